@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sdc_b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline workload (BASELINE.json configs[1], "C2"): Series.rolling(window=100).mean() on a
+100 M-row float64 column per GPU.  A "step" is one pass of the rolling kernel over the column.
+Prints ONE JSON line (see the contract in DESIGN.md, "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_ROWS = 100_000_000
+WINDOW = 100
+BYTES_PER_ROW = 16          # algorithmic: 8 read + 8 written
+WORKLOAD = "C2: Series.rolling(100).mean(), 100M float64 rows per GPU, min_periods=None"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_column(rank=0):
+    return np.random.default_rng(1 + rank).random(N_ROWS)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_rolling_mean(x, repeats):
+    """The oracle (restated reference algorithm, numba prange over all host threads)."""
+    import numba
+    from oracle import rolling as orolling
+    orolling.rolling(x[:100_000], "mean", WINDOW)       # compile
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orolling.rolling(x, "mean", WINDOW)
+        best = min(best, time.perf_counter() - t0)
+    return best, numba.config.NUMBA_NUM_THREADS, numba.threading_layer()
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself cannot be
+    imported or compiled in this image) on the box's host cores, same config / metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numba
+    from oracle import rolling as orolling
+    x = make_column(0)
+    orolling.rolling(x[:100_000], "mean", WINDOW)
+    for _ in range(args.warmup):
+        orolling.rolling(x, "mean", WINDOW)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orolling.rolling(x, "mean", WINDOW)
+    dt = time.perf_counter() - t0
+    value = N_ROWS * args.steps / dt
+    cores = numba.config.NUMBA_NUM_THREADS
+    sample = "full workload: %d rows per step, %d steps" % (N_ROWS, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": "rolling_mean_rows_per_s", "value": value, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows": N_ROWS, "window": WINDOW},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample,
+                         "threading_layer": numba.threading_layer()},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from sdc_b200 import native
+    from sdc_b200.rolling import rolling_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = native.load()
+
+    x_host = make_column(rank)
+    col = torch.from_numpy(x_host).to(dev)
+    out = torch.empty(N_ROWS, dtype=torch.float64, device=dev)
+    halo_n = WINDOW - 1
+    halo = torch.empty(halo_n, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        # row-sharded series: rank r's window needs rank r-1's last win-1 rows
+        h = None
+        if world > 1:
+            ops = []
+            if rank + 1 < world:
+                ops.append(dist.P2POp(dist.isend, col[N_ROWS - halo_n:], rank + 1))
+            if rank > 0:
+                ops.append(dist.P2POp(dist.irecv, halo, rank - 1))
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            h = halo if rank > 0 else None
+        rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=h, row_offset=rank * N_ROWS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = native.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = native.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * N_ROWS * args.steps / (total_ms * 1e-3)
+
+    # kernel-only duration for the roofline: events directly around the launch (N=1: == step)
+    kern_ms = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=None, row_offset=0)
+        b.record()
+        torch.cuda.synchronize()
+        kern_ms.append(a.elapsed_time(b))
+    kern = float(np.mean(kern_ms))
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_ROW * N_ROWS / (kern * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through the C-ABI host entry point (pinned), copies inside the timed region
+    e2e = None
+    if True:
+        import ctypes as ct
+        nbytes = N_ROWS * 8
+        pin_in, pin_out = ct.c_void_p(), ct.c_void_p()
+        native.check(lib.sdcb200_host_alloc(ct.byref(pin_in), nbytes))
+        native.check(lib.sdcb200_host_alloc(ct.byref(pin_out), nbytes))
+        ct.memmove(pin_in.value, x_host.ctypes.data, nbytes)
+        def e2e_step():
+            native.check(lib.sdcb200_host_rolling(1, 9, pin_in.value, pin_out.value, N_ROWS, WINDOW, WINDOW, 1))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res = np.ctypeslib.as_array(ct.cast(pin_out.value, ct.POINTER(ct.c_double)), shape=(N_ROWS,))
+        check = float(np.nanmean(res[::1000]))
+        e2e = {"value": world * N_ROWS * e2e_steps / float(tt.item()), "unit": "rows/s",
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+               "api": "sdcb200_host_rolling (pinned host buffers, 3-stream chunk pipeline)",
+               "result_check_mean": check}
+        lib.sdcb200_host_free(pin_in)
+        lib.sdcb200_host_free(pin_out)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        best, cores, layer = cpu_rolling_mean(x_host, 5)
+        cpu = {"value": N_ROWS / best, "unit": "rows/s", "cores": cores, "kind": "port",
+               "sample": "full workload (100M rows), best of 5", "threading_layer": layer}
+
+    if rank == 0:
+        line = {
+            "metric": "rolling_mean_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rows_per_gpu": N_ROWS, "window": WINDOW,
+                       "l2": "inputs (800 MB in + 800 MB out per step) larger than L2",
+                       "multi_gpu": "row-sharded series, win-1 halo rows from the previous rank (NCCL send/recv)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "rolling_scan_kernel<MEAN,f64>", "kernel_ms": kern,
+                         "algorithmic_bytes_per_launch": BYTES_PER_ROW * N_ROWS},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "ms_per_step_each": per_step,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,101 @@
+/*
+ * sdc_b200.h -- C ABI of libsdc_b200.so, the B200 (sm_100a) relational-kernel
+ * backend for the data-parallel hot path of IntelPython/sdc.
+ *
+ * Conventions
+ *   - Plain C types only.  `stream` is a cudaStream_t passed as void* (NULL = the
+ *     legacy default stream).  Every function returns an int32 status
+ *     (SDCB200_OK == 0); `sdcb200_last_error()` gives the message of the last
+ *     failure on the calling thread.  (The reference natives return void and have
+ *     no error path -- sdc/native/module.cpp:31-92 -- so user-visible argument
+ *     errors are still raised by the Python layer before the call.)
+ *   - Functions named `sdcb200_<op>` take DEVICE pointers and are asynchronous on
+ *     `stream`.  Functions named `sdcb200_host_<op>` take HOST pointers (what the
+ *     reference's natives receive from Numba: NumPy buffers), stage through
+ *     pinned memory and return after the result is in the caller's buffer.
+ *   - The symbols at the end with the reference's own names
+ *     (`parallel_stable_argsort_u64f64`, `stable_argsort`, ...) have the exact
+ *     signatures the reference binds through ctypes / llvmlite.add_symbol, so
+ *     they can replace `sdc.concurrent_sort` / `sdc.hstr_ext` entry points 1:1.
+ *
+ * Reference citations are relative to /root/reference (IntelPython/sdc).
+ */
+#ifndef SDC_B200_H
+#define SDC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+#define SDCB200_OK            0
+#define SDCB200_ERR_ARG       1   /* bad argument (negative length, bad op ...)       */
+#define SDCB200_ERR_CUDA      2   /* a CUDA runtime call or kernel launch failed      */
+#define SDCB200_ERR_NOMEM     3   /* device / pinned allocation failed                */
+#define SDCB200_ERR_CAPACITY  4   /* caller-provided output too small                 */
+#define SDCB200_ERR_HANDLE    5   /* unknown / stale handle                           */
+
+const char* sdcb200_last_error(void);
+const char* sdcb200_version(void);
+/* number of kernel launches issued by this library on the calling process so far
+ * (bench.py reports the delta over the timed region as "gpu_launches").        */
+int64_t sdcb200_launch_count(void);
+int32_t sdcb200_device_info(int32_t* sm_count, int64_t* hbm_bytes, int32_t* cc_major, int32_t* cc_minor);
+
+/* pinned host staging + device scratch used by the host-buffer entry points   */
+int32_t sdcb200_host_alloc(void** p, int64_t bytes);          /* cudaHostAlloc  */
+int32_t sdcb200_host_free(void* p);
+int32_t sdcb200_dev_alloc(void** p, int64_t bytes, void* stream);
+int32_t sdcb200_dev_free(void* p, void* stream);
+int32_t sdcb200_memcpy_h2d(void* dst, const void* src, int64_t bytes, void* stream);
+int32_t sdcb200_memcpy_d2h(void* dst, const void* src, int64_t bytes, void* stream);
+int32_t sdcb200_stream_sync(void* stream);
+
+/* ------------------------------------------------------------------ rolling
+ * Series.rolling(window, min_periods).<op>()
+ * replaces gen_sdc_pandas_series_rolling_impl / _minmax_impl / _ddof_impl
+ * (sdc/datatypes/hpat_pandas_series_rolling_functions.py:586-733) and their
+ * instantiations (:736-754).  Output is always float64[n] (:596).
+ *   op       SDCB200_ROLL_*
+ *   dtype    SDCB200_F64 or SDCB200_I64 input column (ints are read as numbers)
+ *   win,minp already validated (0 <= minp <= win), minp defaulted to win by caller
+ *   ddof     used by VAR / STD only
+ *   halo     optional: the `halo_len` rows (same dtype as `in`) that precede in[0] in the global series
+ *            (row-sharded multi-GPU: the previous rank's last win-1 rows, the
+ *            analogue of the per-chunk prelude at :609-617); NULL / 0 otherwise
+ *   row_offset  global row index of in[0] (count's "rows seen < minp" rule, :249-250)
+ */
+#define SDCB200_ROLL_SUM   0
+#define SDCB200_ROLL_MEAN  1
+#define SDCB200_ROLL_VAR   2
+#define SDCB200_ROLL_STD   3
+#define SDCB200_ROLL_COUNT 4
+#define SDCB200_ROLL_MIN   5
+#define SDCB200_ROLL_MAX   6
+
+#define SDCB200_I8  0
+#define SDCB200_U8  1
+#define SDCB200_I16 2
+#define SDCB200_U16 3
+#define SDCB200_I32 4
+#define SDCB200_U32 5
+#define SDCB200_I64 6
+#define SDCB200_U64 7
+#define SDCB200_F32 8
+#define SDCB200_F64 9
+
+int32_t sdcb200_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
+                        int64_t win, int64_t minp, int64_t ddof,
+                        const void* halo, int64_t halo_len, int64_t row_offset,
+                        void* stream);
+/* host-buffer form: chunks the column through pinned staging, overlapping H2D,
+ * the kernel and D2H on three streams.                                          */
+int32_t sdcb200_host_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
+                             int64_t win, int64_t minp, int64_t ddof);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDC_B200_H */

@@ -1,0 +1,80 @@
+"""ctypes binding of libsdc_b200.so (the C ABI declared in include/sdc_b200.h).
+
+This is the analogue of the reference's FFI idiom A (sdc/functions/sort.py:39-72:
+`ct.cast(address, CFUNCTYPE)` over symbols published by a native module) -- here the
+symbols come straight from a plain shared library.  There is no CPU fallback: if the
+library is missing or a CUDA call fails, an exception is raised.
+"""
+import ctypes as ct
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsdc_b200.so")
+
+OK = 0
+ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
+DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
+               "int64": 6, "uint64": 7, "float32": 8, "float64": 9}
+
+_i32, _i64, _vp, _u8 = ct.c_int32, ct.c_int64, ct.c_void_p, ct.c_uint8
+
+# name -> (restype, argtypes); every symbol include/sdc_b200.h declares
+SIGNATURES = {
+    "sdcb200_last_error": (ct.c_char_p, []),
+    "sdcb200_version": (ct.c_char_p, []),
+    "sdcb200_launch_count": (_i64, []),
+    "sdcb200_device_info": (_i32, [ct.POINTER(_i32), ct.POINTER(_i64), ct.POINTER(_i32), ct.POINTER(_i32)]),
+    "sdcb200_host_alloc": (_i32, [ct.POINTER(_vp), _i64]),
+    "sdcb200_host_free": (_i32, [_vp]),
+    "sdcb200_dev_alloc": (_i32, [ct.POINTER(_vp), _i64, _vp]),
+    "sdcb200_dev_free": (_i32, [_vp, _vp]),
+    "sdcb200_memcpy_h2d": (_i32, [_vp, _vp, _i64, _vp]),
+    "sdcb200_memcpy_d2h": (_i32, [_vp, _vp, _i64, _vp]),
+    "sdcb200_stream_sync": (_i32, [_vp]),
+    "sdcb200_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "sdcb200_host_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                "libsdc_b200.so not found at %s -- build it with "
+                "`python sdc_b200/csrc/build.py` (there is no CPU fallback)" % LIB_PATH)
+        lib = ct.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)        # AttributeError here == ABI drift
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status):
+    if status != OK:
+        msg = load().sdcb200_last_error().decode("utf-8", "replace")
+        raise NativeError("libsdc_b200 status %d: %s" % (status, msg))
+
+
+def launch_count():
+    return int(load().sdcb200_launch_count())
+
+
+def fn_address(name):
+    """Raw address of an exported function (for Numba: ctypes CFUNCTYPE / llvmlite.add_symbol)."""
+    return ct.cast(getattr(load(), name), ct.c_void_p).value
+
+
+def current_stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

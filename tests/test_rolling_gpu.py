@@ -1,0 +1,192 @@
+"""GPU parity: csrc/rolling.cu (through the C ABI) against the oracle and the golden fixtures."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import assert_close, golden_inputs, rolling_golden_cases
+from oracle import rolling as orolling
+
+pytestmark = pytest.mark.gpu
+
+OPS = ("sum", "mean", "var", "std", "count", "min", "max")
+# float64 sum/mean/std/var: 1e-9 relative (north_star); the abs term covers results that are
+# differences of O(window) magnitudes (std/var near zero)
+RTOL, ATOL = 1e-9, 1e-9
+
+
+def _dev(x):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _tol(op):
+    return (0.0, 0.0) if op in ("count", "min", "max") else (RTOL, ATOL)
+
+
+def test_golden_through_host_abi():
+    from sdc_b200.rolling import rolling_host
+    n = 0
+    for op, data, w, mp, ddof, want in rolling_golden_cases():
+        got = rolling_host(data, op, w, mp, ddof)
+        rt, at = _tol(op)
+        assert_close(got, want, rtol=rt, atol=at, msg="%s w=%d mp=%d ddof=%d %s" % (op, w, mp, ddof, data))
+        n += 1
+    assert n > 1000
+
+
+def test_examples_literals():
+    from sdc_b200.rolling import rolling
+    for op, (data, win, want) in golden_inputs.EXAMPLES_ROLLING.items():
+        minp = 0 if op == "count" else None       # see tests/test_oracle_rolling.py
+        got = getattr(rolling(pd.Series(data), win, minp), op)()
+        assert_close(got.to_numpy(), want, rtol=0, atol=6e-7, msg=op)
+    ex = golden_inputs.EXAMPLE_DF_ROLLING_MEAN
+    got = rolling(pd.DataFrame(ex["input"]), ex["window"]).mean()
+    for col in ex["input"]:
+        assert_close(got[col].to_numpy(), ex["expected"][col], rtol=0, atol=6e-7, msg=col)
+
+
+def _mixed(n, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.random(n) * 200 - 100
+    if n > 10:
+        x[rng.integers(0, n, max(1, n // 50))] = np.nan
+        x[rng.integers(0, n, max(1, n // 200))] = np.inf
+        x[rng.integers(0, n, max(1, n // 200))] = -np.inf
+        x[rng.integers(0, n, max(1, n // 100))] = 0.0
+        x[rng.integers(0, n, max(1, n // 300))] = -0.0
+    return x
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 63, 64, 65, 1947, 1948, 1949, 2048, 4097, 100003])
+def test_device_vs_oracle_sizes(n):
+    from sdc_b200.rolling import rolling_device
+    x = _mixed(n, n)
+    d = _dev(x)
+    for win in (1, 2, 3, 5, 31, 32, 33, 63, 64, 65, 100, 127, 128, 129, 191, 192, 193, 194, 200, 257, 1000, 1025, 4096, 4097):
+        for mp in sorted({0, 1, win // 2, win}):
+            for op in OPS:
+                got = rolling_device(d, op, win, mp, 1).cpu().numpy()
+                want = orolling.rolling(x, op, win, mp, 1, nchunks=1)
+                rt, at = _tol(op)
+                assert_close(got, want, rtol=rt, atol=at, msg="%s n=%d w=%d mp=%d" % (op, n, win, mp))
+
+
+def test_window_zero_and_ddof():
+    from sdc_b200.rolling import rolling_device
+    x = _mixed(1000, 5)
+    d = _dev(x)
+    for op in OPS:
+        got = rolling_device(d, op, 0, 0, 1).cpu().numpy()
+        want = orolling.rolling(x, op, 0, 0, 1, nchunks=1)
+        assert_close(got, want, rtol=0, atol=0, msg=op)
+    for ddof in (0, 1, 2, 5, 100):
+        for op in ("var", "std"):
+            got = rolling_device(d, op, 10, 3, ddof).cpu().numpy()
+            want = orolling.rolling(x, op, 10, 3, ddof, nchunks=1)
+            assert_close(got, want, rtol=RTOL, atol=ATOL, msg="%s ddof=%d" % (op, ddof))
+
+
+def test_int64_column():
+    from sdc_b200.rolling import rolling_device
+    x = np.random.default_rng(3).integers(-1000, 1000, 50_000)
+    d = _dev(x)
+    for op in OPS:
+        got = rolling_device(d, op, 100, 100, 1).cpu().numpy()
+        want = orolling.rolling(x, op, 100, 100, 1, nchunks=1)
+        rt, at = _tol(op)
+        assert_close(got, want, rtol=rt, atol=at, msg=op)
+
+
+def test_unaligned_pointers():
+    import torch
+    from sdc_b200.rolling import rolling_device
+    x = _mixed(10_001, 9)
+    base = _dev(np.concatenate([[0.0], x]))
+    col = base[1:]                       # 8-byte aligned only: no TMA, plain loads
+    outbuf = torch.empty(10_002, dtype=torch.float64, device="cuda")
+    for op in OPS:
+        got = rolling_device(col, op, 100, 50, 1, out=outbuf[1:]).cpu().numpy()
+        want = orolling.rolling(x, op, 100, 50, 1, nchunks=1)
+        rt, at = _tol(op)
+        assert_close(got, want, rtol=rt, atol=at, msg=op)
+
+
+@pytest.mark.parametrize("split", [1, 50, 99, 100, 5000])
+def test_row_sharded_halo(split):
+    """Second shard + the previous shard's last win-1 rows == the tail of the whole series."""
+    from sdc_b200.rolling import rolling_device
+    x = _mixed(20_000, 11)
+    win = 100
+    d = _dev(x)
+    for op in OPS:
+        for mp in (0, 100):
+            whole = rolling_device(d, op, win, mp, 1).cpu().numpy()
+            h0 = max(0, split - (win - 1))
+            got = rolling_device(d[split:].clone(), op, win, mp, 1, halo=d[h0:split].clone(),
+                                 row_offset=split).cpu().numpy()
+            assert_close(got, whole[split:], rtol=1e-12, atol=1e-12, msg="%s split=%d" % (op, split))
+
+
+def test_host_abi_chunked_large():
+    """Host entry point with several pipeline chunks (n > 8 Mi rows)."""
+    from sdc_b200.rolling import rolling_host
+    n = (1 << 23) * 2 + 12345
+    x = np.random.default_rng(1).random(n)
+    x[::100003] = np.nan
+    for op in ("mean", "max", "count"):
+        got = rolling_host(x, op, 100, 100, 1)
+        want = orolling.rolling(x, op, 100, 100, 1)
+        rt, at = _tol(op)
+        assert_close(got, want, rtol=rt, atol=at, msg=op)
+
+
+def test_c2_full_size_mean_sum_std():
+    """BASELINE config C2: 100 M float64, window 100 -- whole-column parity with the oracle."""
+    from sdc_b200.rolling import rolling_device
+    n = 100_000_000
+    x = np.random.default_rng(1).random(n)
+    d = _dev(x)
+    for op in ("mean", "sum", "std"):
+        got = rolling_device(d, op, 100, 100, 1).cpu().numpy()
+        want = orolling.rolling(x, op, 100, 100, 1)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        err = np.max(np.abs(got[ok] - want[ok]) / np.maximum(np.abs(want[ok]), 1e-300))
+        assert err < 1e-9, (op, err)
+
+
+def test_adversarial_reference_perf_data():
+    """The reference perf generator's data (choice over test_global_input_data_float64): exact ops."""
+    from sdc_b200.rolling import rolling_device
+    vals = np.asarray(sum(golden_inputs.GLOBAL_FLOAT64, []), dtype=np.float64)
+    x = np.random.default_rng(1).choice(vals, 1_000_000)
+    d = _dev(x)
+    for op in ("count", "min", "max"):
+        got = rolling_device(d, op, 100, 100, 1).cpu().numpy()
+        want = orolling.rolling(x, op, 100, 100, 1)
+        assert_close(got, want, rtol=0, atol=0, msg=op)
+    # sum / mean: NaN pattern (the non-finite counters) must agree exactly
+    for op in ("sum", "mean"):
+        got = rolling_device(d, op, 100, 30, 1).cpu().numpy()
+        want = orolling.rolling(x, op, 100, 30, 1)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), op
+
+
+def test_rolling_class_api_and_errors():
+    from sdc_b200.rolling import rolling
+    s = pd.Series([4., 3., 5., 2., 6.], index=[4, 3, 2, 1, 0], name="A")
+    r = rolling(s, 3).mean()
+    pd.testing.assert_series_equal(r, s.rolling(3).mean())
+    df = pd.DataFrame({"A": [4, 3, 5, 2, 6], "B": [-4., -3., -5., -2., np.nan]})
+    pd.testing.assert_frame_equal(rolling(df, 2, 1).sum(), df.rolling(2, 1).sum())
+    with pytest.raises(ValueError, match="window must be non-negative"):
+        rolling(s, -1)
+    with pytest.raises(ValueError, match="min_periods must be >= 0"):
+        rolling(s, 1, -1)
+    with pytest.raises(ValueError, match="min_periods must be <= window"):
+        rolling(s, 1, 2)
+    with pytest.raises(ValueError, match="center"):
+        rolling(s, 1, 1, center=True)
+    with pytest.raises(TypeError, match="ddof"):
+        rolling(s, 3).std(ddof="1")
