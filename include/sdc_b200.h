@@ -95,6 +95,44 @@ int32_t sdcb200_rolling(int32_t op, int32_t dtype, const void* in, double* out, 
 int32_t sdcb200_host_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
                              int64_t win, int64_t minp, int64_t ddof);
 
+/* ------------------------------------------------------------------ sort / argsort / gather
+ * In-place ascending sort with NaN last: replaces parallel_sort_<t> / parallel_stable_sort_<t>
+ * (sdc/native/sort.cpp:119-121, sdc/native/stable_sort.cpp:308-310; exported at
+ * sdc/native/module.cpp:33-61).  `dtype` is one of the ten SDCB200_* codes.                      */
+int32_t sdcb200_sort(int32_t dtype, void* keys, int64_t n, void* stream);
+/* Stable argsort: index_out[i] = row of the i-th element in the requested order; NaN last for
+ * ascending AND descending, -0.0 == +0.0, ties in input order.  Replaces
+ * parallel_[stable_]argsort_u64<t> (sdc/native/sort.cpp:94-104, stable_sort.cpp:283-293;
+ * called from sdc/functions/sort.py:289-310).                                                     */
+int32_t sdcb200_argsort(int32_t dtype, const void* keys, int64_t n, int32_t ascending, int64_t* index_out, void* stream);
+/* dst[i] = src[idx[i]] for rows of elem_size 1/2/4/8 bytes: numpy_like.take
+ * (sdc/functions/numpy_like.py:1359-1388) and `self._data[sorted_index]`
+ * (sdc/datatypes/hpat_pandas_series_functions.py:3954-3955).                                      */
+int32_t sdcb200_gather(int32_t elem_size, const void* src, const int64_t* idx, int64_t n, void* dst, void* stream);
+int32_t sdcb200_host_sort(int32_t dtype, void* keys, int64_t n);
+int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t ascending, int64_t* index_out);
+
+/* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
+ * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
+ * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and
+ * cannot run on a GPU: not provided.                                                              */
+#define SDCB200_DECL_REF_SORT(T)                                                         \
+    void parallel_sort_##T(void* begin, uint64_t len);                                   \
+    void parallel_stable_sort_##T(void* begin, uint64_t len);                            \
+    void parallel_argsort_u64##T(void* index, void* begin, uint64_t len, uint8_t ascending);        \
+    void parallel_stable_argsort_u64##T(void* index, void* begin, uint64_t len, uint8_t ascending);
+SDCB200_DECL_REF_SORT(i8)
+SDCB200_DECL_REF_SORT(u8)
+SDCB200_DECL_REF_SORT(i16)
+SDCB200_DECL_REF_SORT(u16)
+SDCB200_DECL_REF_SORT(i32)
+SDCB200_DECL_REF_SORT(u32)
+SDCB200_DECL_REF_SORT(i64)
+SDCB200_DECL_REF_SORT(u64)
+SDCB200_DECL_REF_SORT(f32)
+SDCB200_DECL_REF_SORT(f64)
+void set_number_of_threads(uint64_t threads);
+
 #ifdef __cplusplus
 }
 #endif

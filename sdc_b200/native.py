@@ -33,7 +33,21 @@ SIGNATURES = {
     "sdcb200_stream_sync": (_i32, [_vp]),
     "sdcb200_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "sdcb200_host_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64]),
+    "sdcb200_sort": (_i32, [_i32, _vp, _i64, _vp]),
+    "sdcb200_argsort": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp]),
+    "sdcb200_gather": (_i32, [_i32, _vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_host_sort": (_i32, [_i32, _vp, _i64]),
+    "sdcb200_host_argsort": (_i32, [_i32, _vp, _i64, _i32, _vp]),
+    "set_number_of_threads": (None, [ct.c_uint64]),
 }
+
+# the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)
+REF_SORT_TYPES = ("i8", "u8", "i16", "u16", "i32", "u32", "i64", "u64", "f32", "f64")
+for _t in REF_SORT_TYPES:
+    SIGNATURES["parallel_sort_" + _t] = (None, [_vp, ct.c_uint64])
+    SIGNATURES["parallel_stable_sort_" + _t] = (None, [_vp, ct.c_uint64])
+    SIGNATURES["parallel_argsort_u64" + _t] = (None, [_vp, _vp, ct.c_uint64, _u8])
+    SIGNATURES["parallel_stable_argsort_u64" + _t] = (None, [_vp, _vp, ct.c_uint64, _u8])
 
 
 class NativeError(RuntimeError):
