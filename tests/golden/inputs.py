@@ -58,3 +58,17 @@ EXAMPLES_GROUPBY = {   # index is [1, 2, 3] for all
     "count": {"B": [1, 3, 3], "C": [0, 3, 4]},    # on EXAMPLE_GROUPBY_COUNT_DF
 }
 EXAMPLE_SERIES_GROUPBY = {"S": [390., 350., 30., 20.], "by": [0, 1, 0, 1], "mean": [210.0, 185.0], "index": [0, 1]}
+
+# sdc/tests/test_groupby.py:58-64 (_default_df_numeric_data) and :83-100 (key dtypes)
+GROUPBY_DEFAULT_DF = {
+    'A': [2, 1, 2, 1, 2, 2, 1, 0, 3, 1, 3],
+    'B': list(range(11)),
+    'C': [float(i) for i in range(11)],
+    'D': [NAN, 2., -1.3, NAN, 3.5, 0, 10, 0.42, NAN, -2.5, 23],
+    'E': [INF, 2., -1.3, -INF, 3.5, 0, 10, 0.42, NAN, -2.5, 23],
+}
+GROUPBY_KEY_DTYPES = {
+    'int': [2, 1, 1, 1, 2, 2, 1, 0, 3, 1, 3],
+    'float': [2, 1, 1, 1, 2, 2, 1, 3, NAN, 1, NAN],
+    'string': ['b', 'a', 'a', 'a', 'b', 'b', 'a', ' ', None, 'a', None],
+}

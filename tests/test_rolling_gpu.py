@@ -180,11 +180,22 @@ def test_adversarial_reference_perf_data():
         got = rolling_device(d, op, 100, 100, 1).cpu().numpy()
         want = orolling.rolling(x, op, 100, 100, 1)
         assert_close(got, want, rtol=0, atol=0, msg=op)
-    # sum / mean: NaN pattern (the non-finite counters) must agree exactly
+    # sum / mean: rows with fewer than min_periods finite values in the window must be NaN (the
+    # non-finite counters).  Elsewhere finfo.max + finfo.max overflows in BOTH implementations (the
+    # reference's running sum turns inf and stays inf for the rest of its chunk, :1237, :1297), so
+    # the values themselves are not comparable on this data ...
+    nfin = orolling.rolling(np.where(np.isfinite(x), 1.0, np.nan), "count", 100, 0, 1)
     for op in ("sum", "mean"):
         got = rolling_device(d, op, 100, 30, 1).cpu().numpy()
-        want = orolling.rolling(x, op, 100, 30, 1)
-        assert np.array_equal(np.isnan(got), np.isnan(want)), op
+        assert np.all(np.isnan(got[nfin < 30])), op
+    # ... so the same draw with the two overflowing magnitudes scaled down checks the full pattern
+    # and the values
+    y = np.where(np.abs(x) > 1e300, np.sign(x) * 1e10, x)
+    dy = _dev(y)
+    for op in ("sum", "mean", "var", "std"):
+        got = rolling_device(dy, op, 100, 30, 1).cpu().numpy()
+        want = orolling.rolling(y, op, 100, 30, 1)
+        check(op, got, want, y, 100, msg=op)
 
 
 def test_rolling_class_api_and_errors():
