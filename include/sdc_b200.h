@@ -112,6 +112,33 @@ int32_t sdcb200_gather(int32_t elem_size, const void* src, const int64_t* idx, i
 int32_t sdcb200_host_sort(int32_t dtype, void* keys, int64_t n);
 int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t ascending, int64_t* index_out);
 
+/* ------------------------------------------------------------------ groupby
+ * df.groupby(key).{sum,mean,min,max,count,var,std}() / Series.groupby(arr).<agg>():
+ * replaces sdc_pandas_dataframe_groupby (sdc/datatypes/hpat_pandas_dataframe_functions.py:2993-3106),
+ * merge_groupby_dicts_inplace and the per-group take + reduce loop
+ * (sdc/datatypes/hpat_pandas_groupby_functions.py:58-73, 194-283) with one hash aggregate.
+ *   key_dtype        SDCB200_I64 or SDCB200_F64 (NaN keys are skipped, -0.0 == +0.0)
+ *   cols/col_dtypes  ncols (<= 32) value columns, each SDCB200_F64 or SDCB200_I64, device pointers
+ *   agg_mask         OR of SDCB200_AGG_*: every requested aggregate is produced for every column
+ *   sort             1: result ordered by key (stable argsort, groupby_functions.py:209-210);
+ *                    0: first-appearance order (the merged dict's order, :58-73)
+ *   expected_groups  hint (<= 0: unknown) used to size the hash table / pick the shared-memory path
+ * Result values are float64 except: count -> int64; sum/min/max of an int64 column -> int64.
+ * The result lives in a handle; copy keys / values out (device or host destination) and free it.  */
+#define SDCB200_AGG_SUM   1u
+#define SDCB200_AGG_MEAN  2u
+#define SDCB200_AGG_MIN   4u
+#define SDCB200_AGG_MAX   8u
+#define SDCB200_AGG_COUNT 16u
+#define SDCB200_AGG_VAR   32u
+#define SDCB200_AGG_STD   64u
+int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
+                        const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
+                        int64_t expected_groups, void* stream, int64_t* handle_out, int64_t* ngroups_out);
+int32_t sdcb200_groupby_keys(int64_t handle, void* dst, int32_t dst_is_host, void* stream);
+int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* dst, int32_t dst_is_host, void* stream);
+int32_t sdcb200_groupby_free(int64_t handle);
+
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
  * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and

@@ -1,0 +1,201 @@
+"""GPU parity: csrc/groupby.cu (hash groupby-aggregate) against the oracle's dict-of-row-lists restatement.
+
+Keys, counts, min/max and integer sums are compared exactly; float sum/mean/var/std to 1e-9 relative
+(north_star) -- the reduction order differs (atomics vs the reference's per-group serial loop).
+"""
+import numpy as np
+import pandas as pd
+import pytest
+
+from helpers import assert_close, golden_inputs
+from oracle import groupby as ogroupby
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ("min", "max", "count")
+
+
+def _compare(got_keys, got, want_keys, want, agg, msg=""):
+    np.testing.assert_array_equal(np.asarray(got_keys), np.asarray(want_keys), err_msg=msg + " keys")
+    for c in want:
+        g, w = np.asarray(got[c]), np.asarray(want[c])
+        assert g.dtype == w.dtype, "%s %s %s dtype %s vs %s" % (msg, agg, c, g.dtype, w.dtype)
+        if agg in EXACT or g.dtype.kind in "iu":
+            np.testing.assert_array_equal(g, w, err_msg="%s %s %s" % (msg, agg, c))
+        else:
+            # inf - inf style NaNs appear on both sides the same way (sum of +inf and -inf)
+            assert_close(g, w, rtol=1e-9, atol=1e-12, msg="%s %s %s" % (msg, agg, c))
+
+
+def _host(keys, cols, agg, sort=True, ddof=1, expected_groups=0):
+    from sdc_b200.groupby import groupby_host
+    rk, res = groupby_host(keys, cols, (agg,), sort, ddof, expected_groups)
+    return rk, res[agg]
+
+
+def test_example_literals():
+    # examples/dataframe/groupby/dataframe_groupby_{sum,mean,min,max,std,var,count}.py
+    for agg, want in golden_inputs.EXAMPLES_GROUPBY.items():
+        src = golden_inputs.EXAMPLE_GROUPBY_COUNT_DF if agg == "count" else golden_inputs.EXAMPLE_GROUPBY_DF
+        df = pd.DataFrame(src)
+        keys, res = _host(df["A"].to_numpy(), {c: df[c].to_numpy() for c in "BC"}, agg)
+        np.testing.assert_array_equal(keys, [1, 2, 3])
+        for c in ("B", "C"):
+            assert_close(res[c], want[c], rtol=0, atol=6e-7, msg="%s %s" % (agg, c))
+    ex = golden_inputs.EXAMPLE_SERIES_GROUPBY            # examples/series/series_groupby.py
+    keys, res = _host(np.asarray(ex["by"]), {"S": np.asarray(ex["S"])}, "mean")
+    np.testing.assert_array_equal(keys, ex["index"])
+    assert_close(res["S"], ex["mean"], rtol=1e-15, atol=0)
+
+
+@pytest.mark.parametrize("agg", ogroupby.AGGS)
+@pytest.mark.parametrize("sort", [True, False])
+def test_default_df(agg, sort):
+    # sdc/tests/test_groupby.py:58-64, 123-132, 152-212, 244-316: int and float columns with NaN / +-inf
+    df = pd.DataFrame(golden_inputs.GROUPBY_DEFAULT_DF)
+    cols = {c: df[c].to_numpy() for c in "BCDE"}
+    gk, got = _host(df["A"].to_numpy(), cols, agg, sort)
+    wk, want = ogroupby.groupby_agg(df["A"].to_numpy(), cols, agg, sort)
+    _compare(gk, got, wk, want, agg)
+
+
+def test_key_dtypes_float_nan_keys_skipped():
+    # sdc/tests/test_groupby.py:83-100
+    df = pd.DataFrame(golden_inputs.GROUPBY_DEFAULT_DF)
+    for kind in ("int", "float"):
+        key = np.asarray(golden_inputs.GROUPBY_KEY_DTYPES[kind])
+        cols = {c: df[c].to_numpy() for c in "BCDE"}
+        for agg in ("count", "sum", "max"):
+            gk, got = _host(key, cols, agg)
+            wk, want = ogroupby.groupby_agg(key, cols, agg)
+            assert gk.dtype == key.dtype
+            _compare(gk, got, wk, want, agg, kind)
+    # -0.0 and +0.0 are one group; +-inf are ordinary keys
+    key = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.5, -0.0, np.inf])
+    v = {"v": np.arange(8.0)}
+    gk, got = _host(key, v, "sum")
+    wk, want = ogroupby.groupby_agg(key, v, "sum")
+    _compare(gk, got, wk, want, "sum", "zeros")
+    assert len(gk) == 4
+
+
+def test_sort_flag_1000_rows_20_groups():
+    # sdc/tests/test_groupby.py:102-121 (seed 0); sort=False = first-appearance order (dict order)
+    rng = np.random.RandomState(0)
+    a = rng.choice(np.arange(20), 1000)
+    cols = {"B": np.arange(1000)}
+    for sort in (True, False):
+        gk, got = _host(a, cols, "min", sort)
+        wk, want = ogroupby.groupby_agg(a, cols, "min", sort, nchunks=4)
+        _compare(gk, got, wk, want, "min", "sort=%s" % sort)
+
+
+@pytest.mark.parametrize("n,groups", [(1, 1), (31, 7), (4095, 1000), (4096, 3), (200_000, 1000), (300_000, 5000),
+                                      (500_000, 200_000)])
+def test_random_sizes_all_aggs(n, groups):
+    rng = np.random.default_rng(n)
+    a = rng.integers(-groups // 2, groups - groups // 2, n)
+    b = rng.standard_normal(n) * 100
+    if n > 100:
+        b[rng.integers(0, n, n // 100)] = np.nan
+    c = rng.integers(-10**12, 10**12, n)
+    cols = {"b": b, "c": c}
+    for agg in ogroupby.AGGS:
+        for sort in (True, False):
+            gk, got = _host(a, cols, agg, sort)
+            wk, want = ogroupby.groupby_agg(a, cols, agg, sort)
+            _compare(gk, got, wk, want, agg, "n=%d g=%d sort=%s" % (n, groups, sort))
+
+
+def test_expected_groups_hint_paths_agree():
+    """Shared-memory pre-aggregation, direct global table and a too-small hint (regrow) give one answer."""
+    rng = np.random.default_rng(7)
+    n = 400_000
+    a = rng.integers(0, 50_000, n)
+    cols = {"b": rng.random(n)}
+    wk, want = ogroupby.groupby_agg(a, cols, "sum")
+    for hint in (0, 10, 1000, 50_000, 10_000_000):
+        gk, got = _host(a, cols, "sum", True, 1, hint)
+        _compare(gk, got, wk, want, "sum", "hint=%d" % hint)
+
+
+def test_empty_and_degenerate():
+    from sdc_b200.groupby import groupby_host
+    rk, res = groupby_host(np.zeros(0, dtype=np.int64), {"v": np.zeros(0)}, ("sum", "count"))
+    assert len(rk) == 0 and len(res["sum"]["v"]) == 0 and res["count"]["v"].dtype == np.int64
+    # all keys NaN -> no groups
+    rk, res = groupby_host(np.full(100, np.nan), {"v": np.ones(100)}, ("sum",))
+    assert len(rk) == 0
+    # an all-NaN group: sum 0, mean NaN, min/max NaN, count 0, var NaN
+    k = np.array([1, 1, 2, 2])
+    v = {"v": np.array([np.nan, np.nan, 1.0, 3.0])}
+    for agg in ogroupby.AGGS:
+        gk, got = _host(k, v, agg)
+        wk, want = ogroupby.groupby_agg(k, v, agg)
+        _compare(gk, got, wk, want, agg, "all-nan group")
+    # the table's empty-slot sentinel is a legal int64 key
+    sentinel = np.array([0x7ff8dead0000beef], dtype=np.uint64).view(np.int64)[0]
+    k = np.array([sentinel, 5, sentinel, -1, 5], dtype=np.int64)
+    v = {"v": np.array([1.0, 2.0, 3.0, 4.0, 5.0])}
+    for sort in (True, False):
+        gk, got = _host(k, v, "sum", sort)
+        wk, want = ogroupby.groupby_agg(k, v, "sum", sort)
+        _compare(gk, got, wk, want, "sum", "sentinel key")
+    # no value columns: keys only
+    rk, res = groupby_host(np.array([3, 1, 3]), {}, ("count",))
+    np.testing.assert_array_equal(rk, [1, 3])
+
+
+def test_multi_agg_one_pass_and_many_columns():
+    from sdc_b200.groupby import groupby_host
+    rng = np.random.default_rng(3)
+    n = 100_000
+    a = rng.integers(0, 300, n)
+    cols = {"c%d" % i: rng.standard_normal(n) for i in range(12)}
+    aggs = ("sum", "mean", "min", "max", "count")
+    rk, res = groupby_host(a, cols, aggs)
+    for agg in aggs:
+        wk, want = ogroupby.groupby_agg(a, cols, agg)
+        _compare(rk, res[agg], wk, want, agg, "multi")
+
+
+def test_dataframe_and_series_api():
+    from sdc_b200.groupby import groupby
+    df = pd.DataFrame(golden_inputs.GROUPBY_DEFAULT_DF)
+    pd.testing.assert_frame_equal(groupby(df, "A").count(), df.groupby("A").count())
+    pd.testing.assert_frame_equal(groupby(df, "A").max(), df.groupby("A").max())
+    pd.testing.assert_frame_equal(groupby(df, "A")["C", "D"].min(), df.groupby("A")[["C", "D"]].min())
+    pd.testing.assert_series_equal(groupby(df, "A")["D"].mean(), df.groupby("A")["D"].mean())
+    pd.testing.assert_frame_equal(groupby(df, "A", sort=False).sum()[["B", "C", "D"]],
+                                  df.groupby("A", sort=False).sum()[["B", "C", "D"]])
+    pd.testing.assert_frame_equal(groupby(df, "A").std()[["B", "C", "D"]], df.groupby("A").std()[["B", "C", "D"]])
+    s = pd.Series([390., 350., 30., 20.], name="S")
+    pd.testing.assert_series_equal(groupby(s, [0, 1, 0, 1]).mean(), s.groupby(np.array([0, 1, 0, 1])).mean())
+    with pytest.raises(IndexError):
+        groupby(df, "A")["C", "D"]["C"]
+    with pytest.raises(ValueError):
+        groupby(s, [0, 1])
+    with pytest.raises(TypeError):
+        groupby(df, ["A", "B"])
+
+
+def test_c1_full_size_sum_and_multi():
+    """BASELINE config C1: 10 M rows, int64 key with 1 K groups, one float64 value column (1 % NaN variant)."""
+    import torch
+    from sdc_b200.groupby import groupby_device
+    rng = np.random.default_rng(0)
+    n = 10_000_000
+    a = rng.integers(0, 1000, n, dtype=np.int64)
+    b = rng.random(n)
+    for variant in ("plain", "nan"):
+        if variant == "nan":
+            b = b.copy()
+            b[rng.integers(0, n, n // 100)] = np.nan
+        dk, res = groupby_device(torch.from_numpy(a).cuda(), [torch.from_numpy(b).cuda()],
+                                 ("sum", "mean", "min", "max", "count"), True, 1, 1000)
+        want = pd.DataFrame({"A": a, "B": b}).groupby("A")["B"].agg(["sum", "mean", "min", "max", "count"])
+        np.testing.assert_array_equal(dk.cpu().numpy(), want.index.to_numpy())
+        for agg in ("sum", "mean"):
+            np.testing.assert_allclose(res[agg][0].cpu().numpy(), want[agg].to_numpy(), rtol=1e-9, atol=0)
+        for agg in ("min", "max", "count"):
+            np.testing.assert_array_equal(res[agg][0].cpu().numpy(), want[agg].to_numpy())

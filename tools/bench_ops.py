@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Per-operator device timings (CUDA events, inputs resident in HBM) for the kernels that are not
+bench.py's headline: groupby (C1), sort / argsort, join (C3).  One JSON line per case on stdout.
+
+    python tools/bench_ops.py [groupby] [sort] [join] [--reps 10]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def timeit(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def emit(name, rows, alg_bytes, med, best, **kw):
+    d = {"case": name, "rows": rows, "ms_median": med, "ms_best": best, "rows_per_s": rows / (med * 1e-3),
+         "alg_GBps": alg_bytes / (med * 1e-3) / 1e9, "frac_of_measured_peak": alg_bytes / (med * 1e-3) / 1e9 / peak()}
+    d.update(kw)
+    print(json.dumps(d), flush=True)
+
+
+def bench_groupby(reps):
+    from sdc_b200.groupby import groupby_device
+    for n, groups in ((10_000_000, 1000), (100_000_000, 1000), (100_000_000, 1_000_000), (100_000_000, 50_000_000)):
+        rng = np.random.default_rng(0)
+        a = torch.from_numpy(rng.integers(0, groups, n, dtype=np.int64)).cuda()
+        b = torch.from_numpy(rng.random(n)).cuda()
+        for aggs in (("sum",), ("sum", "mean", "min", "max", "count")):
+            med, best = timeit(lambda: groupby_device(a, [b], aggs, True, 1, groups), reps)
+            emit("groupby_%s n=%d groups=%d" % ("+".join(aggs), n, groups), n, 16 * n, med, best)
+        del a, b
+
+
+def bench_sort(reps):
+    from sdc_b200.sort import argsort_device, sort_device
+    for n in (10_000_000, 100_000_000, 200_000_000):
+        rng = np.random.default_rng(4)
+        for name, arr in (("i64_full", rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64)),
+                          ("i64_1k", rng.integers(0, 1000, n, dtype=np.int64)),
+                          ("f64", rng.standard_normal(n))):
+            d = torch.from_numpy(arr).cuda()
+            med, best = timeit(lambda: argsort_device(d), reps)
+            emit("argsort_%s n=%d" % (name, n), n, 16 * n, med, best, note="alg bytes = key read + idx written")
+            w = d.clone()
+            med, best = timeit(lambda: sort_device(w.copy_(d)), reps)
+            emit("sort_inplace+copy_%s n=%d" % (name, n), n, 16 * n, med, best)
+            del d, w
+
+
+def bench_join(reps):
+    from sdc_b200.join import join_device
+    nb, npr = 10_000_000, 100_000_000
+    r = torch.from_numpy(np.random.default_rng(2).permutation(nb).astype(np.int64)).cuda()
+    for name, hi in (("hit100", nb), ("hit50", 2 * nb)):
+        l = torch.from_numpy(np.random.default_rng(3).integers(0, hi, npr, dtype=np.int64)).cuda()
+        for how in ("inner", "left"):
+            out = {}
+            def run():
+                out["r"] = join_device(l, r, how)
+            med, best = timeit(run, reps)
+            n_out = out["r"][0].shape[0]
+            emit("join_%s_%s probe=%d build=%d" % (how, name, npr, nb), npr, 8 * (npr + nb) + 16 * n_out, med, best,
+                 n_out=n_out)
+        del l
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    reps = 10
+    if "--reps" in sys.argv:
+        reps = int(sys.argv[sys.argv.index("--reps") + 1])
+        args = [a for a in args if a != str(reps)]
+    which = args or ["groupby", "sort"]
+    for w in which:
+        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join}[w](reps)
