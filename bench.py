@@ -260,7 +260,7 @@ def run_gpu(args):
                        "multi_gpu": "row-sharded series, win-1 halo rows from the previous rank (NCCL send/recv)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "rolling_scan_kernel<MEAN,f64>", "kernel_ms": kern,
+                         "kernel": "rolling_run_kernel<MEAN,f64,R=17>", "kernel_ms": kern,
                          "algorithmic_bytes_per_launch": BYTES_PER_ROW * N_ROWS},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_each": per_step,

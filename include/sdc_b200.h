@@ -139,6 +139,26 @@ int32_t sdcb200_groupby_keys(int64_t handle, void* dst, int32_t dst_is_host, voi
 int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* dst, int32_t dst_is_host, void* stream);
 int32_t sdcb200_groupby_free(int64_t handle);
 
+/* ------------------------------------------------------------------ join
+ * pd.merge(left, right, on=key, how='inner' | 'left') on one int64 / float64 key column.  The
+ * reference snapshot has no merge overload (sdc/hiframes/join.py:34-43 is a stub; every test of
+ * sdc/tests/test_join.py:51-394 is skipped): behaviour follows pandas.merge, the artefact follows
+ * the reference's live indexer convention (_sdc_internal_join,
+ * sdc/datatypes/common_functions.py:225-455): two int64 row-position arrays, -1 = no partner
+ * (how='left'), duplicate keys give the cross product.  Pairs come out in left-row order; the order
+ * of several right matches of one left row is unspecified.  Float keys: NaN == NaN, -0.0 == +0.0
+ * (pandas).  Build (right) side < 2^32 - 1 rows.  The result lives in a handle.                   */
+#define SDCB200_JOIN_INNER 0
+#define SDCB200_JOIN_LEFT  1
+int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                     void* stream, int64_t* handle_out, int64_t* n_out);
+int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_idx, int32_t dst_is_host, void* stream);
+int32_t sdcb200_join_free(int64_t handle, void* stream);
+/* dst[i] = idx[i] < 0 ? NaN : (double)src[idx[i]] -- payload gather of a left join
+ * (setitem_arr_nan, sdc/hiframes/join.py:34-43); src_dtype SDCB200_I64 or SDCB200_F64.            */
+int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int64_t* idx, int64_t n, double* dst,
+                                  void* stream);
+
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
  * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and

@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsdc_b200.so")
 
 OK = 0
+JOIN_HOW = {"inner": 0, "left": 1}
 AGG_BITS = {"sum": 1, "mean": 2, "min": 4, "max": 8, "count": 16, "var": 32, "std": 64}
 ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
@@ -45,6 +46,10 @@ SIGNATURES = {
     "sdcb200_groupby_keys": (_i32, [_i64, _vp, _i32, _vp]),
     "sdcb200_groupby_values": (_i32, [_i64, _i32, ct.c_uint32, _vp, _i32, _vp]),
     "sdcb200_groupby_free": (_i32, [_i64]),
+    "sdcb200_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
+    "sdcb200_join_indexers": (_i32, [_i64, _vp, _vp, _i32, _vp]),
+    "sdcb200_join_free": (_i32, [_i64, _vp]),
+    "sdcb200_take_nullable_f64": (_i32, [_i32, _vp, _vp, _i64, _vp, _vp]),
 }
 
 # the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)

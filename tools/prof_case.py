@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""One short invocation of one operator, for `ncu` (launch list or --set full) under gpurun.
+
+    python tools/prof_case.py groupby|rolling|sort|join [reps]
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+what = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+rng = np.random.default_rng(0)
+if what == "groupby":
+    from sdc_b200.groupby import groupby_device
+    n = 10_000_000
+    a = torch.from_numpy(rng.integers(0, 1000, n, dtype=np.int64)).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    for _ in range(reps):
+        groupby_device(a, [b], ("sum",), True, 1, 1000)
+elif what == "groupby_hi":
+    from sdc_b200.groupby import groupby_device
+    n = 100_000_000
+    a = torch.from_numpy(rng.integers(0, 1_000_000, n, dtype=np.int64)).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    for _ in range(reps):
+        groupby_device(a, [b], ("sum",), True, 1, 1_000_000)
+elif what == "rolling":
+    from sdc_b200.rolling import rolling_device
+    x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
+    out = torch.empty_like(x)
+    for _ in range(reps):
+        rolling_device(x, "mean", 100, 100, 1, out=out)
+elif what == "sort":
+    from sdc_b200.sort import argsort_device
+    x = torch.from_numpy(rng.integers(-2**63, 2**63 - 1, 100_000_000, dtype=np.int64)).cuda()
+    for _ in range(reps):
+        argsort_device(x)
+elif what == "join":
+    from sdc_b200.join import join_device
+    r = torch.from_numpy(np.random.default_rng(2).permutation(10_000_000).astype(np.int64)).cuda()
+    l = torch.from_numpy(np.random.default_rng(3).integers(0, 10_000_000, 100_000_000, dtype=np.int64)).cuda()
+    for _ in range(reps):
+        join_device(l, r, "inner")
+torch.cuda.synchronize()
+print("ok")
