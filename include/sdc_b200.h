@@ -159,6 +159,36 @@ int32_t sdcb200_join_free(int64_t handle, void* stream);
 int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int64_t* idx, int64_t n, double* dst,
                                   void* stream);
 
+/* ------------------------------------------------------------------ string columns (str_arr)
+ * Layout = the reference's StringArray (sdc/str_arr_type.py:33-101, sdc/native/str_ext/sdc_str_arr.hpp:160-176):
+ * uint32 offsets[n + 1], uint8 chars[offsets[n]] (UTF-8, no terminators), validity bitmap LSB-first with
+ * 1 = valid (NULL bitmap pointer = all valid).  All pointers below are DEVICE pointers.
+ *
+ * sdcb200_str_argsort: replaces `stable_argsort` (sdc_str_arr.hpp:565-593; bound at sdc/str_arr_ext.py:94-99):
+ * unsigned byte-lexicographic order, a proper prefix first, ties in input order for both directions;
+ * writes uint64 row positions like the reference.                                                   */
+int32_t sdcb200_str_argsort(const uint8_t* chars, const uint32_t* offsets, int64_t n, int32_t ascending, uint64_t* index_out,
+                            void* stream);
+/* String keys -> exact dense group ids (gid_out[i] = id of row i's string, -1 for NA rows, which groupby
+ * skips: sdc/datatypes/hpat_pandas_dataframe_functions.py:3088-3089).  The ids feed sdcb200_groupby as an
+ * int64 key column; sdcb200_str_group_rows maps result ids back to one representative input row each
+ * (to materialise the key strings with sdcb200_str_gather_*); the table is released with
+ * sdcb200_str_table_free.                                                                           */
+int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n,
+                              int64_t expected_groups, int64_t* gid_out, int64_t* ngroups_out, int64_t* table_handle_out,
+                              int64_t* table_cap_out, void* stream);
+int32_t sdcb200_str_group_rows(int64_t table_handle, const int64_t* gids, int64_t ng, int64_t* rows_out, void* stream);
+int32_t sdcb200_str_table_free(int64_t table_handle, void* stream);
+/* take() on a str_arr (sdc/functions/numpy_like.py:1359-1388 for strings; convert_len_arr_to_offset,
+ * sdc_str_arr.hpp:242-252): step 1 writes out_offsets[m + 1] and returns the char total, step 2 copies
+ * the bytes and builds the bitmap.  rows[i] < 0 gives an empty NA string.                           */
+int32_t sdcb200_str_gather_sizes(const uint32_t* offsets, const int64_t* rows, int64_t m, uint32_t* out_offsets,
+                                 int64_t* total_chars, void* stream);
+int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, const int64_t* rows,
+                                 int64_t m, const uint32_t* out_offsets, uint8_t* out_chars, uint8_t* out_bitmap, void* stream);
+/* the reference's own symbol (HOST buffers, void return), exactly as sdc/str_arr_ext.py:94-99 declares it */
+void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result);
+
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
  * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and

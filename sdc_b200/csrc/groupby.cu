@@ -226,15 +226,70 @@ struct SmemLayout {
     int bytes;
 };
 
+// strided sample of the key column -> dense-key window for the direct-addressed mode of gb_smem_kernel:
+// direct[0] = lo, direct[1] = range (0 = use hashing).  int64 keys only.
+constexpr int kSampleThreads = 1024;
+constexpr int kSamplePerThread = 4;
+__global__ void __launch_bounds__(kSampleThreads) gb_sample_kernel(const long long* __restrict__ keys, int64_t n, int scap,
+                                                                   long long* direct) {
+    __shared__ long long smin[kSampleThreads / 32], smax[kSampleThreads / 32];
+    const int64_t total = (int64_t)kSampleThreads * kSamplePerThread;
+    const int64_t stride = n > total ? n / total : 1;
+    long long mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
+    long long kv[kSamplePerThread];
+#pragma unroll
+    for (int e = 0; e < kSamplePerThread; ++e) {        // independent loads, all in flight together
+        const int64_t r = ((int64_t)e * kSampleThreads + threadIdx.x) * stride;
+        kv[e] = r < n ? __ldg(keys + r) : keys[0];
+    }
+#pragma unroll
+    for (int e = 0; e < kSamplePerThread; ++e) {
+        mn = kv[e] < mn ? kv[e] : mn;
+        mx = kv[e] > mx ? kv[e] : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kSampleThreads / 32; ++w) {
+            mn = smin[w] < mn ? smin[w] : mn;
+            mx = smax[w] > mx ? smax[w] : mx;
+        }
+        // work in the order-preserving unsigned image of int64 so that extreme keys cannot overflow
+        const unsigned long long top = 0x8000000000000000ull;
+        const unsigned long long umn = (unsigned long long)mn ^ top, umx = (unsigned long long)mx ^ top;
+        long long lo = 0, range = 0;
+        if (mx >= mn && umx - umn < (unsigned long long)scap) {
+            // centre the scap-wide window on the sampled keys, clamped to the int64 range
+            unsigned long long shift = ((unsigned long long)scap - (umx - umn) - 1) / 2;
+            if (shift > umn) shift = umn;
+            unsigned long long ulo = umn - shift;
+            if (ulo > ~0ull - (unsigned long long)scap) ulo = ~0ull - (unsigned long long)scap;
+            lo = (long long)(ulo ^ top);
+            range = scap;
+        }
+        direct[0] = lo;
+        direct[1] = range;
+    }
+}
+
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restrict__ keys, int64_t n, Cols cols, Table t,
-                                                             int need, SmemLayout lay) {
+                                                             int need, SmemLayout lay, const long long* __restrict__ direct) {
     extern __shared__ __align__(16) unsigned char sm[];
     unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);
     unsigned long long* sfirst = reinterpret_cast<unsigned long long*>(sm + (lay.off_first >= 0 ? lay.off_first : 0));
     const int scap = lay.scap;
     const int tid = threadIdx.x;
     const int rep = blockIdx.x % t.nrep;
+    // dense int64 keys: slot = key - lo, no hashing, no probing (window chosen by gb_sample_kernel)
+    const unsigned long long dlo = KEY_F64 ? 0ull : (unsigned long long)direct[0];
+    const unsigned long long drange = KEY_F64 ? 0ull : (unsigned long long)direct[1];
     for (int i = tid; i < scap; i += kGbThreads) {
         skeys[i] = kEmptyKey();
         if (need & NEED_FIRST) sfirst[i] = ~0ull;
@@ -248,6 +303,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restr
     __syncthreads();
     const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncwarp();
         const int64_t base = tile * kGbTile;
         unsigned long long kb[kRows], v0[kRows];
         load4(keys, base, n, tid, cols.vec_ok, kb);
@@ -257,27 +313,39 @@ __global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restr
         unsigned long long g[kRows];
 #pragma unroll
         for (int e = 0; e < kRows; ++e) {
-            unsigned long long k;
-            slot[e] = -1;
+            unsigned long long k = 0;
+            const bool valid = tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k);
+            int sl = -1;
             g[e] = ~0ull;
-            if (!(tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k))) continue;
-            if (k != kEmptyKey()) {
-                unsigned s = (unsigned)mix64(k) & (unsigned)(scap - 1);
-#pragma unroll 1
+            bool pending = valid && k != kEmptyKey();
+            if (drange) {
+                const unsigned long long d = k - dlo;
+                if (pending && d < drange) {
+                    sl = (int)d;
+                    if (skeys[sl] != k) skeys[sl] = k;          // presence marker; every writer stores the same value
+                }
+            } else {
+                unsigned s = (unsigned)((k * 0x9E3779B97F4A7C15ull) >> 40) & (unsigned)(scap - 1);
+                // the warp probes in lock step: the loop exit is warp-uniform, no divergence to undo
                 for (int p = 0; p < kSmemProbes; ++p) {
-                    const unsigned long long cur = skeys[s];
-                    if (cur == k) { slot[e] = (int)s; break; }
-                    if (cur == kEmptyKey()) {
-                        const unsigned long long old = atomicCAS(&skeys[s], kEmptyKey(), k);
-                        if (old == kEmptyKey() || old == k) { slot[e] = (int)s; break; }
+                    if (!__any_sync(0xffffffffu, pending)) break;
+                    if (pending) {
+                        const unsigned long long cur = skeys[s];
+                        if (cur == k) { sl = (int)s; pending = false; }
+                        else if (cur == kEmptyKey()) {
+                            const unsigned long long old = atomicCAS(&skeys[s], kEmptyKey(), k);
+                            if (old == kEmptyKey() || old == k) { sl = (int)s; pending = false; }
+                            else s = (s + 1) & (unsigned)(scap - 1);
+                        } else s = (s + 1) & (unsigned)(scap - 1);
                     }
-                    s = (s + 1) & (unsigned)(scap - 1);
                 }
             }
-            if (slot[e] < 0) {      // shared table full around this key: aggregate in the global table
+            if (valid && sl < 0) {      // outside the window / shared table full around this key: global table
                 g[e] = global_upsert(t, rep, k);
-                slot[e] = g[e] != ~0ull ? -2 : -1;
+                sl = g[e] != ~0ull ? -2 : -1;
             }
+            slot[e] = sl;
+            __syncwarp();
         }
         if (need & NEED_FIRST) {
 #pragma unroll
@@ -286,6 +354,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restr
                 if (slot[e] >= 0) { if (row < sfirst[slot[e]]) atomicMin(&sfirst[slot[e]], row); }
                 else if (slot[e] == -2) atomicMin(&t.first[g[e]], row);
             }
+            __syncwarp();
         }
         for (int c = 0; c < cols.ncols; ++c) {
             if (c > 0) load4(cols.data[c], base, n, tid, cols.vec_ok, v0);
@@ -296,22 +365,25 @@ __global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restr
             unsigned long long* smx = reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c]);
 #pragma unroll
             for (int e = 0; e < kRows; ++e) {
-                if (slot[e] == -1) continue;
-                if (slot[e] == -2) { global_accumulate(t, c, f, need, g[e], v0[e]); continue; }
                 const int sl = slot[e];
-                if (f) {
-                    const double v = __longlong_as_double((long long)v0[e]);
-                    if (v != v) continue;
-                    if (need & NEED_SUM) atomicAdd(ssum + sl, v);
-                    if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                    if (need & NEED_MIN) atomicMin(smn + sl, f64_to_ordered(v));
-                    if (need & NEED_MAX) atomicMax(smx + sl, f64_to_ordered(v));
-                } else {
-                    if (need & NEED_SUM) atomicAdd(reinterpret_cast<unsigned long long*>(ssum) + sl, v0[e]);
-                    if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                    if (need & NEED_MIN) atomicMin(smn + sl, i64_to_ordered((long long)v0[e]));
-                    if (need & NEED_MAX) atomicMax(smx + sl, i64_to_ordered((long long)v0[e]));
+                if (sl == -2) global_accumulate(t, c, f, need, g[e], v0[e]);
+                if (sl >= 0) {
+                    if (f) {
+                        const double v = __longlong_as_double((long long)v0[e]);
+                        if (v == v) {
+                            if (need & NEED_SUM) atomicAdd(ssum + sl, v);
+                            if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
+                            if (need & NEED_MIN) atomicMin(smn + sl, f64_to_ordered(v));
+                            if (need & NEED_MAX) atomicMax(smx + sl, f64_to_ordered(v));
+                        }
+                    } else {
+                        if (need & NEED_SUM) atomicAdd(reinterpret_cast<unsigned long long*>(ssum) + sl, v0[e]);
+                        if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
+                        if (need & NEED_MIN) atomicMin(smn + sl, i64_to_ordered((long long)v0[e]));
+                        if (need & NEED_MAX) atomicMax(smx + sl, i64_to_ordered((long long)v0[e]));
+                    }
                 }
+                __syncwarp();
             }
         }
     }
@@ -493,16 +565,25 @@ __global__ void __launch_bounds__(kSmallThreads) gb_finalize_small_kernel(Table 
     if (threadIdx.x == 0) counter = 0;
     __syncthreads();
     const unsigned nslots = (unsigned)t.cap + 1;
-    for (unsigned i = threadIdx.x; i < nslots; i += kSmallThreads) {
-        const unsigned long long k = t.keys[i];
+    constexpr int kPer = (kSmallSlots + kSmallThreads - 1) / kSmallThreads;
+    unsigned long long kk[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {               // independent loads, all in flight together
+        const unsigned i = e * kSmallThreads + threadIdx.x;
+        kk[e] = i < nslots ? t.keys[i] : kEmptyKey();
+    }
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+        const unsigned i = e * kSmallThreads + threadIdx.x;
+        const unsigned long long k = kk[e];
         if (k == kEmptyKey()) continue;
         const unsigned j = atomicAdd(&counter, 1u);
         if (j >= (unsigned)kSmallSort) continue;
         unsigned long long sk;
         if (by_first) sk = t.first[i];
         else {
-            const unsigned long long kk = (i == (unsigned)t.cap) ? kEmptyKey() : k;
-            sk = key_f64 ? f64_to_ordered(__longlong_as_double((long long)kk)) : i64_to_ordered((long long)kk);
+            const unsigned long long key = (i == (unsigned)t.cap) ? kEmptyKey() : k;
+            sk = key_f64 ? f64_to_ordered(__longlong_as_double((long long)key)) : i64_to_ordered((long long)key);
         }
         skey[j] = sk;
         sslot[j] = i;
@@ -609,14 +690,22 @@ SmemLayout make_layout(int ncols, int need, int want_slots, int budget_bytes) {
     return L;
 }
 
+// one stream-ordered allocation per attempt, carved into the table arrays (256-byte aligned pieces)
 struct TableMem {
-    std::vector<Scratch*> blocks;
-    ~TableMem() { for (auto* b : blocks) delete b; }
-    int32_t get(void** p, size_t bytes, cudaStream_t s) {
-        Scratch* b = new Scratch();
-        blocks.push_back(b);
-        SDC_TRY(b->alloc(bytes, s));
-        *p = b->p;
+    Scratch block;
+    char* cur = nullptr;
+    char* end = nullptr;
+    int32_t reserve(size_t bytes, cudaStream_t s) {
+        SDC_TRY(block.alloc(bytes, s));
+        cur = block.as<char>();
+        end = cur + bytes;
+        return SDCB200_OK;
+    }
+    int32_t get(void** p, size_t bytes, cudaStream_t) {
+        const size_t b = (bytes + 255) & ~size_t(255);
+        if (cur + b > end) { set_error("groupby: table arena exhausted"); return SDCB200_ERR_NOMEM; }
+        *p = cur;
+        cur += b;
         return SDCB200_OK;
     }
 };
@@ -674,6 +763,12 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         InitPlan ip;
         ip.count = 0;
         void* p;
+        {
+            int narr = 1 + ((need & NEED_FIRST) ? 1 : 0);
+            narr += cols.ncols * (((need & NEED_SUM) ? 1 : 0) + ((need & NEED_CNT) ? 1 : 0) + ((need & NEED_MIN) ? 1 : 0) +
+                                  ((need & NEED_MAX) ? 1 : 0) + (need_ssd ? 1 : 0));
+            SDC_TRY(mem.reserve((size_t)narr * ((slots_n * 8 + 255) & ~size_t(255)) + 256, s));
+        }
         auto add = [&](void** dst, unsigned long long init) -> int32_t {
             SDC_TRY(mem.get(&p, slots_n * 8, s));
             *dst = p;
@@ -711,13 +806,22 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
                 SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 configured = true;
             }
-            int occ = 1;
-            SDC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kGbThreads, lay.bytes));
+            static thread_local int occ_bytes = -1, occ_cached = 1;
+            if (occ_bytes != lay.bytes) {
+                SDC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, kern, kGbThreads, lay.bytes));
+                occ_bytes = lay.bytes;
+            }
+            int occ = occ_cached;
             if (occ < 1) occ = 1;
             if (occ > 6) occ = 6;
             int64_t grid = (int64_t)sms * occ;
             if (grid > ntiles) grid = ntiles;
-            kern<<<(unsigned)grid, kGbThreads, lay.bytes, s>>>(keys, n, cols, t, need, lay);
+            long long* direct = reinterpret_cast<long long*>(dmeta + 2);      // zeroed: range 0 = hashing
+            if (!KEY_F64) {
+                gb_sample_kernel<<<1, kSampleThreads, 0, s>>>(reinterpret_cast<const long long*>(keys), n, lay.scap, direct);
+                SDC_CHECK_LAUNCH();
+            }
+            kern<<<(unsigned)grid, kGbThreads, lay.bytes, s>>>(keys, n, cols, t, need, lay, direct);
             SDC_CHECK_LAUNCH();
             if (t.nrep > 1) {
                 const int64_t total = (int64_t)per * (t.nrep - 1);

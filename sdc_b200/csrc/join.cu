@@ -23,16 +23,16 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "common.cuh"
+#include "scan.cuh"
 
 namespace sdcb200 {
 namespace {
 
 constexpr unsigned long long kEmptyKey = 0x7ff8dead0000beefull;   // never a canonical float key; an int64 key
                                                                   // equal to it lives in the spare slot [cap]
-constexpr int kJoinThreads = 256;
-constexpr int kItems = 8;                          // rows per thread in the probe tiles
-constexpr int kTile = kJoinThreads * kItems;       // 2048 rows per CTA
+constexpr int kJoinThreads = kScanThreads;         // 256
+constexpr int kItems = kScanItems;                 // 8 rows per thread in the probe tiles
+constexpr int kTile = kScanTile;                   // 2048 rows per CTA
 
 __host__ __device__ inline unsigned long long jmix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -101,8 +101,6 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
     }
 }
 
-// ---- device-wide exclusive scan, reduce-then-scan over tiles of kTile entries ----
-// LOAD(i) -> u64 value of entry i; STORE(i, exclusive prefix, value)
 struct SlotCountLoad {
     const ulonglong2* slots;
     __device__ unsigned long long operator()(int64_t i) const { return slots[i].y; }
@@ -113,100 +111,6 @@ struct SlotStartStore {          // val = start << 32 | count
         slots[i].y = (excl << 32) | v;
     }
 };
-struct ArrayLoad {
-    const unsigned long long* p;
-    __device__ unsigned long long operator()(int64_t i) const { return p[i]; }
-};
-struct ArrayStore {
-    unsigned long long* p;
-    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long) const { p[i] = excl; }
-};
-
-__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* total,
-                                                                  unsigned long long* wsum /* [8] shared */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    unsigned long long base = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < kJoinThreads / 32; ++w) {
-        const unsigned long long x = wsum[w];
-        if (w < warp) base += x;
-        tot += x;
-    }
-    __syncthreads();
-    *total = tot;
-    return base + incl - v;
-}
-
-template <typename LOAD>
-__global__ void __launch_bounds__(kJoinThreads) scan_reduce_kernel(LOAD load, int64_t n, unsigned long long* tsum) {
-    __shared__ unsigned long long wsum[kJoinThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kTile;
-    unsigned long long v = 0;
-#pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-        const int64_t i = base + e * kJoinThreads + threadIdx.x;
-        if (i < n) v += load(i);
-    }
-    unsigned long long tot;
-    block_excl_scan_u64(v, &tot, wsum);
-    if (threadIdx.x == 0) tsum[blockIdx.x] = tot;
-}
-
-// one CTA: exclusive scan of the tile sums in place; total -> tsum[nt]
-__global__ void __launch_bounds__(kJoinThreads) scan_tiles_kernel(unsigned long long* tsum, int64_t nt) {
-    __shared__ unsigned long long wsum[kJoinThreads / 32];
-    unsigned long long carry = 0;
-    for (int64_t b = 0; b < nt; b += kJoinThreads) {
-        const int64_t i = b + threadIdx.x;
-        const unsigned long long v = i < nt ? tsum[i] : 0ull;
-        unsigned long long tot;
-        const unsigned long long ex = block_excl_scan_u64(v, &tot, wsum);
-        if (i < nt) tsum[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) tsum[nt] = carry;
-}
-
-template <typename LOAD, typename STORE>
-__global__ void __launch_bounds__(kJoinThreads) scan_apply_kernel(LOAD load, STORE store, int64_t n,
-                                                                  const unsigned long long* __restrict__ tsum) {
-    __shared__ unsigned long long wsum[kJoinThreads / 32];
-    const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;   // thread-contiguous items
-    unsigned long long v[kItems], s = 0;
-#pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-        v[e] = (i0 + e < n) ? load(i0 + e) : 0ull;
-        s += v[e];
-    }
-    unsigned long long tot;
-    unsigned long long ex = tsum[blockIdx.x] + block_excl_scan_u64(s, &tot, wsum);
-#pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-        if (i0 + e < n) store(i0 + e, ex, v[e]);
-        ex += v[e];
-    }
-}
-
-template <typename LOAD, typename STORE>
-int32_t device_exclusive_scan(LOAD load, STORE store, int64_t n, unsigned long long* tsum /* [nt + 1] */, cudaStream_t s) {
-    const int64_t nt = ceil_div(n, kTile);
-    scan_reduce_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(load, n, tsum);
-    SDC_CHECK_LAUNCH();
-    scan_tiles_kernel<<<1, kJoinThreads, 0, s>>>(tsum, nt);
-    SDC_CHECK_LAUNCH();
-    scan_apply_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(load, store, n, tsum);
-    SDC_CHECK_LAUNCH();
-    return SDCB200_OK;
-}
-
 __global__ void __launch_bounds__(kJoinThreads) jt_scatter_kernel(const uint32_t* __restrict__ rslot,
                                                                   const uint32_t* __restrict__ rrank, int64_t n, JTable t,
                                                                   uint32_t* __restrict__ rid) {

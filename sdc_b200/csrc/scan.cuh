@@ -1,0 +1,111 @@
+// scan.cuh -- device-wide exclusive scan (reduce-then-scan over tiles) shared by join.cu / strings.cu.
+// Everything here is a template or static, so each translation unit gets its own copy.
+#pragma once
+#include "common.cuh"
+
+namespace sdcb200 {
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;       // 2048 entries per CTA
+
+// ---- device-wide exclusive scan, reduce-then-scan over tiles of kScanTile entries ----
+// LOAD(i) -> u64 value of entry i; STORE(i, exclusive prefix, value)
+struct ArrayLoad {
+    const unsigned long long* p;
+    __device__ unsigned long long operator()(int64_t i) const { return p[i]; }
+};
+struct ArrayStore {
+    unsigned long long* p;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long) const { p[i] = excl; }
+};
+
+__device__ __forceinline__ unsigned long long block_excl_scan_u64(unsigned long long v, unsigned long long* total,
+                                                                  unsigned long long* wsum /* [8] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        const unsigned long long x = wsum[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + incl - v;
+}
+
+template <typename LOAD>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(LOAD load, int64_t n, unsigned long long* tsum) {
+    __shared__ unsigned long long wsum[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    unsigned long long v = 0;
+#pragma unroll
+    for (int e = 0; e < kScanItems; ++e) {
+        const int64_t i = base + e * kScanThreads + threadIdx.x;
+        if (i < n) v += load(i);
+    }
+    unsigned long long tot;
+    block_excl_scan_u64(v, &tot, wsum);
+    if (threadIdx.x == 0) tsum[blockIdx.x] = tot;
+}
+
+// one CTA: exclusive scan of the tile sums in place; total -> tsum[nt]
+static __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(unsigned long long* tsum, int64_t nt) {
+    __shared__ unsigned long long wsum[kScanThreads / 32];
+    unsigned long long carry = 0;
+    for (int64_t b = 0; b < nt; b += kScanThreads) {
+        const int64_t i = b + threadIdx.x;
+        const unsigned long long v = i < nt ? tsum[i] : 0ull;
+        unsigned long long tot;
+        const unsigned long long ex = block_excl_scan_u64(v, &tot, wsum);
+        if (i < nt) tsum[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) tsum[nt] = carry;
+}
+
+template <typename LOAD, typename STORE>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(LOAD load, STORE store, int64_t n,
+                                                                  const unsigned long long* __restrict__ tsum) {
+    __shared__ unsigned long long wsum[kScanThreads / 32];
+    const int64_t i0 = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;   // thread-contiguous items
+    unsigned long long v[kScanItems], s = 0;
+#pragma unroll
+    for (int e = 0; e < kScanItems; ++e) {
+        v[e] = (i0 + e < n) ? load(i0 + e) : 0ull;
+        s += v[e];
+    }
+    unsigned long long tot;
+    unsigned long long ex = tsum[blockIdx.x] + block_excl_scan_u64(s, &tot, wsum);
+#pragma unroll
+    for (int e = 0; e < kScanItems; ++e) {
+        if (i0 + e < n) store(i0 + e, ex, v[e]);
+        ex += v[e];
+    }
+}
+
+template <typename LOAD, typename STORE>
+int32_t device_exclusive_scan(LOAD load, STORE store, int64_t n, unsigned long long* tsum /* [nt + 1] */, cudaStream_t s) {
+    const int64_t nt = ceil_div(n, kScanTile);
+    scan_reduce_kernel<<<(unsigned)nt, kScanThreads, 0, s>>>(load, n, tsum);
+    SDC_CHECK_LAUNCH();
+    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(tsum, nt);
+    SDC_CHECK_LAUNCH();
+    scan_apply_kernel<<<(unsigned)nt, kScanThreads, 0, s>>>(load, store, n, tsum);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+
+}  // namespace
+}  // namespace sdcb200

@@ -1,0 +1,378 @@
+// strings.cu -- str_arr columns (offsets + chars in device memory) as sort and groupby keys (K4, K6).
+//
+// Column layout = the reference's StringArray unchanged (sdc/str_arr_type.py:33-101,
+// sdc/native/str_ext/sdc_str_arr.hpp:160-176): uint32 offsets[n + 1] (offsets[0] = 0,
+// offsets[n] = total chars), uint8 chars[total] UTF-8 without terminators, validity bitmap
+// LSB-first with bit = 1 meaning valid; NA strings are stored empty (:389-393).
+//
+//   sdcb200_str_argsort   replaces `stable_argsort` (sdc_str_arr.hpp:565-593, bound at
+//       sdc/str_arr_ext.py:94-99): the reference copies every string into a std::string and runs a
+//       SERIAL std::stable_sort of (string, idx) pairs with std::string `<` / `>` -- unsigned
+//       byte-lexicographic order, a proper prefix first, ties in input order for both directions.
+//       Here: LSD radix sort over the strings' 8-byte big-endian chunks, last chunk first, preceded by
+//       one pass on the length (the least significant key: zero padding makes "ab" and "ab\0" equal
+//       chunk-wise, the length puts the prefix first).  Every pass is the library's stable onesweep
+//       sort of (u64 chunk key, u32 row), so constant digits are skipped and ties keep input order.
+//   sdcb200_str_factorize  string keys -> dense group ids for the hash groupby: open-addressing table
+//       of 64-bit words (32-bit fingerprint << 32 | representative row) claimed with one atomicCAS; a
+//       fingerprint hit is confirmed by comparing the bytes with the representative row, so ids are
+//       exact.  gid = slot index, -1 for NA rows (None keys are skipped, reference
+//       hpat_pandas_dataframe_functions.py:3088-3089).  The numeric groupby then runs on the ids.
+//   sdcb200_str_gather     rows -> a new str_arr (lengths, exclusive scan, byte copy).
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace sdcb200 {
+namespace {
+
+constexpr int kStrThreads = 256;
+
+__device__ __forceinline__ uint64_t chunk_key(const uint8_t* __restrict__ chars, uint32_t beg, uint32_t end, uint32_t chunk) {
+    // big-endian bytes [8*chunk, 8*chunk + 8) of the string, zero padded
+    const uint64_t p = (uint64_t)beg + 8ull * chunk;
+    uint64_t k = 0;
+    if (p >= end) return 0;
+    const uint32_t avail = (uint32_t)(end - p < 8 ? end - p : 8);
+#pragma unroll
+    for (uint32_t b = 0; b < 8; ++b) {
+        k <<= 8;
+        if (b < avail) k |= chars[p + b];
+    }
+    return k;
+}
+
+// keys for one LSD pass: chunk < 0 -> the length, else the chunk's bytes; rows taken through `perm`
+__global__ void __launch_bounds__(kStrThreads) str_pass_keys_kernel(const uint8_t* __restrict__ chars,
+                                                                    const uint32_t* __restrict__ offsets,
+                                                                    const uint32_t* __restrict__ perm, int64_t n, int chunk,
+                                                                    uint64_t* __restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)kStrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStrThreads) {
+        const uint32_t r = perm ? perm[i] : (uint32_t)i;
+        const uint32_t beg = offsets[r], end = offsets[r + 1];
+        keys[i] = chunk < 0 ? (uint64_t)(end - beg) : chunk_key(chars, beg, end, (uint32_t)chunk);
+    }
+}
+
+__global__ void __launch_bounds__(kStrThreads) str_maxlen_kernel(const uint32_t* __restrict__ offsets, int64_t n,
+                                                                 unsigned* __restrict__ out /* [2]: max, min */) {
+    unsigned mx = 0, mn = 0xffffffffu;
+    for (int64_t i = blockIdx.x * (int64_t)kStrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStrThreads) {
+        const unsigned len = offsets[i + 1] - offsets[i];
+        mx = len > mx ? len : mx;
+        mn = len < mn ? len : mn;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned a = __shfl_xor_sync(0xffffffffu, mx, d), b = __shfl_xor_sync(0xffffffffu, mn, d);
+        mx = a > mx ? a : mx;
+        mn = b < mn ? b : mn;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mx);
+        atomicMin(out + 1, mn);
+    }
+}
+
+__global__ void widen_rows_kernel(const uint32_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in ? in[i] : (uint64_t)i;
+}
+
+inline int grid_for(int64_t n, int threads, int per_sm) {
+    const int64_t want = ceil_div(n, threads);
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+// ---- factorize ----
+__device__ __forceinline__ uint64_t str_hash(const uint8_t* __restrict__ p, uint32_t len) {
+    // FNV-1a over the bytes, finished with a 64-bit mixer
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (uint32_t i = 0; i < len; ++i) {
+        h ^= p[i];
+        h *= 0x100000001b3ull;
+    }
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33;
+    return h;
+}
+
+__device__ __forceinline__ bool str_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len) {
+    for (uint32_t i = 0; i < len; ++i)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+constexpr uint64_t kStrEmpty = ~0ull;     // fingerprint 0xffffffff is remapped, so no live word equals this
+
+__global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_t* __restrict__ chars,
+                                                                    const uint32_t* __restrict__ offsets,
+                                                                    const uint8_t* __restrict__ bitmap, int64_t n,
+                                                                    unsigned long long* __restrict__ table, uint64_t cap,
+                                                                    int64_t* __restrict__ gid,
+                                                                    unsigned long long* __restrict__ counters /* [0] groups, [1] overflow */,
+                                                                    uint64_t limit) {
+    for (int64_t i = blockIdx.x * (int64_t)kStrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStrThreads) {
+        if (bitmap && !((bitmap[i >> 3] >> (i & 7)) & 1)) { gid[i] = -1; continue; }
+        const uint32_t beg = offsets[i], len = offsets[i + 1] - beg;
+        const uint64_t h = str_hash(chars + beg, len);
+        uint64_t fp = h >> 32;
+        if (fp == 0xffffffffull) fp = 0xfffffffeull;
+        const uint64_t mine = (fp << 32) | (uint64_t)(uint32_t)i;
+        uint64_t s = h & (cap - 1);
+        int64_t out = -2;
+        for (uint64_t probes = 0; probes <= cap; ++probes) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&table[s]);
+            if (cur == kStrEmpty) {
+                if (*reinterpret_cast<volatile unsigned long long*>(&counters[1])) break;
+                const unsigned long long old = atomicCAS(&table[s], kStrEmpty, mine);
+                if (old == kStrEmpty) {
+                    if (atomicAdd(&counters[0], 1ull) + 1 > limit) atomicExch(&counters[1], 1ull);
+                    out = (int64_t)s;
+                    break;
+                }
+                cur = old;
+            }
+            if ((cur >> 32) == fp) {
+                const uint32_t rep = (uint32_t)cur;
+                const uint32_t rbeg = offsets[rep], rlen = offsets[rep + 1] - rbeg;
+                if (rlen == len && str_equal(chars + rbeg, chars + beg, len)) { out = (int64_t)s; break; }
+            }
+            s = (s + 1) & (cap - 1);
+        }
+        gid[i] = out;      // -2 only after an overflow; the caller retries with a larger table
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// representative row of each group id (for the result's key strings)
+__global__ void str_group_rows_kernel(const unsigned long long* __restrict__ table, const int64_t* __restrict__ gids,
+                                      int64_t ng, int64_t* __restrict__ rows) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t g = gids[j];
+        rows[j] = g < 0 ? -1 : (int64_t)(uint32_t)table[g];
+    }
+}
+
+// ---- gather ----
+struct RowLenLoad {
+    const uint32_t* offsets;
+    const int64_t* rows;
+    __device__ unsigned long long operator()(int64_t i) const {
+        const int64_t r = rows[i];
+        return r < 0 ? 0ull : (unsigned long long)(offsets[r + 1] - offsets[r]);
+    }
+};
+struct OffsetStore {
+    uint32_t* out;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long) const { out[i] = (uint32_t)excl; }
+};
+
+__global__ void __launch_bounds__(kStrThreads) str_copy_kernel(const uint8_t* __restrict__ chars,
+                                                               const uint32_t* __restrict__ offsets,
+                                                               const int64_t* __restrict__ rows, int64_t m,
+                                                               const uint32_t* __restrict__ out_offsets,
+                                                               uint8_t* __restrict__ out_chars, uint8_t* __restrict__ out_bitmap,
+                                                               const uint8_t* __restrict__ in_bitmap) {
+    // one warp per output string: coalesced byte copy
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)kStrThreads + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * kStrThreads) >> 5;
+    for (int64_t i = warp0; i < m; i += nwarps) {
+        const int64_t r = rows[i];
+        if (r < 0) continue;
+        const uint32_t beg = offsets[r], len = offsets[r + 1] - beg;
+        const uint32_t ob = out_offsets[i];
+        for (uint32_t b = lane; b < len; b += 32) out_chars[ob + b] = chars[beg + b];
+    }
+    if (out_bitmap) {
+        // bitmap bytes: one thread per output byte
+        const int64_t nbytes = (m + 7) >> 3;
+        for (int64_t b = blockIdx.x * (int64_t)kStrThreads + threadIdx.x; b < nbytes; b += (int64_t)gridDim.x * kStrThreads) {
+            uint8_t v = 0;
+            for (int k = 0; k < 8; ++k) {
+                const int64_t i = b * 8 + k;
+                if (i >= m) break;
+                const int64_t r = rows[i];
+                const bool valid = r >= 0 && (!in_bitmap || ((in_bitmap[r >> 3] >> (r & 7)) & 1));
+                if (valid) v |= (uint8_t)(1u << k);
+            }
+            out_bitmap[b] = v;
+        }
+    }
+}
+
+}  // namespace
+
+// stable argsort of a device str_arr -> uint32 rows in *rows_out (a scratch-owned buffer pointer is returned
+// through the ping-pong arguments, so the caller passes its own buffers)
+static int32_t str_argsort_device(const uint8_t* chars, const uint32_t* offsets, int64_t n, bool ascending, uint64_t* index_out,
+                                  cudaStream_t s) {
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(n < 0xffffffffll, "str_argsort: fewer than 2^32 - 1 rows");
+    Scratch meta, keys, kA, kB, pA, pB;
+    SDC_TRY(meta.alloc(16, s));
+    unsigned init[2] = {0u, 0xffffffffu};
+    SDC_CUDA_TRY(cudaMemcpyAsync(meta.p, init, 8, cudaMemcpyHostToDevice, s));
+    str_maxlen_kernel<<<grid_for(n, kStrThreads, 8), kStrThreads, 0, s>>>(offsets, n, meta.as<unsigned>());
+    SDC_CHECK_LAUNCH();
+    unsigned lens[2];
+    SDC_CUDA_TRY(cudaMemcpyAsync(lens, meta.p, 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    const int nchunks = (int)((lens[0] + 7) / 8);
+    SDC_TRY(keys.alloc((size_t)n * 8, s));
+    SDC_TRY(kA.alloc((size_t)n * 8, s));
+    SDC_TRY(kB.alloc((size_t)n * 8, s));
+    SDC_TRY(pA.alloc((size_t)n * 4, s));
+    SDC_TRY(pB.alloc((size_t)n * 4, s));
+    const uint32_t* perm = nullptr;          // nullptr = identity
+    const int grid = grid_for(n, kStrThreads, 8);
+    // passes from the least significant key to the most: length, last chunk, ..., chunk 0
+    for (int pass = -1; pass < nchunks; ++pass) {
+        const int chunk = pass < 0 ? -1 : nchunks - 1 - pass;
+        if (chunk < 0 && lens[0] == lens[1]) continue;            // all lengths equal: nothing to order
+        str_pass_keys_kernel<<<grid, kStrThreads, 0, s>>>(chars, offsets, perm, n, chunk, keys.as<uint64_t>());
+        SDC_CHECK_LAUNCH();
+        const void* rk = nullptr;
+        const void* rp = nullptr;
+        // the pass reads the current perm in its first digit pass only and alternates its outputs
+        // starting with the first one given, so the first output must be the buffer perm is NOT in
+        const bool in_a = (perm == pA.as<uint32_t>());
+        SDC_TRY(radix_sort_core(SDCB200_U64, keys.p, kA.p, kB.p, 4, perm, in_a ? pB.p : pA.p, in_a ? pA.p : pB.p, n,
+                                perm == nullptr, !ascending, &rk, &rp, s));
+        if (rp == nullptr || rp == (const void*)perm) continue;   // no digit varied: order unchanged
+        perm = reinterpret_cast<const uint32_t*>(rp);
+    }
+    widen_rows_kernel<<<grid, 256, 0, s>>>(perm, index_out, n);
+    SDC_CHECK_LAUNCH();
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));      // scratch buffers go out of scope
+    return SDCB200_OK;
+}
+
+}  // namespace sdcb200
+
+using namespace sdcb200;
+
+extern "C" {
+
+int32_t sdcb200_str_argsort(const uint8_t* chars, const uint32_t* offsets, int64_t n, int32_t ascending, uint64_t* index_out,
+                            void* stream) {
+    SDC_ARG_CHECK(n >= 0, "n");
+    SDC_ARG_CHECK(n == 0 || (offsets && index_out), "null pointer");
+    return str_argsort_device(chars, offsets, n, ascending != 0, index_out, (cudaStream_t)stream);
+}
+
+int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n,
+                              int64_t expected_groups, int64_t* gid_out, int64_t* ngroups_out, int64_t* table_handle_words,
+                              int64_t* table_cap_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(n >= 0 && n < 0xffffffffll, "row count (< 2^32 - 1)");
+    SDC_ARG_CHECK(ngroups_out && table_handle_words && table_cap_out, "null out pointer");
+    *ngroups_out = 0;
+    *table_handle_words = 0;
+    *table_cap_out = 0;
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(offsets && gid_out, "null pointer");
+    uint64_t worst = 64;
+    while (worst < 2ull * (uint64_t)n) worst <<= 1;
+    uint64_t cap = 1ull << 16;
+    if (expected_groups > 0) { cap = 1024; while (cap < 2ull * (uint64_t)expected_groups) cap <<= 1; }
+    if (cap > worst) cap = worst;
+    for (;;) {
+        void* table = nullptr;
+        SDC_TRY(dev_alloc(&table, (size_t)cap * 8 + 16, s));
+        unsigned long long* counters = reinterpret_cast<unsigned long long*>(table) + cap;
+        fill_u64_kernel<<<grid_for((int64_t)cap, 256, 8), 256, 0, s>>>(reinterpret_cast<unsigned long long*>(table), kStrEmpty, cap);
+        SDC_CHECK_LAUNCH();
+        SDC_CUDA_TRY(cudaMemsetAsync(counters, 0, 16, s));
+        str_factorize_kernel<<<grid_for(n, kStrThreads, 8), kStrThreads, 0, s>>>(chars, offsets, bitmap, n,
+                                                                                reinterpret_cast<unsigned long long*>(table), cap,
+                                                                                gid_out, counters, cap / 2 + 1);
+        SDC_CHECK_LAUNCH();
+        unsigned long long h[2];
+        SDC_CUDA_TRY(cudaMemcpyAsync(h, counters, 16, cudaMemcpyDeviceToHost, s));
+        SDC_CUDA_TRY(cudaStreamSynchronize(s));
+        if (h[1] == 0) {
+            *ngroups_out = (int64_t)h[0];
+            *table_handle_words = (int64_t)reinterpret_cast<uintptr_t>(table);
+            *table_cap_out = (int64_t)cap;
+            return SDCB200_OK;
+        }
+        dev_free(table, s);
+        if (cap >= worst) { set_error("str_factorize: table overflow at capacity %llu", (unsigned long long)cap); return SDCB200_ERR_CAPACITY; }
+        cap = cap * 16 < worst ? cap * 16 : worst;
+    }
+}
+
+int32_t sdcb200_str_group_rows(int64_t table_handle_words, const int64_t* gids, int64_t ng, int64_t* rows_out, void* stream) {
+    SDC_ARG_CHECK(ng >= 0, "ng");
+    if (ng == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(table_handle_words && gids && rows_out, "null pointer");
+    str_group_rows_kernel<<<grid_for(ng, 256, 4), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const unsigned long long*>((uintptr_t)table_handle_words), gids, ng, rows_out);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_table_free(int64_t table_handle_words, void* stream) {
+    if (table_handle_words) return dev_free(reinterpret_cast<void*>((uintptr_t)table_handle_words), (cudaStream_t)stream);
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_gather_sizes(const uint32_t* offsets, const int64_t* rows, int64_t m, uint32_t* out_offsets, int64_t* total_chars,
+                                 void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(m >= 0 && total_chars && out_offsets, "args");
+    *total_chars = 0;
+    if (m == 0) {
+        SDC_CUDA_TRY(cudaMemsetAsync(out_offsets, 0, 4, s));
+        return SDCB200_OK;
+    }
+    Scratch tsum;
+    SDC_TRY(tsum.alloc((size_t)(ceil_div(m, kScanTile) + 1) * 8, s));
+    SDC_TRY(device_exclusive_scan(RowLenLoad{offsets, rows}, OffsetStore{out_offsets}, m, tsum.as<unsigned long long>(), s));
+    unsigned long long total = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&total, tsum.as<unsigned long long>() + ceil_div(m, kScanTile), 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    SDC_ARG_CHECK(total < 0xffffffffull, "gathered chars exceed the uint32 offset range (sdc_str_arr.hpp:206)");
+    const uint32_t t32 = (uint32_t)total;
+    SDC_CUDA_TRY(cudaMemcpyAsync(out_offsets + m, &t32, 4, cudaMemcpyHostToDevice, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    *total_chars = (int64_t)total;
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, const int64_t* rows, int64_t m,
+                                 const uint32_t* out_offsets, uint8_t* out_chars, uint8_t* out_bitmap, void* stream) {
+    SDC_ARG_CHECK(m >= 0, "m");
+    if (m == 0) return SDCB200_OK;
+    str_copy_kernel<<<grid_for(m * 32, kStrThreads, 8), kStrThreads, 0, (cudaStream_t)stream>>>(chars, offsets, rows, m, out_offsets,
+                                                                                               out_chars, out_bitmap, bitmap);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+// The reference's own symbol (sdc/native/str_ext/sdc_str_arr.hpp:565-593, bound in sdc/str_arr_ext.py:94-99):
+// HOST buffers, void return.
+void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result) {
+    if (len == 0) return;
+    uint32_t total = offsets[len];
+    void *dchars = nullptr, *doffs = nullptr, *dout = nullptr;
+    cudaStream_t s = nullptr;
+    auto fail = [&](const char* what) {
+        fprintf(stderr, "sdc_b200 stable_argsort: %s: %s\n", what, sdcb200_last_error());
+    };
+    if (dev_alloc(&dchars, (size_t)total + 16, s) || dev_alloc(&doffs, (size_t)(len + 1) * 4, s) ||
+        dev_alloc(&dout, (size_t)len * 8, s)) { fail("alloc"); return; }
+    bool ok = cudaMemcpyAsync(dchars, data, total, cudaMemcpyHostToDevice, s) == cudaSuccess &&
+              cudaMemcpyAsync(doffs, offsets, (size_t)(len + 1) * 4, cudaMemcpyHostToDevice, s) == cudaSuccess;
+    if (ok) ok = sdcb200_str_argsort((const uint8_t*)dchars, (const uint32_t*)doffs, (int64_t)len, ascending, (uint64_t*)dout, s) == SDCB200_OK;
+    if (ok) ok = cudaMemcpyAsync(result, dout, (size_t)len * 8, cudaMemcpyDeviceToHost, s) == cudaSuccess &&
+                 cudaStreamSynchronize(s) == cudaSuccess;
+    if (!ok) fail("run");
+    dev_free(dchars, s); dev_free(doffs, s); dev_free(dout, s);
+}
+
+}  // extern "C"

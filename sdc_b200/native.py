@@ -50,6 +50,14 @@ SIGNATURES = {
     "sdcb200_join_indexers": (_i32, [_i64, _vp, _vp, _i32, _vp]),
     "sdcb200_join_free": (_i32, [_i64, _vp]),
     "sdcb200_take_nullable_f64": (_i32, [_i32, _vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_argsort": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "sdcb200_str_factorize": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64),
+                                     ct.POINTER(_i64), _vp]),
+    "sdcb200_str_group_rows": (_i32, [_i64, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_table_free": (_i32, [_i64, _vp]),
+    "sdcb200_str_gather_sizes": (_i32, [_vp, _vp, _i64, _vp, ct.POINTER(_i64), _vp]),
+    "sdcb200_str_gather_chars": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "stable_argsort": (None, [_vp, _vp, ct.c_uint64, ct.c_int8, _vp]),
 }
 
 # the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)

@@ -1,0 +1,175 @@
+"""String columns on the B200 backend: the reference's str_arr layout held in device memory.
+
+Host-side mirror of
+  * StringArrayType / payload (offsets uint32[n+1], chars uint8[total], validity bitmap LSB-first,
+    1 = valid; NA strings stored empty) ............ sdc/str_arr_type.py:33-101, sdc/native/str_ext/sdc_str_arr.hpp:160-176, 310-314, 389-393
+  * str_arr_stable_argosort -> hstr_ext.stable_argsort  sdc/str_arr_ext.py:1468-1476, sdc_str_arr.hpp:565-593
+  * Series.sort_values on strings (NaN split, argsort of the rest, na_position) sdc/datatypes/hpat_pandas_series_functions.py:3924-3957
+  * groupby with string keys (None keys skipped) ...... sdc/datatypes/hpat_pandas_dataframe_functions.py:3076-3104
+Ordering, hashing and gathering run in libsdc_b200.so (csrc/strings.cu, groupby.cu); the Python <-> str_arr
+conversion below is boxing (the reference does it element by element under the GIL, sdc_str_arr.hpp:323-477).
+"""
+import ctypes as ct
+
+import numpy as np
+
+from . import native
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class StringArray:
+    """offsets / chars / bitmap as NumPy arrays (host) or torch CUDA tensors (device)."""
+
+    def __init__(self, offsets, chars, bitmap, n):
+        self.offsets, self.chars, self.bitmap, self.n = offsets, chars, bitmap, int(n)
+
+    # ---- boxing ----
+    @classmethod
+    def from_pylist(cls, values):
+        n = len(values)
+        enc = [b"" if v is None or (isinstance(v, float) and v != v) else str(v).encode("utf-8") for v in values]
+        lens = np.fromiter((len(e) for e in enc), dtype=np.int64, count=n)
+        total = int(lens.sum())
+        if total >= 2**32:
+            raise ValueError("string array exceeds the uint32 offset range")          # sdc_str_arr.hpp:206
+        offsets = np.zeros(n + 1, dtype=np.uint32)
+        np.cumsum(lens, out=offsets[1:], dtype=np.uint64) if n else None
+        chars = np.frombuffer(b"".join(enc), dtype=np.uint8).copy() if total else np.zeros(0, dtype=np.uint8)
+        valid = np.fromiter((not (v is None or (isinstance(v, float) and v != v)) for v in values), dtype=bool, count=n)
+        bitmap = np.packbits(valid, bitorder="little") if n else np.zeros(0, dtype=np.uint8)
+        return cls(offsets, chars, bitmap, n)
+
+    @classmethod
+    def from_fixed_width(cls, codes_u8):
+        """n x w uint8 matrix of characters -> str_arr without touching Python strings (benchmarks)."""
+        n, w = codes_u8.shape
+        offsets = (np.arange(n + 1, dtype=np.uint64) * w).astype(np.uint32)
+        return cls(offsets, np.ascontiguousarray(codes_u8).reshape(-1), np.full((n + 7) // 8, 0xFF, dtype=np.uint8), n)
+
+    def is_device(self):
+        return not isinstance(self.offsets, np.ndarray)
+
+    def cuda(self):
+        torch = _torch()
+        if self.is_device():
+            return self
+        pad = lambda a: a if a.size else np.zeros(1, dtype=a.dtype)      # keep data_ptr() valid for empty parts
+        return StringArray(torch.from_numpy(self.offsets.view(np.int32)).cuda(), torch.from_numpy(pad(self.chars)).cuda(),
+                           torch.from_numpy(pad(self.bitmap)).cuda(), self.n)
+
+    def cpu(self):
+        if not self.is_device():
+            return self
+        return StringArray(self.offsets.cpu().numpy().view(np.uint32), self.chars.cpu().numpy(), self.bitmap.cpu().numpy(), self.n)
+
+    def valid_mask(self):
+        h = self.cpu()
+        return np.unpackbits(h.bitmap, bitorder="little")[:h.n].astype(bool) if h.n else np.zeros(0, dtype=bool)
+
+    def to_pylist(self):
+        h = self.cpu()
+        valid = h.valid_mask()
+        buf = h.chars.tobytes()
+        o = h.offsets
+        return [buf[o[i]:o[i + 1]].decode("utf-8") if valid[i] else None for i in range(h.n)]
+
+    # ---- kernels ----
+    def argsort(self, ascending=True):
+        """Stable argsort in the reference's string order (NA rows sort as empty strings) -> CUDA int64."""
+        torch = _torch()
+        lib = native.load()
+        d = self.cuda()
+        out = torch.empty(d.n, dtype=torch.int64, device=d.offsets.device)
+        with torch.cuda.device(d.offsets.device):
+            native.check(lib.sdcb200_str_argsort(d.chars.data_ptr(), d.offsets.data_ptr(), d.n, 1 if ascending else 0,
+                                                 out.data_ptr(), native.current_stream_ptr()))
+        return out
+
+    def take(self, rows):
+        """rows: CUDA int64 tensor; rows < 0 give NA.  -> device StringArray."""
+        torch = _torch()
+        lib = native.load()
+        d = self.cuda()
+        m = rows.shape[0]
+        dev = d.offsets.device
+        out_off = torch.empty(m + 1, dtype=torch.int32, device=dev)
+        total = ct.c_int64(0)
+        with torch.cuda.device(dev):
+            stream = native.current_stream_ptr()
+            native.check(lib.sdcb200_str_gather_sizes(d.offsets.data_ptr(), rows.data_ptr(), m, out_off.data_ptr(),
+                                                      ct.byref(total), stream))
+            out_chars = torch.empty(max(1, total.value), dtype=torch.uint8, device=dev)
+            out_bm = torch.empty(max(1, (m + 7) // 8), dtype=torch.uint8, device=dev)
+            native.check(lib.sdcb200_str_gather_chars(d.chars.data_ptr(), d.offsets.data_ptr(), d.bitmap.data_ptr(),
+                                                      rows.data_ptr(), m, out_off.data_ptr(), out_chars.data_ptr(),
+                                                      out_bm.data_ptr(), stream))
+        return StringArray(out_off, out_chars[:total.value] if total.value else out_chars[:0], out_bm[:(m + 7) // 8], m)
+
+    def factorize(self, expected_groups=0):
+        """-> (gid int64 CUDA tensor with -1 for NA rows, n_groups, table handle, table capacity)."""
+        torch = _torch()
+        lib = native.load()
+        d = self.cuda()
+        gid = torch.empty(d.n, dtype=torch.int64, device=d.offsets.device)
+        ng, handle, cap = ct.c_int64(0), ct.c_int64(0), ct.c_int64(0)
+        with torch.cuda.device(d.offsets.device):
+            native.check(lib.sdcb200_str_factorize(d.chars.data_ptr(), d.offsets.data_ptr(), d.bitmap.data_ptr(), d.n,
+                                                   int(expected_groups), gid.data_ptr(), ct.byref(ng), ct.byref(handle),
+                                                   ct.byref(cap), native.current_stream_ptr()))
+        return gid, ng.value, handle.value, cap.value
+
+
+def groupby_str_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
+    """Hash groupby with a string key column: factorize -> numeric groupby on the ids -> key strings.
+
+    keys: StringArray (device);  cols: list of CUDA tensors -> (result key StringArray, {agg: [tensor per column]})
+    sort=True orders the groups by the reference's string order, sort=False by first appearance."""
+    torch = _torch()
+    lib = native.load()
+    from .groupby import groupby_device
+    from .sort import gather_device
+    d = keys.cuda()
+    dev = d.offsets.device
+    gid, ng, handle, cap = d.factorize(expected_groups)
+    try:
+        # ids are table slots; NA rows carry -1 and form one extra group that is dropped below.
+        # first-appearance order comes from the numeric groupby itself (sort=False).
+        gk, res = groupby_device(gid, cols, aggs, False, ddof, max(ng + 1, 1))
+        keep = torch.nonzero(gk >= 0).reshape(-1)
+        if keep.shape[0] != gk.shape[0]:
+            gk = gather_device(gk, keep)
+            res = {a: [gather_device(t, keep) for t in ts] for a, ts in res.items()}
+        rows = torch.empty(gk.shape[0], dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            native.check(lib.sdcb200_str_group_rows(handle, gk.data_ptr(), gk.shape[0], rows.data_ptr(),
+                                                    native.current_stream_ptr()))
+    finally:
+        with torch.cuda.device(dev):
+            native.check(lib.sdcb200_str_table_free(handle, native.current_stream_ptr()))
+    rkeys = d.take(rows)
+    if sort and rkeys.n > 1:
+        order = rkeys.argsort(True)
+        rkeys = rkeys.take(order)
+        res = {a: [gather_device(t, order) for t in ts] for a, ts in res.items()}
+    return rkeys, res
+
+
+def series_sort_values_str(series, ascending=True, na_position="last"):
+    """Series.sort_values for a string Series (reference :3924-3957): None/NaN rows are split off, the rest
+    is argsorted with the native stable string sort, the NA block goes last or first."""
+    import pandas as pd
+    torch = _torch()
+    values = series.to_numpy(dtype=object)
+    sa = StringArray.from_pylist(list(values))
+    valid = sa.valid_mask()
+    good = np.flatnonzero(valid)
+    bad = np.flatnonzero(~valid)
+    sub = StringArray.from_pylist([values[i] for i in good]).cuda()
+    order = sub.argsort(bool(ascending)).cpu().numpy()
+    pos = good[order]
+    idx = np.concatenate([bad, pos]) if na_position == "first" else np.concatenate([pos, bad])
+    return pd.Series(values[idx], index=series.index.take(idx), name=series.name, dtype=series.dtype)

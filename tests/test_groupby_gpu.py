@@ -146,6 +146,34 @@ def test_empty_and_degenerate():
     np.testing.assert_array_equal(rk, [1, 3])
 
 
+def test_dense_window_outliers_and_extreme_keys():
+    """Dense int64 keys take the direct-addressed shared table; keys outside the sampled window (and
+    INT64_MIN / INT64_MAX) must still aggregate exactly through the global table."""
+    rng = np.random.default_rng(21)
+    n = 300_000
+    a = rng.integers(-400, 600, n)
+    a[rng.integers(0, n, 50)] = rng.integers(10**9, 10**12, 50)
+    a[7] = np.iinfo(np.int64).min
+    a[8] = np.iinfo(np.int64).max
+    a[9] = np.iinfo(np.int64).max
+    cols = {"b": rng.standard_normal(n), "c": rng.integers(-5, 5, n)}
+    for agg in ("sum", "min", "count", "mean"):
+        for sort in (True, False):
+            gk, got = _host(a, cols, agg, sort, 1, 1000)
+            wk, want = ogroupby.groupby_agg(a, cols, agg, sort)
+            _compare(gk, got, wk, want, agg, "dense+outliers sort=%s" % sort)
+    # keys clustered at the top of the int64 range (window clamp)
+    a2 = np.iinfo(np.int64).max - rng.integers(0, 100, n)
+    gk, got = _host(a2, cols, "sum", True, 1, 100)
+    wk, want = ogroupby.groupby_agg(a2, cols, "sum", True)
+    _compare(gk, got, wk, want, "sum", "top of range")
+    # sorted keys: the strided sample still sees the whole range
+    a3 = np.sort(rng.integers(0, 2000, n))
+    gk, got = _host(a3, cols, "max", True, 1, 2000)
+    wk, want = ogroupby.groupby_agg(a3, cols, "max", True)
+    _compare(gk, got, wk, want, "max", "sorted keys")
+
+
 def test_multi_agg_one_pass_and_many_columns():
     from sdc_b200.groupby import groupby_host
     rng = np.random.default_rng(3)
