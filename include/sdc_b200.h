@@ -189,6 +189,18 @@ int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, 
 /* the reference's own symbol (HOST buffers, void return), exactly as sdc/str_arr_ext.py:94-99 declares it */
 void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result);
 
+/* ------------------------------------------------------------------ multi-GPU hash shuffle
+ * Partition step of the reference's (dead) MPI shuffle (sdc/shuffle_utils.py:119-163: per-row destination
+ * and per-destination counts); the exchange -- c_alltoall of the counts and c_alltoallv per column,
+ * sdc/distributed_api.py:439-466, sdc/transport/hpat_transport_single_process.cpp:106-119 -- is an NCCL
+ * all-to-all issued by sdc_b200/distributed.py.  perm_out = row numbers grouped by destination rank
+ * (rows of one destination keep their input order), counts_out[nparts] = rows per destination (int64).
+ * Columns are packed for sending with sdcb200_gather(perm).                                           */
+int32_t sdcb200_hash_partition(int32_t key_dtype, const void* keys, int64_t n, int32_t nparts, int64_t* perm_out,
+                               int64_t* counts_out, void* stream);
+/* out[i] = cnt[i] ? sum[i] / cnt[i] : NaN: final step of a distributed mean (partials are exchanged).  */
+int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, int64_t n, double* out, void* stream);
+
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
  * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and

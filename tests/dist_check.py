@@ -1,0 +1,105 @@
+"""Multi-GPU parity check, one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_check.py
+
+Every rank builds the SAME global synthetic table (seeded), takes its block of rows
+(sdc/_distributed.h:77-102), runs the distributed groupby / join / rolling, and the gathered results are
+compared with the oracle on the global table.  Exits non-zero on any mismatch.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    from oracle import groupby as ogroupby
+    from oracle import join as ojoin
+    from oracle import rolling as orolling
+    from sdc_b200 import distributed as D
+
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    P = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rng = np.random.default_rng(5)
+    n = 400_003
+    keys_lo = rng.integers(0, 1000, n)
+    keys_hi = rng.integers(0, 150_000, n)
+    vals = rng.standard_normal(n)
+    vals[rng.integers(0, n, n // 100)] = np.nan
+    ivals = rng.integers(-1000, 1000, n)
+    s, e = D.block_range(n, rank, P)
+    cols = [torch.from_numpy(vals[s:e].copy()).to(dev), torch.from_numpy(ivals[s:e].copy()).to(dev)]
+    names = {"v": vals, "w": ivals}
+
+    def check_groupby(keys, aggs, mode, sort, hint):
+        k = torch.from_numpy(keys[s:e].copy()).to(dev)
+        gk, res, layout = D.groupby_distributed(k, cols, aggs, sort, 1, hint, None, mode)
+        if layout == "sharded":
+            gk_all, _ = D.allgather_ragged(gk)
+            res = {a: [D.allgather_ragged(t)[0] for t in ts] for a, ts in res.items()}
+            order = torch.argsort(gk_all)                       # test-side canonical order
+            gk = gk_all[order]
+            res = {a: [t[order] for t in ts] for a, ts in res.items()}
+            sort_cmp = True
+        else:
+            sort_cmp = sort
+        for a in aggs:
+            wk, want = ogroupby.groupby_agg(keys, names, a, sort_cmp)
+            np.testing.assert_array_equal(gk.cpu().numpy(), wk, err_msg="%s %s keys" % (mode, a))
+            for i, c in enumerate(("v", "w")):
+                g, w = res[a][i].cpu().numpy(), want[c]
+                if a in ("min", "max", "count") or w.dtype.kind == "i":
+                    np.testing.assert_array_equal(g, w, err_msg="%s %s %s" % (mode, a, c))
+                else:
+                    np.testing.assert_allclose(g, w, rtol=1e-9, atol=1e-12, equal_nan=True, err_msg="%s %s %s" % (mode, a, c))
+
+    check_groupby(keys_lo, ("sum", "mean", "min", "max", "count"), "combine", True, 1000)
+    check_groupby(keys_lo, ("sum", "count"), "combine", False, 1000)
+    check_groupby(keys_hi, ("sum", "mean", "min", "max", "count"), "shuffle", True, 150_000)
+    check_groupby(keys_hi, ("var", "std"), "shuffle", True, 150_000)
+
+    # join: probe rows sharded, build rows sharded; global row numbers come back
+    nb = 20_011
+    build = rng.permutation(60_000)[:nb].astype(np.int64)
+    probe = rng.integers(0, 60_000, n)
+    bs, be = D.block_range(nb, rank, P)
+    for mode in ("broadcast", "shuffle"):
+        for how in ("inner", "left"):
+            li, ri = D.join_distributed(torch.from_numpy(probe[s:e].copy()).to(dev), torch.from_numpy(build[bs:be].copy()).to(dev),
+                                        how, None, mode)
+            li_all, _ = D.allgather_ragged(li)
+            ri_all, _ = D.allgather_ragged(ri)
+            got = ojoin.canonical(li_all.cpu().numpy(), ri_all.cpu().numpy())
+            want = ojoin.join_indexers(probe, build, how)
+            np.testing.assert_array_equal(got[0], want[0], err_msg="%s %s" % (mode, how))
+            np.testing.assert_array_equal(got[1], want[1], err_msg="%s %s" % (mode, how))
+
+    # rolling: row-sharded with the halo from the previous rank
+    x = rng.random(n)
+    x[::977] = np.nan
+    for op in ("mean", "std", "count", "max"):
+        out = D.rolling_distributed(torch.from_numpy(x[s:e].copy()).to(dev), op, 100, 100, 1)
+        full, _ = D.allgather_ragged(out)
+        want = orolling.rolling(x, op, 100, 100, 1)
+        g = full.cpu().numpy()
+        assert np.array_equal(np.isnan(g), np.isnan(want)), op
+        ok = ~np.isnan(want)
+        np.testing.assert_allclose(g[ok], want[ok], rtol=1e-9, atol=1e-11, err_msg=op)
+
+    dist.barrier()
+    if rank == 0:
+        print("dist_check ok: world=%d" % P)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+"""N > 1 host logic under gloo (world_size 2, CPU): the shuffle protocol, ragged all-gather, halo exchange
+and block partition of sdc_b200/distributed.py against the oracle's restatement of the reference protocol.
+The device kernels are not involved (those run in tests/dist_check.py on >= 2 GPUs)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, fn_name, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        ret[rank] = globals()[fn_name](rank, world_size)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name, world_size=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world_size, _free_port(), fn_name, ret), nprocs=world_size, join=True)
+    return [ret[r] for r in range(world_size)]
+
+
+def _data(rank):
+    rng = np.random.default_rng(100 + rank)
+    n = 1000 + 37 * rank
+    keys = rng.integers(0, 50, n)
+    vals = rng.standard_normal(n)
+    dest = (keys * 2654435761 % 7) % 2
+    return keys, vals, dest
+
+
+def _shuffle_case(rank, P):
+    from sdc_b200 import distributed as D
+    keys, vals, dest = _data(rank)
+    perm = np.argsort(dest, kind="stable")                    # what sdcb200_hash_partition returns on a GPU
+    counts = torch.from_numpy(np.bincount(dest, minlength=P).astype(np.int64))
+    recv = D.exchange_counts(counts)
+    k2 = D.exchange_rows(torch.from_numpy(keys[perm]), counts, recv)
+    v2 = D.exchange_rows(torch.from_numpy(vals[perm]), counts, recv)
+    return recv.numpy(), k2.numpy(), v2.numpy()
+
+
+def test_shuffle_protocol_matches_reference_restatement():
+    from oracle import shuffle as oshuffle
+    got = _run("_shuffle_case")
+    cols = [[_data(r)[0], _data(r)[1]] for r in range(2)]
+    dests = [_data(r)[2] for r in range(2)]
+    want, send_counts = oshuffle.shuffle(cols, dests)
+    for r in range(2):
+        np.testing.assert_array_equal(got[r][0], send_counts[:, r])
+        np.testing.assert_array_equal(got[r][1], want[r][0])
+        np.testing.assert_array_equal(got[r][2], want[r][1])
+        # every key landed on the rank its destination names
+        assert np.all((got[r][1] * 2654435761 % 7) % 2 == r)
+
+
+def _ragged_case(rank, P):
+    from sdc_b200 import distributed as D
+    t = torch.arange(3 + 4 * rank, dtype=torch.float64) + 100 * rank
+    cat, sizes = D.allgather_ragged(t)
+    return cat.numpy(), sizes
+
+
+def test_allgather_ragged():
+    got = _run("_ragged_case")
+    want = np.concatenate([np.arange(3) + 0.0, np.arange(7) + 100.0])
+    for r in range(2):
+        np.testing.assert_array_equal(got[r][0], want)
+        assert got[r][1] == [3, 7]
+
+
+def _halo_case(rank, P):
+    from sdc_b200 import distributed as D
+    x = np.arange(10.0) + 10 * rank
+    h = D.halo_exchange(torch.from_numpy(x), 3)
+    return None if h is None else h.numpy()
+
+
+def test_halo_exchange_and_block_partition():
+    from oracle import shuffle as oshuffle
+    from sdc_b200 import distributed as D
+    got = _run("_halo_case")
+    assert got[0] is None
+    np.testing.assert_array_equal(got[1], [7.0, 8.0, 9.0])
+    for n, P in ((9, 4), (10, 3), (1, 2), (0, 2), (100, 8)):
+        for r in range(P):
+            assert D.block_range(n, r, P) == oshuffle.block_range(n, r, P)
+    # sdc/_distributed.h:77-102: ceil(n / P) rows per rank, the tail ranks may be short or empty
+    assert [D.block_range(9, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 9)]
+
+
+def _rolling_halo_oracle_case(rank, P):
+    """Row-sharded rolling with the halo exchange, the window arithmetic done by the oracle on each shard:
+    shard + halo must reproduce the tail of the whole-series result."""
+    from oracle import rolling as orolling
+    from sdc_b200 import distributed as D
+    x = np.random.default_rng(7).random(400)
+    s, e = D.block_range(len(x), rank, P)
+    h = D.halo_exchange(torch.from_numpy(x[s:e].copy()), 9)
+    loc = x[s:e] if h is None else np.concatenate([h.numpy(), x[s:e]])
+    out = orolling.rolling(loc, "mean", 10, 10, 1)
+    return out[len(loc) - (e - s):]
+
+
+def test_row_sharded_rolling_via_halo():
+    from oracle import rolling as orolling
+    got = np.concatenate(_run("_rolling_halo_oracle_case"))
+    x = np.random.default_rng(7).random(400)
+    want = orolling.rolling(x, "mean", 10, 10, 1)
+    # rank 1's first rows see the halo, so only rank 0's own warm-up rows are NaN
+    np.testing.assert_allclose(got[200:], want[200:], rtol=1e-12)
+    np.testing.assert_allclose(got[:200], want[:200], rtol=1e-12, equal_nan=True)
