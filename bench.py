@@ -133,6 +133,106 @@ def run_reference(args):
     }))
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rolling kernel, from the committed
+    `ncu --set full` summary (profiles/); None when no capture of the current kernel is on file."""
+    p = os.path.join(ROOT, "profiles", "r1_rolling_ncu_summary.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
+def _event_times(fn, reps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def bench_other_ops(dev, peak, cpu_legs=True):
+    """The other two operators BASELINE.json's metric names, at their configs, inputs resident in HBM:
+    C1 groupby-sum (10 M rows, 1 K int64 groups, one f64 column) and C3 inner hash join (100 M probe x
+    10 M build, int64 keys).  Whole-operator device time through the public Python API (CUDA events)."""
+    import torch
+    from sdc_b200.groupby import groupby_device
+    from sdc_b200.join import join_device
+    out = {}
+    rng = np.random.default_rng(0)
+    n = 10_000_000
+    a_h = rng.integers(0, 1000, n, dtype=np.int64)
+    b_h = rng.random(n)
+    a, b = torch.from_numpy(a_h).to(dev), torch.from_numpy(b_h).to(dev)
+    med, best = _event_times(lambda: groupby_device(a, [b], ("sum",), True, 1, 1000), 20)
+    gb = {"workload": "C1: df.groupby('A').sum(), 10M rows, int64 key with 1K groups, one float64 column, sort=True",
+          "rows_per_s": n / (med * 1e-3), "ms_median": med, "ms_best": best, "algorithmic_bytes": 16 * n,
+          "achieved_GBps": 16 * n / (med * 1e-3) / 1e9, "frac_of_measured_peak": 16 * n / (med * 1e-3) / 1e9 / peak}
+    n2 = 100_000_000
+    a2 = torch.from_numpy(rng.integers(0, 1000, n2, dtype=np.int64)).to(dev)
+    b2 = torch.from_numpy(rng.random(n2)).to(dev)
+    med2, _ = _event_times(lambda: groupby_device(a2, [b2], ("sum",), True, 1, 1000), 10)
+    gb["rows_per_s_100M"] = n2 / (med2 * 1e-3)
+    gb["frac_of_measured_peak_100M"] = 16 * n2 / (med2 * 1e-3) / 1e9 / peak
+    del a2, b2
+    if cpu_legs:
+        import numba
+        import pandas as pd
+        from oracle import groupby as ogroupby
+        ns = 2_000_000          # the dict-of-row-lists algorithm is ~5 Mrows/s: bounded sample
+        ogroupby.groupby_agg(a_h[:10000], {"B": b_h[:10000]}, "sum")
+        t0 = time.perf_counter()
+        ogroupby.groupby_agg(a_h[:ns], {"B": b_h[:ns]}, "sum")
+        dt = time.perf_counter() - t0
+        df = pd.DataFrame({"A": a_h, "B": b_h})
+        t0 = time.perf_counter()
+        df.groupby("A").sum()
+        dtp = time.perf_counter() - t0
+        gb["cpu_baseline"] = {"value": ns / dt, "unit": "rows/s", "cores": numba.config.NUMBA_NUM_THREADS, "kind": "port",
+                              "sample": "first 2M rows of the workload, one call after a compile call",
+                              "pandas_rows_per_s": n / dtp}
+    out["groupby_sum_c1"] = gb
+    del a, b
+
+    nb, npr = 10_000_000, 100_000_000
+    r_h = np.random.default_rng(2).permutation(nb).astype(np.int64)
+    l_h = np.random.default_rng(3).integers(0, nb, npr, dtype=np.int64)
+    r, l = torch.from_numpy(r_h).to(dev), torch.from_numpy(l_h).to(dev)
+    res = {}
+
+    def run():
+        res["o"] = join_device(l, r, "inner")
+    med, best = _event_times(run, 5, warm=2)
+    n_out = int(res["o"][0].shape[0])
+    alg = 8 * (npr + nb) + 16 * n_out
+    jn = {"workload": "C3: pd.merge inner, 100M-row probe x 10M-row build (unique), int64 keys -> int64 indexers",
+          "rows_per_s": npr / (med * 1e-3), "ms_median": med, "ms_best": best, "n_out": n_out, "algorithmic_bytes": alg,
+          "achieved_GBps": alg / (med * 1e-3) / 1e9, "frac_of_measured_peak": alg / (med * 1e-3) / 1e9 / peak}
+    res.clear()
+    if cpu_legs:
+        import pandas as pd
+        ns = 10_000_000
+        L = pd.DataFrame({"k": l_h[:ns], "li": np.arange(ns)})
+        R = pd.DataFrame({"k": r_h, "ri": np.arange(nb)})
+        t0 = time.perf_counter()
+        L.merge(R, on="k", how="inner")
+        dt = time.perf_counter() - t0
+        jn["cpu_baseline"] = {"value": ns / dt, "unit": "probe rows/s", "cores": 1, "kind": "pandas.merge (the reference ships no merge)",
+                              "sample": "first 10M probe rows x the full 10M-row build side"}
+    out["join_inner_c3"] = jn
+    return out
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def run_gpu(args):
     import torch
@@ -243,6 +343,10 @@ def run_gpu(args):
         lib.sdcb200_host_free(pin_in)
         lib.sdcb200_host_free(pin_out)
 
+    ops = None
+    if rank == 0 and world == 1 and not args.no_ops:
+        ops = bench_other_ops(dev, peak, cpu_legs=not args.no_cpu)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         best, cores, layer = cpu_rolling_mean(x_host, 5)
@@ -259,11 +363,12 @@ def run_gpu(args):
                        "l2": "inputs (800 MB in + 800 MB out per step) larger than L2",
                        "multi_gpu": "row-sharded series, win-1 halo rows from the previous rank (NCCL send/recv)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
                          "kernel": "rolling_run_kernel<MEAN,f64,R=17>", "kernel_ms": kern,
                          "algorithmic_bytes_per_launch": BYTES_PER_ROW * N_ROWS},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_each": per_step,
+            "other_ops": ops,
         }
         print(json.dumps(line))
     if world > 1:
@@ -277,6 +382,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ops", action="store_true", help="skip the groupby (C1) / join (C3) side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

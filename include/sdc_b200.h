@@ -153,6 +153,9 @@ int32_t sdcb200_groupby_free(int64_t handle);
 int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                      void* stream, int64_t* handle_out, int64_t* n_out);
 int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_idx, int32_t dst_is_host, void* stream);
+/* zero-copy access: device pointers of the handle's indexer arrays (n_out int64 each), valid until
+ * sdcb200_join_free                                                                                  */
+int32_t sdcb200_join_result(int64_t handle, int64_t** left_idx, int64_t** right_idx);
 int32_t sdcb200_join_free(int64_t handle, void* stream);
 /* dst[i] = idx[i] < 0 ? NaN : (double)src[idx[i]] -- payload gather of a left join
  * (setitem_arr_nan, sdc/hiframes/join.py:34-43); src_dtype SDCB200_I64 or SDCB200_F64.            */

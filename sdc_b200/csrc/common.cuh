@@ -138,6 +138,42 @@ __device__ __forceinline__ void st_stream_v2f64(double* p, double a, double b) {
     asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
 }
 
+// ---- L2 eviction-priority hints (createpolicy + ld/st ... L2::cache_hint) ----
+// evict_first for data streamed once (probe keys, emitted pairs), evict_last for the random-access
+// table that should stay L2-resident while the streams pass through.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_hint_u32(const uint32_t* a, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_hint_u64(const unsigned long long* a, uint64_t pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ld_hint_v2u64(const void* a, uint64_t pol) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+                 : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint_v2s64(void* a, long long x, long long y, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(a), "l"(x), "l"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint_s64(void* a, long long x, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(a), "l"(x), "l"(pol) : "memory");
+}
+
 __device__ __forceinline__ double shfl_up_f64(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 
 __device__ __forceinline__ bool is_finite_f64(double v) {

@@ -17,6 +17,15 @@
 //                        a scan of the tile counts gives every tile its output offset (and n_out);
 //                        pass B: block scan of the per-row counts, then (left row, right row) pairs are
 //                        written in LEFT ROW ORDER (how='left' keeps the left order like pandas).
+//   dense keys           int64 build keys whose range is <= 4x the build rows (found by a min/max pass) skip hashing:
+//                        the table is an array of 8-byte vals indexed by key - min (80 MB for C3: L2-resident),
+//                        build = one atomicAdd per row, probe = one 8-byte load.
+//   unique build keys    (every count <= 1, detected on the fly): ONE probe kernel -- tiles take a ticket, a
+//                        decoupled look-back chains the per-tile output counts, pairs are staged in shared
+//                        memory and written coalesced; how='left' needs no scan at all (output row = left row).
+//                        Uniqueness is known after the build (the insert raises a flag on a second row of a key);
+//                        with dense keys the unique table is just uint32 right-row + 1 per key (40 MB for C3).
+//                        Streams (probe keys, emitted pairs) carry L2 evict_first hints, table loads evict_last.
 // Keys: int64, or float64 canonicalised so that -0.0 == +0.0 and NaN == NaN (pandas merges NaN keys).
 // Limits: build side < 2^32 - 1 rows.
 #include <cstring>
@@ -50,8 +59,11 @@ __device__ __forceinline__ unsigned long long canon_key(unsigned long long b) {
 }
 
 struct JTable {
-    ulonglong2* slots;          // [cap + 1]
+    ulonglong2* slots;          // hash mode: [cap + 1]
     unsigned long long cap;     // power of two
+    unsigned long long* dense;  // dense mode: val of key k at dense[k - dlo]
+    uint32_t* dense32;          // dense mode with unique build keys: right row + 1 (0 = absent), 4 bytes per key
+    unsigned long long dlo, drange;   // drange == 0: hash mode
 };
 
 __device__ __forceinline__ unsigned long long jt_upsert(const JTable& t, unsigned long long key) {
@@ -70,6 +82,10 @@ __device__ __forceinline__ unsigned long long jt_upsert(const JTable& t, unsigne
 
 // -> val of the key's slot, 0 when the key is absent
 __device__ __forceinline__ unsigned long long jt_lookup(const JTable& t, unsigned long long key) {
+    if (t.drange) {
+        const unsigned long long d = key - t.dlo;
+        return d < t.drange ? __ldg(t.dense + d) : 0ull;
+    }
     if (key == kEmptyKey) return t.slots[t.cap].y;
     unsigned long long s = jmix64(key) & (t.cap - 1);
     while (true) {
@@ -90,15 +106,72 @@ __global__ void jt_init_kernel(JTable t) {
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                  JTable t, uint32_t* __restrict__ rslot,
-                                                                 uint32_t* __restrict__ rrank) {
+                                                                 uint32_t* __restrict__ rrank,
+                                                                 unsigned long long* __restrict__ dup_flag) {
     const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
     for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride) {
         const unsigned long long k = canon_key<KEY_F64>(keys[j]);
         const unsigned long long s = jt_upsert(t, k);
         const unsigned long long rank = atomicAdd(&t.slots[s].y, 1ull);
+        if (rank) *dup_flag = 1ull;
         rslot[j] = (uint32_t)s;
         rrank[j] = (uint32_t)rank;
     }
+}
+
+// ---- dense mode ----
+__global__ void __launch_bounds__(kJoinThreads) key_minmax_kernel(const long long* __restrict__ keys, int64_t n,
+                                                                  unsigned long long* __restrict__ mm /* [0] min, [1] max, ordered */) {
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)kJoinThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kJoinThreads) {
+        const unsigned long long u = (unsigned long long)keys[i] ^ 0x8000000000000000ull;
+        mn = u < mn ? u : mn;
+        mx = u > mx ? u : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, mn);
+        atomicMax(mm + 1, mx);
+    }
+}
+
+// unique build keys: the table holds the right row itself; a second row of a key raises the flag
+__global__ void __launch_bounds__(kJoinThreads) dense_insert_unique_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                           JTable t, unsigned long long* __restrict__ dup_flag) {
+    const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
+    for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride) {
+        const unsigned long long d = keys[j] - t.dlo;          // in range by construction
+        if (atomicCAS(&t.dense32[d], 0u, (uint32_t)j + 1u) != 0u) *dup_flag = 1ull;
+    }
+}
+
+__global__ void __launch_bounds__(kJoinThreads) dense_insert_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                    JTable t, uint32_t* __restrict__ rslot,
+                                                                    uint32_t* __restrict__ rrank) {
+    const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
+    for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride) {
+        const unsigned long long d = keys[j] - t.dlo;          // in range by construction
+        rslot[j] = (uint32_t)d;
+        rrank[j] = (uint32_t)atomicAdd(&t.dense[d], 1ull);
+    }
+}
+
+struct DenseStartStore {          // val = start << 32 | count
+    unsigned long long* p;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const { p[i] = (excl << 32) | v; }
+};
+
+__global__ void __launch_bounds__(kJoinThreads) dense_scatter_kernel(const uint32_t* __restrict__ rslot,
+                                                                     const uint32_t* __restrict__ rrank, int64_t n, JTable t,
+                                                                     uint32_t* __restrict__ rid) {
+    const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
+    for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride)
+        rid[(t.dense[rslot[j]] >> 32) + rrank[j]] = (uint32_t)j;
 }
 
 struct SlotCountLoad {
@@ -213,6 +286,136 @@ __global__ void __launch_bounds__(kJoinThreads) probe_emit_kernel(const unsigned
     }
 }
 
+// ---- unique build keys: one probe kernel ----
+// right row + 1 of the key, 0 when absent (valid only when every build key is unique)
+__device__ __forceinline__ uint32_t lookup_row1(const JTable& t, const uint32_t* __restrict__ rid, unsigned long long key,
+                                                uint64_t keep) {
+    if (t.dense32) {
+        const unsigned long long d = key - t.dlo;
+        return d < t.drange ? ld_hint_u32(t.dense32 + d, keep) : 0u;
+    }
+    const unsigned long long v = jt_lookup(t, key);
+    return (unsigned)v ? rid[v >> 32] + 1u : 0u;
+}
+
+template <bool KEY_F64>
+__device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t i0, int64_t n,
+                                                uint64_t stream_pol, unsigned long long k[kItems]) {
+    if (i0 + kItems <= n) {
+#pragma unroll
+        for (int e = 0; e < kItems; e += 2) {
+            const ulonglong2 kk = ld_hint_v2u64(keys + i0 + e, stream_pol);
+            k[e] = canon_key<KEY_F64>(kk.x);
+            k[e + 1] = canon_key<KEY_F64>(kk.y);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kItems; ++e) k[e] = (i0 + e < n) ? canon_key<KEY_F64>(keys[i0 + e]) : 0ull;
+    }
+}
+
+// meta[0] ticket, meta[1] n_out.  status[tile] = flag << 62 | value; flag 1: tile aggregate, 2: inclusive prefix
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kJoinThreads) probe_unique_inner_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                          JTable t, const uint32_t* __restrict__ rid,
+                                                                          unsigned long long* __restrict__ status,
+                                                                          unsigned long long* __restrict__ meta, int64_t ntiles,
+                                                                          int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+    __shared__ unsigned long long wsum[kJoinThreads / 32];
+    __shared__ unsigned long long s_tile, s_base;
+    __shared__ int64_t sl[kTile];
+    __shared__ int64_t sr[kTile];
+    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
+    if (threadIdx.x == 0) s_tile = atomicAdd(&meta[0], 1ull);
+    __syncthreads();
+    const int64_t tile = (int64_t)s_tile;
+    const int64_t i0 = tile * kTile + (int64_t)threadIdx.x * kItems;
+    unsigned long long k[kItems];
+    uint32_t row1[kItems];
+    load_probe_keys<KEY_F64>(keys, i0, n, stream_pol, k);
+    unsigned c = 0;
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) {
+        row1[e] = (i0 + e < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
+        c += row1[e] ? 1u : 0u;
+    }
+    unsigned long long tot;
+    const unsigned long long ex = block_excl_scan_u64(c, &tot, wsum);
+    // decoupled look-back over the tile totals (warp 0)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long base = 0;
+        if (tile == 0) {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[0]) = (2ull << 62) | tot;
+        } else {
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = (1ull << 62) | tot;
+            int64_t idx = tile - 1;
+            while (true) {
+                const int64_t j = idx - lane;
+                unsigned long long sv = (2ull << 62);                      // before tile 0: prefix 0
+                if (j >= 0) sv = *reinterpret_cast<volatile unsigned long long*>(&status[j]);
+                const unsigned ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
+                if (ready != 0xffffffffu) continue;                         // a predecessor has not published yet
+                const unsigned pref = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+                const int first = pref ? __ffs(pref) - 1 : 31;
+                unsigned long long val = (lane <= first) ? (sv & 0x3fffffffffffffffull) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                base += val;
+                if (pref) break;
+                idx -= 32;
+            }
+            if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = (2ull << 62) | (base + tot);
+        }
+        if (lane == 0) {
+            s_base = base;
+            if (tile == ntiles - 1) meta[1] = base + tot;
+        }
+    }
+    // stage the tile's pairs, then coalesced streaming stores
+    unsigned p = (unsigned)ex;
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) {
+        if (row1[e]) {
+            sl[p] = i0 + e;
+            sr[p] = (int64_t)row1[e] - 1;
+            ++p;
+        }
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    for (unsigned q = threadIdx.x; q < (unsigned)tot; q += kJoinThreads) {
+        st_hint_s64(lidx + base + q, sl[q], stream_pol);
+        st_hint_s64(ridx + base + q, sr[q], stream_pol);
+    }
+}
+
+// how='left' with unique build keys: output row i = left row i, no scan
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                         JTable t, const uint32_t* __restrict__ rid,
+                                                                         int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
+    const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
+    if (i0 >= n) return;
+    unsigned long long k[kItems];
+    int64_t rr[kItems];
+    load_probe_keys<KEY_F64>(keys, i0, n, stream_pol, k);
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) rr[e] = (i0 + e < n) ? (int64_t)lookup_row1(t, rid, k[e], keep_pol) - 1 : -1;
+    if (i0 + kItems <= n) {
+#pragma unroll
+        for (int e = 0; e < kItems; e += 2) {
+            st_hint_v2s64(lidx + i0 + e, i0 + e, i0 + e + 1, stream_pol);
+            st_hint_v2s64(ridx + i0 + e, rr[e], rr[e + 1], stream_pol);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kItems; ++e)
+            if (i0 + e < n) { lidx[i0 + e] = i0 + e; ridx[i0 + e] = rr[e]; }
+    }
+}
+
 // dst[i] = idx[i] < 0 ? NaN : (double)src[idx[i]]  -- the payload gather of a left join
 // (setitem_arr_nan, sdc/hiframes/join.py:34-43: unmatched rows become NaN, ints are promoted)
 template <typename T>
@@ -239,33 +442,114 @@ template <bool KEY_F64, bool LEFT>
 int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long long* r, int64_t nr, cudaStream_t s,
                  JoinResult* res) {
     const int sms = sm_count();
+    const int wide = sms * 8;
     // ---- build ----
     JTable t;
-    t.cap = 1024;
-    while (t.cap * 3 < (unsigned long long)nr * 4) t.cap <<= 1;        // load factor <= 0.75
-    Scratch slots, rslot, rrank, rid, tsum_b;
-    SDC_TRY(slots.alloc((size_t)(t.cap + 1) * 16, s));
-    t.slots = slots.as<ulonglong2>();
-    SDC_TRY(rslot.alloc((size_t)nr * 4, s));
-    SDC_TRY(rrank.alloc((size_t)nr * 4, s));
-    SDC_TRY(rid.alloc((size_t)nr * 4, s));
-    const int64_t nslots = (int64_t)t.cap + 1;
-    SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
-    const int wide = sms * 8;
-    jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
-    SDC_CHECK_LAUNCH();
-    if (nr > 0) {
-        const int grid = (int)(ceil_div(nr, kJoinThreads) < wide ? ceil_div(nr, kJoinThreads) : wide);
-        jt_insert_kernel<KEY_F64><<<grid, kJoinThreads, 0, s>>>(r, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>());
+    memset(&t, 0, sizeof(t));
+    Scratch slots, slots32, rslot, rrank, rid, tsum_b, meta;
+    SDC_TRY(meta.alloc(64, s));                  // [0] ticket, [1] n_out, [2] duplicate build key seen, [4] min, [5] max
+    unsigned long long* dmeta = meta.as<unsigned long long>();
+    {
+        const unsigned long long init[8] = {0, 0, 0, 0, ~0ull, 0ull, 0, 0};
+        SDC_CUDA_TRY(cudaMemcpyAsync(dmeta, init, 64, cudaMemcpyHostToDevice, s));
+    }
+    SDC_TRY(rid.alloc((size_t)nr * 4 + 16, s));
+    const int bgrid = (int)(ceil_div(nr, kJoinThreads) < wide ? (nr > 0 ? ceil_div(nr, kJoinThreads) : 1) : wide);
+    bool dense = false, unique = true;
+    unsigned long long hdup = 0;
+    if (!KEY_F64 && nr > 0) {
+        key_minmax_kernel<<<bgrid, kJoinThreads, 0, s>>>(reinterpret_cast<const long long*>(r), nr, dmeta + 4);
         SDC_CHECK_LAUNCH();
-        SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
-                                      tsum_b.as<unsigned long long>(), s));
-        jt_scatter_kernel<<<grid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
+        unsigned long long mm[2];
+        SDC_CUDA_TRY(cudaMemcpyAsync(mm, dmeta + 4, 16, cudaMemcpyDeviceToHost, s));
+        SDC_CUDA_TRY(cudaStreamSynchronize(s));
+        const unsigned long long span = mm[1] - mm[0];          // ordered (sign-flipped) image: no overflow
+        unsigned long long lim = 4ull * (unsigned long long)nr;
+        if (lim < (1ull << 16)) lim = 1ull << 16;
+        if (span < lim && span < 0xfffffff0ull) {
+            dense = true;
+            t.dlo = mm[0] ^ 0x8000000000000000ull;
+            t.drange = span + 1;
+        }
+    }
+    if (dense) {
+        // optimistic: unique build keys -> 4-byte table of right rows, no scan, no scatter
+        const int64_t nslots = (int64_t)t.drange;
+        SDC_TRY(slots32.alloc((size_t)nslots * 4, s));
+        t.dense32 = slots32.as<uint32_t>();
+        SDC_CUDA_TRY(cudaMemsetAsync(t.dense32, 0, (size_t)nslots * 4, s));
+        dense_insert_unique_kernel<<<bgrid, kJoinThreads, 0, s>>>(r, nr, t, dmeta + 2);
         SDC_CHECK_LAUNCH();
+        SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+        SDC_CUDA_TRY(cudaStreamSynchronize(s));
+        unique = hdup == 0;
+        if (!unique) {
+            t.dense32 = nullptr;
+            SDC_TRY(rslot.alloc((size_t)nr * 4 + 16, s));
+            SDC_TRY(rrank.alloc((size_t)nr * 4 + 16, s));
+            SDC_TRY(slots.alloc((size_t)nslots * 8, s));
+            t.dense = slots.as<unsigned long long>();
+            SDC_CUDA_TRY(cudaMemsetAsync(t.dense, 0, (size_t)nslots * 8, s));
+            SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
+            dense_insert_kernel<<<bgrid, kJoinThreads, 0, s>>>(r, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>());
+            SDC_CHECK_LAUNCH();
+            SDC_TRY(device_exclusive_scan(ArrayLoad{t.dense}, DenseStartStore{t.dense}, nslots, tsum_b.as<unsigned long long>(), s));
+            dense_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
+            SDC_CHECK_LAUNCH();
+        }
+    } else {
+        t.cap = 1024;
+        while (t.cap * 3 < (unsigned long long)nr * 4) t.cap <<= 1;        // load factor <= 0.75
+        const int64_t nslots = (int64_t)t.cap + 1;
+        SDC_TRY(rslot.alloc((size_t)nr * 4 + 16, s));
+        SDC_TRY(rrank.alloc((size_t)nr * 4 + 16, s));
+        SDC_TRY(slots.alloc((size_t)nslots * 16, s));
+        t.slots = slots.as<ulonglong2>();
+        SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
+        jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
+        SDC_CHECK_LAUNCH();
+        if (nr > 0) {
+            jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(r, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2);
+            SDC_CHECK_LAUNCH();
+            SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
+                                          tsum_b.as<unsigned long long>(), s));
+            jt_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
+            SDC_CHECK_LAUNCH();
+            SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            unique = hdup == 0;
+        }
     }
     // ---- probe ----
     if (nl == 0) return SDCB200_OK;
     const int64_t nt = ceil_div(nl, kTile);
+    void* p = nullptr;
+    if (unique) {
+        // every left row has at most one partner: one kernel, n_out <= nl
+        SDC_TRY(dev_alloc(&p, (size_t)nl * 8, s));
+        res->lidx = reinterpret_cast<int64_t*>(p);
+        SDC_TRY(dev_alloc(&p, (size_t)nl * 8, s));
+        res->ridx = reinterpret_cast<int64_t*>(p);
+        if (LEFT) {
+            probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx);
+            SDC_CHECK_LAUNCH();
+            res->n_out = nl;                                 // scratch is freed in stream order: no sync needed
+        } else {
+            Scratch status;
+            SDC_TRY(status.alloc((size_t)nt * 8, s));
+            SDC_CUDA_TRY(cudaMemsetAsync(status.p, 0, (size_t)nt * 8, s));
+            probe_unique_inner_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(),
+                                                                                    status.as<unsigned long long>(), dmeta, nt,
+                                                                                    res->lidx, res->ridx);
+            SDC_CHECK_LAUNCH();
+            unsigned long long h[2] = {0, 0};
+            SDC_CUDA_TRY(cudaMemcpyAsync(h, dmeta, 16, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            res->n_out = (int64_t)h[1];
+        }
+        return SDCB200_OK;
+    }
+    // general two-pass path (duplicate build keys): count, scan, emit
     Scratch pval, tcnt;
     SDC_TRY(pval.alloc((size_t)nl * 8, s));
     SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
@@ -274,8 +558,8 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     probe_count_kernel<KEY_F64, LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, pval.as<unsigned long long>(), tile_counts);
     SDC_CHECK_LAUNCH();
     // exclusive scan of the tile counts in place; total lands in tile_counts[nt]
-    if (nt <= 64 * 1024) {
-        scan_tiles_kernel<<<1, kJoinThreads, 0, s>>>(tile_counts, nt);
+    if (nt <= 256 * 1024) {
+        scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tile_counts, nt);
         SDC_CHECK_LAUNCH();
     } else {
         SDC_TRY(device_exclusive_scan(ArrayLoad{tile_counts}, ArrayStore{tile_counts}, nt, tsum_p, s));
@@ -287,7 +571,6 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     SDC_CUDA_TRY(cudaStreamSynchronize(s));
     res->n_out = (int64_t)total;
     if (total == 0) return SDCB200_OK;
-    void* p = nullptr;
     SDC_TRY(dev_alloc(&p, (size_t)total * 8, s));
     res->lidx = reinterpret_cast<int64_t*>(p);
     SDC_TRY(dev_alloc(&p, (size_t)total * 8, s));
@@ -353,6 +636,15 @@ int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_
     if (left_idx) SDC_CUDA_TRY(cudaMemcpyAsync(left_idx, r->lidx, (size_t)r->n_out * 8, kind, s));
     if (right_idx) SDC_CUDA_TRY(cudaMemcpyAsync(right_idx, r->ridx, (size_t)r->n_out * 8, kind, s));
     if (dst_is_host) SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_join_result(int64_t handle, int64_t** left_idx, int64_t** right_idx) {
+    std::lock_guard<std::mutex> lk(g_jmu);
+    auto it = g_joins.find(handle);
+    if (it == g_joins.end()) { set_error("join: unknown handle %lld", (long long)handle); return SDCB200_ERR_HANDLE; }
+    if (left_idx) *left_idx = it->second->lidx;
+    if (right_idx) *right_idx = it->second->ridx;
     return SDCB200_OK;
 }
 

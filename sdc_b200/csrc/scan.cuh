@@ -59,19 +59,38 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(LOAD load, in
     if (threadIdx.x == 0) tsum[blockIdx.x] = tot;
 }
 
-// one CTA: exclusive scan of the tile sums in place; total -> tsum[nt]
-static __global__ void __launch_bounds__(kScanThreads) scan_tiles_kernel(unsigned long long* tsum, int64_t nt) {
-    __shared__ unsigned long long wsum[kScanThreads / 32];
-    unsigned long long carry = 0;
-    for (int64_t b = 0; b < nt; b += kScanThreads) {
-        const int64_t i = b + threadIdx.x;
-        const unsigned long long v = i < nt ? tsum[i] : 0ull;
-        unsigned long long tot;
-        const unsigned long long ex = block_excl_scan_u64(v, &tot, wsum);
-        if (i < nt) tsum[i] = carry + ex;
-        carry += tot;
+// one CTA of 1024 threads: exclusive scan of the tile sums in place (thread-contiguous chunks, one block
+// scan); total -> tsum[nt]
+constexpr int kScanTilesThreads = 1024;
+static __global__ void __launch_bounds__(kScanTilesThreads) scan_tiles_kernel(unsigned long long* tsum, int64_t nt) {
+    __shared__ unsigned long long wsum[kScanTilesThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t per = (nt + kScanTilesThreads - 1) / kScanTilesThreads;
+    const int64_t lo = (int64_t)threadIdx.x * per;
+    const int64_t hi = lo + per < nt ? lo + per : nt;
+    unsigned long long s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += tsum[i];
+    unsigned long long incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
-    if (threadIdx.x == 0) tsum[nt] = carry;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+    for (int w = 0; w < kScanTilesThreads / 32; ++w) {
+        const unsigned long long x = wsum[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    unsigned long long run = base + incl - s;
+    for (int64_t i = lo; i < hi; ++i) {
+        const unsigned long long v = tsum[i];
+        tsum[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) tsum[nt] = tot;
 }
 
 template <typename LOAD, typename STORE>
@@ -99,7 +118,7 @@ int32_t device_exclusive_scan(LOAD load, STORE store, int64_t n, unsigned long l
     const int64_t nt = ceil_div(n, kScanTile);
     scan_reduce_kernel<<<(unsigned)nt, kScanThreads, 0, s>>>(load, n, tsum);
     SDC_CHECK_LAUNCH();
-    scan_tiles_kernel<<<1, kScanThreads, 0, s>>>(tsum, nt);
+    scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tsum, nt);
     SDC_CHECK_LAUNCH();
     scan_apply_kernel<<<(unsigned)nt, kScanThreads, 0, s>>>(load, store, n, tsum);
     SDC_CHECK_LAUNCH();

@@ -42,13 +42,38 @@ def join_device(left_keys, right_keys, how="inner"):
         native.check(lib.sdcb200_join(native.JOIN_HOW[how], native.DTYPE_CODES[name], left_keys.data_ptr(),
                                       left_keys.shape[0], right_keys.data_ptr(), right_keys.shape[0], stream,
                                       ct.byref(handle), ct.byref(n_out)))
-        try:
-            li = torch.empty(n_out.value, dtype=torch.int64, device=left_keys.device)
-            ri = torch.empty(n_out.value, dtype=torch.int64, device=left_keys.device)
-            native.check(lib.sdcb200_join_indexers(handle.value, li.data_ptr(), ri.data_ptr(), 0, stream))
-        finally:
-            native.check(lib.sdcb200_join_free(handle.value, stream))
+        owner = _JoinHandle(handle.value, left_keys.device)
+        if n_out.value == 0:
+            e = torch.empty(0, dtype=torch.int64, device=left_keys.device)
+            return e, e.clone()
+        lp, rp = ct.c_void_p(), ct.c_void_p()
+        native.check(lib.sdcb200_join_result(handle.value, ct.byref(lp), ct.byref(rp)))
+        # the indexers stay where the library wrote them; the tensors keep the handle alive
+        li = torch.as_tensor(_DeviceView(lp.value, n_out.value, owner), device=left_keys.device)
+        ri = torch.as_tensor(_DeviceView(rp.value, n_out.value, owner), device=left_keys.device)
     return li, ri
+
+
+class _JoinHandle:
+    """Owns a join result handle; frees it when the last tensor viewing it is gone."""
+
+    def __init__(self, handle, device):
+        self.handle, self.device = handle, device
+
+    def __del__(self):
+        try:
+            native.load().sdcb200_join_free(self.handle, None)
+        except Exception:
+            pass
+
+
+class _DeviceView:
+    """int64[n] device buffer exposed through __cuda_array_interface__ (zero-copy into torch)."""
+
+    def __init__(self, ptr, n, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2,
+                                         "strides": None}
 
 
 def take_nullable_device(col, idx):
