@@ -137,6 +137,11 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
                         int64_t expected_groups, void* stream, int64_t* handle_out, int64_t* ngroups_out);
 int32_t sdcb200_groupby_keys(int64_t handle, void* dst, int32_t dst_is_host, void* stream);
 int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* dst, int32_t dst_is_host, void* stream);
+/* zero-copy access: device pointers of the handle's result, valid until sdcb200_groupby_free.
+ * keys[ngroups]; vals is a matrix of rows of `stride` elements, row (rank(agg) * ncols + col) holds
+ * that aggregate of that column in its first ngroups entries (rank = position of the aggregate among
+ * the requested ones in ascending bit order).                                                       */
+int32_t sdcb200_groupby_result(int64_t handle, void** keys, void** vals, int64_t* stride);
 int32_t sdcb200_groupby_free(int64_t handle);
 
 /* ------------------------------------------------------------------ join

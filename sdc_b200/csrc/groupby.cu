@@ -24,6 +24,7 @@
 //
 // Skipna semantics: sum of an all-NaN group = 0, mean = NaN, min/max = NaN,
 // count = 0; +-inf take part in min/max/sum; integer columns: sum/min/max/count are int64.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -60,23 +61,24 @@ __device__ __forceinline__ unsigned long long i64_to_ordered(long long v) {
     return (unsigned long long)v ^ 0x8000000000000000ull;
 }
 
-// The global table.  `nrep` replicas of (cap + 1) slots each: the shared-memory path flushes CTA b
-// into replica b % nrep so that the flush atomics of hundreds of CTAs do not serialise on the same
-// few addresses; replicas 1.. are folded into replica 0 afterwards.  Slot indices below are
-// "global": replica * (cap + 1) + slot.
+// The global table.  ONE key array of cap + 1 slots (slot cap = the spare slot for key == kEmpty) and
+// `nrep` replicas of every value array: the shared-memory path flushes CTA b into replica b % nrep so
+// that the flush atomics of hundreds of CTAs do not serialise on the same few addresses (the key of a
+// group is claimed once and only read afterwards, so the key array needs no replicas).  The last CTA
+// to finish folds replicas 1.. into replica 0.  Value index = replica * (cap + 1) + slot.
 struct Table {
-    unsigned long long* keys;       // [nrep][cap + 1]; slot cap = the spare slot for key == kEmpty
-    unsigned long long* first;      // first row of the group (NEED_FIRST)
-    // per column c (nullptr when not needed)
+    unsigned long long* keys;       // [cap + 1]
+    unsigned long long* first;      // [nrep][cap + 1] first row of the group (NEED_FIRST)
+    // per column c (nullptr when not needed), each [nrep][cap + 1]
     void* sum[kMaxCols];            // double or long long
     unsigned long long* cnt[kMaxCols];
     unsigned long long* mn[kMaxCols];   // ordered u64
     unsigned long long* mx[kMaxCols];
     double* ssd[kMaxCols];          // second pass: sum of squared deviations (replica 0 only)
     unsigned long long cap;         // power of two
-    unsigned long long limit;       // max occupied slots per replica before "overflow"
-    unsigned long long* occupied;   // [nrep] device counters
-    int* overflow;                  // device flag
+    unsigned long long limit;       // max occupied slots before "overflow"
+    unsigned long long* occupied;   // device counter
+    int* overflow;                  // device flag: 1 = table too small, 2 = a key fell outside the direct window
     int nrep;
 };
 
@@ -98,24 +100,23 @@ __device__ __forceinline__ bool canon_key(unsigned long long b, unsigned long lo
     return true;
 }
 
-// find-or-insert in replica `rep`; returns the global slot, or ~0 when the table overflowed
-__device__ __forceinline__ unsigned long long global_upsert(const Table& t, int rep, unsigned long long key) {
-    const unsigned long long off = (unsigned long long)rep * (t.cap + 1);
+// find-or-insert; returns the slot, or ~0 when the table overflowed
+__device__ __forceinline__ unsigned long long global_upsert(const Table& t, unsigned long long key) {
     if (key == kEmptyKey()) {
-        if (atomicCAS(&t.keys[off + t.cap], kEmptyKey(), key + 1) == kEmptyKey()) atomicAdd(&t.occupied[rep], 1ull);
-        return off + t.cap;
+        if (atomicCAS(&t.keys[t.cap], kEmptyKey(), key + 1) == kEmptyKey()) atomicAdd(t.occupied, 1ull);
+        return t.cap;
     }
     unsigned long long slot = mix64(key) & (t.cap - 1);
     for (unsigned long long probes = 0; probes <= t.cap; ++probes) {
-        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.keys[off + slot]);
-        if (cur == key) return off + slot;
+        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.keys[slot]);
+        if (cur == key) return slot;
         if (cur == kEmptyKey()) {
-            const unsigned long long old = atomicCAS(&t.keys[off + slot], kEmptyKey(), key);
+            const unsigned long long old = atomicCAS(&t.keys[slot], kEmptyKey(), key);
             if (old == kEmptyKey()) {
-                if (atomicAdd(&t.occupied[rep], 1ull) + 1 > t.limit) { *(volatile int*)t.overflow = 1; return ~0ull; }
-                return off + slot;
+                if (atomicAdd(t.occupied, 1ull) + 1 > t.limit) { *(volatile int*)t.overflow = 1; return ~0ull; }
+                return slot;
             }
-            if (old == key) return off + slot;
+            if (old == key) return slot;
         }
         slot = (slot + 1) & (t.cap - 1);
     }
@@ -123,8 +124,11 @@ __device__ __forceinline__ unsigned long long global_upsert(const Table& t, int 
     return ~0ull;
 }
 
-// read-only lookup in replica 0 (second pass); the key is known to be present
-__device__ __forceinline__ unsigned long long global_find(const Table& t, unsigned long long key) {
+// read-only lookup (second pass); the key is known to be present.  drange != 0: the table is
+// direct-addressed (slot = key - dlo), as the shared-memory path left it for dense int64 keys.
+__device__ __forceinline__ unsigned long long global_find(const Table& t, unsigned long long key, unsigned long long dlo,
+                                                          unsigned long long drange) {
+    if (drange) return key - dlo;
     if (key == kEmptyKey()) return t.cap;
     unsigned long long slot = mix64(key) & (t.cap - 1);
     while (t.keys[slot] != key) slot = (slot + 1) & (t.cap - 1);
@@ -149,22 +153,24 @@ __device__ __forceinline__ void global_accumulate(const Table& t, int c, bool is
     }
 }
 
-// ---- tile loads: a CTA works on kGbTile = 256 threads x 4 rows; thread t holds rows
-// base + 2t, 2t+1, 512 + 2t, 512 + 2t + 1, so each column costs two coalesced 128-bit loads per
-// thread and all loads of a tile are in flight together.
+// ---- tile loads: a CTA of THREADS threads works on THREADS x 4 rows; thread t holds rows
+// base + 2t, 2t+1, 2 THREADS + 2t, 2 THREADS + 2t + 1, so each column costs two coalesced 128-bit
+// loads per thread and all loads of a tile are in flight together.
 constexpr int kRows = 4;
 constexpr int kGbTile = kGbThreads * kRows;
 
+template <int THREADS = kGbThreads>
 __device__ __forceinline__ int64_t tile_row(int64_t base, int tid, int e) {
-    return base + (e >> 1) * (2 * kGbThreads) + 2 * tid + (e & 1);
+    return base + (e >> 1) * (2 * THREADS) + 2 * tid + (e & 1);
 }
 
+template <int THREADS = kGbThreads>
 __device__ __forceinline__ void load4(const void* col, int64_t base, int64_t n, int tid, bool vec,
                                       unsigned long long v[kRows]) {
     const unsigned long long* p = reinterpret_cast<const unsigned long long*>(col);
-    if (vec && base + kGbTile <= n) {
+    if (vec && base + THREADS * kRows <= n) {
         const int4 a = ld_stream_v4(p + base + 2 * tid);
-        const int4 b = ld_stream_v4(p + base + 2 * kGbThreads + 2 * tid);
+        const int4 b = ld_stream_v4(p + base + 2 * THREADS + 2 * tid);
         v[0] = (unsigned long long)(unsigned)a.x | ((unsigned long long)(unsigned)a.y << 32);
         v[1] = (unsigned long long)(unsigned)a.z | ((unsigned long long)(unsigned)a.w << 32);
         v[2] = (unsigned long long)(unsigned)b.x | ((unsigned long long)(unsigned)b.y << 32);
@@ -172,7 +178,7 @@ __device__ __forceinline__ void load4(const void* col, int64_t base, int64_t n, 
     } else {
 #pragma unroll
         for (int e = 0; e < kRows; ++e) {
-            const int64_t r = tile_row(base, tid, e);
+            const int64_t r = tile_row<THREADS>(base, tid, e);
             v[e] = r < n ? p[r] : 0ull;
         }
     }
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
         for (int e = 0; e < kRows; ++e) {
             unsigned long long k;
             g[e] = ~0ull;
-            if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_upsert(t, 0, k);
+            if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_upsert(t, k);
         }
         if (need & NEED_FIRST) {
 #pragma unroll
@@ -209,292 +215,6 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
             for (int e = 0; e < kRows; ++e)
                 if (g[e] != ~0ull) global_accumulate(t, c, f, need, g[e], v0[e]);
         }
-    }
-}
-
-// ------------------------------------------------------------------ low-cardinality path
-// Per-CTA shared-memory table of SCAP slots; layout (SoA):
-//   keys[SCAP] u64 | first[SCAP] u64 | per column: sum[SCAP] 8B, mn[SCAP] u64, mx[SCAP] u64 | cnt[SCAP] u32 per column
-// (only the arrays `need` asks for are carved out).  Rows that cannot get a slot within
-// kSmemProbes probes go to the global table directly.  HBM traffic = keys + values read once.
-constexpr int kSmemProbes = 16;
-
-struct SmemLayout {
-    int scap;
-    int off_first;          // byte offsets from the table base; -1 = absent
-    int off_sum[kMaxCols], off_cnt[kMaxCols], off_mn[kMaxCols], off_mx[kMaxCols];
-    int bytes;
-};
-
-// strided sample of the key column -> dense-key window for the direct-addressed mode of gb_smem_kernel:
-// direct[0] = lo, direct[1] = range (0 = use hashing).  int64 keys only.
-constexpr int kSampleThreads = 1024;
-constexpr int kSamplePerThread = 4;
-__global__ void __launch_bounds__(kSampleThreads) gb_sample_kernel(const long long* __restrict__ keys, int64_t n, int scap,
-                                                                   long long* direct) {
-    __shared__ long long smin[kSampleThreads / 32], smax[kSampleThreads / 32];
-    const int64_t total = (int64_t)kSampleThreads * kSamplePerThread;
-    const int64_t stride = n > total ? n / total : 1;
-    long long mn = 0x7fffffffffffffffLL, mx = -0x7fffffffffffffffLL - 1;
-    long long kv[kSamplePerThread];
-#pragma unroll
-    for (int e = 0; e < kSamplePerThread; ++e) {        // independent loads, all in flight together
-        const int64_t r = ((int64_t)e * kSampleThreads + threadIdx.x) * stride;
-        kv[e] = r < n ? __ldg(keys + r) : keys[0];
-    }
-#pragma unroll
-    for (int e = 0; e < kSamplePerThread; ++e) {
-        mn = kv[e] < mn ? kv[e] : mn;
-        mx = kv[e] > mx ? kv[e] : mx;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
-        mn = a < mn ? a : mn;
-        mx = b > mx ? b : mx;
-    }
-    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = mn; smax[threadIdx.x >> 5] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < kSampleThreads / 32; ++w) {
-            mn = smin[w] < mn ? smin[w] : mn;
-            mx = smax[w] > mx ? smax[w] : mx;
-        }
-        // work in the order-preserving unsigned image of int64 so that extreme keys cannot overflow
-        const unsigned long long top = 0x8000000000000000ull;
-        const unsigned long long umn = (unsigned long long)mn ^ top, umx = (unsigned long long)mx ^ top;
-        long long lo = 0, range = 0;
-        if (mx >= mn && umx - umn < (unsigned long long)scap) {
-            // centre the scap-wide window on the sampled keys, clamped to the int64 range
-            unsigned long long shift = ((unsigned long long)scap - (umx - umn) - 1) / 2;
-            if (shift > umn) shift = umn;
-            unsigned long long ulo = umn - shift;
-            if (ulo > ~0ull - (unsigned long long)scap) ulo = ~0ull - (unsigned long long)scap;
-            lo = (long long)(ulo ^ top);
-            range = scap;
-        }
-        direct[0] = lo;
-        direct[1] = range;
-    }
-}
-
-template <bool KEY_F64>
-__global__ void __launch_bounds__(kGbThreads) gb_smem_kernel(const void* __restrict__ keys, int64_t n, Cols cols, Table t,
-                                                             int need, SmemLayout lay, const long long* __restrict__ direct) {
-    extern __shared__ __align__(16) unsigned char sm[];
-    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);
-    unsigned long long* sfirst = reinterpret_cast<unsigned long long*>(sm + (lay.off_first >= 0 ? lay.off_first : 0));
-    const int scap = lay.scap;
-    const int tid = threadIdx.x;
-    const int rep = blockIdx.x % t.nrep;
-    // dense int64 keys: slot = key - lo, no hashing, no probing (window chosen by gb_sample_kernel)
-    const unsigned long long dlo = KEY_F64 ? 0ull : (unsigned long long)direct[0];
-    const unsigned long long drange = KEY_F64 ? 0ull : (unsigned long long)direct[1];
-    for (int i = tid; i < scap; i += kGbThreads) {
-        skeys[i] = kEmptyKey();
-        if (need & NEED_FIRST) sfirst[i] = ~0ull;
-        for (int c = 0; c < cols.ncols; ++c) {
-            if (need & NEED_SUM) reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i] = 0ull;
-            if (need & NEED_CNT) reinterpret_cast<unsigned*>(sm + lay.off_cnt[c])[i] = 0u;
-            if (need & NEED_MIN) reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c])[i] = ~0ull;
-            if (need & NEED_MAX) reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c])[i] = 0ull;
-        }
-    }
-    __syncthreads();
-    const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncwarp();
-        const int64_t base = tile * kGbTile;
-        unsigned long long kb[kRows], v0[kRows];
-        load4(keys, base, n, tid, cols.vec_ok, kb);
-        if (cols.ncols > 0) load4(cols.data[0], base, n, tid, cols.vec_ok, v0);
-        if (*(volatile int*)t.overflow) break;
-        int slot[kRows];                      // >= 0 shared slot, -1 row skipped, -2 row lives in the global table
-        unsigned long long g[kRows];
-#pragma unroll
-        for (int e = 0; e < kRows; ++e) {
-            unsigned long long k = 0;
-            const bool valid = tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k);
-            int sl = -1;
-            g[e] = ~0ull;
-            bool pending = valid && k != kEmptyKey();
-            if (drange) {
-                const unsigned long long d = k - dlo;
-                if (pending && d < drange) {
-                    sl = (int)d;
-                    if (skeys[sl] != k) skeys[sl] = k;          // presence marker; every writer stores the same value
-                }
-            } else {
-                unsigned s = (unsigned)((k * 0x9E3779B97F4A7C15ull) >> 40) & (unsigned)(scap - 1);
-                // the warp probes in lock step: the loop exit is warp-uniform, no divergence to undo
-                for (int p = 0; p < kSmemProbes; ++p) {
-                    if (!__any_sync(0xffffffffu, pending)) break;
-                    if (pending) {
-                        const unsigned long long cur = skeys[s];
-                        if (cur == k) { sl = (int)s; pending = false; }
-                        else if (cur == kEmptyKey()) {
-                            const unsigned long long old = atomicCAS(&skeys[s], kEmptyKey(), k);
-                            if (old == kEmptyKey() || old == k) { sl = (int)s; pending = false; }
-                            else s = (s + 1) & (unsigned)(scap - 1);
-                        } else s = (s + 1) & (unsigned)(scap - 1);
-                    }
-                }
-            }
-            if (valid && sl < 0) {      // outside the window / shared table full around this key: global table
-                g[e] = global_upsert(t, rep, k);
-                sl = g[e] != ~0ull ? -2 : -1;
-            }
-            slot[e] = sl;
-            __syncwarp();
-        }
-        if (need & NEED_FIRST) {
-#pragma unroll
-            for (int e = 0; e < kRows; ++e) {
-                const unsigned long long row = (unsigned long long)tile_row(base, tid, e);
-                if (slot[e] >= 0) { if (row < sfirst[slot[e]]) atomicMin(&sfirst[slot[e]], row); }
-                else if (slot[e] == -2) atomicMin(&t.first[g[e]], row);
-            }
-            __syncwarp();
-        }
-        for (int c = 0; c < cols.ncols; ++c) {
-            if (c > 0) load4(cols.data[c], base, n, tid, cols.vec_ok, v0);
-            const bool f = cols.is_f64[c] != 0;
-            double* ssum = reinterpret_cast<double*>(sm + lay.off_sum[c]);
-            unsigned* scnt = reinterpret_cast<unsigned*>(sm + lay.off_cnt[c]);
-            unsigned long long* smn = reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c]);
-            unsigned long long* smx = reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c]);
-#pragma unroll
-            for (int e = 0; e < kRows; ++e) {
-                const int sl = slot[e];
-                if (sl == -2) global_accumulate(t, c, f, need, g[e], v0[e]);
-                if (sl >= 0) {
-                    if (f) {
-                        const double v = __longlong_as_double((long long)v0[e]);
-                        if (v == v) {
-                            if (need & NEED_SUM) atomicAdd(ssum + sl, v);
-                            if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                            if (need & NEED_MIN) atomicMin(smn + sl, f64_to_ordered(v));
-                            if (need & NEED_MAX) atomicMax(smx + sl, f64_to_ordered(v));
-                        }
-                    } else {
-                        if (need & NEED_SUM) atomicAdd(reinterpret_cast<unsigned long long*>(ssum) + sl, v0[e]);
-                        if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                        if (need & NEED_MIN) atomicMin(smn + sl, i64_to_ordered((long long)v0[e]));
-                        if (need & NEED_MAX) atomicMax(smx + sl, i64_to_ordered((long long)v0[e]));
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    }
-    __syncthreads();
-    // flush the occupied shared slots into this CTA's replica of the global table
-    for (int i = tid; i < scap; i += kGbThreads) {
-        const unsigned long long k = skeys[i];
-        if (k == kEmptyKey()) continue;
-        const unsigned long long g = global_upsert(t, rep, k);
-        if (g == ~0ull) continue;
-        if (need & NEED_FIRST) atomicMin(&t.first[g], sfirst[i]);
-        for (int c = 0; c < cols.ncols; ++c) {
-            if (need & NEED_CNT) {
-                const unsigned cn = reinterpret_cast<unsigned*>(sm + lay.off_cnt[c])[i];
-                if (cn) atomicAdd(&t.cnt[c][g], (unsigned long long)cn);
-            }
-            if (need & NEED_SUM) {
-                if (cols.is_f64[c]) {
-                    const double v = reinterpret_cast<double*>(sm + lay.off_sum[c])[i];
-                    if (v != 0.0) atomicAdd(reinterpret_cast<double*>(t.sum[c]) + g, v);
-                } else {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(t.sum[c]) + g,
-                              reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i]);
-                }
-            }
-            if (need & NEED_MIN) atomicMin(&t.mn[c][g], reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c])[i]);
-            if (need & NEED_MAX) atomicMax(&t.mx[c][g], reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c])[i]);
-        }
-    }
-}
-
-// fold replicas 1 .. nrep-1 into replica 0
-__global__ void gb_merge_replicas_kernel(Table t, int ncols, unsigned is_f64_mask, int need) {
-    const unsigned long long per = t.cap + 1;
-    const unsigned long long total = per * (unsigned long long)(t.nrep - 1);
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long src = per + i;
-        const unsigned long long kraw = t.keys[src];
-        if (kraw == kEmptyKey()) continue;
-        const bool spare = (src % per) == t.cap;
-        const unsigned long long g = global_upsert(t, 0, spare ? kEmptyKey() : kraw);
-        if (g == ~0ull) continue;
-        if (need & NEED_FIRST) atomicMin(&t.first[g], t.first[src]);
-        for (int c = 0; c < ncols; ++c) {
-            if (need & NEED_CNT) { const unsigned long long cn = t.cnt[c][src]; if (cn) atomicAdd(&t.cnt[c][g], cn); }
-            if (need & NEED_SUM) {
-                if ((is_f64_mask >> c) & 1u) {
-                    const double v = reinterpret_cast<const double*>(t.sum[c])[src];
-                    if (v != 0.0) atomicAdd(reinterpret_cast<double*>(t.sum[c]) + g, v);
-                } else {
-                    atomicAdd(reinterpret_cast<unsigned long long*>(t.sum[c]) + g,
-                              reinterpret_cast<const unsigned long long*>(t.sum[c])[src]);
-                }
-            }
-            if (need & NEED_MIN) atomicMin(&t.mn[c][g], t.mn[c][src]);
-            if (need & NEED_MAX) atomicMax(&t.mx[c][g], t.mx[c][src]);
-        }
-    }
-}
-
-// second pass for var / std: ssd[slot] += (x - mean)^2  (nanvar's two passes, numpy_like.py:850-872)
-template <bool KEY_F64>
-__global__ void __launch_bounds__(kGbThreads) gb_ssd_kernel(const void* __restrict__ keys, int64_t n, Cols cols, Table t) {
-    const int tid = threadIdx.x;
-    const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t base = tile * kGbTile;
-        unsigned long long kb[kRows], v0[kRows], g[kRows];
-        load4(keys, base, n, tid, cols.vec_ok, kb);
-#pragma unroll
-        for (int e = 0; e < kRows; ++e) {
-            unsigned long long k;
-            g[e] = ~0ull;
-            if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_find(t, k);
-        }
-        for (int c = 0; c < cols.ncols; ++c) {
-            load4(cols.data[c], base, n, tid, cols.vec_ok, v0);
-#pragma unroll
-            for (int e = 0; e < kRows; ++e) {
-                if (g[e] == ~0ull) continue;
-                double v, mean;
-                const double cnt = (double)t.cnt[c][g[e]];
-                if (cols.is_f64[c]) {
-                    v = __longlong_as_double((long long)v0[e]);
-                    if (v != v) continue;
-                    mean = reinterpret_cast<const double*>(t.sum[c])[g[e]] / cnt;
-                } else {
-                    v = (double)(long long)v0[e];
-                    mean = (double)reinterpret_cast<const long long*>(t.sum[c])[g[e]] / cnt;
-                }
-                const double d = v - mean;
-                atomicAdd(&t.ssd[c][g[e]], d * d);
-            }
-        }
-    }
-}
-
-// every table array gets its initial value in one launch
-struct InitPlan {
-    unsigned long long* ptr[4 + 5 * kMaxCols];
-    unsigned long long val[4 + 5 * kMaxCols];
-    int count;
-};
-__global__ void gb_init_kernel(InitPlan plan, unsigned long long n) {
-    for (int a = blockIdx.y; a < plan.count; a += gridDim.y) {
-        unsigned long long* p = plan.ptr[a];
-        const unsigned long long v = plan.val[a];
-        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-             i += (unsigned long long)gridDim.x * blockDim.x)
-            p[i] = v;
     }
 }
 
@@ -546,57 +266,394 @@ __device__ __forceinline__ void write_group(const Table& t, int ncols, unsigned 
     }
 }
 
-// ---- small tables (cap + 1 <= kSmallSlots): ONE CTA compacts the occupied slots, orders them with a
-// bitonic sort in shared memory and writes every aggregate -- no host round trip, no radix sort.
-constexpr int kSmallSlots = 8192 + 1;
-constexpr int kSmallSort = 8192;          // groups <= limit = cap / 2 + 1 <= 4097 fit twice over
-constexpr int kSmallThreads = 1024;
+// ------------------------------------------------------------------ low-cardinality path
+// ONE kernel.  Every CTA (512 threads, two per SM, persistent over tiles of 2048 rows):
+//   1. samples the key column (int64 keys): if the sampled keys span fewer values than the shared
+//      table has slots, the table is DIRECT-ADDRESSED (slot = key - lo: no hashing, no probing, and
+//      slot order = key order); every CTA reads the same samples, so all agree on the window.
+//      A later key outside the window raises overflow = 2 and the host reruns with hashing.
+//   2. aggregates its rows into a private shared-memory table (SoA):
+//        keys[SCAP] u64 | first[SCAP] u64 | per column: sum[SCAP] 8B, mn[SCAP] u64, mx[SCAP] u64 | cnt[SCAP] u32 per column
+//      (only the arrays `need` asks for are carved out).  Hashing mode: rows that cannot get a slot
+//      within kSmemProbes probes go to the global table directly.
+//   3. flushes its occupied slots into replica (blockIdx % nrep) of the small global table.
+//   4. takes a ticket; the LAST CTA folds the replicas into replica 0, compacts the groups, orders
+//      them (direct + sort=True: already in key order, a block scan; otherwise a bitonic sort of
+//      (key | first row, slot) in shared memory) and writes every aggregate -- no second launch.
+// HBM traffic = keys + values read once.
+constexpr int kSmThreads = 512;                 // two CTAs per SM: two private tables halve the CAS contention
+constexpr int kSmemProbes = 16;
+constexpr int kSamplePerThread = 4;              // 2048 strided samples per CTA
+constexpr int kSmallReplicas = 8;                // replicas of the small global table's value arrays
 
-__global__ void __launch_bounds__(kSmallThreads) gb_finalize_small_kernel(Table t, int ncols, unsigned is_f64_mask,
-                                                                          unsigned agg_mask, long long ddof, int by_first,
-                                                                          int key_f64, int64_t ngcap,
-                                                                          unsigned long long* out_keys,
-                                                                          unsigned long long* out_vals,
-                                                                          unsigned long long* ng_out) {
+struct SmemLayout {
+    int scap;
+    int off_first;          // byte offsets from the table base; -1 = absent
+    int off_sum[kMaxCols], off_cnt[kMaxCols], off_mn[kMaxCols], off_mx[kMaxCols];
+    int bytes;              // table bytes
+    int alloc_bytes;        // dynamic shared memory of the launch (table or the finalize's sort arrays)
+};
+
+struct SmallFin {
+    unsigned long long* out_keys;
+    unsigned long long* out_vals;
+    int64_t ngcap;
+    unsigned agg_mask, is_f64_mask;
+    long long ddof;
+    int by_first, key_f64;
+    int write_out;                  // 0: only fold the replicas (var / std continue on the host path)
+    int allow_direct;
+    unsigned long long* meta;       // [0] groups written, [1] CTAs done, [2] direct lo, [3] direct range
+};
+
+// SPEC >= 0: compile-time `need` mask for ONE float64 value column (the common df.groupby(k).agg() shapes get a
+// tight loop); SPEC < 0: any columns / aggregates, decided at run time.
+template <bool KEY_F64, int SPEC>
+__global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __restrict__ keys, int64_t n, Cols cols_rt, Table t,
+                                                                int need_rt, SmemLayout lay, SmallFin fin) {
+    const int need = SPEC >= 0 ? SPEC : need_rt;
+    struct ColsView {
+        const Cols& c;
+        __device__ __forceinline__ int ncols() const { return SPEC >= 0 ? 1 : c.ncols; }
+        __device__ __forceinline__ bool is_f64(int i) const { return SPEC >= 0 ? true : c.is_f64[i] != 0; }
+    };
+    const ColsView cv{cols_rt};
+    const Cols& cols = cols_rt;
+    constexpr int kSmTile = kSmThreads * kRows;
+    constexpr int kSmWarps = kSmThreads / 32;
     extern __shared__ __align__(16) unsigned char sm[];
-    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);          // [kSmallSort]
-    unsigned* sslot = reinterpret_cast<unsigned*>(skey + kSmallSort);              // [kSmallSort]
-    __shared__ unsigned counter;
-    if (threadIdx.x == 0) counter = 0;
-    __syncthreads();
-    const unsigned nslots = (unsigned)t.cap + 1;
-    constexpr int kPer = (kSmallSlots + kSmallThreads - 1) / kSmallThreads;
-    unsigned long long kk[kPer];
-#pragma unroll
-    for (int e = 0; e < kPer; ++e) {               // independent loads, all in flight together
-        const unsigned i = e * kSmallThreads + threadIdx.x;
-        kk[e] = i < nslots ? t.keys[i] : kEmptyKey();
+    __shared__ unsigned long long s_red[2 * kSmWarps];
+    __shared__ unsigned long long s_dlo, s_drange;
+    __shared__ unsigned s_counter;
+    __shared__ int s_last;
+    unsigned long long* skeys = reinterpret_cast<unsigned long long*>(sm);
+    unsigned long long* sfirst = reinterpret_cast<unsigned long long*>(sm + (lay.off_first >= 0 ? lay.off_first : 0));
+    const int scap = lay.scap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rep = blockIdx.x % t.nrep;
+    const unsigned long long per = t.cap + 1;
+
+    // the first tile's loads go out before anything else; inside the loop the next tile is always in flight
+    const int64_t ntiles = (n + kSmTile - 1) / kSmTile;
+    unsigned long long kbn[kRows], v0n[kRows];
+    if ((int64_t)blockIdx.x < ntiles) {
+        load4<kSmThreads>(keys, (int64_t)blockIdx.x * kSmTile, n, tid, cols.vec_ok, kbn);
+        if (cv.ncols() > 0) load4<kSmThreads>(cols.data[0], (int64_t)blockIdx.x * kSmTile, n, tid, cols.vec_ok, v0n);
     }
+
+    // ---- 1. key sample -> direct window
+    if (!KEY_F64 && fin.allow_direct) {
+        const long long* kp = reinterpret_cast<const long long*>(keys);
+        const int64_t total = (int64_t)kSmThreads * kSamplePerThread;
+        const int64_t stride = n > total ? n / total : 1;
+        long long kv[kSamplePerThread];
 #pragma unroll
-    for (int e = 0; e < kPer; ++e) {
-        const unsigned i = e * kSmallThreads + threadIdx.x;
-        const unsigned long long k = kk[e];
+        for (int e = 0; e < kSamplePerThread; ++e) {        // independent loads, all in flight together
+            const int64_t r = ((int64_t)e * kSmThreads + tid) * stride;
+            kv[e] = r < n ? __ldg(kp + r) : __ldg(kp);
+        }
+        const unsigned long long top = 0x8000000000000000ull;   // order-preserving unsigned image: no overflow
+        unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll
+        for (int e = 0; e < kSamplePerThread; ++e) {
+            const unsigned long long u = (unsigned long long)kv[e] ^ top;
+            mn = u < mn ? u : mn;
+            mx = u > mx ? u : mx;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
+        }
+        if (lane == 0) { s_red[warp] = mn; s_red[kSmWarps + warp] = mx; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kSmWarps; ++w) {
+                mn = s_red[w] < mn ? s_red[w] : mn;
+                mx = s_red[kSmWarps + w] > mx ? s_red[kSmWarps + w] : mx;
+            }
+            unsigned long long lo = 0, range = 0;
+            if (mx - mn < (unsigned long long)scap) {
+                // centre the scap-wide window on the sampled keys, clamped to the int64 range
+                unsigned long long shift = ((unsigned long long)scap - (mx - mn) - 1) / 2;
+                if (shift > mn) shift = mn;
+                unsigned long long ulo = mn - shift;
+                if (ulo > ~0ull - (unsigned long long)scap) ulo = ~0ull - (unsigned long long)scap;
+                lo = ulo ^ top;
+                range = (unsigned long long)scap;
+            }
+            s_dlo = lo;
+            s_drange = range;
+            if (blockIdx.x == 0) { fin.meta[2] = lo; fin.meta[3] = range; }
+        }
+    } else if (tid == 0) {
+        s_dlo = 0ull;
+        s_drange = 0ull;
+    }
+    for (int i = tid; i < scap; i += kSmThreads) {
+        skeys[i] = kEmptyKey();
+        if (need & NEED_FIRST) sfirst[i] = ~0ull;
+        for (int c = 0; c < cv.ncols(); ++c) {
+            if (need & NEED_SUM) reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i] = 0ull;
+            if (need & NEED_CNT) reinterpret_cast<unsigned*>(sm + lay.off_cnt[c])[i] = 0u;
+            if (need & NEED_MIN) reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c])[i] = ~0ull;
+            if (need & NEED_MAX) reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c])[i] = 0ull;
+        }
+    }
+    __syncthreads();
+    const unsigned long long dlo = s_dlo, drange = s_drange;
+
+    // ---- 2. aggregate
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncwarp();
+        const int64_t base = tile * kSmTile;
+        unsigned long long kb[kRows], v0[kRows];
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) { kb[e] = kbn[e]; v0[e] = v0n[e]; }
+        if (tile + gridDim.x < ntiles) {
+            const int64_t nbase = (tile + gridDim.x) * kSmTile;
+            load4<kSmThreads>(keys, nbase, n, tid, cols.vec_ok, kbn);
+            if (cv.ncols() > 0) load4<kSmThreads>(cols.data[0], nbase, n, tid, cols.vec_ok, v0n);
+        }
+        const int ovf = *(volatile int*)t.overflow;      // consumed at the end of the iteration
+        int slot[kRows];                      // >= 0 shared slot, -1 row skipped, -2 row lives in the global table
+        unsigned long long g[kRows];
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) {
+            unsigned long long k = 0;
+            const bool valid = tile_row<kSmThreads>(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k);
+            int sl = -1;
+            g[e] = ~0ull;
+            if (drange) {
+                const unsigned long long d = k - dlo;
+                if (valid) {
+                    if (d < drange && k != kEmptyKey()) {
+                        sl = (int)d;
+                        // presence marker: one native 32-bit shared atomic on the slot's key word (the key itself is
+                        // dlo + slot); it cannot wrap back to the empty pattern within a CTA's rows
+                        atomicAdd(reinterpret_cast<unsigned*>(skeys + sl), 1u);
+                    } else {
+                        *(volatile int*)t.overflow = 2;             // outside the sampled window: rerun with hashing
+                    }
+                }
+            } else {
+                bool pending = valid && k != kEmptyKey();
+                unsigned s = (unsigned)((k * 0x9E3779B97F4A7C15ull) >> 40) & (unsigned)(scap - 1);
+                // the warp probes in lock step: the loop exit is warp-uniform, no divergence to undo
+                for (int p = 0; p < kSmemProbes; ++p) {
+                    if (!__any_sync(0xffffffffu, pending)) break;
+                    if (pending) {
+                        const unsigned long long cur = skeys[s];
+                        if (cur == k) { sl = (int)s; pending = false; }
+                        else if (cur == kEmptyKey()) {
+                            const unsigned long long old = atomicCAS(&skeys[s], kEmptyKey(), k);
+                            if (old == kEmptyKey() || old == k) { sl = (int)s; pending = false; }
+                            else s = (s + 1) & (unsigned)(scap - 1);
+                        } else s = (s + 1) & (unsigned)(scap - 1);
+                    }
+                }
+                if (valid && sl < 0) {      // shared table full around this key (or key == kEmpty): global table
+                    const unsigned long long gs = global_upsert(t, k);
+                    if (gs != ~0ull) { g[e] = (unsigned long long)rep * per + gs; sl = -2; }
+                }
+            }
+            slot[e] = sl;
+            __syncwarp();
+        }
+        if (need & NEED_FIRST) {
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) {
+                const unsigned long long row = (unsigned long long)tile_row<kSmThreads>(base, tid, e);
+                if (slot[e] >= 0) { if (row < sfirst[slot[e]]) atomicMin(&sfirst[slot[e]], row); }
+                else if (slot[e] == -2) atomicMin(&t.first[g[e]], row);
+            }
+            __syncwarp();
+        }
+        for (int c = 0; c < cv.ncols(); ++c) {
+            if (c > 0) load4<kSmThreads>(cols.data[c], base, n, tid, cols.vec_ok, v0);
+            const bool f = cv.is_f64(c);
+            double* ssum = reinterpret_cast<double*>(sm + lay.off_sum[c]);
+            unsigned* scnt = reinterpret_cast<unsigned*>(sm + lay.off_cnt[c]);
+            unsigned long long* smn = reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c]);
+            unsigned long long* smx = reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c]);
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) {
+                const int sl = slot[e];
+                if (sl == -2) global_accumulate(t, c, f, need, g[e], v0[e]);
+                if (sl >= 0) {
+                    if (f) {
+                        const double v = __longlong_as_double((long long)v0[e]);
+                        if (v == v) {
+                            if (need & NEED_SUM) atomicAdd(ssum + sl, v);
+                            if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
+                            if (need & NEED_MIN) atomicMin(smn + sl, f64_to_ordered(v));
+                            if (need & NEED_MAX) atomicMax(smx + sl, f64_to_ordered(v));
+                        }
+                    } else {
+                        if (need & NEED_SUM) atomicAdd(reinterpret_cast<unsigned long long*>(ssum) + sl, v0[e]);
+                        if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
+                        if (need & NEED_MIN) atomicMin(smn + sl, i64_to_ordered((long long)v0[e]));
+                        if (need & NEED_MAX) atomicMax(smx + sl, i64_to_ordered((long long)v0[e]));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        if (ovf) break;
+    }
+    __syncthreads();
+
+    // ---- 3. flush the occupied shared slots into this CTA's replica of the global value arrays
+    for (int i = tid; i < scap; i += kSmThreads) {
+        unsigned long long k = skeys[i];
         if (k == kEmptyKey()) continue;
-        const unsigned j = atomicAdd(&counter, 1u);
-        if (j >= (unsigned)kSmallSort) continue;
+        unsigned long long gs;
+        if (drange) {
+            k = dlo + (unsigned long long)i;
+            gs = (unsigned long long)i;
+            if (*reinterpret_cast<volatile unsigned long long*>(&t.keys[gs]) != k) t.keys[gs] = k;   // same value from every CTA
+        } else {
+            gs = global_upsert(t, k);
+            if (gs == ~0ull) continue;
+        }
+        const unsigned long long g = (unsigned long long)rep * per + gs;
+        if (need & NEED_FIRST) atomicMin(&t.first[g], sfirst[i]);
+        for (int c = 0; c < cv.ncols(); ++c) {
+            if (need & NEED_CNT) {
+                const unsigned cn = reinterpret_cast<unsigned*>(sm + lay.off_cnt[c])[i];
+                if (cn) atomicAdd(&t.cnt[c][g], (unsigned long long)cn);
+            }
+            if (need & NEED_SUM) {
+                if (cv.is_f64(c)) {
+                    const double v = reinterpret_cast<double*>(sm + lay.off_sum[c])[i];
+                    if (v != 0.0) atomicAdd(reinterpret_cast<double*>(t.sum[c]) + g, v);
+                } else {
+                    atomicAdd(reinterpret_cast<unsigned long long*>(t.sum[c]) + g,
+                              reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i]);
+                }
+            }
+            if (need & NEED_MIN) atomicMin(&t.mn[c][g], reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c])[i]);
+            if (need & NEED_MAX) atomicMax(&t.mx[c][g], reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c])[i]);
+        }
+    }
+
+    // ---- 4. the last CTA to get here finishes the job
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long ticket = atomicAdd(&fin.meta[1], 1ull);
+        s_last = ticket == (unsigned long long)gridDim.x - 1;
+        s_counter = 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (*(volatile int*)t.overflow) return;
+    const unsigned nslots = (unsigned)per;
+    // fold replicas 1.. into replica 0: plain L2 loads (every other CTA is done), unconditional (an empty slot folds
+    // its initial values), two slots per step so that 2 x nrep loads are in flight per thread
+    if (t.nrep > 1) {
+        auto comb = [](unsigned long long a, unsigned long long b, int mode) -> unsigned long long {
+            if (mode == 0) return a + b;
+            if (mode == 1) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+            if (mode == 2) return b < a ? b : a;
+            return b > a ? b : a;
+        };
+        auto fold = [&](unsigned long long* arr, int mode /* 0 add u64, 1 add f64, 2 min, 3 max */) {
+            for (unsigned i = tid; i < nslots; i += 2 * kSmThreads) {
+                const unsigned i2 = i + kSmThreads;
+                const bool two = i2 < nslots;
+                unsigned long long v[kSmallReplicas], w[kSmallReplicas];
+#pragma unroll
+                for (int r = 0; r < kSmallReplicas; ++r) {
+                    v[r] = __ldcg(arr + (r < t.nrep ? r : 0) * per + i);
+                    w[r] = __ldcg(arr + (r < t.nrep ? r : 0) * per + (two ? i2 : i));
+                }
+                unsigned long long a = v[0], c = w[0];
+#pragma unroll
+                for (int r = 1; r < kSmallReplicas; ++r) {
+                    if (r < t.nrep) { a = comb(a, v[r], mode); c = comb(c, w[r], mode); }
+                }
+                arr[i] = a;
+                if (two) arr[i2] = c;
+            }
+        };
+        if (need & NEED_FIRST) fold(t.first, 2);
+        for (int c = 0; c < cv.ncols(); ++c) {
+            if (need & NEED_SUM) fold(reinterpret_cast<unsigned long long*>(t.sum[c]), cv.is_f64(c) ? 1 : 0);
+            if (need & NEED_CNT) fold(t.cnt[c], 0);
+            if (need & NEED_MIN) fold(t.mn[c], 2);
+            if (need & NEED_MAX) fold(t.mx[c], 3);
+        }
+    }
+    __syncthreads();       // each thread reads back only what it wrote itself (same i striding) or after this barrier
+    if (!fin.write_out) {
+        // var / std: the host continues with the second pass; it needs the group count
+        unsigned cntp = 0;
+        for (unsigned i = tid; i < nslots; i += kSmThreads) cntp += __ldcg(&t.keys[i]) != kEmptyKey();
+        atomicAdd(&s_counter, cntp);
+        __syncthreads();
+        if (tid == 0) fin.meta[0] = s_counter;
+        return;
+    }
+    if (drange && !fin.by_first) {
+        // direct slots are already in key order: ordered compaction by a block scan over contiguous chunks
+        const unsigned chunk = (nslots + kSmThreads - 1) / kSmThreads;
+        const unsigned lo = tid * chunk, hi = lo + chunk < nslots ? lo + chunk : nslots;
+        unsigned c = 0;
+        for (unsigned i = lo; i < hi; ++i) c += __ldcg(&t.keys[i]) != kEmptyKey();
+        unsigned incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        unsigned* wsum = reinterpret_cast<unsigned*>(s_red);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned basec = 0, tot = 0;
+        for (int w = 0; w < kSmWarps; ++w) {
+            const unsigned x = wsum[w];
+            if (w < warp) basec += x;
+            tot += x;
+        }
+        unsigned j = basec + incl - c;
+        for (unsigned i = lo; i < hi; ++i) {
+            if (__ldcg(&t.keys[i]) == kEmptyKey()) continue;
+            write_group(t, cv.ncols(), fin.is_f64_mask, fin.agg_mask, fin.ddof, i, j, fin.ngcap, fin.out_keys, fin.out_vals);
+            ++j;
+        }
+        if (tid == 0) fin.meta[0] = tot;
+        return;
+    }
+    // hashed slots (or sort=False): compact, bitonic sort of (key | first row, slot) in shared memory, write
+    const unsigned sort_cap = (unsigned)(lay.alloc_bytes / 12);
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(sm);          // [sort_cap]
+    unsigned* sslot = reinterpret_cast<unsigned*>(skey + sort_cap);                // [sort_cap]
+    for (unsigned i = tid; i < nslots; i += kSmThreads) {
+        const unsigned long long k = __ldcg(&t.keys[i]);
+        if (k == kEmptyKey()) continue;
+        const unsigned j = atomicAdd(&s_counter, 1u);
+        if (j >= sort_cap) continue;
         unsigned long long sk;
-        if (by_first) sk = t.first[i];
+        if (fin.by_first) sk = t.first[i];
         else {
             const unsigned long long key = (i == (unsigned)t.cap) ? kEmptyKey() : k;
-            sk = key_f64 ? f64_to_ordered(__longlong_as_double((long long)key)) : i64_to_ordered((long long)key);
+            sk = fin.key_f64 ? f64_to_ordered(__longlong_as_double((long long)key)) : i64_to_ordered((long long)key);
         }
         skey[j] = sk;
         sslot[j] = i;
     }
     __syncthreads();
-    const unsigned ng = counter < (unsigned)kSmallSort ? counter : (unsigned)kSmallSort;
+    const unsigned ng = s_counter < sort_cap ? s_counter : sort_cap;
     unsigned P = 1;
     while (P < ng) P <<= 1;
-    for (unsigned i = ng + threadIdx.x; i < P; i += kSmallThreads) { skey[i] = ~0ull; sslot[i] = 0xffffffffu; }
+    for (unsigned i = ng + tid; i < P; i += kSmThreads) { skey[i] = ~0ull; sslot[i] = 0xffffffffu; }
     __syncthreads();
     for (unsigned k = 2; k <= P; k <<= 1) {
         for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned i = threadIdx.x; i < P; i += kSmallThreads) {
+            for (unsigned i = tid; i < P; i += kSmThreads) {
                 const unsigned ixj = i ^ j;
                 if (ixj > i) {
                     const unsigned long long a = skey[i], b = skey[ixj];
@@ -609,9 +666,64 @@ __global__ void __launch_bounds__(kSmallThreads) gb_finalize_small_kernel(Table 
             __syncthreads();
         }
     }
-    for (unsigned j = threadIdx.x; j < ng; j += kSmallThreads)
-        write_group(t, ncols, is_f64_mask, agg_mask, ddof, sslot[j], j, ngcap, out_keys, out_vals);
-    if (threadIdx.x == 0) *ng_out = ng;
+    for (unsigned j = tid; j < ng; j += kSmThreads)
+        write_group(t, cv.ncols(), fin.is_f64_mask, fin.agg_mask, fin.ddof, sslot[j], j, fin.ngcap, fin.out_keys, fin.out_vals);
+    if (tid == 0) fin.meta[0] = ng;
+}
+
+// second pass for var / std: ssd[slot] += (x - mean)^2  (nanvar's two passes, numpy_like.py:850-872)
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kGbThreads) gb_ssd_kernel(const void* __restrict__ keys, int64_t n, Cols cols, Table t,
+                                                            unsigned long long dlo, unsigned long long drange) {
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * kGbTile;
+        unsigned long long kb[kRows], v0[kRows], g[kRows];
+        load4(keys, base, n, tid, cols.vec_ok, kb);
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) {
+            unsigned long long k;
+            g[e] = ~0ull;
+            if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_find(t, k, dlo, drange);
+        }
+        for (int c = 0; c < cols.ncols; ++c) {
+            load4(cols.data[c], base, n, tid, cols.vec_ok, v0);
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) {
+                if (g[e] == ~0ull) continue;
+                double v, mean;
+                const double cnt = (double)t.cnt[c][g[e]];
+                if (cols.is_f64[c]) {
+                    v = __longlong_as_double((long long)v0[e]);
+                    if (v != v) continue;
+                    mean = reinterpret_cast<const double*>(t.sum[c])[g[e]] / cnt;
+                } else {
+                    v = (double)(long long)v0[e];
+                    mean = (double)reinterpret_cast<const long long*>(t.sum[c])[g[e]] / cnt;
+                }
+                const double d = v - mean;
+                atomicAdd(&t.ssd[c][g[e]], d * d);
+            }
+        }
+    }
+}
+
+// every table array gets its initial value in one launch
+struct InitPlan {
+    unsigned long long* ptr[4 + 5 * kMaxCols];
+    unsigned long long val[4 + 5 * kMaxCols];
+    unsigned long long len[4 + 5 * kMaxCols];
+    int count;
+};
+__global__ void gb_init_kernel(InitPlan plan) {
+    for (int a = blockIdx.y; a < plan.count; a += gridDim.y) {
+        unsigned long long* p = plan.ptr[a];
+        const unsigned long long v = plan.val[a], n = plan.len[a];
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x)
+            p[i] = v;
+    }
 }
 
 // ---- large tables: compaction, radix argsort of the group keys, gather ----
@@ -666,7 +778,7 @@ int need_for(unsigned agg_mask, bool sort) {
     return need;
 }
 
-SmemLayout make_layout(int ncols, int need, int want_slots, int budget_bytes) {
+SmemLayout make_layout(int ncols, int need, int want_slots, int budget_bytes, unsigned long long cap) {
     SmemLayout L;
     int per_slot = 8 + ((need & NEED_FIRST) ? 8 : 0);
     per_slot += ncols * (((need & NEED_SUM) ? 8 : 0) + ((need & NEED_CNT) ? 4 : 0) + ((need & NEED_MIN) ? 8 : 0) +
@@ -687,6 +799,9 @@ SmemLayout make_layout(int ncols, int need, int want_slots, int budget_bytes) {
     for (int c = 0; c < ncols; ++c)
         if (need & NEED_CNT) { L.off_cnt[c] = off; off += scap * 4; }
     L.bytes = off;
+    // the last CTA's bitonic sort holds up to `cap` (key, slot) pairs of 12 bytes in the same allocation
+    const int sort_bytes = (int)cap * 12;
+    L.alloc_bytes = off > sort_bytes ? off : sort_bytes;
     return L;
 }
 
@@ -716,6 +831,13 @@ struct Attempt {
     int nrep;
 };
 
+// pinned landing zone for the control-block read-back (a pageable destination makes the copy a staged one)
+unsigned long long* pinned_meta() {
+    static thread_local unsigned long long* p = nullptr;
+    if (!p && cudaMallocHost(reinterpret_cast<void**>(&p), 256) != cudaSuccess) p = nullptr;
+    return p;
+}
+
 unsigned long long pow2_at_least(unsigned long long v, unsigned long long lo) {
     unsigned long long c = lo;
     while (c < v) c <<= 1;
@@ -740,16 +862,17 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     Attempt plan[3];
     int nattempts = 0;
     if (expected_groups <= 0) {
-        if (n >= 4096) plan[nattempts++] = {true, 8192, 8};
+        if (n >= 4096) plan[nattempts++] = {true, 8192, kSmallReplicas};
         if ((1ull << 22) < worst) plan[nattempts++] = {false, 1ull << 22, 1};
     } else if (expected_groups <= 4096 && n >= 4096) {
-        plan[nattempts++] = {true, pow2_at_least(2ull * (unsigned long long)expected_groups, 1024), 8};
+        plan[nattempts++] = {true, pow2_at_least(2ull * (unsigned long long)expected_groups, 1024), kSmallReplicas};
     } else {
         const unsigned long long c = pow2_at_least(2ull * (unsigned long long)expected_groups, 1024);
         if (c < worst) plan[nattempts++] = {false, c, 1};
     }
     plan[nattempts++] = {false, worst, 1};
 
+    int allow_direct = 1;
     for (int attempt = 0; attempt < nattempts; ++attempt) {
         const Attempt& at = plan[attempt];
         TableMem mem;
@@ -769,118 +892,121 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
                                   ((need & NEED_MAX) ? 1 : 0) + (need_ssd ? 1 : 0));
             SDC_TRY(mem.reserve((size_t)narr * ((slots_n * 8 + 255) & ~size_t(255)) + 256, s));
         }
-        auto add = [&](void** dst, unsigned long long init) -> int32_t {
-            SDC_TRY(mem.get(&p, slots_n * 8, s));
+        auto add = [&](void** dst, unsigned long long init, unsigned long long len) -> int32_t {
+            SDC_TRY(mem.get(&p, len * 8, s));
             *dst = p;
             ip.ptr[ip.count] = reinterpret_cast<unsigned long long*>(p);
+            ip.len[ip.count] = len;
             ip.val[ip.count++] = init;
             return SDCB200_OK;
         };
-        SDC_TRY(add(reinterpret_cast<void**>(&t.keys), kEmptyKey()));
-        if (need & NEED_FIRST) SDC_TRY(add(reinterpret_cast<void**>(&t.first), ~0ull));
+        SDC_TRY(add(reinterpret_cast<void**>(&t.keys), kEmptyKey(), per));
+        if (need & NEED_FIRST) SDC_TRY(add(reinterpret_cast<void**>(&t.first), ~0ull, slots_n));
         for (int c = 0; c < cols.ncols; ++c) {
-            if (need & NEED_SUM) SDC_TRY(add(&t.sum[c], 0ull));
-            if (need & NEED_CNT) SDC_TRY(add(reinterpret_cast<void**>(&t.cnt[c]), 0ull));
-            if (need & NEED_MIN) SDC_TRY(add(reinterpret_cast<void**>(&t.mn[c]), ~0ull));
-            if (need & NEED_MAX) SDC_TRY(add(reinterpret_cast<void**>(&t.mx[c]), 0ull));
-            if (need_ssd) SDC_TRY(add(reinterpret_cast<void**>(&t.ssd[c]), 0ull));
+            if (need & NEED_SUM) SDC_TRY(add(&t.sum[c], 0ull, slots_n));
+            if (need & NEED_CNT) SDC_TRY(add(reinterpret_cast<void**>(&t.cnt[c]), 0ull, slots_n));
+            if (need & NEED_MIN) SDC_TRY(add(reinterpret_cast<void**>(&t.mn[c]), ~0ull, slots_n));
+            if (need & NEED_MAX) SDC_TRY(add(reinterpret_cast<void**>(&t.mx[c]), 0ull, slots_n));
+            if (need_ssd) SDC_TRY(add(reinterpret_cast<void**>(&t.ssd[c]), 0ull, per));
         }
+        // one 256-byte control block: [0] occupied, [8] overflow flag, [16] groups written, [17] CTAs done,
+        // [18] direct lo, [19] direct range, [20] compaction counter
         SDC_TRY(mem.get(&p, 256, s));
-        SDC_CUDA_TRY(cudaMemsetAsync(p, 0, 256, s));
-        t.occupied = reinterpret_cast<unsigned long long*>(p);                // [nrep <= 8]
+        ip.ptr[ip.count] = reinterpret_cast<unsigned long long*>(p);
+        ip.len[ip.count] = 32;
+        ip.val[ip.count++] = 0ull;
+        t.occupied = reinterpret_cast<unsigned long long*>(p);
         t.overflow = reinterpret_cast<int*>(reinterpret_cast<char*>(p) + 64);
-        unsigned long long* dmeta = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p) + 128);   // ng / compact counter
+        unsigned long long* dmeta = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(p) + 128);
         {
             unsigned gx = (unsigned)(ceil_div((int64_t)slots_n, 1024) < (int64_t)sms * 4 ? ceil_div((int64_t)slots_n, 1024) : (int64_t)sms * 4);
             if (gx == 0) gx = 1;
             dim3 grid(gx, ip.count < 16 ? ip.count : 16);
-            gb_init_kernel<<<grid, 256, 0, s>>>(ip, slots_n);
+            gb_init_kernel<<<grid, 256, 0, s>>>(ip);
             SDC_CHECK_LAUNCH();
         }
-        const int64_t ntiles = ceil_div(n, kGbTile);
+        unsigned long long hstack[32];
+        unsigned long long* hmeta = pinned_meta();
+        if (!hmeta) hmeta = hstack;
+        unsigned long long dlo = 0, drange = 0;
         if (at.smem) {
-            SmemLayout lay = make_layout(cols.ncols, need, (int)(2 * (expected_groups > 0 ? expected_groups : 2048)), 160 * 1024);
-            auto kern = gb_smem_kernel<KEY_F64>;
-            static thread_local bool configured = false;
-            if (!configured) {
-                SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                configured = true;
-            }
-            static thread_local int occ_bytes = -1, occ_cached = 1;
-            if (occ_bytes != lay.bytes) {
-                SDC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cached, kern, kGbThreads, lay.bytes));
-                occ_bytes = lay.bytes;
-            }
-            int occ = occ_cached;
-            if (occ < 1) occ = 1;
-            if (occ > 6) occ = 6;
-            int64_t grid = (int64_t)sms * occ;
+            // ---- low cardinality: one kernel aggregates, folds and (unless var / std) writes the result
+            SmemLayout lay = make_layout(cols.ncols, need, (int)(2 * (expected_groups > 0 ? expected_groups : 2048)), 100 * 1024, t.cap);
+            // one float64 column with a common aggregate set: compile-time specialised loop
+            int spec = -1;
+            if (cols.ncols == 1 && cols.is_f64[0] && (need == 1 || need == 2 || need == 3 || need == 15)) spec = need;
+            void (*kern)(const void*, int64_t, Cols, Table, int, SmemLayout, SmallFin) = gb_smem_kernel<KEY_F64, -1>;
+            if (spec == 1) kern = gb_smem_kernel<KEY_F64, 1>;
+            else if (spec == 2) kern = gb_smem_kernel<KEY_F64, 2>;
+            else if (spec == 3) kern = gb_smem_kernel<KEY_F64, 3>;
+            else if (spec == 15) kern = gb_smem_kernel<KEY_F64, 15>;
+            SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            const int64_t ntiles = ceil_div(n, (int64_t)kSmThreads * kRows);
+            int64_t grid = (int64_t)sms * 2;
             if (grid > ntiles) grid = ntiles;
-            long long* direct = reinterpret_cast<long long*>(dmeta + 2);      // zeroed: range 0 = hashing
-            if (!KEY_F64) {
-                gb_sample_kernel<<<1, kSampleThreads, 0, s>>>(reinterpret_cast<const long long*>(keys), n, lay.scap, direct);
-                SDC_CHECK_LAUNCH();
+            SmallFin fin;
+            memset(&fin, 0, sizeof(fin));
+            const int64_t ngcap = (int64_t)per;
+            if (!need_ssd) {
+                SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ngcap * 8, s));
+                SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ngcap * 8 * (nagg * cols.ncols + 1), s));
+                res->ngcap = ngcap;
             }
-            kern<<<(unsigned)grid, kGbThreads, lay.bytes, s>>>(keys, n, cols, t, need, lay, direct);
+            fin.out_keys = res->keys;
+            fin.out_vals = res->vals;
+            fin.ngcap = ngcap;
+            fin.agg_mask = agg_mask;
+            fin.is_f64_mask = is_f64_mask;
+            fin.ddof = ddof;
+            fin.by_first = sort ? 0 : 1;
+            fin.key_f64 = KEY_F64 ? 1 : 0;
+            fin.write_out = need_ssd ? 0 : 1;
+            fin.allow_direct = allow_direct;
+            fin.meta = dmeta;
+            kern<<<(unsigned)grid, kSmThreads, lay.alloc_bytes, s>>>(keys, n, cols, t, need, lay, fin);
             SDC_CHECK_LAUNCH();
-            if (t.nrep > 1) {
-                const int64_t total = (int64_t)per * (t.nrep - 1);
-                gb_merge_replicas_kernel<<<(unsigned)(ceil_div(total, 256) < (int64_t)sms * 4 ? ceil_div(total, 256) : (int64_t)sms * 4), 256, 0, s>>>(
-                    t, cols.ncols, is_f64_mask, need);
-                SDC_CHECK_LAUNCH();
-            }
-        } else {
-            int64_t grid = (int64_t)sms * 8;
-            if (grid > ntiles) grid = ntiles;
-            gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need);
-            SDC_CHECK_LAUNCH();
-        }
-        const bool small = per <= (unsigned long long)kSmallSlots;
-        if (small && !need_ssd) {
-            // everything else happens in one CTA; the group count comes back with the overflow flag
-            const int64_t ngcap = (int64_t)t.limit + 1;
-            SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ngcap * 8, s));
-            SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ngcap * 8 * (nagg * cols.ncols + 1), s));
-            res->ngcap = ngcap;
-            auto fk = gb_finalize_small_kernel;
-            static thread_local bool fconfigured = false;
-            const int fsmem = kSmallSort * 12;
-            if (!fconfigured) {
-                SDC_CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem));
-                fconfigured = true;
-            }
-            fk<<<1, kSmallThreads, fsmem, s>>>(t, cols.ncols, is_f64_mask, agg_mask, ddof, sort ? 0 : 1, KEY_F64 ? 1 : 0,
-                                               ngcap, res->keys, res->vals, dmeta);
-            SDC_CHECK_LAUNCH();
-            unsigned long long hmeta[17];
-            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 136, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
-            if ((int)(hmeta[8] & 0xffffffffull)) {
-                dev_free(res->keys, s); dev_free(res->vals, s);
+            const int ovf = (int)(hmeta[8] & 0xffffffffull);
+            if (ovf) {
+                if (res->keys) dev_free(res->keys, s);
+                if (res->vals) dev_free(res->vals, s);
                 res->keys = res->vals = nullptr;
+                if (ovf == 2 && allow_direct) { allow_direct = 0; --attempt; continue; }   // same table, hashing this time
                 if (attempt + 1 < nattempts) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);
                 return SDCB200_ERR_CAPACITY;
             }
-            res->ngroups = (int64_t)hmeta[16];
-            return SDCB200_OK;
-        }
-        // large table (or var / std, which need a second pass over the rows once the means are known)
-        unsigned long long hmeta[9];
-        SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 72, cudaMemcpyDeviceToHost, s));
-        SDC_CUDA_TRY(cudaStreamSynchronize(s));
-        if ((int)(hmeta[8] & 0xffffffffull)) {
-            if (attempt + 1 < nattempts) continue;
-            set_error("groupby: hash table overflow at capacity %llu", t.cap);
-            return SDCB200_ERR_CAPACITY;
-        }
-        if (need_ssd) {
+            if (!need_ssd) {
+                res->ngroups = (int64_t)hmeta[16];
+                return SDCB200_OK;
+            }
+            dlo = hmeta[18];
+            drange = hmeta[19];
+            hmeta[0] = hmeta[16];                    // group count for the second-pass path below
+        } else {
+            const int64_t ntiles = ceil_div(n, kGbTile);
             int64_t grid = (int64_t)sms * 8;
             if (grid > ntiles) grid = ntiles;
-            gb_ssd_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t);
+            gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need);
+            SDC_CHECK_LAUNCH();
+            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 72, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            if ((int)(hmeta[8] & 0xffffffffull)) {
+                if (attempt + 1 < nattempts) continue;
+                set_error("groupby: hash table overflow at capacity %llu", t.cap);
+                return SDCB200_ERR_CAPACITY;
+            }
+        }
+        // large table (or var / std, which need a second pass over the rows once the means are known)
+        if (need_ssd) {
+            const int64_t ntiles = ceil_div(n, kGbTile);
+            int64_t grid = (int64_t)sms * 8;
+            if (grid > ntiles) grid = ntiles;
+            gb_ssd_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, dlo, drange);
             SDC_CHECK_LAUNCH();
         }
-        const int64_t ng = (int64_t)hmeta[0];        // replica 0 holds every group after the merge
+        const int64_t ng = (int64_t)hmeta[0];
         res->ngroups = ng;
         res->ngcap = ng;
         if (ng == 0) return SDCB200_OK;
@@ -890,7 +1016,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         SDC_TRY(order.alloc((size_t)ng * 8, s));
         const int cgrid = (int)(ceil_div((int64_t)per, 256) < (int64_t)sms * 8 ? ceil_div((int64_t)per, 256) : (int64_t)sms * 8);
         gb_compact_kernel<<<cgrid, 256, 0, s>>>(t, slots.as<unsigned long long>(), sortkeys.as<unsigned long long>(),
-                                                sort ? 0 : 1, dmeta);
+                                                sort ? 0 : 1, dmeta + 4);
         SDC_CHECK_LAUNCH();
         SDC_TRY(argsort_device(sort ? key_dtype : SDCB200_U64, sortkeys.p, ng, true, order.as<int64_t>(), s));
         SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ng * 8, s));
@@ -978,6 +1104,16 @@ int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* 
     SDC_CUDA_TRY(cudaMemcpyAsync(dst, r->vals + ((int64_t)rank * r->ncols + col) * r->ngcap, (size_t)r->ngroups * 8,
                                  dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     if (dst_is_host) SDC_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_groupby_result(int64_t handle, void** keys, void** vals, int64_t* stride) {
+    GroupbyResult* r = find_result(handle);
+    if (!r) { set_error("groupby: unknown handle %lld", (long long)handle); return SDCB200_ERR_HANDLE; }
+    SDC_ARG_CHECK(keys != nullptr && vals != nullptr && stride != nullptr, "null out pointer");
+    *keys = r->keys;
+    *vals = r->vals;
+    *stride = r->ngcap;
     return SDCB200_OK;
 }
 

@@ -28,6 +28,7 @@
 //                        Streams (probe keys, emitted pairs) carry L2 evict_first hints, table loads evict_last.
 // Keys: int64, or float64 canonicalised so that -0.0 == +0.0 and NaN == NaN (pandas merges NaN keys).
 // Limits: build side < 2^32 - 1 rows.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -298,72 +299,115 @@ __device__ __forceinline__ uint32_t lookup_row1(const JTable& t, const uint32_t*
     return (unsigned)v ? rid[v >> 32] + 1u : 0u;
 }
 
+// Probe tiles are WARP-STRIPED: a warp owns 256 consecutive rows and lane L holds rows
+//   w0 + j * 64 + 2 L + {0, 1},  j = 0 .. 3   (items e = 2 j, 2 j + 1)
+// so every 128-bit access of a warp covers 512 contiguous bytes (whole sectors, whole lines), both for the
+// key loads and for the (left row, right row) stores of how='left'.
+__device__ __forceinline__ int64_t probe_row(int64_t tile0, int warp, int lane, int e) {
+    return tile0 + warp * 256 + (e >> 1) * 64 + 2 * lane + (e & 1);
+}
+
 template <bool KEY_F64>
-__device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t i0, int64_t n,
-                                                uint64_t stream_pol, unsigned long long k[kItems]) {
-    if (i0 + kItems <= n) {
+__device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t tile0, int warp, int lane,
+                                                int64_t n, bool vec, uint64_t stream_pol, unsigned long long k[kItems]) {
+    if (vec && tile0 + kTile <= n) {
 #pragma unroll
         for (int e = 0; e < kItems; e += 2) {
-            const ulonglong2 kk = ld_hint_v2u64(keys + i0 + e, stream_pol);
+            const ulonglong2 kk = ld_hint_v2u64(keys + probe_row(tile0, warp, lane, e), stream_pol);
             k[e] = canon_key<KEY_F64>(kk.x);
             k[e + 1] = canon_key<KEY_F64>(kk.y);
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < kItems; ++e) k[e] = (i0 + e < n) ? canon_key<KEY_F64>(keys[i0 + e]) : 0ull;
+        for (int e = 0; e < kItems; ++e) {
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            k[e] = r < n ? canon_key<KEY_F64>(keys[r]) : 0ull;
+        }
     }
 }
 
 // meta[0] ticket, meta[1] n_out.  status[tile] = flag << 62 | value; flag 1: tile aggregate, 2: inclusive prefix
 template <bool KEY_F64>
-__global__ void __launch_bounds__(kJoinThreads) probe_unique_inner_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+__global__ void __launch_bounds__(kJoinThreads, 5) probe_unique_inner_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                           JTable t, const uint32_t* __restrict__ rid,
                                                                           unsigned long long* __restrict__ status,
                                                                           unsigned long long* __restrict__ meta, int64_t ntiles,
-                                                                          int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
-    __shared__ unsigned long long wsum[kJoinThreads / 32];
-    __shared__ unsigned long long s_tile, s_base;
+                                                                          int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
+                                                                          int vec) {
+    constexpr int kWarps = kJoinThreads / 32;
+    __shared__ unsigned wcnt[kWarps];
+    __shared__ unsigned long long s_base;
     __shared__ int64_t sl[kTile];
     __shared__ int64_t sr[kTile];
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
-    if (threadIdx.x == 0) s_tile = atomicAdd(&meta[0], 1ull);
-    __syncthreads();
-    const int64_t tile = (int64_t)s_tile;
-    const int64_t i0 = tile * kTile + (int64_t)threadIdx.x * kItems;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    // tile = blockIdx.x: CTAs are dispatched in blockIdx order, so a tile's predecessors are resident or done
+    // (the forward-progress assumption every single-pass chained scan makes); no ticket, no start-up barrier
+    const int64_t tile = (int64_t)blockIdx.x;
+    const int64_t tile0 = tile * kTile;
     unsigned long long k[kItems];
     uint32_t row1[kItems];
-    load_probe_keys<KEY_F64>(keys, i0, n, stream_pol, k);
-    unsigned c = 0;
+    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-        row1[e] = (i0 + e < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
-        c += row1[e] ? 1u : 0u;
+    for (int e = 0; e < kItems; ++e)
+        row1[e] = (probe_row(tile0, warp, lane, e) < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
+    // rank of every hit inside the warp's 256 rows, in row order: segment j = 64 rows, lane L holds 2 of them
+    unsigned rank[kItems], wtot = 0;
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const unsigned ba = __ballot_sync(0xffffffffu, row1[2 * j] != 0u);
+        const unsigned bb = __ballot_sync(0xffffffffu, row1[2 * j + 1] != 0u);
+        rank[2 * j] = wtot + __popc(ba & lt_mask) + __popc(bb & lt_mask);
+        rank[2 * j + 1] = rank[2 * j] + (row1[2 * j] != 0u ? 1u : 0u);
+        wtot += __popc(ba) + __popc(bb);
     }
-    unsigned long long tot;
-    const unsigned long long ex = block_excl_scan_u64(c, &tot, wsum);
+    if (lane == 0) wcnt[warp] = wtot;
+    __syncthreads();
+    unsigned wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const unsigned x = wcnt[w];
+        if (w < warp) wbase += x;
+        tot += x;
+    }
     // decoupled look-back over the tile totals (warp 0)
     if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
         unsigned long long base = 0;
         if (tile == 0) {
             if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[0]) = (2ull << 62) | tot;
         } else {
             if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = (1ull << 62) | tot;
+            // kLook windows of 32 predecessors are loaded together (one L2 round trip), then consumed
+            // in order; a window whose entries up to its first inclusive prefix are not all published restarts
+            // the round from there
+            constexpr int kLook = 1;
             int64_t idx = tile - 1;
-            while (true) {
-                const int64_t j = idx - lane;
-                unsigned long long sv = (2ull << 62);                      // before tile 0: prefix 0
-                if (j >= 0) sv = *reinterpret_cast<volatile unsigned long long*>(&status[j]);
-                const unsigned ready = __ballot_sync(0xffffffffu, (sv >> 62) != 0);
-                if (ready != 0xffffffffu) continue;                         // a predecessor has not published yet
-                const unsigned pref = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
-                const int first = pref ? __ffs(pref) - 1 : 31;
-                unsigned long long val = (lane <= first) ? (sv & 0x3fffffffffffffffull) : 0ull;
+            bool done = false;
+            while (!done) {
+                unsigned long long sv[kLook];
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                base += val;
-                if (pref) break;
-                idx -= 32;
+                for (int m = 0; m < kLook; ++m) {
+                    const int64_t j = idx - lane - 32 * m;
+                    sv[m] = (2ull << 62);                                       // before tile 0: prefix 0
+                    if (j >= 0) sv[m] = *reinterpret_cast<volatile unsigned long long*>(&status[j]);
+                }
+                bool retry = false;
+#pragma unroll
+                for (int m = 0; m < kLook; ++m) {
+                    if (done || retry) continue;                                // warp-uniform
+                    const unsigned ready = __ballot_sync(0xffffffffu, (sv[m] >> 62) != 0);
+                    const unsigned pref = __ballot_sync(0xffffffffu, (sv[m] >> 62) == 2);
+                    const int first = pref ? __ffs(pref) - 1 : 31;
+                    const unsigned need_mask = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+                    if ((ready & need_mask) != need_mask) { retry = true; continue; }
+                    unsigned long long val = (lane <= first) ? (sv[m] & 0x3fffffffffffffffull) : 0ull;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                    base += val;
+                    if (pref) done = true;
+                    else idx -= 32;
+                }
             }
             if (lane == 0) *reinterpret_cast<volatile unsigned long long*>(&status[tile]) = (2ull << 62) | (base + tot);
         }
@@ -372,21 +416,25 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_inner_kernel(const 
             if (tile == ntiles - 1) meta[1] = base + tot;
         }
     }
-    // stage the tile's pairs, then coalesced streaming stores
-    unsigned p = (unsigned)ex;
+    // stage the tile's pairs (consecutive hits -> consecutive words: conflict-free), then coalesced streaming stores
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
         if (row1[e]) {
-            sl[p] = i0 + e;
+            const unsigned p = wbase + rank[e];
+            sl[p] = probe_row(tile0, warp, lane, e);
             sr[p] = (int64_t)row1[e] - 1;
-            ++p;
         }
     }
     __syncthreads();
     const unsigned long long base = s_base;
-    for (unsigned q = threadIdx.x; q < (unsigned)tot; q += kJoinThreads) {
-        st_hint_s64(lidx + base + q, sl[q], stream_pol);
-        st_hint_s64(ridx + base + q, sr[q], stream_pol);
+    // 16-byte stores over the aligned body, scalar head / tail
+    const unsigned head = (unsigned)(base & 1ull) < tot ? (unsigned)(base & 1ull) : tot;
+    const unsigned body = (tot - head) & ~1u;
+    if (threadIdx.x == 0 && head) { lidx[base] = sl[0]; ridx[base] = sr[0]; }
+    if (threadIdx.x == 1 && head + body < tot) { lidx[base + tot - 1] = sl[tot - 1]; ridx[base + tot - 1] = sr[tot - 1]; }
+    for (unsigned q = head + 2 * threadIdx.x; q < head + body; q += 2 * kJoinThreads) {
+        st_hint_v2s64(lidx + base + q, sl[q], sl[q + 1], stream_pol);
+        st_hint_v2s64(ridx + base + q, sr[q], sr[q + 1], stream_pol);
     }
 }
 
@@ -394,25 +442,30 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_inner_kernel(const 
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                          JTable t, const uint32_t* __restrict__ rid,
-                                                                         int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+                                                                         int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
+                                                                         int vec) {
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
-    const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
-    if (i0 >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
     unsigned long long k[kItems];
     int64_t rr[kItems];
-    load_probe_keys<KEY_F64>(keys, i0, n, stream_pol, k);
+    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e) rr[e] = (i0 + e < n) ? (int64_t)lookup_row1(t, rid, k[e], keep_pol) - 1 : -1;
-    if (i0 + kItems <= n) {
+    for (int e = 0; e < kItems; ++e)
+        rr[e] = (probe_row(tile0, warp, lane, e) < n) ? (int64_t)lookup_row1(t, rid, k[e], keep_pol) - 1 : -1;
+    if (tile0 + kTile <= n) {
 #pragma unroll
         for (int e = 0; e < kItems; e += 2) {
-            st_hint_v2s64(lidx + i0 + e, i0 + e, i0 + e + 1, stream_pol);
-            st_hint_v2s64(ridx + i0 + e, rr[e], rr[e + 1], stream_pol);
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            st_hint_v2s64(lidx + r, r, r + 1, stream_pol);
+            st_hint_v2s64(ridx + r, rr[e], rr[e + 1], stream_pol);
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < kItems; ++e)
-            if (i0 + e < n) { lidx[i0 + e] = i0 + e; ridx[i0 + e] = rr[e]; }
+        for (int e = 0; e < kItems; ++e) {
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            if (r < n) { lidx[r] = r; ridx[r] = rr[e]; }
+        }
     }
 }
 
@@ -530,18 +583,22 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         res->lidx = reinterpret_cast<int64_t*>(p);
         SDC_TRY(dev_alloc(&p, (size_t)nl * 8, s));
         res->ridx = reinterpret_cast<int64_t*>(p);
+        const int vec = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
         if (LEFT) {
-            probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx);
+            probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx, vec);
             SDC_CHECK_LAUNCH();
-            res->n_out = nl;                                 // scratch is freed in stream order: no sync needed
         } else {
             Scratch status;
             SDC_TRY(status.alloc((size_t)nt * 8, s));
             SDC_CUDA_TRY(cudaMemsetAsync(status.p, 0, (size_t)nt * 8, s));
             probe_unique_inner_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(),
                                                                                     status.as<unsigned long long>(), dmeta, nt,
-                                                                                    res->lidx, res->ridx);
+                                                                                    res->lidx, res->ridx, vec);
             SDC_CHECK_LAUNCH();
+        }
+        if (LEFT) {
+            res->n_out = nl;                                 // scratch is freed in stream order: no sync needed
+        } else {
             unsigned long long h[2] = {0, 0};
             SDC_CUDA_TRY(cudaMemcpyAsync(h, dmeta, 16, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));

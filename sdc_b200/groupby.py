@@ -64,22 +64,54 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
         native.check(lib.sdcb200_groupby(native.DTYPE_CODES[kname], keys.data_ptr(), n, len(cols), ptrs, dts, mask,
                                          1 if sort else 0, int(ddof), int(expected_groups), stream,
                                          ct.byref(handle), ct.byref(ng)))
-        try:
-            g = ng.value
-            out_keys = torch.empty(g, dtype=keys.dtype, device=keys.device)
-            native.check(lib.sdcb200_groupby_keys(handle.value, out_keys.data_ptr(), 0, stream))
-            res = {}
+        g = ng.value
+        owner = _ResultHandle(handle.value)
+        if g == 0:
+            out_keys = torch.empty(0, dtype=keys.dtype, device=keys.device)
+            return out_keys, {a: [torch.empty(0, dtype=_out_dtype(torch, a, c), device=keys.device) for c in cols]
+                              for a in aggs}
+        # the result stays where the library wrote it: tensors view the handle's buffers and keep it alive
+        kp, vp, stride = ct.c_void_p(), ct.c_void_p(), ct.c_int64(0)
+        native.check(lib.sdcb200_groupby_result(handle.value, ct.byref(kp), ct.byref(vp), ct.byref(stride)))
+        out_keys = torch.as_tensor(_DeviceView(kp.value, (g,), "<i8", owner), device=keys.device).view(keys.dtype)
+        ranks = sorted(set(aggs), key=lambda a: native.AGG_BITS[a])
+        res = {}
+        if cols:
+            vals = torch.as_tensor(_DeviceView(vp.value, (len(ranks) * len(cols), stride.value), "<i8", owner),
+                                   device=keys.device)
             for a in aggs:
-                outs = []
-                for i, c in enumerate(cols):
-                    is_int = a == "count" or (c.dtype == torch.int64 and a in ("sum", "min", "max"))
-                    o = torch.empty(g, dtype=torch.int64 if is_int else torch.float64, device=keys.device)
-                    native.check(lib.sdcb200_groupby_values(handle.value, i, native.AGG_BITS[a], o.data_ptr(), 0, stream))
-                    outs.append(o)
-                res[a] = outs
-        finally:
-            native.check(lib.sdcb200_groupby_free(handle.value))
+                r = ranks.index(a)
+                res[a] = [vals[r * len(cols) + i, :g].view(_out_dtype(torch, a, c)) for i, c in enumerate(cols)]
+        else:
+            res = {a: [] for a in aggs}
     return out_keys, res
+
+
+def _out_dtype(torch, agg, col):
+    is_int = agg == "count" or (col.dtype == torch.int64 and agg in ("sum", "min", "max"))
+    return torch.int64 if is_int else torch.float64
+
+
+class _ResultHandle:
+    """Owns a groupby result handle; frees it when the last tensor viewing it is gone."""
+
+    def __init__(self, handle):
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            native.load().sdcb200_groupby_free(self.handle)
+        except Exception:
+            pass
+
+
+class _DeviceView:
+    """Device buffer exposed through __cuda_array_interface__ (zero-copy into torch)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
 
 
 def _value_column(values):

@@ -21,6 +21,13 @@ if what == "groupby":
     b = torch.from_numpy(rng.random(n)).cuda()
     for _ in range(reps):
         groupby_device(a, [b], ("sum",), True, 1, 1000)
+elif what == "groupby_small":
+    from sdc_b200.groupby import groupby_device
+    n = 200_000
+    a = torch.from_numpy(rng.integers(0, 1000, n, dtype=np.int64)).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    for _ in range(reps):
+        groupby_device(a, [b], ("sum",), True, 1, 1000)
 elif what == "groupby_hi":
     from sdc_b200.groupby import groupby_device
     n = 100_000_000
@@ -28,6 +35,13 @@ elif what == "groupby_hi":
     b = torch.from_numpy(rng.random(n)).cuda()
     for _ in range(reps):
         groupby_device(a, [b], ("sum",), True, 1, 1_000_000)
+elif what == "groupby_50m":
+    from sdc_b200.groupby import groupby_device
+    n = 100_000_000
+    a = torch.from_numpy(rng.integers(0, 50_000_000, n, dtype=np.int64)).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    for _ in range(reps):
+        groupby_device(a, [b], ("sum",), True, 1, 50_000_000)
 elif what == "rolling":
     from sdc_b200.rolling import rolling_device
     x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
@@ -39,6 +53,12 @@ elif what == "sort":
     x = torch.from_numpy(rng.integers(-2**63, 2**63 - 1, 100_000_000, dtype=np.int64)).cuda()
     for _ in range(reps):
         argsort_device(x)
+elif what == "join_left":
+    from sdc_b200.join import join_device
+    r = torch.from_numpy(np.random.default_rng(2).permutation(10_000_000).astype(np.int64)).cuda()
+    l = torch.from_numpy(np.random.default_rng(3).integers(0, 10_000_000, 100_000_000, dtype=np.int64)).cuda()
+    for _ in range(reps):
+        join_device(l, r, "left")
 elif what == "join":
     from sdc_b200.join import join_device
     r = torch.from_numpy(np.random.default_rng(2).permutation(10_000_000).astype(np.int64)).cuda()
