@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "radix_sort.cuh"
+#include "scan.cuh"
 
 namespace sdcb200 {
 namespace {
@@ -709,6 +710,164 @@ __global__ void __launch_bounds__(kGbThreads) gb_ssd_kernel(const void* __restri
     }
 }
 
+// ------------------------------------------------------------------ very high cardinality: sort, then segments
+// When the table of a hash aggregate would be far larger than L2 (tens of millions of groups) every row costs
+// two random HBM sectors; sorting (key, row) pairs with the onesweep radix sort and reducing equal-key runs
+// streams instead, and leaves the groups in key order for free.  Rows are visited in sorted order:
+//   gb_seg_count_kernel   per tile of 2048 sorted rows: number of run heads
+//   (scan of the tile counts -> group id of every head, number of groups)
+//   gb_seg_kernel         per thread 8 consecutive sorted rows: values gathered by row number, equal-key
+//                         runs folded in registers, one atomic per run and aggregate into the group arrays
+//                         (runs crossing thread or tile borders meet in the atomics)
+// NaN keys sort last (sort.cu canon_key) and are skipped like in the hash path.  The stable sort keeps rows of a
+// group in input order, so the head of a run is the group's first row (sort=False ordering).
+// thresholds of the sort path (overridable for tests: SDCB200_GB_SORT_ROWS / SDCB200_GB_SORT_GROUPS)
+int64_t sort_path_rows() {          // inputs below this keep the worst-case hash table
+    const char* e = getenv("SDCB200_GB_SORT_ROWS");
+    return e ? atoll(e) : (8ll << 20);
+}
+int64_t sort_path_groups() {        // expected groups above this go straight to the sort path
+    const char* e = getenv("SDCB200_GB_SORT_GROUPS");
+    return e ? atoll(e) : (4ll << 20);
+}
+constexpr int kSegItems = 8;
+constexpr int kSegTile = kGbThreads * kSegItems;
+
+template <bool KEY_F64>
+__device__ __forceinline__ unsigned seg_heads(const unsigned long long* __restrict__ sk, int64_t i0, int64_t n,
+                                              unsigned long long k[kSegItems], unsigned& valid) {
+    // bit e of the result: row i0 + e starts a run; bit e of valid: row exists and its key is not NaN
+    unsigned heads = 0;
+    valid = 0;
+    unsigned long long prev = 0;
+    bool have_prev = false;
+    if (i0 > 0 && i0 < n) have_prev = canon_key<KEY_F64>(sk[i0 - 1], prev);
+#pragma unroll
+    for (int e = 0; e < kSegItems; ++e) {
+        k[e] = 0;
+        if (i0 + e < n && canon_key<KEY_F64>(sk[i0 + e], k[e])) {
+            valid |= 1u << e;
+            if (!have_prev || k[e] != prev) heads |= 1u << e;
+            prev = k[e];
+            have_prev = true;
+        }
+    }
+    return heads;
+}
+
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kGbThreads) gb_seg_count_kernel(const unsigned long long* __restrict__ sk, int64_t n,
+                                                                  unsigned long long* __restrict__ tile_counts) {
+    __shared__ unsigned wcnt[kGbThreads / 32];
+    const int64_t i0 = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+    unsigned long long k[kSegItems];
+    unsigned valid;
+    unsigned c = __popc(seg_heads<KEY_F64>(sk, i0, n, k, valid));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < kGbThreads / 32; ++w) t += wcnt[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// pass 0: sum / count / min / max / first into the group arrays; pass 1: sum of squared deviations (var / std)
+template <bool KEY_F64, typename ROW>
+__global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long long* __restrict__ sk,
+                                                            const ROW* __restrict__ rows, int64_t n, Cols cols, Table t,
+                                                            int need, int pass,
+                                                            const unsigned long long* __restrict__ tile_offs) {
+    __shared__ unsigned long long wsum[kGbThreads / 32];
+    const int64_t i0 = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
+    unsigned long long k[kSegItems];
+    unsigned valid;
+    const unsigned heads = seg_heads<KEY_F64>(sk, i0, n, k, valid);
+    unsigned long long tot;
+    // group id of the run that is open when this thread starts (= heads before it, minus one)
+    unsigned long long gid = tile_offs[blockIdx.x] + block_excl_scan_u64(__popc(heads), &tot, wsum) - 1ull;
+    if (!valid) return;
+    ROW r[kSegItems];
+#pragma unroll
+    for (int e = 0; e < kSegItems; ++e) r[e] = (valid >> e) & 1u ? rows[i0 + e] : ROW(0);
+    if (pass == 0) {
+        unsigned long long g = gid;
+#pragma unroll
+        for (int e = 0; e < kSegItems; ++e) {
+            if ((heads >> e) & 1u) {
+                ++g;
+                t.keys[g] = k[e];
+                if (need & NEED_FIRST) t.first[g] = (unsigned long long)r[e];
+            }
+        }
+    }
+    for (int c = 0; c < cols.ncols; ++c) {
+        const bool f = cols.is_f64[c] != 0;
+        const unsigned long long* col = reinterpret_cast<const unsigned long long*>(cols.data[c]);
+        unsigned long long bits[kSegItems];
+#pragma unroll
+        for (int e = 0; e < kSegItems; ++e) bits[e] = (valid >> e) & 1u ? __ldg(col + r[e]) : 0ull;   // gathers in flight together
+        unsigned long long g = gid;
+        // open run: folded in registers, flushed with atomics when the next head (or the thread's end) comes
+        double fs = 0.0;
+        long long is = 0;
+        unsigned long long cn = 0, mn = ~0ull, mx = 0ull;
+        bool open = false;
+        auto flush = [&]() {
+            if (!open) return;
+            if (pass == 1) { if (cn) atomicAdd(&t.ssd[c][g], fs); }
+            else {
+                if (need & NEED_SUM) {
+                    if (f) { if (cn) atomicAdd(reinterpret_cast<double*>(t.sum[c]) + g, fs); }
+                    else atomicAdd(reinterpret_cast<unsigned long long*>(t.sum[c]) + g, (unsigned long long)is);
+                }
+                if ((need & NEED_CNT) && cn) atomicAdd(&t.cnt[c][g], cn);
+                if ((need & NEED_MIN) && cn) atomicMin(&t.mn[c][g], mn);
+                if ((need & NEED_MAX) && cn) atomicMax(&t.mx[c][g], mx);
+            }
+            fs = 0.0; is = 0; cn = 0; mn = ~0ull; mx = 0ull;
+        };
+#pragma unroll
+        for (int e = 0; e < kSegItems; ++e) {
+            if (!((valid >> e) & 1u)) continue;
+            if ((heads >> e) & 1u) { flush(); ++g; }
+            open = true;
+            if (pass == 1) {
+                const double cnt = (double)t.cnt[c][g];
+                double v, mean;
+                if (f) {
+                    v = __longlong_as_double((long long)bits[e]);
+                    if (v != v) continue;
+                    mean = reinterpret_cast<const double*>(t.sum[c])[g] / cnt;
+                } else {
+                    v = (double)(long long)bits[e];
+                    mean = (double)reinterpret_cast<const long long*>(t.sum[c])[g] / cnt;
+                }
+                const double d = v - mean;
+                fs += d * d;
+                ++cn;
+            } else if (f) {
+                const double v = __longlong_as_double((long long)bits[e]);
+                if (v != v) continue;                                    // skipna
+                fs += v;
+                ++cn;
+                const unsigned long long o = f64_to_ordered(v);
+                mn = o < mn ? o : mn;
+                mx = o > mx ? o : mx;
+            } else {
+                is += (long long)bits[e];
+                ++cn;
+                const unsigned long long o = i64_to_ordered((long long)bits[e]);
+                mn = o < mn ? o : mn;
+                mx = o > mx ? o : mx;
+            }
+        }
+        flush();
+    }
+}
+
 // every table array gets its initial value in one launch
 struct InitPlan {
     unsigned long long* ptr[4 + 5 * kMaxCols];
@@ -744,6 +903,15 @@ __global__ void gb_finalize_kernel(Table t, int ncols, unsigned is_f64_mask, uns
                                    int64_t ng, unsigned long long* out_keys, unsigned long long* out_vals) {
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x)
         write_group(t, ncols, is_f64_mask, agg_mask, ddof, slots[order[j]], j, ng, out_keys, out_vals);
+}
+
+// segment path: the group arrays are already dense (group j at index j, in key order); `order` (sort=False)
+// permutes them into first-appearance order
+__global__ void gb_finalize_seg_kernel(Table t, int ncols, unsigned is_f64_mask, unsigned agg_mask, long long ddof,
+                                       const int64_t* __restrict__ order, int64_t ng, unsigned long long* out_keys,
+                                       unsigned long long* out_vals) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x)
+        write_group(t, ncols, is_f64_mask, agg_mask, ddof, (unsigned long long)(order ? order[j] : j), j, ng, out_keys, out_vals);
 }
 
 // ------------------------------------------------------------------ host side
@@ -844,6 +1012,102 @@ unsigned long long pow2_at_least(unsigned long long v, unsigned long long lo) {
     return c;
 }
 
+// very high cardinality: radix sort of (key, row), then one streaming pass over equal-key runs
+template <bool KEY_F64>
+int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_mask, bool sort, long long ddof,
+                           int key_dtype, cudaStream_t s, GroupbyResult* res) {
+    const int need = need_for(agg_mask, sort);
+    const bool need_ssd = (agg_mask & (AGG_VAR | AGG_STD)) != 0;
+    const int sms = sm_count();
+    const int nagg = __builtin_popcount(agg_mask);
+    unsigned is_f64_mask = 0;
+    for (int c = 0; c < cols.ncols; ++c) if (cols.is_f64[c]) is_f64_mask |= 1u << c;
+    const bool small_rows = n <= 0xffffffffll;
+    const int pay = small_rows ? 4 : 8;
+    Scratch ka, kb, pa, pb, tcnt;
+    SDC_TRY(ka.alloc((size_t)n * 8, s));
+    SDC_TRY(kb.alloc((size_t)n * 8, s));
+    SDC_TRY(pa.alloc((size_t)n * pay, s));
+    SDC_TRY(pb.alloc((size_t)n * pay, s));
+    const void *rk, *rp;
+    SDC_TRY(radix_sort_core(key_dtype, keys, ka.p, kb.p, pay, nullptr, pa.p, pb.p, n, true, false, &rk, &rp, s));
+    const unsigned long long* sk = reinterpret_cast<const unsigned long long*>(rk);
+    const int64_t nt = ceil_div(n, kSegTile);
+    SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8, s));
+    gb_seg_count_kernel<KEY_F64><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, n, tcnt.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tcnt.as<unsigned long long>(), nt);
+    SDC_CHECK_LAUNCH();
+    unsigned long long total = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&total, tcnt.as<unsigned long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    const int64_t ng = (int64_t)total;
+    res->ngroups = ng;
+    res->ngcap = ng;
+    if (ng == 0) return SDCB200_OK;
+
+    TableMem mem;
+    Table t;
+    memset(&t, 0, sizeof(t));
+    t.cap = ~0ull;                    // no spare slot: group j lives at index j
+    t.nrep = 1;
+    InitPlan ip;
+    ip.count = 0;
+    {
+        int narr = 1 + ((need & NEED_FIRST) ? 1 : 0);
+        narr += cols.ncols * (((need & NEED_SUM) ? 1 : 0) + ((need & NEED_CNT) ? 1 : 0) + ((need & NEED_MIN) ? 1 : 0) +
+                              ((need & NEED_MAX) ? 1 : 0) + (need_ssd ? 1 : 0));
+        SDC_TRY(mem.reserve((size_t)narr * (((size_t)ng * 8 + 255) & ~size_t(255)) + 256, s));
+    }
+    void* p;
+    auto add = [&](void** dst, unsigned long long init, bool do_init) -> int32_t {
+        SDC_TRY(mem.get(&p, (size_t)ng * 8, s));
+        *dst = p;
+        if (do_init) {
+            ip.ptr[ip.count] = reinterpret_cast<unsigned long long*>(p);
+            ip.len[ip.count] = (unsigned long long)ng;
+            ip.val[ip.count++] = init;
+        }
+        return SDCB200_OK;
+    };
+    SDC_TRY(add(reinterpret_cast<void**>(&t.keys), 0ull, false));                 // every entry is written by its head
+    if (need & NEED_FIRST) SDC_TRY(add(reinterpret_cast<void**>(&t.first), 0ull, false));
+    for (int c = 0; c < cols.ncols; ++c) {
+        if (need & NEED_SUM) SDC_TRY(add(&t.sum[c], 0ull, true));
+        if (need & NEED_CNT) SDC_TRY(add(reinterpret_cast<void**>(&t.cnt[c]), 0ull, true));
+        if (need & NEED_MIN) SDC_TRY(add(reinterpret_cast<void**>(&t.mn[c]), ~0ull, true));
+        if (need & NEED_MAX) SDC_TRY(add(reinterpret_cast<void**>(&t.mx[c]), 0ull, true));
+        if (need_ssd) SDC_TRY(add(reinterpret_cast<void**>(&t.ssd[c]), 0ull, true));
+    }
+    if (ip.count) {
+        unsigned gx = (unsigned)(ceil_div(ng, 1024) < (int64_t)sms * 4 ? ceil_div(ng, 1024) : (int64_t)sms * 4);
+        dim3 grid(gx ? gx : 1, ip.count < 16 ? ip.count : 16);
+        gb_init_kernel<<<grid, 256, 0, s>>>(ip);
+        SDC_CHECK_LAUNCH();
+    }
+    for (int pass = 0; pass < (need_ssd ? 2 : 1); ++pass) {
+        if (small_rows)
+            gb_seg_kernel<KEY_F64, uint32_t><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, reinterpret_cast<const uint32_t*>(rp), n, cols, t,
+                                                                                need, pass, tcnt.as<unsigned long long>());
+        else
+            gb_seg_kernel<KEY_F64, unsigned long long><<<(unsigned)nt, kGbThreads, 0, s>>>(
+                sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, tcnt.as<unsigned long long>());
+        SDC_CHECK_LAUNCH();
+    }
+    Scratch order;
+    if (!sort) {
+        SDC_TRY(order.alloc((size_t)ng * 8, s));
+        SDC_TRY(argsort_device(SDCB200_U64, t.first, ng, true, order.as<int64_t>(), s));
+    }
+    SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ng * 8, s));
+    SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ng * 8 * (nagg * cols.ncols + 1), s));
+    const int fgrid = (int)(ceil_div(ng, 256) < (int64_t)sms * 8 ? ceil_div(ng, 256) : (int64_t)sms * 8);
+    gb_finalize_seg_kernel<<<fgrid, 256, 0, s>>>(t, cols.ncols, is_f64_mask, agg_mask, ddof,
+                                                 sort ? nullptr : order.as<int64_t>(), ng, res->keys, res->vals);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
 template <bool KEY_F64>
 int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, bool sort, long long ddof,
                     int key_dtype, int64_t expected_groups, cudaStream_t s, GroupbyResult* res) {
@@ -856,9 +1120,13 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     cols.vec_ok = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
     for (int c = 0; c < cols.ncols; ++c) if (reinterpret_cast<uintptr_t>(cols.data[c]) & 15) cols.vec_ok = 0;
 
-    // plan: shared-memory pre-aggregation + small replicated table when the cardinality is (or may be)
-    // low; a single global table sized from the hint; the worst case (every row its own group) last
+    // plan: shared-memory pre-aggregation + small replicated table when the cardinality is (or may be) low;
+    // a single global table sized from the hint while it stays around the size of L2; beyond that (hint or
+    // overflow) the sort-and-segment path, whose cost does not depend on the number of groups
     const unsigned long long worst = pow2_at_least(2ull * (unsigned long long)n, 64);
+    const bool big = n >= sort_path_rows();
+    if (big && expected_groups > sort_path_groups())
+        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, s, res);
     Attempt plan[3];
     int nattempts = 0;
     if (expected_groups <= 0) {
@@ -870,7 +1138,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         const unsigned long long c = pow2_at_least(2ull * (unsigned long long)expected_groups, 1024);
         if (c < worst) plan[nattempts++] = {false, c, 1};
     }
-    plan[nattempts++] = {false, worst, 1};
+    if (!big) plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
 
     int allow_direct = 1;
     for (int attempt = 0; attempt < nattempts; ++attempt) {
@@ -973,7 +1241,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
                 if (res->vals) dev_free(res->vals, s);
                 res->keys = res->vals = nullptr;
                 if (ovf == 2 && allow_direct) { allow_direct = 0; --attempt; continue; }   // same table, hashing this time
-                if (attempt + 1 < nattempts) continue;
+                if (attempt + 1 < nattempts || big) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);
                 return SDCB200_ERR_CAPACITY;
             }
@@ -993,7 +1261,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 72, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
             if ((int)(hmeta[8] & 0xffffffffull)) {
-                if (attempt + 1 < nattempts) continue;
+                if (attempt + 1 < nattempts || big) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);
                 return SDCB200_ERR_CAPACITY;
             }
@@ -1028,6 +1296,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         SDC_CUDA_TRY(cudaStreamSynchronize(s));   // table scratch is released when `mem` goes out of scope
         return SDCB200_OK;
     }
+    if (big) return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, s, res);
     return SDCB200_ERR_CAPACITY;
 }
 

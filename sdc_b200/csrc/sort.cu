@@ -112,30 +112,37 @@ __global__ void __launch_bounds__(256) scan_kernel(const unsigned long long* __r
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 
-template <typename U> struct Items { static constexpr int v = sizeof(U) == 8 ? 12 : 16; };
+// rows per thread: tiles of 4096 rows keep the number of tiles in flight (and so the length of the
+// look-back chains) down without costing a resident CTA
+template <typename U> struct Items { static constexpr int v = 16; };
 
 struct NoPay {};
 
-template <typename U, typename P, bool HAS_PAY>
-__global__ void __launch_bounds__(kSortThreads)
+// look-back status word: bits 0-1 flag (1 = tile count, 2 = inclusive prefix), bits 2-9 epoch (the pass
+// number + 1: entries of earlier passes are simply stale, so the buffer is zeroed once per sort, not once
+// per pass), bits 10.. value
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long v, unsigned flag, unsigned epoch) {
+    return (v << 10) | ((unsigned long long)epoch << 2) | flag;
+}
+
+template <typename U, typename P, bool HAS_PAY, int KIND, bool DESC, int ITEMS>
+__global__ void __launch_bounds__(kSortThreads, 3)
 onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __restrict__ pin, P* __restrict__ pout,
-                int64_t n, int shift, int kind, int desc, int iota,
-                const unsigned long long* __restrict__ gbase, unsigned long long* lookback, unsigned* tile_counter) {
-    constexpr int ITEMS = Items<U>::v;
+                int64_t n, int shift, int iota,
+                const unsigned long long* __restrict__ gbase, unsigned long long* lookback, unsigned epoch) {
     constexpr int TILE = kSortThreads * ITEMS;
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned* wh = reinterpret_cast<unsigned*>(smem);                        // [kSortWarps][256]
     unsigned* tile_off = wh + kSortWarps * 256;                              // [256]
     long long* digit_dst = reinterpret_cast<long long*>(tile_off + 256);    // [256]
-    unsigned* warp_tot = reinterpret_cast<unsigned*>(digit_dst + 256);      // [8] + tile id
+    unsigned* warp_tot = reinterpret_cast<unsigned*>(digit_dst + 256);      // [8]
     U* skeys = reinterpret_cast<U*>(warp_tot + 16);
     P* spay = reinterpret_cast<P*>(skeys + TILE);
+    unsigned char* sdig = reinterpret_cast<unsigned char*>(spay + (HAS_PAY ? TILE : 0));   // [TILE] digit of the staged row
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) warp_tot[8] = atomicAdd(tile_counter, 1u);
-    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) wh[i] = 0;
-    __syncthreads();
-    const unsigned tile = warp_tot[8];
+    // tile = blockIdx.x: CTAs are dispatched in blockIdx order, so a tile's predecessors are resident or done
+    const unsigned tile = blockIdx.x;
     const int64_t tile_base = (int64_t)tile * TILE;
     const int tile_n = (int)((n - tile_base) < (int64_t)TILE ? (n - tile_base) : (int64_t)TILE);
 
@@ -148,6 +155,17 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         const int pos = wbase + i * 32 + lane;
         key[i] = pos < tile_n ? kin[tile_base + pos] : U(0);
     }
+    // the payload rides along in registers: its loads are in flight while the tile is ranked
+    P pay[HAS_PAY ? ITEMS : 1];
+    if (HAS_PAY) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int pos = wbase + i * 32 + lane;
+            pay[i] = iota ? P(tile_base + pos) : (pos < tile_n ? pin[tile_base + pos] : P(0));
+        }
+    }
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) wh[i] = 0;
+    __syncthreads();
     // ---- rank inside the warp: ballot multisplit, stable in lane order ----
     unsigned* mywh = wh + w * 256;
     const unsigned lt = (1u << lane) - 1u;
@@ -155,7 +173,7 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = wbase + i * 32 + lane;
         const bool valid = pos < tile_n;
-        const unsigned d = (unsigned)(canon_key<U>(key[i], kind, desc != 0) >> shift) & 255u;
+        const unsigned d = (unsigned)(canon_key<U>(key[i], KIND, DESC) >> shift) & 255u;
         unsigned peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
@@ -170,7 +188,9 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         rank[i] = (unsigned short)(prior + __popc(peers & lt));
     }
     __syncthreads();
-    // ---- per digit (thread d): prefix over warps, tile count, look-back ----
+    // ---- per digit (thread d): prefix over warps, tile count published at once, scan over digits ----
+    volatile unsigned long long* lb = lookback;
+    unsigned long long cnt;
     {
         const int d = tid;
         unsigned run = 0;
@@ -180,24 +200,8 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             wh[ww * 256 + d] = run;
             run += t;
         }
-        const unsigned long long cnt = run;
-        volatile unsigned long long* lb = lookback;
-        unsigned long long excl = 0;
-        if (tile == 0) {
-            lb[d] = (cnt << 2) | 2ull;
-        } else {
-            lb[(size_t)tile * 256 + d] = (cnt << 2) | 1ull;
-            long long t = (long long)tile - 1;
-            while (true) {
-                unsigned long long v;
-                do { v = lb[(size_t)t * 256 + d]; } while ((v & 3ull) == 0);
-                excl += v >> 2;
-                if ((v & 3ull) == 2ull) break;
-                --t;
-            }
-            lb[(size_t)tile * 256 + d] = ((excl + cnt) << 2) | 2ull;
-        }
-        // exclusive scan of the tile counts over digits
+        cnt = run;
+        lb[(size_t)tile * 256 + d] = lb_pack(cnt, tile == 0 ? 2u : 1u, epoch);
         unsigned x = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -208,29 +212,43 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         __syncthreads();
         unsigned add = 0;
         for (int i = 0; i < w; ++i) add += warp_tot[i];
-        const unsigned off = add + x - run;
-        tile_off[d] = off;
-        digit_dst[d] = (long long)(gbase[d] + excl) - (long long)off;
+        tile_off[d] = add + x - run;
     }
     __syncthreads();
-    // ---- stage the tile in digit order ----
+    // ---- stage the tile in digit order (needs only tile-local offsets; predecessors publish meanwhile) ----
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = wbase + i * 32 + lane;
         if (pos < tile_n) {
-            const unsigned d = (unsigned)(canon_key<U>(key[i], kind, desc != 0) >> shift) & 255u;
+            const unsigned d = (unsigned)(canon_key<U>(key[i], KIND, DESC) >> shift) & 255u;
             const unsigned p = tile_off[d] + mywh[d] + rank[i];
             skeys[p] = key[i];
-            if (HAS_PAY) spay[p] = iota ? P(tile_base + pos) : pin[tile_base + pos];
+            sdig[p] = (unsigned char)d;
+            if (HAS_PAY) spay[p] = pay[i];
         }
+    }
+    // ---- decoupled look-back per digit ----
+    {
+        const int d = tid;
+        unsigned long long excl = 0;
+        if (tile != 0) {
+            long long t = (long long)tile - 1;
+            while (true) {
+                unsigned long long v;
+                do { v = lb[(size_t)t * 256 + d]; } while ((v & 3ull) == 0 || (unsigned)((v >> 2) & 255ull) != epoch);
+                excl += v >> 10;
+                if ((v & 3ull) == 2ull) break;
+                --t;
+            }
+            lb[(size_t)tile * 256 + d] = lb_pack(excl + cnt, 2u, epoch);
+        }
+        digit_dst[d] = (long long)(gbase[d] + excl) - (long long)tile_off[d];
     }
     __syncthreads();
     // ---- scatter: consecutive staged slots of one digit go to consecutive global slots ----
     for (int p = tid; p < tile_n; p += kSortThreads) {
-        const U k = skeys[p];
-        const unsigned d = (unsigned)(canon_key<U>(k, kind, desc != 0) >> shift) & 255u;
-        const long long dst = digit_dst[d] + p;
-        kout[dst] = k;
+        const long long dst = digit_dst[sdig[p]] + p;
+        kout[dst] = skeys[p];
         if (HAS_PAY) pout[dst] = spay[p];
     }
 }
@@ -252,11 +270,10 @@ __global__ void gather_kernel(const T* __restrict__ src, const int64_t* __restri
         dst[i] = src[idx[i]];
 }
 
-template <typename U, typename P, bool HAS_PAY>
-int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, int64_t n, int kind, bool iota,
+template <typename U, typename P, bool HAS_PAY, int ITEMS>
+int32_t sort_impl_items(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, int64_t n, int kind, bool iota,
                   bool desc, const void** rkeys, const void** rpay, cudaStream_t s) {
     constexpr int NP = sizeof(U);
-    constexpr int ITEMS = Items<U>::v;
     constexpr int TILE = kSortThreads * ITEMS;
     const int64_t ntiles = ceil_div(n, TILE);
     Scratch meta, lb;
@@ -269,6 +286,7 @@ int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, i
     unsigned* counters = reinterpret_cast<unsigned*>(gbase + NP * 256);
     int* trivial = reinterpret_cast<int*>(counters + NP);
     SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, meta_bytes, s));
+    SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
     int hgrid = (int)(ceil_div(n, kHistThreads * 8) < (int64_t)sm_count() * 4 ? ceil_div(n, kHistThreads * 8) : (int64_t)sm_count() * 4);
     if (hgrid < 1) hgrid = 1;
     hist_kernel<U><<<hgrid, kHistThreads, 0, s>>>(src, n, kind, desc ? 1 : 0, ghist);
@@ -279,14 +297,14 @@ int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, i
     SDC_CUDA_TRY(cudaMemcpyAsync(htriv, trivial, NP * sizeof(int), cudaMemcpyDeviceToHost, s));
     SDC_CUDA_TRY(cudaStreamSynchronize(s));
 
-    auto kern = onesweep_kernel<U, P, HAS_PAY>;
+    using KernT = void (*)(const U*, U*, const P*, P*, int64_t, int, int, const unsigned long long*, unsigned long long*, unsigned);
+    KernT kern = nullptr;
+    if (kind == KIND_FLOAT) kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_FLOAT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_FLOAT, false, ITEMS>;
+    else if (kind == KIND_SINT) kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_SINT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_SINT, false, ITEMS>;
+    else kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_UINT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_UINT, false, ITEMS>;
     const size_t smem = (size_t)kSortWarps * 256 * 4 + 256 * 4 + 256 * 8 + 16 * 4 + (size_t)TILE * sizeof(U) +
-                        (HAS_PAY ? (size_t)TILE * sizeof(P) : 0);
-    static thread_local bool configured = false;
-    if (!configured) {
-        SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+                        (HAS_PAY ? (size_t)TILE * sizeof(P) : 0) + (size_t)TILE;
+    SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const U* kcur = src;
     const P* pcur = psrc;
     bool first = true;
@@ -295,10 +313,9 @@ int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, i
         if (htriv[p]) continue;
         U* kdst = flip ? bufB : bufA;
         P* pdst = flip ? pB : pA;
-        SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
-        kern<<<(unsigned)ntiles, kSortThreads, smem, s>>>(kcur, kdst, pcur, pdst, n, 8 * p, kind, desc ? 1 : 0,
+        kern<<<(unsigned)ntiles, kSortThreads, smem, s>>>(kcur, kdst, pcur, pdst, n, 8 * p,
                                                           (first && iota) ? 1 : 0, gbase + p * 256,
-                                                          lb.as<unsigned long long>(), counters + p);
+                                                          lb.as<unsigned long long>(), (unsigned)(p + 1));
         SDC_CHECK_LAUNCH();
         kcur = kdst;
         pcur = pdst;
@@ -313,6 +330,12 @@ int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, i
     *rkeys = kcur;
     *rpay = pcur;
     return SDCB200_OK;
+}
+
+template <typename U, typename P, bool HAS_PAY>
+int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, int64_t n, int kind, bool iota,
+                  bool desc, const void** rkeys, const void** rpay, cudaStream_t s) {
+    return sort_impl_items<U, P, HAS_PAY, 16>(src, bufA, bufB, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
 }
 
 template <typename U>

@@ -119,6 +119,35 @@ def test_expected_groups_hint_paths_agree():
         _compare(gk, got, wk, want, "sum", "hint=%d" % hint)
 
 
+@pytest.mark.parametrize("keykind", ["int", "float"])
+def test_sort_and_segment_path(keykind, monkeypatch):
+    """Very high cardinality goes through radix sort + segmented reduction (csrc/groupby.cu run_groupby_sorted);
+    the thresholds are lowered so that the oracle finishes in seconds."""
+    monkeypatch.setenv("SDCB200_GB_SORT_ROWS", "1000")
+    monkeypatch.setenv("SDCB200_GB_SORT_GROUPS", "1000")
+    rng = np.random.default_rng(11)
+    n, groups = 300_000, 120_000
+    a = rng.integers(-groups // 2, groups - groups // 2, n)
+    if keykind == "float":
+        a = a.astype(np.float64) * 0.5
+        a[rng.integers(0, n, 500)] = np.nan          # NaN keys are skipped
+        a[rng.integers(0, n, 50)] = -0.0             # -0.0 == +0.0
+        a[rng.integers(0, n, 50)] = np.inf
+    b = rng.standard_normal(n) * 100
+    b[rng.integers(0, n, n // 100)] = np.nan
+    c = rng.integers(-10**12, 10**12, n)
+    cols = {"b": b, "c": c}
+    for agg in ogroupby.AGGS:
+        for sort in (True, False):
+            gk, got = _host(a, cols, agg, sort, 1, groups)           # hint above the threshold: sort path at once
+            wk, want = ogroupby.groupby_agg(a, cols, agg, sort)
+            _compare(gk, got, wk, want, agg, "sorted path %s %s sort=%s" % (keykind, agg, sort))
+    # unknown hint: shared table overflows, 4 M-slot table is skipped by the tiny threshold -> sort path as the fallback
+    gk, got = _host(a, cols, "sum", True, 1, 10)
+    wk, want = ogroupby.groupby_agg(a, cols, "sum", True)
+    _compare(gk, got, wk, want, "sum", "sorted path fallback")
+
+
 def test_empty_and_degenerate():
     from sdc_b200.groupby import groupby_host
     rk, res = groupby_host(np.zeros(0, dtype=np.int64), {"v": np.zeros(0)}, ("sum", "count"))
