@@ -85,6 +85,9 @@ int32_t sdcb200_stream_sync(void* stream);
 #define SDCB200_U64 7
 #define SDCB200_F32 8
 #define SDCB200_F64 9
+/* groupby key column of dense int64 group ids in [0, expected_groups); negative ids skip the row
+ * (what sdcb200_str_factorize produces: the table of the aggregate is direct-addressed, no hashing) */
+#define SDCB200_GID 100
 
 int32_t sdcb200_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
                         int64_t win, int64_t minp, int64_t ddof,
@@ -117,7 +120,7 @@ int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t
  * replaces sdc_pandas_dataframe_groupby (sdc/datatypes/hpat_pandas_dataframe_functions.py:2993-3106),
  * merge_groupby_dicts_inplace and the per-group take + reduce loop
  * (sdc/datatypes/hpat_pandas_groupby_functions.py:58-73, 194-283) with one hash aggregate.
- *   key_dtype        SDCB200_I64 or SDCB200_F64 (NaN keys are skipped, -0.0 == +0.0)
+ *   key_dtype        SDCB200_I64 or SDCB200_F64 (NaN keys are skipped, -0.0 == +0.0), or SDCB200_GID
  *   cols/col_dtypes  ncols (<= 32) value columns, each SDCB200_F64 or SDCB200_I64, device pointers
  *   agg_mask         OR of SDCB200_AGG_*: every requested aggregate is produced for every column
  *   sort             1: result ordered by key (stable argsort, groupby_functions.py:209-210);

@@ -167,6 +167,13 @@ __device__ __forceinline__ ulonglong2 ld_hint_v2u64(const void* a, uint64_t pol)
                  : "=l"(v.x), "=l"(v.y) : "l"(a), "l"(pol));
     return v;
 }
+__device__ __forceinline__ int4 ld_hint_v4(const void* p, uint64_t pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ void st_hint_v2s64(void* a, long long x, long long y, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1,%2}, %3;" ::"l"(a), "l"(x), "l"(y), "l"(pol) : "memory");
 }

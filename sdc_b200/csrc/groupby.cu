@@ -170,8 +170,10 @@ __device__ __forceinline__ void load4(const void* col, int64_t base, int64_t n, 
                                       unsigned long long v[kRows]) {
     const unsigned long long* p = reinterpret_cast<const unsigned long long*>(col);
     if (vec && base + THREADS * kRows <= n) {
-        const int4 a = ld_stream_v4(p + base + 2 * tid);
-        const int4 b = ld_stream_v4(p + base + 2 * THREADS + 2 * tid);
+        // streamed once: first in line for L2 eviction, so the table lines the atomics work on stay resident
+        const uint64_t pol = l2_policy_evict_first();
+        const int4 a = ld_hint_v4(p + base + 2 * tid, pol);
+        const int4 b = ld_hint_v4(p + base + 2 * THREADS + 2 * tid, pol);
         v[0] = (unsigned long long)(unsigned)a.x | ((unsigned long long)(unsigned)a.y << 32);
         v[1] = (unsigned long long)(unsigned)a.z | ((unsigned long long)(unsigned)a.w << 32);
         v[2] = (unsigned long long)(unsigned)b.x | ((unsigned long long)(unsigned)b.y << 32);
@@ -186,12 +188,92 @@ __device__ __forceinline__ void load4(const void* col, int64_t base, int64_t n, 
 }
 
 // ------------------------------------------------------------------ high-cardinality path
+// strided sample of an int64 key column by the whole CTA -> window [lo, lo + width) centred on the sampled
+// keys when they span fewer than `width` values (range 0 otherwise).  Every CTA reads the same samples, so
+// all CTAs agree.  s_red: 2 * THREADS / 32 words of shared scratch; the result is valid for thread 0 only.
+template <int THREADS, int PER>
+__device__ __forceinline__ void sample_window(const long long* __restrict__ kp, int64_t n, unsigned long long width,
+                                              unsigned long long* s_red, unsigned long long& lo, unsigned long long& range) {
+    constexpr int WARPS = THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t total = (int64_t)THREADS * PER;
+    const int64_t stride = n > total ? n / total : 1;
+    long long kv[PER];
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {        // independent loads, all in flight together
+        const int64_t r = ((int64_t)e * THREADS + tid) * stride;
+        kv[e] = r < n ? __ldg(kp + r) : __ldg(kp);
+    }
+    const unsigned long long top = 0x8000000000000000ull;   // order-preserving unsigned image: no overflow
+    unsigned long long mn = ~0ull, mx = 0ull;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+        const unsigned long long u = (unsigned long long)kv[e] ^ top;
+        mn = u < mn ? u : mn;
+        mx = u > mx ? u : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (lane == 0) { s_red[warp] = mn; s_red[WARPS + warp] = mx; }
+    __syncthreads();
+    lo = 0;
+    range = 0;
+    if (tid == 0) {
+        for (int w = 1; w < WARPS; ++w) {
+            mn = s_red[w] < mn ? s_red[w] : mn;
+            mx = s_red[WARPS + w] > mx ? s_red[WARPS + w] : mx;
+        }
+        if (mx - mn < width) {
+            unsigned long long shift = (width - (mx - mn) - 1) / 2;
+            if (shift > mn) shift = mn;
+            unsigned long long ulo = mn - shift;
+            if (ulo > ~0ull - width) ulo = ~0ull - width;
+            lo = ulo ^ top;
+            range = width;
+        }
+    }
+}
+
+// key modes of the int64 path
+enum { KEYS_PLAIN = 0, KEYS_GID = 1 };      // GID: dense group ids in [0, range), negative = skip the row
+
+struct DirectHint {
+    int mode;                       // KEYS_PLAIN: sample the keys (allow != 0); KEYS_GID: window [0, range)
+    int allow;                      // 0: hashing only (a previous attempt saw a key outside its window)
+    unsigned long long range;       // KEYS_GID: the id range
+    unsigned long long* out;        // [2] device: the window the kernel used (lo, range), read back by the host
+};
+
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __restrict__ keys, int64_t n, Cols cols,
-                                                               Table t, int need) {
+                                                               Table t, int need, DirectHint dh) {
+    __shared__ unsigned long long s_red[2 * kGbThreads / 32];
+    __shared__ unsigned long long s_dlo, s_drange;
     const int tid = threadIdx.x;
+    // dense int64 keys: the table is direct-addressed (slot = key - lo): no hashing, no CAS, presence = the key word
+    if (!KEY_F64 && dh.mode == KEYS_GID) {
+        if (tid == 0) { s_dlo = 0ull; s_drange = dh.range; }
+    } else if (!KEY_F64 && dh.allow) {
+        unsigned long long lo, range;
+        sample_window<kGbThreads, 4>(reinterpret_cast<const long long*>(keys), n, t.cap, s_red, lo, range);
+        if (tid == 0) { s_dlo = lo; s_drange = range; }
+    } else if (tid == 0) {
+        s_dlo = 0ull;
+        s_drange = 0ull;
+    }
+    __syncthreads();
+    const unsigned long long dlo = s_dlo, drange = s_drange;
+    if (blockIdx.x == 0 && tid == 0) { dh.out[0] = dlo; dh.out[1] = drange; }
+    const bool skip_neg = !KEY_F64 && dh.mode == KEYS_GID;
     const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // probe loops end at different times per lane; a warp that stays split would issue the next tile's
+        // 128-bit loads as several partial requests
+        __syncwarp();
         const int64_t base = tile * kGbTile;
         unsigned long long kb[kRows], v0[kRows];
         load4(keys, base, n, tid, cols.vec_ok, kb);
@@ -202,7 +284,20 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
         for (int e = 0; e < kRows; ++e) {
             unsigned long long k;
             g[e] = ~0ull;
-            if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_upsert(t, k);
+            __syncwarp();
+            if (!(tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k))) continue;
+            if (skip_neg && (long long)k < 0) continue;
+            if (drange) {
+                const unsigned long long d = k - dlo;
+                if (d < drange && k != kEmptyKey()) {
+                    g[e] = d;
+                    if (t.keys[d] != k) t.keys[d] = k;              // every writer stores the same value
+                } else {
+                    *(volatile int*)t.overflow = 2;                 // outside the window: rerun with hashing
+                }
+            } else {
+                g[e] = global_upsert(t, k);
+            }
         }
         if (need & NEED_FIRST) {
 #pragma unroll
@@ -303,7 +398,7 @@ struct SmallFin {
     long long ddof;
     int by_first, key_f64;
     int write_out;                  // 0: only fold the replicas (var / std continue on the host path)
-    int allow_direct;
+    DirectHint dh;                  // dh.out = meta + 2
     unsigned long long* meta;       // [0] groups written, [1] CTAs done, [2] direct lo, [3] direct range
 };
 
@@ -343,55 +438,18 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     }
 
     // ---- 1. key sample -> direct window
-    if (!KEY_F64 && fin.allow_direct) {
-        const long long* kp = reinterpret_cast<const long long*>(keys);
-        const int64_t total = (int64_t)kSmThreads * kSamplePerThread;
-        const int64_t stride = n > total ? n / total : 1;
-        long long kv[kSamplePerThread];
-#pragma unroll
-        for (int e = 0; e < kSamplePerThread; ++e) {        // independent loads, all in flight together
-            const int64_t r = ((int64_t)e * kSmThreads + tid) * stride;
-            kv[e] = r < n ? __ldg(kp + r) : __ldg(kp);
-        }
-        const unsigned long long top = 0x8000000000000000ull;   // order-preserving unsigned image: no overflow
-        unsigned long long mn = ~0ull, mx = 0ull;
-#pragma unroll
-        for (int e = 0; e < kSamplePerThread; ++e) {
-            const unsigned long long u = (unsigned long long)kv[e] ^ top;
-            mn = u < mn ? u : mn;
-            mx = u > mx ? u : mx;
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
-            mn = a < mn ? a : mn;
-            mx = b > mx ? b : mx;
-        }
-        if (lane == 0) { s_red[warp] = mn; s_red[kSmWarps + warp] = mx; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < kSmWarps; ++w) {
-                mn = s_red[w] < mn ? s_red[w] : mn;
-                mx = s_red[kSmWarps + w] > mx ? s_red[kSmWarps + w] : mx;
-            }
-            unsigned long long lo = 0, range = 0;
-            if (mx - mn < (unsigned long long)scap) {
-                // centre the scap-wide window on the sampled keys, clamped to the int64 range
-                unsigned long long shift = ((unsigned long long)scap - (mx - mn) - 1) / 2;
-                if (shift > mn) shift = mn;
-                unsigned long long ulo = mn - shift;
-                if (ulo > ~0ull - (unsigned long long)scap) ulo = ~0ull - (unsigned long long)scap;
-                lo = ulo ^ top;
-                range = (unsigned long long)scap;
-            }
-            s_dlo = lo;
-            s_drange = range;
-            if (blockIdx.x == 0) { fin.meta[2] = lo; fin.meta[3] = range; }
-        }
+    if (!KEY_F64 && fin.dh.mode == KEYS_GID) {
+        if (tid == 0) { s_dlo = 0ull; s_drange = fin.dh.range <= (unsigned long long)scap ? (unsigned long long)scap : 0ull; }
+    } else if (!KEY_F64 && fin.dh.allow) {
+        unsigned long long lo, range;
+        sample_window<kSmThreads, kSamplePerThread>(reinterpret_cast<const long long*>(keys), n, (unsigned long long)scap, s_red, lo, range);
+        if (tid == 0) { s_dlo = lo; s_drange = range; }
     } else if (tid == 0) {
         s_dlo = 0ull;
         s_drange = 0ull;
     }
+    if (blockIdx.x == 0 && tid == 0) { fin.dh.out[0] = s_dlo; fin.dh.out[1] = s_drange; }
+    const bool skip_neg = !KEY_F64 && fin.dh.mode == KEYS_GID;
     for (int i = tid; i < scap; i += kSmThreads) {
         skeys[i] = kEmptyKey();
         if (need & NEED_FIRST) sfirst[i] = ~0ull;
@@ -423,7 +481,8 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
 #pragma unroll
         for (int e = 0; e < kRows; ++e) {
             unsigned long long k = 0;
-            const bool valid = tile_row<kSmThreads>(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k);
+            bool valid = tile_row<kSmThreads>(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k);
+            if (skip_neg && (long long)k < 0) valid = false;
             int sl = -1;
             g[e] = ~0ull;
             if (drange) {
@@ -681,14 +740,17 @@ __global__ void __launch_bounds__(kGbThreads) gb_ssd_kernel(const void* __restri
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * kGbTile;
         unsigned long long kb[kRows], v0[kRows], g[kRows];
+        __syncwarp();
         load4(keys, base, n, tid, cols.vec_ok, kb);
 #pragma unroll
         for (int e = 0; e < kRows; ++e) {
             unsigned long long k;
             g[e] = ~0ull;
             if (tile_row(base, tid, e) < n && canon_key<KEY_F64>(kb[e], k)) g[e] = global_find(t, k, dlo, drange);
+            __syncwarp();
         }
         for (int c = 0; c < cols.ncols; ++c) {
+            __syncwarp();
             load4(cols.data[c], base, n, tid, cols.vec_ok, v0);
 #pragma unroll
             for (int e = 0; e < kRows; ++e) {
@@ -734,18 +796,23 @@ constexpr int kSegItems = 8;
 constexpr int kSegTile = kGbThreads * kSegItems;
 
 template <bool KEY_F64>
-__device__ __forceinline__ unsigned seg_heads(const unsigned long long* __restrict__ sk, int64_t i0, int64_t n,
+__device__ __forceinline__ bool seg_key(unsigned long long raw, bool skip_neg, unsigned long long& k) {
+    return canon_key<KEY_F64>(raw, k) && !(skip_neg && (long long)k < 0);
+}
+
+template <bool KEY_F64>
+__device__ __forceinline__ unsigned seg_heads(const unsigned long long* __restrict__ sk, int64_t i0, int64_t n, bool skip_neg,
                                               unsigned long long k[kSegItems], unsigned& valid) {
     // bit e of the result: row i0 + e starts a run; bit e of valid: row exists and its key is not NaN
     unsigned heads = 0;
     valid = 0;
     unsigned long long prev = 0;
     bool have_prev = false;
-    if (i0 > 0 && i0 < n) have_prev = canon_key<KEY_F64>(sk[i0 - 1], prev);
+    if (i0 > 0 && i0 < n) have_prev = seg_key<KEY_F64>(sk[i0 - 1], skip_neg, prev);
 #pragma unroll
     for (int e = 0; e < kSegItems; ++e) {
         k[e] = 0;
-        if (i0 + e < n && canon_key<KEY_F64>(sk[i0 + e], k[e])) {
+        if (i0 + e < n && seg_key<KEY_F64>(sk[i0 + e], skip_neg, k[e])) {
             valid |= 1u << e;
             if (!have_prev || k[e] != prev) heads |= 1u << e;
             prev = k[e];
@@ -757,12 +824,12 @@ __device__ __forceinline__ unsigned seg_heads(const unsigned long long* __restri
 
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kGbThreads) gb_seg_count_kernel(const unsigned long long* __restrict__ sk, int64_t n,
-                                                                  unsigned long long* __restrict__ tile_counts) {
+                                                                  int skip_neg, unsigned long long* __restrict__ tile_counts) {
     __shared__ unsigned wcnt[kGbThreads / 32];
     const int64_t i0 = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
     unsigned long long k[kSegItems];
     unsigned valid;
-    unsigned c = __popc(seg_heads<KEY_F64>(sk, i0, n, k, valid));
+    unsigned c = __popc(seg_heads<KEY_F64>(sk, i0, n, skip_neg != 0, k, valid));
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
     if ((threadIdx.x & 31) == 0) wcnt[threadIdx.x >> 5] = c;
@@ -778,13 +845,13 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_count_kernel(const unsigned
 template <bool KEY_F64, typename ROW>
 __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long long* __restrict__ sk,
                                                             const ROW* __restrict__ rows, int64_t n, Cols cols, Table t,
-                                                            int need, int pass,
+                                                            int need, int pass, int skip_neg,
                                                             const unsigned long long* __restrict__ tile_offs) {
     __shared__ unsigned long long wsum[kGbThreads / 32];
     const int64_t i0 = (int64_t)blockIdx.x * kSegTile + (int64_t)threadIdx.x * kSegItems;
     unsigned long long k[kSegItems];
     unsigned valid;
-    const unsigned heads = seg_heads<KEY_F64>(sk, i0, n, k, valid);
+    const unsigned heads = seg_heads<KEY_F64>(sk, i0, n, skip_neg != 0, k, valid);
     unsigned long long tot;
     // group id of the run that is open when this thread starts (= heads before it, minus one)
     unsigned long long gid = tile_offs[blockIdx.x] + block_excl_scan_u64(__popc(heads), &tot, wsum) - 1ull;
@@ -1015,7 +1082,8 @@ unsigned long long pow2_at_least(unsigned long long v, unsigned long long lo) {
 // very high cardinality: radix sort of (key, row), then one streaming pass over equal-key runs
 template <bool KEY_F64>
 int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_mask, bool sort, long long ddof,
-                           int key_dtype, cudaStream_t s, GroupbyResult* res) {
+                           int key_dtype, int key_mode, cudaStream_t s, GroupbyResult* res) {
+    const int skip_neg = key_mode == KEYS_GID ? 1 : 0;
     const int need = need_for(agg_mask, sort);
     const bool need_ssd = (agg_mask & (AGG_VAR | AGG_STD)) != 0;
     const int sms = sm_count();
@@ -1034,7 +1102,7 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     const unsigned long long* sk = reinterpret_cast<const unsigned long long*>(rk);
     const int64_t nt = ceil_div(n, kSegTile);
     SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8, s));
-    gb_seg_count_kernel<KEY_F64><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, n, tcnt.as<unsigned long long>());
+    gb_seg_count_kernel<KEY_F64><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, n, skip_neg, tcnt.as<unsigned long long>());
     SDC_CHECK_LAUNCH();
     scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tcnt.as<unsigned long long>(), nt);
     SDC_CHECK_LAUNCH();
@@ -1088,10 +1156,10 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     for (int pass = 0; pass < (need_ssd ? 2 : 1); ++pass) {
         if (small_rows)
             gb_seg_kernel<KEY_F64, uint32_t><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, reinterpret_cast<const uint32_t*>(rp), n, cols, t,
-                                                                                need, pass, tcnt.as<unsigned long long>());
+                                                                                need, pass, skip_neg, tcnt.as<unsigned long long>());
         else
             gb_seg_kernel<KEY_F64, unsigned long long><<<(unsigned)nt, kGbThreads, 0, s>>>(
-                sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, tcnt.as<unsigned long long>());
+                sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, skip_neg, tcnt.as<unsigned long long>());
         SDC_CHECK_LAUNCH();
     }
     Scratch order;
@@ -1110,7 +1178,7 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
 
 template <bool KEY_F64>
 int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, bool sort, long long ddof,
-                    int key_dtype, int64_t expected_groups, cudaStream_t s, GroupbyResult* res) {
+                    int key_dtype, int key_mode, int64_t expected_groups, cudaStream_t s, GroupbyResult* res) {
     const int need = need_for(agg_mask, sort);
     const bool need_ssd = (agg_mask & (AGG_VAR | AGG_STD)) != 0;
     const int sms = sm_count();
@@ -1126,7 +1194,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     const unsigned long long worst = pow2_at_least(2ull * (unsigned long long)n, 64);
     const bool big = n >= sort_path_rows();
     if (big && expected_groups > sort_path_groups())
-        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, s, res);
+        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     Attempt plan[3];
     int nattempts = 0;
     if (expected_groups <= 0) {
@@ -1134,11 +1202,13 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         if ((1ull << 22) < worst) plan[nattempts++] = {false, 1ull << 22, 1};
     } else if (expected_groups <= 4096 && n >= 4096) {
         plan[nattempts++] = {true, pow2_at_least(2ull * (unsigned long long)expected_groups, 1024), kSmallReplicas};
+    } else if (key_mode == KEYS_GID) {
+        plan[nattempts++] = {false, pow2_at_least((unsigned long long)expected_groups, 1024), 1};   // direct: one slot per id
     } else {
         const unsigned long long c = pow2_at_least(2ull * (unsigned long long)expected_groups, 1024);
         if (c < worst) plan[nattempts++] = {false, c, 1};
     }
-    if (!big) plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
+    if (!big && key_mode != KEYS_GID) plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
 
     int allow_direct = 1;
     for (int attempt = 0; attempt < nattempts; ++attempt) {
@@ -1229,7 +1299,10 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             fin.by_first = sort ? 0 : 1;
             fin.key_f64 = KEY_F64 ? 1 : 0;
             fin.write_out = need_ssd ? 0 : 1;
-            fin.allow_direct = allow_direct;
+            fin.dh.mode = key_mode;
+            fin.dh.allow = allow_direct;
+            fin.dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
+            fin.dh.out = dmeta + 2;
             fin.meta = dmeta;
             kern<<<(unsigned)grid, kSmThreads, lay.alloc_bytes, s>>>(keys, n, cols, t, need, lay, fin);
             SDC_CHECK_LAUNCH();
@@ -1256,15 +1329,25 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             const int64_t ntiles = ceil_div(n, kGbTile);
             int64_t grid = (int64_t)sms * 8;
             if (grid > ntiles) grid = ntiles;
-            gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need);
+            DirectHint dh;
+            dh.mode = key_mode;
+            dh.allow = allow_direct;
+            dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
+            dh.out = dmeta + 2;
+            gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need, dh);
             SDC_CHECK_LAUNCH();
-            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 72, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
-            if ((int)(hmeta[8] & 0xffffffffull)) {
+            const int ovf = (int)(hmeta[8] & 0xffffffffull);
+            if (ovf) {
+                if (ovf == 2 && allow_direct && key_mode != KEYS_GID) { allow_direct = 0; --attempt; continue; }
+                if (ovf == 2 && key_mode == KEYS_GID) { set_error("groupby: a group id lies outside [0, %lld)", (long long)expected_groups); return SDCB200_ERR_ARG; }
                 if (attempt + 1 < nattempts || big) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);
                 return SDCB200_ERR_CAPACITY;
             }
+            dlo = hmeta[18];
+            drange = hmeta[19];
         }
         // large table (or var / std, which need a second pass over the rows once the means are known)
         if (need_ssd) {
@@ -1274,18 +1357,26 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             gb_ssd_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, dlo, drange);
             SDC_CHECK_LAUNCH();
         }
-        const int64_t ng = (int64_t)hmeta[0];
-        res->ngroups = ng;
-        res->ngcap = ng;
-        if (ng == 0) return SDCB200_OK;
+        // a direct-addressed table counts its groups while compacting; a hashed one counted them on insert
+        const bool count_late = !at.smem && drange != 0;
+        int64_t ng = count_late ? (int64_t)(n < (int64_t)per ? n : (int64_t)per) : (int64_t)hmeta[0];
+        if (ng == 0) { res->ngroups = 0; res->ngcap = 0; return SDCB200_OK; }
         Scratch slots, sortkeys, order;
         SDC_TRY(slots.alloc((size_t)ng * 8, s));
         SDC_TRY(sortkeys.alloc((size_t)ng * 8, s));
-        SDC_TRY(order.alloc((size_t)ng * 8, s));
         const int cgrid = (int)(ceil_div((int64_t)per, 256) < (int64_t)sms * 8 ? ceil_div((int64_t)per, 256) : (int64_t)sms * 8);
         gb_compact_kernel<<<cgrid, 256, 0, s>>>(t, slots.as<unsigned long long>(), sortkeys.as<unsigned long long>(),
                                                 sort ? 0 : 1, dmeta + 4);
         SDC_CHECK_LAUNCH();
+        if (count_late) {
+            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, dmeta + 4, 8, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            ng = (int64_t)hmeta[0];
+        }
+        res->ngroups = ng;
+        res->ngcap = ng;
+        if (ng == 0) return SDCB200_OK;
+        SDC_TRY(order.alloc((size_t)ng * 8, s));
         SDC_TRY(argsort_device(sort ? key_dtype : SDCB200_U64, sortkeys.p, ng, true, order.as<int64_t>(), s));
         SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ng * 8, s));
         SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ng * 8 * (nagg * cols.ncols + 1), s));
@@ -1296,7 +1387,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         SDC_CUDA_TRY(cudaStreamSynchronize(s));   // table scratch is released when `mem` goes out of scope
         return SDCB200_OK;
     }
-    if (big) return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, s, res);
+    if (big) return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     return SDCB200_ERR_CAPACITY;
 }
 
@@ -1311,7 +1402,13 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
                         const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
                         int64_t expected_groups, void* stream, int64_t* handle_out, int64_t* ngroups_out) {
     cudaStream_t s = (cudaStream_t)stream;
-    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
+    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64 || key_dtype == SDCB200_GID, "key dtype must be I64, F64 or GID");
+    int key_mode = KEYS_PLAIN;
+    if (key_dtype == SDCB200_GID) {
+        SDC_ARG_CHECK(expected_groups > 0, "GID keys: expected_groups is the id range and must be > 0");
+        key_mode = KEYS_GID;
+        key_dtype = SDCB200_I64;
+    }
     SDC_ARG_CHECK(n >= 0 && ncols >= 0 && ncols <= kMaxCols, "n / ncols");
     SDC_ARG_CHECK(agg_mask != 0 && (agg_mask & ~0x7fu) == 0, "agg mask");
     SDC_ARG_CHECK(handle_out != nullptr && ngroups_out != nullptr, "null out pointer");
@@ -1332,8 +1429,8 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
     int32_t rc = SDCB200_OK;
     if (n > 0) {
         rc = key_dtype == SDCB200_F64
-                 ? run_groupby<true>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, expected_groups, s, res)
-                 : run_groupby<false>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, expected_groups, s, res);
+                 ? run_groupby<true>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, KEYS_PLAIN, expected_groups, s, res)
+                 : run_groupby<false>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, key_mode, expected_groups, s, res);
     }
     if (rc != SDCB200_OK) {
         free_result(res);

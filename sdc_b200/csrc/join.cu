@@ -110,13 +110,23 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
                                                                  uint32_t* __restrict__ rrank,
                                                                  unsigned long long* __restrict__ dup_flag) {
     const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
-    for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride) {
-        const unsigned long long k = canon_key<KEY_F64>(keys[j]);
-        const unsigned long long s = jt_upsert(t, k);
-        const unsigned long long rank = atomicAdd(&t.slots[s].y, 1ull);
-        if (rank) *dup_flag = 1ull;
-        rslot[j] = (uint32_t)s;
-        rrank[j] = (uint32_t)rank;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop; the probe loop of jt_upsert ends at different times per lane, so reconverge before the
+    // coalesced stores (a split warp issues them as partial requests)
+    for (int64_t w0 = (int64_t)blockIdx.x * kJoinThreads + (threadIdx.x & ~31); w0 < n; w0 += stride) {
+        const int64_t j = w0 + lane;
+        unsigned long long s = 0, rank = 0;
+        if (j < n) {
+            const unsigned long long k = canon_key<KEY_F64>(keys[j]);
+            s = jt_upsert(t, k);
+            rank = atomicAdd(&t.slots[s].y, 1ull);
+            if (rank) *dup_flag = 1ull;
+        }
+        __syncwarp();
+        if (j < n) {
+            rslot[j] = (uint32_t)s;
+            rrank[j] = (uint32_t)rank;
+        }
     }
 }
 
@@ -218,6 +228,7 @@ __global__ void __launch_bounds__(kJoinThreads) probe_count_kernel(const unsigne
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
         v[e] = (i0 + e < n) ? jt_lookup(t, canon_key<KEY_F64>(k[e])) : 0ull;
+        __syncwarp();                                  // hash probes end at different times per lane
         const unsigned long long cnt = v[e] & 0xffffffffull;
         if (i0 + e < n) c += LEFT ? (cnt ? cnt : 1ull) : cnt;
     }
@@ -350,8 +361,10 @@ __global__ void __launch_bounds__(kJoinThreads, 5) probe_unique_inner_kernel(con
     uint32_t row1[kItems];
     load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e)
+    for (int e = 0; e < kItems; ++e) {
         row1[e] = (probe_row(tile0, warp, lane, e) < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
+        __syncwarp();                                  // hash probes end at different times per lane
+    }
     // rank of every hit inside the warp's 256 rows, in row order: segment j = 64 rows, lane L holds 2 of them
     unsigned rank[kItems], wtot = 0;
 #pragma unroll
@@ -451,8 +464,10 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const u
     int64_t rr[kItems];
     load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e)
+    for (int e = 0; e < kItems; ++e) {
         rr[e] = (probe_row(tile0, warp, lane, e) < n) ? (int64_t)lookup_row1(t, rid, k[e], keep_pol) - 1 : -1;
+        __syncwarp();                                  // hash probes end at different times per lane
+    }
     if (tile0 + kTile <= n) {
 #pragma unroll
         for (int e = 0; e < kItems; e += 2) {

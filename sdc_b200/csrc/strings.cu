@@ -14,10 +14,11 @@
 //       chunk-wise, the length puts the prefix first).  Every pass is the library's stable onesweep
 //       sort of (u64 chunk key, u32 row), so constant digits are skipped and ties keep input order.
 //   sdcb200_str_factorize  string keys -> dense group ids for the hash groupby: open-addressing table
-//       of 64-bit words (32-bit fingerprint << 32 | representative row) claimed with one atomicCAS; a
-//       fingerprint hit is confirmed by comparing the bytes with the representative row, so ids are
-//       exact.  gid = slot index, -1 for NA rows (None keys are skipped, reference
-//       hpat_pandas_dataframe_functions.py:3088-3089).  The numeric groupby then runs on the ids.
+//       of 16-byte slots {key word, length << 32 | representative row}; strings of up to 8 bytes ARE the
+//       key word (no look at the representative), longer ones hash into it and a hit is confirmed by
+//       comparing the bytes, so ids are exact.  gid = slot index in [0, cap], -1 for NA rows (None keys
+//       are skipped, reference hpat_pandas_dataframe_functions.py:3088-3089).  The numeric groupby then
+//       runs on the ids (key dtype SDCB200_GID: direct-addressed table).
 //   sdcb200_str_gather     rows -> a new str_arr (lengths, exclusive scan, byte copy).
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -85,74 +86,123 @@ inline int grid_for(int64_t n, int threads, int per_sm) {
 }
 
 // ---- factorize ----
-__device__ __forceinline__ uint64_t str_hash(const uint8_t* __restrict__ p, uint32_t len) {
-    // FNV-1a over the bytes, finished with a 64-bit mixer
-    uint64_t h = 0xcbf29ce484222325ull;
-    for (uint32_t i = 0; i < len; ++i) {
-        h ^= p[i];
-        h *= 0x100000001b3ull;
+// Table of 16-byte slots {key word, len << 32 | representative row}, linear probing, the key word claimed
+// with one 64-bit atomicCAS; the second word is published right after and readers wait for it.
+//   len <= 8 : key word = the string's bytes (little-endian, zero padded) -- together with the length in
+//              the second word that IS the string, so a match needs no look at the representative row:
+//              one 16-byte slot load per probe, no dependent random reads (C4's 8-character keys)
+//   len  > 8 : key word = 64-bit hash of the bytes; a (word, length) match is confirmed by comparing the bytes
+//              with the representative row, so ids are exact
+// A key word equal to the empty marker lives in the spare slot [cap].
+constexpr uint64_t kStrEmpty = ~0ull;
+constexpr uint64_t kStrPending = ~0ull;
+
+// bytes [beg, beg + len) with len <= 8 as a little-endian word, zero padded
+__device__ __forceinline__ uint64_t load_word(const uint8_t* __restrict__ chars, uint64_t beg, uint32_t len, uint64_t total) {
+    if (len == 0) return 0ull;
+    if ((beg & 7ull) == 0 && beg + 8 <= total) {
+        const uint64_t w = *reinterpret_cast<const uint64_t*>(chars + beg);
+        return len >= 8 ? w : (w & ((1ull << (8 * len)) - 1ull));
     }
-    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33;
+    uint64_t w = 0;
+    for (uint32_t b = 0; b < len; ++b) w |= (uint64_t)chars[beg + b] << (8 * b);
+    return w;
+}
+
+__device__ __forceinline__ uint64_t smix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ uint64_t str_hash(const uint8_t* __restrict__ chars, uint64_t beg, uint32_t len, uint64_t total) {
+    uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
+    for (uint32_t o = 0; o < len; o += 8) h = smix64(h ^ load_word(chars, beg + o, len - o < 8 ? len - o : 8, total));
     return h;
 }
 
-__device__ __forceinline__ bool str_equal(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint32_t len) {
-    for (uint32_t i = 0; i < len; ++i)
-        if (a[i] != b[i]) return false;
+__device__ __forceinline__ bool str_equal(const uint8_t* __restrict__ chars, uint64_t a, uint64_t b, uint32_t len, uint64_t total) {
+    for (uint32_t o = 0; o < len; o += 8) {
+        const uint32_t m = len - o < 8 ? len - o : 8;
+        if (load_word(chars, a + o, m, total) != load_word(chars, b + o, m, total)) return false;
+    }
     return true;
 }
-
-constexpr uint64_t kStrEmpty = ~0ull;     // fingerprint 0xffffffff is remapped, so no live word equals this
 
 __global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_t* __restrict__ chars,
                                                                     const uint32_t* __restrict__ offsets,
                                                                     const uint8_t* __restrict__ bitmap, int64_t n,
-                                                                    unsigned long long* __restrict__ table, uint64_t cap,
+                                                                    ulonglong2* __restrict__ table, uint64_t cap,
                                                                     int64_t* __restrict__ gid,
                                                                     unsigned long long* __restrict__ counters /* [0] groups, [1] overflow */,
                                                                     uint64_t limit) {
-    for (int64_t i = blockIdx.x * (int64_t)kStrThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kStrThreads) {
-        if (bitmap && !((bitmap[i >> 3] >> (i & 7)) & 1)) { gid[i] = -1; continue; }
-        const uint32_t beg = offsets[i], len = offsets[i + 1] - beg;
-        const uint64_t h = str_hash(chars + beg, len);
-        uint64_t fp = h >> 32;
-        if (fp == 0xffffffffull) fp = 0xfffffffeull;
-        const uint64_t mine = (fp << 32) | (uint64_t)(uint32_t)i;
-        uint64_t s = h & (cap - 1);
-        int64_t out = -2;
-        for (uint64_t probes = 0; probes <= cap; ++probes) {
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&table[s]);
-            if (cur == kStrEmpty) {
-                if (*reinterpret_cast<volatile unsigned long long*>(&counters[1])) break;
-                const unsigned long long old = atomicCAS(&table[s], kStrEmpty, mine);
-                if (old == kStrEmpty) {
-                    if (atomicAdd(&counters[0], 1ull) + 1 > limit) atomicExch(&counters[1], 1ull);
-                    out = (int64_t)s;
-                    break;
+    const uint64_t total = offsets[n];
+    const uint64_t stream_pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop (a warp owns 32 consecutive rows per step) and an explicit reconvergence before the
+    // coalesced accesses: the probe loop's trip count differs per lane, and a warp that stays split issues its
+    // loads and stores as several partial requests
+    for (int64_t w0 = blockIdx.x * (int64_t)kStrThreads + (threadIdx.x & ~31); w0 < n; w0 += (int64_t)gridDim.x * kStrThreads) {
+        __syncwarp();
+        const int64_t i = w0 + lane;
+        const bool in = i < n;
+        const bool valid = in && !(bitmap && !((bitmap[i >> 3] >> (i & 7)) & 1));
+        uint32_t beg = 0, len = 0;
+        if (valid) { beg = offsets[i]; len = offsets[i + 1] - beg; }
+        uint64_t kw = 0;
+        if (valid) kw = len <= 8 ? load_word(chars, beg, len, total) : str_hash(chars, beg, len, total);
+        if (len > 8 && kw == kStrEmpty) kw = kStrEmpty - 1;      // only the 8-byte string of 0xFF uses the spare slot
+        const uint64_t mine2 = ((uint64_t)len << 32) | (uint64_t)(uint32_t)i;
+        int64_t out = valid ? -2 : -1;
+        if (valid && kw == kStrEmpty) {
+            // the spare slot holds this one key; it is claimed through its second word
+            const unsigned long long old = atomicCAS(&table[cap].y, kStrPending, mine2);
+            if (old == kStrPending) atomicAdd(&counters[0], 1ull);
+            out = (int64_t)cap;
+        } else if (valid) {
+            uint64_t s = smix64(kw ^ ((uint64_t)len << 56)) & (cap - 1);
+            for (uint64_t probes = 0; probes <= cap; ++probes) {
+                // published slots never change, so a cached load is fine: a stale copy can only look emptier
+                // than the slot is, and then the CAS (or the volatile re-read) sees the truth
+                ulonglong2 sl = *reinterpret_cast<const ulonglong2*>(&table[s]);
+                if (sl.x == kStrEmpty) {
+                    if (*reinterpret_cast<volatile unsigned long long*>(&counters[1])) break;
+                    const unsigned long long old = atomicCAS(&table[s].x, kStrEmpty, kw);
+                    if (old == kStrEmpty) {
+                        *reinterpret_cast<volatile unsigned long long*>(&table[s].y) = mine2;
+                        if (atomicAdd(&counters[0], 1ull) + 1 > limit) atomicExch(&counters[1], 1ull);
+                        out = (int64_t)s;
+                        break;
+                    }
+                    sl.x = old;
+                    sl.y = kStrPending;
                 }
-                cur = old;
+                if (sl.x == kw) {
+                    while (sl.y == kStrPending) sl.y = *reinterpret_cast<volatile unsigned long long*>(&table[s].y);
+                    if ((uint32_t)(sl.y >> 32) == len) {
+                        if (len <= 8) { out = (int64_t)s; break; }
+                        const uint32_t rep = (uint32_t)sl.y;
+                        if (str_equal(chars, offsets[rep], beg, len, total)) { out = (int64_t)s; break; }
+                    }
+                }
+                s = (s + 1) & (cap - 1);
             }
-            if ((cur >> 32) == fp) {
-                const uint32_t rep = (uint32_t)cur;
-                const uint32_t rbeg = offsets[rep], rlen = offsets[rep + 1] - rbeg;
-                if (rlen == len && str_equal(chars + rbeg, chars + beg, len)) { out = (int64_t)s; break; }
-            }
-            s = (s + 1) & (cap - 1);
         }
-        gid[i] = out;      // -2 only after an overflow; the caller retries with a larger table
+        __syncwarp();
+        if (in) st_hint_s64(gid + i, out, stream_pol);      // -2 only after an overflow; the caller retries with a larger table
     }
 }
 
-__global__ void fill_u64_kernel(unsigned long long* p, unsigned long long v, uint64_t n) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+__global__ void fill_slots_kernel(ulonglong2* p, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = make_ulonglong2(kStrEmpty, kStrPending);
 }
 
 // representative row of each group id (for the result's key strings)
-__global__ void str_group_rows_kernel(const unsigned long long* __restrict__ table, const int64_t* __restrict__ gids,
+__global__ void str_group_rows_kernel(const ulonglong2* __restrict__ table, const int64_t* __restrict__ gids,
                                       int64_t ng, int64_t* __restrict__ rows) {
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t g = gids[j];
-        rows[j] = g < 0 ? -1 : (int64_t)(uint32_t)table[g];
+        rows[j] = g < 0 ? -1 : (int64_t)(uint32_t)table[g].y;
     }
 }
 
@@ -282,13 +332,13 @@ int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, con
     if (cap > worst) cap = worst;
     for (;;) {
         void* table = nullptr;
-        SDC_TRY(dev_alloc(&table, (size_t)cap * 8 + 16, s));
-        unsigned long long* counters = reinterpret_cast<unsigned long long*>(table) + cap;
-        fill_u64_kernel<<<grid_for((int64_t)cap, 256, 8), 256, 0, s>>>(reinterpret_cast<unsigned long long*>(table), kStrEmpty, cap);
+        SDC_TRY(dev_alloc(&table, (size_t)(cap + 1) * 16 + 16, s));
+        unsigned long long* counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<ulonglong2*>(table) + cap + 1);
+        fill_slots_kernel<<<grid_for((int64_t)cap + 1, 256, 8), 256, 0, s>>>(reinterpret_cast<ulonglong2*>(table), cap + 1);
         SDC_CHECK_LAUNCH();
         SDC_CUDA_TRY(cudaMemsetAsync(counters, 0, 16, s));
         str_factorize_kernel<<<grid_for(n, kStrThreads, 8), kStrThreads, 0, s>>>(chars, offsets, bitmap, n,
-                                                                                reinterpret_cast<unsigned long long*>(table), cap,
+                                                                                reinterpret_cast<ulonglong2*>(table), cap,
                                                                                 gid_out, counters, cap / 2 + 1);
         SDC_CHECK_LAUNCH();
         unsigned long long h[2];
@@ -311,7 +361,7 @@ int32_t sdcb200_str_group_rows(int64_t table_handle_words, const int64_t* gids, 
     if (ng == 0) return SDCB200_OK;
     SDC_ARG_CHECK(table_handle_words && gids && rows_out, "null pointer");
     str_group_rows_kernel<<<grid_for(ng, 256, 4), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const unsigned long long*>((uintptr_t)table_handle_words), gids, ng, rows_out);
+        reinterpret_cast<const ulonglong2*>((uintptr_t)table_handle_words), gids, ng, rows_out);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

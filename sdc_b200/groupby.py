@@ -27,10 +27,11 @@ def _tname(t):
     return str(t.dtype).replace("torch.", "")
 
 
-def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
+def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, gid_range=0):
     """Hash groupby-aggregate of device columns.
 
-    keys : 1-D contiguous CUDA tensor, int64 or float64 (NaN keys are skipped, -0.0 == +0.0)
+    keys : 1-D contiguous CUDA tensor, int64 or float64 (NaN keys are skipped, -0.0 == +0.0);
+           gid_range > 0: int64 group ids in [0, gid_range), negative ids skip the row (SDCB200_GID)
     cols : list of 1-D contiguous CUDA tensors (int64 / float64) of the same length
     aggs : iterable of names from AGGS -- every aggregate is produced for every column
     -> (group_keys tensor[ng], {agg: [tensor[ng] per column]})
@@ -61,8 +62,14 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
     handle, ng = ct.c_int64(0), ct.c_int64(0)
     with torch.cuda.device(keys.device):
         stream = native.current_stream_ptr()
-        native.check(lib.sdcb200_groupby(native.DTYPE_CODES[kname], keys.data_ptr(), n, len(cols), ptrs, dts, mask,
-                                         1 if sort else 0, int(ddof), int(expected_groups), stream,
+        if gid_range > 0:
+            if kname != "int64":
+                raise TypeError("groupby: group ids must be int64")
+            kcode, hint = native.DTYPE_GID, int(gid_range)
+        else:
+            kcode, hint = native.DTYPE_CODES[kname], int(expected_groups)
+        native.check(lib.sdcb200_groupby(kcode, keys.data_ptr(), n, len(cols), ptrs, dts, mask,
+                                         1 if sort else 0, int(ddof), hint, stream,
                                          ct.byref(handle), ct.byref(ng)))
         g = ng.value
         owner = _ResultHandle(handle.value)

@@ -17,6 +17,7 @@ AGG_BITS = {"sum": 1, "mean": 2, "min": 4, "max": 8, "count": 16, "var": 32, "st
 ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
                "int64": 6, "uint64": 7, "float32": 8, "float64": 9}
+DTYPE_GID = 100     # SDCB200_GID: dense int64 group ids as a groupby key column
 
 _i32, _i64, _vp, _u8 = ct.c_int32, ct.c_int64, ct.c_void_p, ct.c_uint8
 

@@ -136,13 +136,11 @@ def groupby_str_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
     dev = d.offsets.device
     gid, ng, handle, cap = d.factorize(expected_groups)
     try:
-        # ids are table slots; NA rows carry -1 and form one extra group that is dropped below.
-        # first-appearance order comes from the numeric groupby itself (sort=False).
-        gk, res = groupby_device(gid, cols, aggs, False, ddof, max(ng + 1, 1))
-        keep = torch.nonzero(gk >= 0).reshape(-1)
-        if keep.shape[0] != gk.shape[0]:
-            gk = gather_device(gk, keep)
-            res = {a: [gather_device(t, keep) for t in ts] for a, ts in res.items()}
+        # ids are table slots in [0, cap]; NA rows carry -1 and are skipped by the aggregate (SDCB200_GID keys:
+        # direct-addressed table).
+        # sort=True reorders by string order below, so the id order of the aggregate is as good as any (and cheaper
+        # than tracking first rows); sort=False needs the first-appearance order from the aggregate itself
+        gk, res = groupby_device(gid, cols, aggs, bool(sort), ddof, gid_range=cap + 1)
         rows = torch.empty(gk.shape[0], dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             native.check(lib.sdcb200_str_group_rows(handle, gk.data_ptr(), gk.shape[0], rows.data_ptr(),

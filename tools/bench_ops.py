@@ -53,6 +53,11 @@ def bench_groupby(reps):
         for aggs in (("sum",), ("sum", "mean", "min", "max", "count")):
             med, best = timeit(lambda: groupby_device(a, [b], aggs, True, 1, groups), reps)
             emit("groupby_%s n=%d groups=%d" % ("+".join(aggs), n, groups), n, 16 * n, med, best)
+        if groups == 1_000_000:        # the same groups under non-dense keys: the hashed global table
+            a2 = a * 1000003
+            med, best = timeit(lambda: groupby_device(a2, [b], ("sum",), True, 1, groups), reps)
+            emit("groupby_sum_sparsekeys n=%d groups=%d" % (n, groups), n, 16 * n, med, best)
+            del a2
         del a, b
 
 
@@ -76,8 +81,13 @@ def bench_join(reps):
     from sdc_b200.join import join_device
     nb, npr = 10_000_000, 100_000_000
     r = torch.from_numpy(np.random.default_rng(2).permutation(nb).astype(np.int64)).cuda()
-    for name, hi in (("hit100", nb), ("hit50", 2 * nb)):
+    r0 = r
+    for name, hi in (("hit100", nb), ("hit50", 2 * nb), ("sparsekeys_hit100", nb)):
         l = torch.from_numpy(np.random.default_rng(3).integers(0, hi, npr, dtype=np.int64)).cuda()
+        r = r0
+        if name.startswith("sparse"):      # keys spread over a wide range: the hash-table path instead of the dense one
+            l = l * 1000003
+            r = r0 * 1000003
         for how in ("inner", "left"):
             out = {}
             def run():
@@ -89,6 +99,30 @@ def bench_join(reps):
         del l
 
 
+def bench_strings(reps, n=200_000_000):
+    """C4: sort_values + groupby multi-agg on 200 M rows with 8-char string keys (str_arr offsets + chars built
+    on the device from a host dictionary of G distinct strings)."""
+    from sdc_b200.str_arr import StringArray, groupby_str_device
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789", dtype=np.uint8)
+    for groups in (1000, 1_000_000):
+        rng = np.random.default_rng(4)
+        dic = torch.from_numpy(alphabet[rng.integers(0, alphabet.size, (groups, 8))]).cuda()       # [G, 8] uint8
+        ids = torch.randint(0, groups, (n,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+        chars = dic[ids].reshape(-1).contiguous()
+        del ids
+        offsets = (torch.arange(n + 1, device="cuda", dtype=torch.int64) * 8).to(torch.int32)
+        bitmap = torch.full(((n + 7) // 8,), 0xFF, dtype=torch.uint8, device="cuda")
+        sa = StringArray(offsets, chars, bitmap, n)
+        vals = torch.rand(n, device="cuda", dtype=torch.float64)
+        med, best = timeit(lambda: sa.argsort(True), reps, warm=1)
+        emit("str_argsort n=%d G=%d" % (n, groups), n, n * (12 + 8), med, best, note="alg bytes = offsets + chars read + idx written")
+        aggs = ("sum", "mean", "min", "max", "count")
+        med, best = timeit(lambda: groupby_str_device(sa, [vals], aggs, True, 1, groups), reps, warm=1)
+        emit("str_groupby_multiagg n=%d G=%d" % (n, groups), n, n * (4 + 8 + 8), med, best,
+             note="alg bytes = offsets + chars + value read once")
+        del sa, vals, chars, offsets, bitmap
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     reps = 10
@@ -97,4 +131,4 @@ if __name__ == "__main__":
         args = [a for a in args if a != str(reps)]
     which = args or ["groupby", "sort"]
     for w in which:
-        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join}[w](reps)
+        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join, "strings": bench_strings}[w](reps)
