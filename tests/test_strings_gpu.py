@@ -106,6 +106,45 @@ def test_groupby_string_keys():
                     np.testing.assert_allclose(res[agg][c], want[c], rtol=1e-9)
 
 
+def test_groupby_string_keys_inline_and_hashed_slots():
+    """csrc/strings.cu str_factorize: strings of <= 8 bytes ARE the slot's key word (zero padded, so "ab" and
+    "ab\\0" differ only by length), longer ones hash into it and are confirmed byte by byte; the 8-byte string of
+    0xFF collides with the empty marker and lives in the spare slot.  Groups must be exact in every case."""
+    import torch
+    from sdc_b200.str_arr import StringArray, groupby_str_device
+    rng = np.random.default_rng(9)
+    pool = ["", "a", "ab", "ab\x00", "ab\x00\x00", "abcdefgh", "abcdefg", "abcdefghi", "abcdefghij" * 3,
+            "abcdefghij" * 3 + "k", "x" * 8, "x" * 9, "x" * 16, "x" * 17, "\u00e9t\u00e9", "\u00e9t\u00e9s longs et accentu\u00e9s"]
+    keys = [pool[i] for i in rng.integers(0, len(pool), 50_000)]
+    keys[7] = None
+    keys[4242] = None
+    v = {"v": rng.standard_normal(50_000)}
+    from sdc_b200.groupby import groupby_host
+    for sort in (True, False):
+        rk, res = groupby_host(keys, v, ("sum", "count"), sort)
+        for agg in ("sum", "count"):
+            wk, want = ogroupby.groupby_agg(keys, v, agg, sort)
+            assert list(rk) == list(wk), (sort, rk, wk)
+            if agg == "count":
+                np.testing.assert_array_equal(res[agg]["v"], want["v"])
+            else:
+                np.testing.assert_allclose(res[agg]["v"], want["v"], rtol=1e-9)
+    # raw bytes (not UTF-8): 8 x 0xFF is the table's empty marker -> spare slot; 8 x 0xFE is an ordinary key
+    codes = np.full((1000, 8), 0xFE, dtype=np.uint8)
+    codes[::3] = 0xFF
+    codes[1::7, 3] = 0x41
+    sa = StringArray.from_fixed_width(codes).cuda()
+    val = torch.ones(1000, dtype=torch.float64, device="cuda")
+    rk, res = groupby_str_device(sa, [val], ("count",), True, 1, 0)
+    as_int = np.ascontiguousarray(codes).view(">u8").reshape(-1)
+    uniq, cnt = np.unique(as_int, return_counts=True)
+    assert rk.n == len(uniq)
+    got = rk.cpu()
+    got_int = got.chars.reshape(-1, 8).view(">u8").reshape(-1)
+    np.testing.assert_array_equal(got_int, uniq)                     # byte-lexicographic order == big-endian value order
+    np.testing.assert_array_equal(res["count"][0].cpu().numpy(), cnt)
+
+
 def test_c4_shape_scaled_properties():
     """BASELINE config C4 (string keys, sort + multi-agg) at 20 M rows: fixed-width 8-char keys built natively;
     checked through invariants -- sorted order is non-decreasing, counts sum to n, sums match a float64 total."""

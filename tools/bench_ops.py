@@ -99,6 +99,21 @@ def bench_join(reps):
         del l
 
 
+def bench_rolling(reps, n=100_000_000):
+    """C2: every Series.rolling(100) reduction on 100 M float64 rows, each as its own pass (16 B / row)."""
+    from sdc_b200.rolling import rolling_device
+    x = torch.from_numpy(np.random.default_rng(1).random(n)).cuda()
+    out = torch.empty_like(x)
+    for op in ("sum", "mean", "std", "var", "count", "min", "max"):
+        med, best = timeit(lambda: rolling_device(x, op, 100, 100, 1, out=out), reps)
+        emit("rolling_%s w=100 n=%d" % (op, n), n, 16 * n, med, best)
+    x[::1000] = float("nan")
+    x[7::100_000] = float("inf")
+    for op in ("mean", "std", "min"):
+        med, best = timeit(lambda: rolling_device(x, op, 100, 100, 1, out=out), reps)
+        emit("rolling_%s w=100 n=%d, 0.1%% NaN + a few inf" % (op, n), n, 16 * n, med, best)
+
+
 def bench_strings(reps, n=200_000_000):
     """C4: sort_values + groupby multi-agg on 200 M rows with 8-char string keys (str_arr offsets + chars built
     on the device from a host dictionary of G distinct strings)."""
@@ -131,4 +146,5 @@ if __name__ == "__main__":
         args = [a for a in args if a != str(reps)]
     which = args or ["groupby", "sort"]
     for w in which:
-        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join, "strings": bench_strings}[w](reps)
+        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join, "strings": bench_strings,
+         "rolling": bench_rolling}[w](reps)
