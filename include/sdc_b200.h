@@ -212,6 +212,36 @@ int32_t sdcb200_hash_partition(int32_t key_dtype, const void* keys, int64_t n, i
 /* out[i] = cnt[i] ? sum[i] / cnt[i] : NaN: final step of a distributed mean (partials are exchanged).  */
 int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, int64_t n, double* out, void* stream);
 
+/* ---- peer-memory shuffle over NVLink (one node, one process per GPU) --------------------------------------
+ * Replaces the per-column alltoallv of the reference's shuffle (sdc/shuffle_utils.py:268-270,
+ * sdc/distributed_api.py:439-466) with ONE pack-and-send kernel that stores rows straight into the
+ * destination ranks' receive arenas (CUDA IPC + NVLink P2P stores).
+ *   ipc_alloc / ipc_free      arena memory (cudaMalloc: exportable, unlike the stream-ordered pool)
+ *   ipc_get_handle / ipc_open 64-byte CUDA IPC handle of an arena / a peer's arena mapped into this process
+ *   shuffle_scatter           rows perm[seg_start[d] .. seg_start[d+1]) of every column go to rank d's arena,
+ *                             column c at peer_bases[d] + (c * arena_rows + dst_off[d] + k) * 8.  seg_start,
+ *                             dst_off, peer_bases are HOST arrays; cols / perm device pointers; 8-byte rows.
+ * The caller orders the kernel between two collectives on the same stream (counts exchange before, barrier
+ * after); see sdc_b200/distributed.py: PeerShuffle.                                                         */
+int32_t sdcb200_ipc_alloc(void** p, int64_t bytes);
+int32_t sdcb200_ipc_free(void* p);
+int32_t sdcb200_ipc_get_handle(void* p, void* handle64);
+int32_t sdcb200_ipc_open(const void* handle64, void** p);
+int32_t sdcb200_ipc_close(void* p);
+int32_t sdcb200_shuffle_scatter(int32_t ncols, const void* const* cols, const int64_t* perm, int64_t n, int32_t nparts,
+                                const int64_t* seg_start, const int64_t* dst_off, void* const* peer_bases,
+                                int64_t arena_rows, void* stream);
+/* fused form (no row permutation is ever materialised): shuffle_plan hashes the keys once and leaves the per-tile
+ * (4096 rows) exclusive offsets per destination in tile_off[ceil(n / 4096) * 8] (device, uint32) and the totals in
+ * counts_out[nparts] (device); after the totals of every rank are known, shuffle_send re-hashes, ranks the rows of
+ * each destination inside the tile in row order, stages them in shared memory and stores each destination's run
+ * into that rank's arena.  cols[0] must be the key column.  Row order in the arenas = the NCCL path's.            */
+int32_t sdcb200_shuffle_plan(int32_t key_dtype, const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off,
+                             int64_t* counts_out, void* stream);
+int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t ncols, const void* const* cols, int64_t n, int32_t nparts,
+                             const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
+                             int64_t arena_rows, void* stream);
+
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The
  * generic-comparator forms (parallel_sort(begin,len,size,compare) etc.) take a host callback and

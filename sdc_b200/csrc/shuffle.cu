@@ -12,6 +12,8 @@
 //              destination's rows stay in input order (left-order joins and first-appearance groupby
 //              survive the shuffle)
 // Columns are then packed with sdcb200_gather(perm) into contiguous per-destination send buffers.
+#include <cstring>
+
 #include "radix_sort.cuh"
 
 namespace sdcb200 {
@@ -19,6 +21,7 @@ namespace {
 
 constexpr int kPartThreads = 256;
 constexpr int kMaxParts = 256;
+constexpr int kMaxCols = 32;
 
 __host__ __device__ inline unsigned long long pmix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -96,6 +99,317 @@ extern "C" int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, i
     int64_t grid = ceil_div(n, 256);
     if (grid > (int64_t)sm_count() * 4) grid = (int64_t)sm_count() * 4;
     combine_mean_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(sum, reinterpret_cast<const long long*>(cnt), n, out);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+// ------------------------------------------------------------------ peer-memory shuffle (NVLink P2P stores)
+// One node, one process per GPU: every rank owns a receive arena (cudaMalloc, exported with a CUDA IPC handle and
+// opened by its peers).  After the per-destination counts are known on every rank (one small all-gather), ONE
+// kernel packs and sends: thread i takes row perm[i], finds its destination d (perm is grouped by destination)
+// and stores every column's value straight into rank d's arena at the slot reserved for this source rank --
+// NVLink carries 8-byte stores coalesced per destination run; there is no packed send buffer and no per-column
+// all-to-all.  A barrier on the stream after the kernel makes the arenas readable.
+namespace sdcb200 { namespace {
+constexpr int kPeerMax = 8;
+struct ScatterArgs {
+    const unsigned long long* cols[kMaxCols];   // local source columns (8-byte rows)
+    unsigned long long* peer[kPeerMax];          // arena base of every destination rank (peer[me] is local)
+    long long seg_start[kPeerMax + 1];           // perm[seg_start[d] .. seg_start[d+1]) go to rank d
+    long long dst_off[kPeerMax];                 // first row of this source's block in rank d's arena
+    long long cap;                               // arena rows per column: column c starts at base + c * cap
+    int ncols, nparts;
+};
+
+__global__ void __launch_bounds__(256) shuffle_scatter_kernel(ScatterArgs a, const long long* __restrict__ perm, long long n) {
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256ll) {
+        int d = 0;
+#pragma unroll
+        for (int q = 1; q < kPeerMax; ++q) d += (q < a.nparts && i >= a.seg_start[q]) ? 1 : 0;
+        const long long row = perm[i];
+        const long long pos = a.dst_off[d] + (i - a.seg_start[d]);
+        unsigned long long* base = a.peer[d];
+        for (int c = 0; c < a.ncols; ++c) base[(long long)c * a.cap + pos] = a.cols[c][row];
+    }
+}
+}}
+
+extern "C" int32_t sdcb200_ipc_alloc(void** p, int64_t bytes) {
+    SDC_ARG_CHECK(p != nullptr && bytes > 0, "ipc_alloc");
+    SDC_CUDA_TRY(cudaMalloc(p, (size_t)bytes));
+    return SDCB200_OK;
+}
+extern "C" int32_t sdcb200_ipc_free(void* p) {
+    if (p) SDC_CUDA_TRY(cudaFree(p));
+    return SDCB200_OK;
+}
+extern "C" int32_t sdcb200_ipc_get_handle(void* p, void* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    SDC_ARG_CHECK(p != nullptr && handle64 != nullptr, "ipc_get_handle");
+    cudaIpcMemHandle_t h;
+    SDC_CUDA_TRY(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    return SDCB200_OK;
+}
+extern "C" int32_t sdcb200_ipc_open(const void* handle64, void** p) {
+    SDC_ARG_CHECK(p != nullptr && handle64 != nullptr, "ipc_open");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    SDC_CUDA_TRY(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess));
+    return SDCB200_OK;
+}
+extern "C" int32_t sdcb200_ipc_close(void* p) {
+    if (p) SDC_CUDA_TRY(cudaIpcCloseMemHandle(p));
+    return SDCB200_OK;
+}
+
+extern "C" int32_t sdcb200_shuffle_scatter(int32_t ncols, const void* const* cols, const int64_t* perm, int64_t n, int32_t nparts,
+                                           const int64_t* seg_start, const int64_t* dst_off, void* const* peer_bases,
+                                           int64_t arena_rows, void* stream) {
+    SDC_ARG_CHECK(ncols >= 1 && ncols <= kMaxCols, "ncols");
+    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax, "nparts (<= 8 GPUs of one node)");
+    SDC_ARG_CHECK(n >= 0 && seg_start && dst_off && peer_bases && cols, "null pointer");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(perm != nullptr, "null perm");
+    ScatterArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < ncols; ++c) a.cols[c] = reinterpret_cast<const unsigned long long*>(cols[c]);
+    for (int d = 0; d < nparts; ++d) {
+        a.peer[d] = reinterpret_cast<unsigned long long*>(peer_bases[d]);
+        a.seg_start[d] = seg_start[d];
+        a.dst_off[d] = dst_off[d];
+        SDC_ARG_CHECK(dst_off[d] >= 0 && dst_off[d] + (seg_start[d + 1] - seg_start[d]) <= arena_rows, "arena too small");
+    }
+    a.seg_start[nparts] = seg_start[nparts];
+    a.cap = arena_rows;
+    a.ncols = ncols;
+    a.nparts = nparts;
+    int64_t grid = ceil_div(n, 256 * 4);
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    shuffle_scatter_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, reinterpret_cast<const long long*>(perm), n);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+// ------------------------------------------------------------------ fused partition + send
+// The perm-based scatter above still materialises the row permutation (a radix pass + a widen pass).  The fused
+// form never does: tiles of 4096 rows, two kernels.
+//   shuffle_count_kernel   destination of every row (same hash as sdcb200_hash_partition), per-tile counts per
+//                          destination (ballots), total counts
+//   shuffle_tile_scan      exclusive scan of the tile counts per destination -> tile_off[tile][d]
+//   (host: all-gather of the totals -> this source's first row in every destination arena)
+//   shuffle_send_kernel    recomputes the destinations, ranks the rows of each destination inside the tile in row
+//                          order (ballot multisplit + warp prefix: stable), stages one column at a time in shared
+//                          memory in destination order and copies every destination's run -- ~4 KB contiguous --
+//                          to that rank's arena over NVLink.  Same row order in the arenas as the NCCL path.
+namespace sdcb200 { namespace {
+constexpr int kShThreads = 256;
+constexpr int kShItems = 16;
+constexpr int kShTile = kShThreads * kShItems;      // 4096 rows
+constexpr int kShWarps = kShThreads / 32;
+
+template <bool KEY_F64>
+__device__ __forceinline__ unsigned shuffle_dest(unsigned long long b, unsigned nparts) {
+    if (KEY_F64) {
+        const unsigned long long mag = b & 0x7fffffffffffffffull;
+        if (mag > 0x7ff0000000000000ull) b = 0x7ff8000000000000ull;
+        else if (mag == 0) b = 0;
+    }
+    return (unsigned)(((pmix64(b) >> 32) * (unsigned long long)nparts) >> 32);
+}
+
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kShThreads) shuffle_count_kernel(const unsigned long long* __restrict__ keys, long long n,
+                                                                   unsigned nparts, unsigned* __restrict__ tile_counts,
+                                                                   unsigned long long* __restrict__ counts) {
+    __shared__ unsigned wtot[kShWarps][kPeerMax];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * kShTile + w * 32 * kShItems;
+    unsigned run[kPeerMax];
+#pragma unroll
+    for (int d = 0; d < kPeerMax; ++d) run[d] = 0;
+#pragma unroll
+    for (int i = 0; i < kShItems; ++i) {
+        const long long r = base + i * 32 + lane;
+        const unsigned d = r < n ? shuffle_dest<KEY_F64>(keys[r], nparts) : 0xffu;
+#pragma unroll
+        for (int q = 0; q < kPeerMax; ++q) run[q] += __popc(__ballot_sync(0xffffffffu, d == (unsigned)q));
+    }
+#pragma unroll
+    for (int q = 0; q < kPeerMax; ++q) if (lane == q) wtot[w][q] = run[q];
+    __syncthreads();
+    if (threadIdx.x < kPeerMax) {
+        unsigned t = 0;
+        for (int ww = 0; ww < kShWarps; ++ww) t += wtot[ww][threadIdx.x];
+        tile_counts[(size_t)blockIdx.x * kPeerMax + threadIdx.x] = t;
+        if (t) atomicAdd(&counts[threadIdx.x], (unsigned long long)t);
+    }
+}
+
+// grid = kPeerMax CTAs of 1024 threads: CTA d scans column d of tile_counts in place (exclusive)
+__global__ void __launch_bounds__(1024) shuffle_tile_scan(unsigned* __restrict__ tile_counts, long long ntiles) {
+    __shared__ unsigned wsum[32];
+    const int d = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long per = (ntiles + 1023) / 1024;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < ntiles ? lo + per : ntiles;
+    unsigned s = 0;
+    for (long long t = lo; t < hi; ++t) s += tile_counts[t * kPeerMax + d];
+    unsigned incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned basev = 0;
+    for (int ww = 0; ww < warp; ++ww) basev += wsum[ww];
+    unsigned run = basev + incl - s;
+    for (long long t = lo; t < hi; ++t) {
+        const unsigned v = tile_counts[t * kPeerMax + d];
+        tile_counts[t * kPeerMax + d] = run;
+        run += v;
+    }
+}
+
+struct SendArgs {
+    const unsigned long long* cols[kMaxCols];   // cols[0] = the key column
+    unsigned long long* peer[kPeerMax];
+    long long dst_off[kPeerMax];
+    long long cap;
+    int ncols, nparts;
+};
+
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kShThreads) shuffle_send_kernel(SendArgs a, long long n, const unsigned* __restrict__ tile_off) {
+    __shared__ unsigned long long stage[kShTile];
+    __shared__ unsigned wtot[kShWarps][kPeerMax];
+    __shared__ unsigned wbase[kShWarps][kPeerMax];
+    __shared__ unsigned stage_off[kPeerMax + 1];
+    __shared__ long long run_dst[kPeerMax];            // global row of the first staged row of destination d
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long tile_base = (long long)blockIdx.x * kShTile;
+    const long long base = tile_base + w * 32 * kShItems;
+    const int tile_n = (int)(n - tile_base < kShTile ? n - tile_base : kShTile);
+    const unsigned lt = (1u << lane) - 1u;
+    unsigned long long key[kShItems];
+    unsigned short slot[kShItems];       // rank inside (warp, destination) first, staged slot later
+    unsigned char dd[kShItems];
+    unsigned run[kPeerMax];
+#pragma unroll
+    for (int d = 0; d < kPeerMax; ++d) run[d] = 0;
+#pragma unroll
+    for (int i = 0; i < kShItems; ++i) {
+        const long long r = base + i * 32 + lane;
+        key[i] = r < n ? a.cols[0][r] : 0ull;
+    }
+#pragma unroll
+    for (int i = 0; i < kShItems; ++i) {
+        const long long r = base + i * 32 + lane;
+        const unsigned d = r < n ? shuffle_dest<KEY_F64>(key[i], (unsigned)a.nparts) : 0xffu;
+        dd[i] = (unsigned char)d;
+        unsigned mine = 0;
+#pragma unroll
+        for (int q = 0; q < kPeerMax; ++q) {
+            const unsigned b = __ballot_sync(0xffffffffu, d == (unsigned)q);
+            if (d == (unsigned)q) mine = run[q] + __popc(b & lt);
+            run[q] += __popc(b);
+        }
+        slot[i] = (unsigned short)mine;
+    }
+#pragma unroll
+    for (int q = 0; q < kPeerMax; ++q) if (lane == q) wtot[w][q] = run[q];
+    __syncthreads();
+    if (tid < kShWarps * kPeerMax) {
+        const int ww = tid / kPeerMax, d = tid % kPeerMax;
+        unsigned b = 0;
+        for (int x = 0; x < ww; ++x) b += wtot[x][d];
+        wbase[ww][d] = b;
+    }
+    if (tid == 0) {
+        unsigned acc = 0;
+        for (int d = 0; d < kPeerMax; ++d) {
+            unsigned t = 0;
+            for (int x = 0; x < kShWarps; ++x) t += wtot[x][d];
+            stage_off[d] = acc;
+            run_dst[d] = d < a.nparts ? a.dst_off[d] + (long long)tile_off[(size_t)blockIdx.x * kPeerMax + d] : 0;
+            acc += t;
+        }
+        stage_off[kPeerMax] = acc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kShItems; ++i)
+        if (dd[i] != 0xff) slot[i] = (unsigned short)(stage_off[dd[i]] + wbase[w][dd[i]] + slot[i]);
+    for (int c = 0; c < a.ncols; ++c) {
+        const unsigned long long* col = a.cols[c];
+#pragma unroll
+        for (int i = 0; i < kShItems; ++i) {
+            const long long r = base + i * 32 + lane;
+            if (dd[i] != 0xff) stage[slot[i]] = c == 0 ? key[i] : col[r];
+        }
+        __syncthreads();
+        for (int q = tid; q < tile_n; q += kShThreads) {
+            int d = 0;
+#pragma unroll
+            for (int x = 1; x < kPeerMax; ++x) d += (q >= (int)stage_off[x]) ? 1 : 0;
+            a.peer[d][(long long)c * a.cap + run_dst[d] + (q - (int)stage_off[d])] = stage[q];
+        }
+        __syncthreads();
+    }
+}
+}}
+
+extern "C" int32_t sdcb200_shuffle_plan(int32_t key_dtype, const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off,
+                                        int64_t* counts_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
+    SDC_ARG_CHECK(n >= 0 && n < 0xffffffffll && nparts >= 1 && nparts <= kPeerMax, "n (< 2^32) / nparts (<= 8)");
+    SDC_ARG_CHECK(counts_out != nullptr && (n == 0 || (keys && tile_off)), "null pointer");
+    SDC_CUDA_TRY(cudaMemsetAsync(counts_out, 0, (size_t)nparts * 8, s));
+    if (n == 0) return SDCB200_OK;
+    const int64_t ntiles = ceil_div(n, kShTile);
+    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(keys);
+    Scratch cnt8;                                   // the kernels always keep kPeerMax counters
+    SDC_TRY(cnt8.alloc(kPeerMax * 8, s));
+    SDC_CUDA_TRY(cudaMemsetAsync(cnt8.p, 0, kPeerMax * 8, s));
+    if (key_dtype == SDCB200_F64)
+        shuffle_count_kernel<true><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, (unsigned)nparts, tile_off, cnt8.as<unsigned long long>());
+    else
+        shuffle_count_kernel<false><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, (unsigned)nparts, tile_off, cnt8.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    shuffle_tile_scan<<<kPeerMax, 1024, 0, s>>>(tile_off, ntiles);
+    SDC_CHECK_LAUNCH();
+    SDC_CUDA_TRY(cudaMemcpyAsync(counts_out, cnt8.p, (size_t)nparts * 8, cudaMemcpyDeviceToDevice, s));
+    return SDCB200_OK;
+}
+
+extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t ncols, const void* const* cols, int64_t n, int32_t nparts,
+                                        const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
+                                        int64_t arena_rows, void* stream) {
+    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
+    SDC_ARG_CHECK(ncols >= 1 && ncols <= kMaxCols, "ncols");
+    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax, "nparts (<= 8 GPUs of one node)");
+    SDC_ARG_CHECK(n >= 0 && dst_off && peer_bases && cols, "null pointer");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(tile_off != nullptr, "null tile offsets");
+    SendArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < ncols; ++c) a.cols[c] = reinterpret_cast<const unsigned long long*>(cols[c]);
+    for (int d = 0; d < nparts; ++d) {
+        a.peer[d] = reinterpret_cast<unsigned long long*>(peer_bases[d]);
+        a.dst_off[d] = dst_off[d];
+        SDC_ARG_CHECK(dst_off[d] >= 0 && dst_off[d] <= arena_rows, "arena offset");
+    }
+    a.cap = arena_rows;
+    a.ncols = ncols;
+    a.nparts = nparts;
+    const int64_t ntiles = ceil_div(n, kShTile);
+    if (key_dtype == SDCB200_F64)
+        shuffle_send_kernel<true><<<(unsigned)ntiles, kShThreads, 0, (cudaStream_t)stream>>>(a, n, tile_off);
+    else
+        shuffle_send_kernel<false><<<(unsigned)ntiles, kShThreads, 0, (cudaStream_t)stream>>>(a, n, tile_off);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

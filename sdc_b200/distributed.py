@@ -114,12 +114,180 @@ def hash_partition_device(keys, nparts):
     return perm, counts
 
 
-def hash_shuffle(keys, cols, group=None):
-    """Route every row to rank hash(key) % P.  -> (keys', [cols'...]) now owned by this rank."""
+class _ArenaView:
+    """int64[n] window of a receive arena exposed through __cuda_array_interface__ (zero-copy into torch)."""
+
+    def __init__(self, ptr, n, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2, "strides": None}
+
+
+class PeerShuffle:
+    """Hash shuffle over NVLink peer memory (one node, one process per GPU, P <= 8).
+
+    Every rank owns `narenas` receive arenas of `max_cols` columns x `capacity_rows` 8-byte rows (cudaMalloc,
+    exported with CUDA IPC handles, opened by the peers once, here).  shuffle() then costs: one counting pass over
+    the keys (`sdcb200_shuffle_plan`), ONE small all-gather of the per-destination counts, ONE fused partition-and-
+    send kernel (`sdcb200_shuffle_send`: rows ranked per destination inside 4096-row tiles, staged in shared memory,
+    stored into the peers' arenas over NVLink) and a barrier -- instead of a radix partition, a gather kernel and an
+    NCCL all-to-all per column.  The returned tensors VIEW the arena used by this call; arenas rotate, so
+    they stay valid for the next `narenas - 1` calls."""
+
+    def __init__(self, capacity_rows, max_cols=4, narenas=2, group=None):
+        torch, dist = _torch(), _dist()
+        self.group = group
+        self.rank, self.P = world(group)
+        if self.P > 8:
+            raise ValueError("PeerShuffle: at most 8 ranks (one NVSwitch node)")
+        self.cap, self.max_cols, self.narenas = int(capacity_rows), int(max_cols), int(narenas)
+        self.lib = native.load()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.mine, self.peers, self.turn = [], [], 0
+        nbytes = self.cap * self.max_cols * 8
+        for _ in range(self.narenas):
+            p = ct.c_void_p()
+            native.check(self.lib.sdcb200_ipc_alloc(ct.byref(p), nbytes))
+            h = (ct.c_uint8 * 64)()
+            native.check(self.lib.sdcb200_ipc_get_handle(p, h))
+            handles = [None] * self.P
+            dist.all_gather_object(handles, bytes(h), group=group)
+            bases = []
+            for r, hb in enumerate(handles):
+                if r == self.rank:
+                    bases.append(p.value)
+                else:
+                    q = ct.c_void_p()
+                    native.check(self.lib.sdcb200_ipc_open((ct.c_uint8 * 64).from_buffer_copy(hb), ct.byref(q)))
+                    bases.append(q.value)
+            self.mine.append(p.value)
+            self.peers.append(bases)
+
+    def close(self):
+        torch = _torch()
+        torch.cuda.synchronize()
+        for a, bases in enumerate(self.peers):
+            for r, b in enumerate(bases):
+                if r != self.rank:
+                    self.lib.sdcb200_ipc_close(b)
+        _dist().barrier(group=self.group)          # nobody frees an arena a peer still maps
+        for p in self.mine:
+            self.lib.sdcb200_ipc_free(p)
+        self.mine, self.peers = [], []
+
+    def shuffle(self, keys, cols):
+        """Route every row to rank hash(key) % P.  -> (keys', [cols'...]) views of this rank's arena."""
+        torch, dist = _torch(), _dist()
+        P, me = self.P, self.rank
+        allc = [keys] + list(cols)
+        if len(allc) > self.max_cols:
+            raise ValueError("PeerShuffle: %d columns, arena holds %d" % (len(allc), self.max_cols))
+        for c in allc:
+            if c.element_size() != 8 or not c.is_contiguous():
+                raise TypeError("PeerShuffle: contiguous 8-byte columns only")
+        n = keys.shape[0]
+        kname = str(keys.dtype).replace("torch.", "")
+        if kname not in ("int64", "float64"):
+            raise TypeError("PeerShuffle: key dtype %s" % kname)
+        kcode = native.DTYPE_CODES[kname]
+        counts = torch.empty(P, dtype=torch.int64, device=keys.device)
+        tile_off = torch.empty(max(1, -(-n // 4096)) * 8, dtype=torch.int32, device=keys.device)
+        with torch.cuda.device(keys.device):
+            native.check(self.lib.sdcb200_shuffle_plan(kcode, keys.data_ptr(), n, P, tile_off.data_ptr(), counts.data_ptr(),
+                                                       native.current_stream_ptr()))
+        # counts[s][d] on every rank; entering the collective also orders this call after every rank's use of the
+        # arena that is about to be overwritten (each rank's consumers run before it on the same stream)
+        mat = torch.empty(P * P, dtype=torch.int64, device=keys.device)
+        dist.all_gather_into_tensor(mat, counts, group=self.group)
+        m = mat.cpu().view(P, P)
+        recv_total = int(m[:, me].sum())
+        if int(m.sum(0).max()) > self.cap:
+            raise ArenaOverflow(int(m.sum(0).max()), self.cap)
+        dst_off = [int(m[:me, d].sum()) for d in range(P)]       # my block in rank d's arena starts after lower ranks'
+        a = self.turn
+        self.turn = (self.turn + 1) % self.narenas
+        cptr = (ct.c_void_p * len(allc))(*[c.data_ptr() for c in allc])
+        offc = (ct.c_int64 * P)(*dst_off)
+        basec = (ct.c_void_p * P)(*self.peers[a])
+        with torch.cuda.device(keys.device):
+            native.check(self.lib.sdcb200_shuffle_send(kcode, len(allc), cptr, n, P, tile_off.data_ptr(), offc, basec,
+                                                       self.cap, native.current_stream_ptr()))
+        # every rank's stores have landed once every rank's kernel is done: a collective on the same stream
+        dist.barrier(group=self.group, device_ids=[self.dev.index])
+        out = []
+        for c, col in enumerate(allc):
+            if recv_total == 0:
+                out.append(torch.empty(0, dtype=col.dtype, device=col.device))
+                continue
+            v = torch.as_tensor(_ArenaView(self.mine[a] + c * self.cap * 8, recv_total, self), device=col.device)
+            out.append(v.view(col.dtype))
+        return out[0], out[1:]
+
+
+_AUTO_PEERS = {}     # id(group) -> PeerShuffle | False (peer memory unavailable for this group)
+
+
+class ArenaOverflow(native.NativeError):
+    """Raised by PeerShuffle.shuffle on EVERY rank (the decision is taken on the all-gathered count matrix)."""
+
+    def __init__(self, needed, cap):
+        super().__init__("PeerShuffle: a rank would receive %d rows, arena holds %d" % (needed, cap))
+        self.needed = needed
+
+
+def auto_peer(group, n_rows, ncols, min_rows=0):
+    """The cached PeerShuffle context of `group`, created (or re-created larger) collectively; None when the group is
+    not one NCCL node of <= 8 GPUs or SDCB200_PEER_SHUFFLE=0.  Every decision depends only on values all ranks
+    share (ncols, all-reduced sizes, the all-gathered count matrix), so all ranks take the same path."""
+    import os
+    import socket
+    torch, dist = _torch(), _dist()
+    key = id(group)
+    ctx = _AUTO_PEERS.get(key)
+    if ctx is False or os.environ.get("SDCB200_PEER_SHUFFLE", "1") == "0":
+        return None
+    _, P = world(group)
+    if ctx is None:
+        if P < 2 or P > 8 or dist.get_backend(group) != "nccl":
+            _AUTO_PEERS[key] = False
+            return None
+        hosts = [None] * P
+        dist.all_gather_object(hosts, socket.gethostname(), group=group)
+        if len(set(hosts)) != 1:
+            _AUTO_PEERS[key] = False
+            return None
+    if ctx is not None and ncols <= ctx.max_cols and min_rows <= ctx.cap:
+        return ctx
+    if ctx is None:
+        need = torch.tensor([n_rows], dtype=torch.int64, device="cuda")
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=group)
+        cap = max(int(need.item()) * 3 // 2 + 4096, min_rows)
+        cols_cap = max(ncols, 2)
+    else:
+        cap = max(ctx.cap, min_rows * 5 // 4)
+        cols_cap = max(ncols, ctx.max_cols)
+        ctx.close()
+    ctx = PeerShuffle(cap, max_cols=cols_cap, narenas=2, group=group)
+    _AUTO_PEERS[key] = ctx
+    return ctx
+
+
+def hash_shuffle(keys, cols, group=None, peer=None):
+    """Route every row to rank hash(key) % P.  -> (keys', [cols'...]) now owned by this rank.
+    peer: a PeerShuffle context -> NVLink peer-memory stores instead of NCCL all-to-all per column."""
     from .sort import gather_device
     _, P = world(group)
     if P == 1:
         return keys, list(cols)
+    if peer == "auto":
+        peer = auto_peer(group, keys.shape[0], 1 + len(cols)) if keys.is_cuda else None
+        if peer is not None:
+            try:
+                return peer.shuffle(keys, cols)
+            except ArenaOverflow as e:           # skewed destinations: every rank is here, grow together and retry
+                peer = auto_peer(group, keys.shape[0], 1 + len(cols), e.needed)
+                return peer.shuffle(keys, cols)
+    if peer is not None:
+        return peer.shuffle(keys, cols)
     perm, counts = hash_partition_device(keys, P)
     recv_counts = exchange_counts(counts, group)
     out = []
@@ -141,7 +309,7 @@ def combine_mean_device(sums, counts):
 _PARTIALS = {"sum": ("sum",), "count": ("count",), "min": ("min",), "max": ("max",), "mean": ("sum", "count")}
 
 
-def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, group=None, mode="auto"):
+def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, group=None, mode="auto", peer="auto"):
     """df.groupby(key).<aggs>() over row-sharded columns.
 
     mode 'combine' (low cardinality): local hash-aggregate -> all-gather of the partial (key, sum, count,
@@ -149,7 +317,9 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
       This is the reference's per-chunk-dict-then-merge idea (hpat_pandas_dataframe_functions.py:3080-3102)
       with GPUs as the chunks.  sum / mean / min / max / count only.
     mode 'shuffle' (high cardinality, or var / std): rows go to rank hash(key) % P, each rank aggregates
-      the keys it owns -> every rank holds a disjoint slice of the groups.
+      the keys it owns -> every rank holds a disjoint slice of the groups.  peer: 'auto' (default: the cached
+      PeerShuffle context of the group -- NVLink peer-memory stores -- when the group is one node of <= 8 GPUs), a
+      PeerShuffle context, or None for NCCL all-to-all.
     -> (group_keys, {agg: [tensor per column]}, 'replicated' | 'sharded')"""
     from .groupby import groupby_device
     torch = _torch()
@@ -162,7 +332,7 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
         simple = all(a in _PARTIALS for a in aggs)
         mode = "combine" if simple and 0 < expected_groups <= (1 << 20) else "shuffle"
     if mode == "shuffle":
-        k2, c2 = hash_shuffle(keys, cols, group)
+        k2, c2 = hash_shuffle(keys, cols, group, peer)
         k, r = groupby_device(k2, c2, aggs, sort, ddof, expected_groups // P if expected_groups > 0 else 0)
         return k, r, "sharded"
     for a in aggs:
@@ -198,7 +368,7 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
     return out_keys, res, "replicated"
 
 
-def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"):
+def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto", peer="auto"):
     """pd.merge indexers over row-sharded key columns.  Row numbers in the result are GLOBAL
     (rank-major: global = rows of lower ranks + local row), the result itself stays sharded.
 
@@ -225,8 +395,8 @@ def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"
     roff = int(nr_all[:rank].sum().item())
     lid = torch.arange(loff, loff + left_keys.shape[0], dtype=torch.int64, device=dev)
     rid = torch.arange(roff, roff + right_keys.shape[0], dtype=torch.int64, device=dev)
-    lk2, (lid2,) = hash_shuffle(left_keys, [lid], group)
-    rk2, (rid2,) = hash_shuffle(right_keys, [rid], group)
+    lk2, (lid2,) = hash_shuffle(left_keys, [lid], group, peer)     # peer: two arenas, both results stay valid
+    rk2, (rid2,) = hash_shuffle(right_keys, [rid], group, peer)
     li, ri = join_device(lk2, rk2, how)
     gl = gather_device(lid2, li)
     if how == "left":

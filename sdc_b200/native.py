@@ -63,6 +63,15 @@ SIGNATURES = {
     "stable_argsort": (None, [_vp, _vp, ct.c_uint64, ct.c_int8, _vp]),
     "sdcb200_hash_partition": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "sdcb200_combine_mean": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_ipc_alloc": (_i32, [ct.POINTER(_vp), _i64]),
+    "sdcb200_ipc_free": (_i32, [_vp]),
+    "sdcb200_ipc_get_handle": (_i32, [_vp, _vp]),
+    "sdcb200_ipc_open": (_i32, [_vp, ct.POINTER(_vp)]),
+    "sdcb200_ipc_close": (_i32, [_vp]),
+    "sdcb200_shuffle_plan": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "sdcb200_shuffle_send": (_i32, [_i32, _i32, ct.POINTER(_vp), _i64, _i32, _vp, ct.POINTER(_i64), ct.POINTER(_vp), _i64, _vp]),
+    "sdcb200_shuffle_scatter": (_i32, [_i32, ct.POINTER(_vp), _vp, _i64, _i32, ct.POINTER(_i64), ct.POINTER(_i64),
+                                       ct.POINTER(_vp), _i64, _vp]),
 }
 
 # the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)

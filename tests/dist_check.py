@@ -40,9 +40,11 @@ def main():
     cols = [torch.from_numpy(vals[s:e].copy()).to(dev), torch.from_numpy(ivals[s:e].copy()).to(dev)]
     names = {"v": vals, "w": ivals}
 
-    def check_groupby(keys, aggs, mode, sort, hint):
+    peer = D.PeerShuffle(2 * n // P + 4096, max_cols=3, narenas=2)      # NVLink peer-memory shuffle (CUDA IPC)
+
+    def check_groupby(keys, aggs, mode, sort, hint, peer=None):          # peer=None: NCCL all-to-all
         k = torch.from_numpy(keys[s:e].copy()).to(dev)
-        gk, res, layout = D.groupby_distributed(k, cols, aggs, sort, 1, hint, None, mode)
+        gk, res, layout = D.groupby_distributed(k, cols, aggs, sort, 1, hint, None, mode, peer)
         if layout == "sharded":
             gk_all, _ = D.allgather_ragged(gk)
             res = {a: [D.allgather_ragged(t)[0] for t in ts] for a, ts in res.items()}
@@ -66,16 +68,27 @@ def main():
     check_groupby(keys_lo, ("sum", "count"), "combine", False, 1000)
     check_groupby(keys_hi, ("sum", "mean", "min", "max", "count"), "shuffle", True, 150_000)
     check_groupby(keys_hi, ("var", "std"), "shuffle", True, 150_000)
+    check_groupby(keys_hi, ("sum", "mean", "min", "max", "count"), "shuffle", True, 150_000, peer)
+    check_groupby(keys_hi, ("sum", "count"), "shuffle", True, 150_000, "auto")        # cached context of the group
+    # the peer-memory shuffle delivers exactly what the NCCL all-to-all delivers: same rows, same order
+    kh = torch.from_numpy(keys_hi[s:e].copy()).to(dev)
+    for rep in range(3):                                   # arenas rotate: results of consecutive calls must not alias
+        k_a, c_a = D.hash_shuffle(kh, cols)
+        k_b, c_b = D.hash_shuffle(kh, cols, None, peer)
+        assert torch.equal(k_a, k_b), "peer shuffle keys differ (rep %d)" % rep
+        for x_a, x_b in zip(c_a, c_b):
+            assert torch.equal(x_a.view(torch.int64), x_b.view(torch.int64)), "peer shuffle column differs (rep %d)" % rep
 
     # join: probe rows sharded, build rows sharded; global row numbers come back
     nb = 20_011
     build = rng.permutation(60_000)[:nb].astype(np.int64)
     probe = rng.integers(0, 60_000, n)
     bs, be = D.block_range(nb, rank, P)
-    for mode in ("broadcast", "shuffle"):
+    for mode in ("broadcast", "shuffle", "shuffle_peer"):
         for how in ("inner", "left"):
             li, ri = D.join_distributed(torch.from_numpy(probe[s:e].copy()).to(dev), torch.from_numpy(build[bs:be].copy()).to(dev),
-                                        how, None, mode)
+                                        how, None, "shuffle" if mode == "shuffle_peer" else mode,
+                                        peer if mode == "shuffle_peer" else None)
             li_all, _ = D.allgather_ragged(li)
             ri_all, _ = D.allgather_ragged(ri)
             got = ojoin.canonical(li_all.cpu().numpy(), ri_all.cpu().numpy())
@@ -95,6 +108,7 @@ def main():
         ok = ~np.isnan(want)
         np.testing.assert_allclose(g[ok], want[ok], rtol=1e-9, atol=1e-11, err_msg=op)
 
+    peer.close()
     dist.barrier()
     if rank == 0:
         print("dist_check ok: world=%d" % P)

@@ -65,6 +65,7 @@ def main():
             print(json.dumps(d), flush=True)
 
     cases = args.cases.split(",")
+    peer = D.PeerShuffle(int(n * 1.25) + 1024, max_cols=2, narenas=2) if P > 1 else None
     vals = torch.rand(n, device=dev, dtype=torch.float64, generator=g)
     if "groupby_lo" in cases:
         keys = torch.randint(0, 1000, (n,), device=dev, generator=g)
@@ -74,26 +75,39 @@ def main():
     if "groupby_hi" in cases:
         K = 100_000_000
         keys = torch.randint(0, K, (n,), device=dev, generator=g)
-        ms = timed(lambda: D.groupby_distributed(keys, [vals], ("sum",), True, 1, K, None, "shuffle"))
+        ms = timed(lambda: D.groupby_distributed(keys, [vals], ("sum",), True, 1, K, None, "shuffle", None))
         out_bytes = n * 16 * (P - 1) / P
         emit("groupby_sum K=100M (hash shuffle of key + value, local aggregate)", ms, n * P,
              shuffle_bytes_out_per_gpu=out_bytes, nvlink_frac_upper=(out_bytes / (ms * 1e-3)) / 900e9 if P > 1 else None)
+        if peer is not None:
+            ms = timed(lambda: D.groupby_distributed(keys, [vals], ("sum",), True, 1, K, None, "shuffle", peer))
+            emit("groupby_sum K=100M, peer-memory shuffle (one pack-and-send kernel over NVLink)", ms, n * P,
+                 shuffle_bytes_out_per_gpu=out_bytes, nvlink_frac_upper=(out_bytes / (ms * 1e-3)) / 900e9)
+            ms_nccl = timed(lambda: D.hash_shuffle(keys, [vals]))
+            ms_peer = timed(lambda: D.hash_shuffle(keys, [vals], None, peer))
+            emit("shuffle alone: NCCL all-to-all per column", ms_nccl, n * P, shuffle_bytes_out_per_gpu=out_bytes,
+                 nvlink_frac=(out_bytes / (ms_nccl * 1e-3)) / 900e9)
+            emit("shuffle alone: peer-memory stores", ms_peer, n * P, shuffle_bytes_out_per_gpu=out_bytes,
+                 nvlink_frac=(out_bytes / (ms_peer * 1e-3)) / 900e9)
         del keys
     nb = max(1, n // 10)
     if "join_bcast" in cases or "join_shuffle" in cases:
         build = (torch.randperm(nb * P, device=dev, generator=torch.Generator(device=dev).manual_seed(99))[rank * nb:(rank + 1) * nb]).contiguous()
         probe = torch.randint(0, nb * P, (n,), device=dev, generator=g)
-        for mode in ("broadcast", "shuffle"):
+        for mode in ("broadcast", "shuffle", "shuffle_peer"):
             if ("join_bcast" if mode == "broadcast" else "join_shuffle") not in cases:
+                continue
+            if mode == "shuffle_peer" and peer is None:
                 continue
             res = {}
 
             def run():
                 res.clear()
-                res["o"] = D.join_distributed(probe, build, "inner", None, mode)
+                res["o"] = D.join_distributed(probe, build, "inner", None, "shuffle" if mode == "shuffle_peer" else mode,
+                                              peer if mode == "shuffle_peer" else None)
             ms = timed(run)
             kw = {}
-            if mode == "shuffle" and P > 1:
+            if mode != "broadcast" and P > 1:
                 out_bytes = (n + nb) * 16 * (P - 1) / P
                 kw = {"shuffle_bytes_out_per_gpu": out_bytes, "nvlink_frac_upper": (out_bytes / (ms * 1e-3)) / 900e9}
             emit("join_inner %s (probe %d x build %d rows per GPU)" % (mode, n, nb), ms, n * P, n_out_rank0=int(res["o"][0].shape[0]), **kw)
@@ -104,6 +118,7 @@ def main():
         ms = timed(lambda: D.rolling_distributed(vals, "mean", 100, 100, 1, None, rank * n, out))
         emit("rolling_mean w=100 (row-sharded, win-1 halo rows from the previous rank)", ms, n * P)
     if P > 1:
+        peer.close()
         dist.barrier()
         dist.destroy_process_group()
 

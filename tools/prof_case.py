@@ -48,6 +48,18 @@ elif what == "rolling":
     out = torch.empty_like(x)
     for _ in range(reps):
         rolling_device(x, "mean", 100, 100, 1, out=out)
+elif what in ("rolling_std", "rolling_min", "rolling_mean_nan"):
+    from sdc_b200.rolling import rolling_device
+    x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
+    if what == "rolling_mean_nan":
+        x[::1000] = float("nan")
+    out = torch.empty_like(x)
+    for _ in range(reps):
+        rolling_device(x, {"rolling_std": "std", "rolling_min": "min", "rolling_mean_nan": "mean"}[what], 100, 100, 1, out=out)
+elif what == "strings":
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_ops
+    bench_ops.bench_strings(1, 50_000_000)
 elif what == "sort":
     from sdc_b200.sort import argsort_device
     x = torch.from_numpy(rng.integers(-2**63, 2**63 - 1, 100_000_000, dtype=np.int64)).cuda()
