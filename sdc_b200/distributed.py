@@ -339,9 +339,39 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
         if a not in _PARTIALS:
             raise ValueError("groupby_distributed: %r needs mode='shuffle'" % (a,))
     need = sorted({p for a in aggs for p in _PARTIALS[a]})
-    lk, lres = groupby_device(keys, cols, need, False, ddof, expected_groups)
-    gk, _ = allgather_ragged(lk, group)
-    part = {p: [allgather_ragged(t, group)[0] for t in lres[p]] for p in need}
+    # sort=False needs every partial table in local first-appearance order (the combine then sees the groups in
+    # global first-appearance order, rank-major); sort=True does not care, and the sorted local path is cheaper
+    lk, lres = groupby_device(keys, cols, need, bool(sort), ddof, expected_groups)
+    gk = part = None
+    cap = int(expected_groups)
+    if 0 < cap <= (1 << 16) and lk.is_cuda:
+        # ONE collective: every rank's partial table (keys + every partial of every column, padded to the hint, its
+        # group count in the extra last column) travels in a single int64 matrix
+        nrows = 1 + len(need) * len(cols)
+        ng = lk.shape[0]
+        buf = torch.zeros((nrows, cap + 1), dtype=torch.int64, device=lk.device)
+        buf[0, cap] = ng
+        if ng <= cap:
+            buf[0, :ng] = lk.view(torch.int64)
+            r = 1
+            for p_ in need:
+                for t in lres[p_]:
+                    buf[r, :ng] = t.view(torch.int64)
+                    r += 1
+        allb = torch.empty((P, nrows, cap + 1), dtype=torch.int64, device=lk.device)
+        _dist().all_gather_into_tensor(allb, buf, group=group)
+        ngs = allb[:, 0, cap].tolist()                                   # the one host read of this path
+        if all(0 <= g <= cap for g in ngs):
+            gk = torch.cat([allb[q, 0, :g] for q, g in enumerate(ngs)]).view(lk.dtype)
+            part, r = {}, 1
+            for p_ in need:
+                part[p_] = []
+                for t in lres[p_]:
+                    part[p_].append(torch.cat([allb[q, r, :g] for q, g in enumerate(ngs)]).view(t.dtype))
+                    r += 1
+    if gk is None:            # no usable hint (or it was too small on some rank -- every rank sees that): ragged gathers
+        gk, _ = allgather_ragged(lk, group)
+        part = {p: [allgather_ragged(t, group)[0] for t in lres[p]] for p in need}
     final = {}
     # sums of sums and of counts, minima of minima, maxima of maxima: one pass of the same kernel each
     summed = [t for p in ("sum", "count") if p in part for t in part[p]]
