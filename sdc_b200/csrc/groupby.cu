@@ -842,7 +842,9 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_count_kernel(const unsigned
 }
 
 // pass 0: sum / count / min / max / first into the group arrays; pass 1: sum of squared deviations (var / std)
-template <bool KEY_F64, typename ROW>
+// VALPAY: the sort carried the (single) value column itself as its payload, so `rows` holds the values in sorted
+// order and nothing is gathered -- a random 8-byte gather costs a whole 128-byte DRAM burst per row.
+template <bool KEY_F64, typename ROW, bool VALPAY>
 __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long long* __restrict__ sk,
                                                             const ROW* __restrict__ rows, int64_t n, Cols cols, Table t,
                                                             int need, int pass, int skip_neg,
@@ -866,7 +868,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
             if ((heads >> e) & 1u) {
                 ++g;
                 t.keys[g] = k[e];
-                if (need & NEED_FIRST) t.first[g] = (unsigned long long)r[e];
+                if (!VALPAY && (need & NEED_FIRST)) t.first[g] = (unsigned long long)r[e];
             }
         }
     }
@@ -875,7 +877,8 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
         const unsigned long long* col = reinterpret_cast<const unsigned long long*>(cols.data[c]);
         unsigned long long bits[kSegItems];
 #pragma unroll
-        for (int e = 0; e < kSegItems; ++e) bits[e] = (valid >> e) & 1u ? __ldg(col + r[e]) : 0ull;   // gathers in flight together
+        for (int e = 0; e < kSegItems; ++e)          // gathers in flight together
+            bits[e] = (valid >> e) & 1u ? (VALPAY ? (unsigned long long)r[e] : __ldg(col + r[e])) : 0ull;
         unsigned long long g = gid;
         // open run: folded in registers, flushed with atomics when the next head (or the thread's end) comes
         double fs = 0.0;
@@ -1091,14 +1094,18 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     unsigned is_f64_mask = 0;
     for (int c = 0; c < cols.ncols; ++c) if (cols.is_f64[c]) is_f64_mask |= 1u << c;
     const bool small_rows = n <= 0xffffffffll;
-    const int pay = small_rows ? 4 : 8;
+    // one value column and no first-row bookkeeping: the values ride through the sort as the payload
+    const bool valpay = cols.ncols == 1 && !(need & NEED_FIRST);
+    const int pay = valpay ? 8 : (small_rows ? 4 : 8);
     Scratch ka, kb, pa, pb, tcnt;
     SDC_TRY(ka.alloc((size_t)n * 8, s));
     SDC_TRY(kb.alloc((size_t)n * 8, s));
     SDC_TRY(pa.alloc((size_t)n * pay, s));
     SDC_TRY(pb.alloc((size_t)n * pay, s));
     const void *rk, *rp;
-    SDC_TRY(radix_sort_core(key_dtype, keys, ka.p, kb.p, pay, nullptr, pa.p, pb.p, n, true, false, &rk, &rp, s));
+    SDC_TRY(radix_sort_core(key_dtype, keys, ka.p, kb.p, pay, valpay ? cols.data[0] : nullptr, pa.p, pb.p, n, !valpay, false,
+                            &rk, &rp, s));
+    if (valpay && rp == nullptr) rp = cols.data[0];          // no pass ran (every digit constant): the column as it is
     const unsigned long long* sk = reinterpret_cast<const unsigned long long*>(rk);
     const int64_t nt = ceil_div(n, kSegTile);
     SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8, s));
@@ -1154,11 +1161,14 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
         SDC_CHECK_LAUNCH();
     }
     for (int pass = 0; pass < (need_ssd ? 2 : 1); ++pass) {
-        if (small_rows)
-            gb_seg_kernel<KEY_F64, uint32_t><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, reinterpret_cast<const uint32_t*>(rp), n, cols, t,
-                                                                                need, pass, skip_neg, tcnt.as<unsigned long long>());
+        if (valpay)
+            gb_seg_kernel<KEY_F64, unsigned long long, true><<<(unsigned)nt, kGbThreads, 0, s>>>(
+                sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, skip_neg, tcnt.as<unsigned long long>());
+        else if (small_rows)
+            gb_seg_kernel<KEY_F64, uint32_t, false><<<(unsigned)nt, kGbThreads, 0, s>>>(sk, reinterpret_cast<const uint32_t*>(rp), n, cols, t,
+                                                                                       need, pass, skip_neg, tcnt.as<unsigned long long>());
         else
-            gb_seg_kernel<KEY_F64, unsigned long long><<<(unsigned)nt, kGbThreads, 0, s>>>(
+            gb_seg_kernel<KEY_F64, unsigned long long, false><<<(unsigned)nt, kGbThreads, 0, s>>>(
                 sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, skip_neg, tcnt.as<unsigned long long>());
         SDC_CHECK_LAUNCH();
     }

@@ -125,8 +125,9 @@ __device__ __forceinline__ unsigned long long lb_pack(unsigned long long v, unsi
     return (v << 10) | ((unsigned long long)epoch << 2) | flag;
 }
 
+// 16-byte rows stage 80 KB per tile: two CTAs per SM fit, so the register budget is that of two
 template <typename U, typename P, bool HAS_PAY, int KIND, bool DESC, int ITEMS>
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, (HAS_PAY && sizeof(U) + sizeof(P) > 12) ? 2 : 3)
 onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __restrict__ pin, P* __restrict__ pout,
                 int64_t n, int shift, int iota,
                 const unsigned long long* __restrict__ gbase, unsigned long long* lookback, unsigned epoch) {
