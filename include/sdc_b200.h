@@ -218,20 +218,16 @@ int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, int64_t n, d
  * destination ranks' receive arenas (CUDA IPC + NVLink P2P stores).
  *   ipc_alloc / ipc_free      arena memory (cudaMalloc: exportable, unlike the stream-ordered pool)
  *   ipc_get_handle / ipc_open 64-byte CUDA IPC handle of an arena / a peer's arena mapped into this process
- *   shuffle_scatter           rows perm[seg_start[d] .. seg_start[d+1]) of every column go to rank d's arena,
- *                             column c at peer_bases[d] + (c * arena_rows + dst_off[d] + k) * 8.  seg_start,
- *                             dst_off, peer_bases are HOST arrays; cols / perm device pointers; 8-byte rows.
- * The caller orders the kernel between two collectives on the same stream (counts exchange before, barrier
- * after); see sdc_b200/distributed.py: PeerShuffle.                                                         */
+ * Column c of the rows this rank sends to rank d lands at peer_bases[d] + (c * arena_rows + dst_off[d] + k) * 8;
+ * dst_off and peer_bases are HOST arrays, cols device pointers, rows 8 bytes.  The caller orders the send kernel
+ * between two collectives on the same stream (counts exchange before, barrier after); see
+ * sdc_b200/distributed.py: PeerShuffle.                                                                      */
 int32_t sdcb200_ipc_alloc(void** p, int64_t bytes);
 int32_t sdcb200_ipc_free(void* p);
 int32_t sdcb200_ipc_get_handle(void* p, void* handle64);
 int32_t sdcb200_ipc_open(const void* handle64, void** p);
 int32_t sdcb200_ipc_close(void* p);
-int32_t sdcb200_shuffle_scatter(int32_t ncols, const void* const* cols, const int64_t* perm, int64_t n, int32_t nparts,
-                                const int64_t* seg_start, const int64_t* dst_off, void* const* peer_bases,
-                                int64_t arena_rows, void* stream);
-/* fused form (no row permutation is ever materialised): shuffle_plan hashes the keys once and leaves the per-tile
+/* shuffle_plan hashes the keys once and leaves the per-tile
  * (4096 rows) exclusive offsets per destination in tile_off[ceil(n / 4096) * 8] (device, uint32) and the totals in
  * counts_out[nparts] (device); after the totals of every rank are known, shuffle_send re-hashes, ranks the rows of
  * each destination inside the tile in row order, stages them in shared memory and stores each destination's run

@@ -104,34 +104,11 @@ extern "C" int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, i
 }
 
 // ------------------------------------------------------------------ peer-memory shuffle (NVLink P2P stores)
-// One node, one process per GPU: every rank owns a receive arena (cudaMalloc, exported with a CUDA IPC handle and
-// opened by its peers).  After the per-destination counts are known on every rank (one small all-gather), ONE
-// kernel packs and sends: thread i takes row perm[i], finds its destination d (perm is grouped by destination)
-// and stores every column's value straight into rank d's arena at the slot reserved for this source rank --
-// NVLink carries 8-byte stores coalesced per destination run; there is no packed send buffer and no per-column
-// all-to-all.  A barrier on the stream after the kernel makes the arenas readable.
+// One node, one process per GPU: every rank owns receive arenas (cudaMalloc, exported with CUDA IPC handles and
+// opened by its peers).  Rows are stored straight into the destination ranks' arenas by the fused
+// partition-and-send kernel below; there is no packed send buffer and no per-column all-to-all.
 namespace sdcb200 { namespace {
 constexpr int kPeerMax = 8;
-struct ScatterArgs {
-    const unsigned long long* cols[kMaxCols];   // local source columns (8-byte rows)
-    unsigned long long* peer[kPeerMax];          // arena base of every destination rank (peer[me] is local)
-    long long seg_start[kPeerMax + 1];           // perm[seg_start[d] .. seg_start[d+1]) go to rank d
-    long long dst_off[kPeerMax];                 // first row of this source's block in rank d's arena
-    long long cap;                               // arena rows per column: column c starts at base + c * cap
-    int ncols, nparts;
-};
-
-__global__ void __launch_bounds__(256) shuffle_scatter_kernel(ScatterArgs a, const long long* __restrict__ perm, long long n) {
-    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (long long)gridDim.x * 256ll) {
-        int d = 0;
-#pragma unroll
-        for (int q = 1; q < kPeerMax; ++q) d += (q < a.nparts && i >= a.seg_start[q]) ? 1 : 0;
-        const long long row = perm[i];
-        const long long pos = a.dst_off[d] + (i - a.seg_start[d]);
-        unsigned long long* base = a.peer[d];
-        for (int c = 0; c < a.ncols; ++c) base[(long long)c * a.cap + pos] = a.cols[c][row];
-    }
-}
 }}
 
 extern "C" int32_t sdcb200_ipc_alloc(void** p, int64_t bytes) {
@@ -163,37 +140,8 @@ extern "C" int32_t sdcb200_ipc_close(void* p) {
     return SDCB200_OK;
 }
 
-extern "C" int32_t sdcb200_shuffle_scatter(int32_t ncols, const void* const* cols, const int64_t* perm, int64_t n, int32_t nparts,
-                                           const int64_t* seg_start, const int64_t* dst_off, void* const* peer_bases,
-                                           int64_t arena_rows, void* stream) {
-    SDC_ARG_CHECK(ncols >= 1 && ncols <= kMaxCols, "ncols");
-    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax, "nparts (<= 8 GPUs of one node)");
-    SDC_ARG_CHECK(n >= 0 && seg_start && dst_off && peer_bases && cols, "null pointer");
-    if (n == 0) return SDCB200_OK;
-    SDC_ARG_CHECK(perm != nullptr, "null perm");
-    ScatterArgs a;
-    memset(&a, 0, sizeof(a));
-    for (int c = 0; c < ncols; ++c) a.cols[c] = reinterpret_cast<const unsigned long long*>(cols[c]);
-    for (int d = 0; d < nparts; ++d) {
-        a.peer[d] = reinterpret_cast<unsigned long long*>(peer_bases[d]);
-        a.seg_start[d] = seg_start[d];
-        a.dst_off[d] = dst_off[d];
-        SDC_ARG_CHECK(dst_off[d] >= 0 && dst_off[d] + (seg_start[d + 1] - seg_start[d]) <= arena_rows, "arena too small");
-    }
-    a.seg_start[nparts] = seg_start[nparts];
-    a.cap = arena_rows;
-    a.ncols = ncols;
-    a.nparts = nparts;
-    int64_t grid = ceil_div(n, 256 * 4);
-    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
-    shuffle_scatter_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(a, reinterpret_cast<const long long*>(perm), n);
-    SDC_CHECK_LAUNCH();
-    return SDCB200_OK;
-}
-
 // ------------------------------------------------------------------ fused partition + send
-// The perm-based scatter above still materialises the row permutation (a radix pass + a widen pass).  The fused
-// form never does: tiles of 4096 rows, two kernels.
+// No row permutation is ever materialised: tiles of 4096 rows, two kernels.
 //   shuffle_count_kernel   destination of every row (same hash as sdcb200_hash_partition), per-tile counts per
 //                          destination (ballots), total counts
 //   shuffle_tile_scan      exclusive scan of the tile counts per destination -> tile_off[tile][d]

@@ -70,8 +70,6 @@ SIGNATURES = {
     "sdcb200_ipc_close": (_i32, [_vp]),
     "sdcb200_shuffle_plan": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "sdcb200_shuffle_send": (_i32, [_i32, _i32, ct.POINTER(_vp), _i64, _i32, _vp, ct.POINTER(_i64), ct.POINTER(_vp), _i64, _vp]),
-    "sdcb200_shuffle_scatter": (_i32, [_i32, ct.POINTER(_vp), _vp, _i64, _i32, ct.POINTER(_i64), ct.POINTER(_i64),
-                                       ct.POINTER(_vp), _i64, _vp]),
 }
 
 # the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)
