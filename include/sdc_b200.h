@@ -116,7 +116,7 @@ int32_t sdcb200_host_sort(int32_t dtype, void* keys, int64_t n);
 int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t ascending, int64_t* index_out);
 
 /* ------------------------------------------------------------------ groupby
- * df.groupby(key).{sum,mean,min,max,count,var,std}() / Series.groupby(arr).<agg>():
+ * df.groupby(key).{sum,mean,min,max,count,var,std,prod,median}() / Series.groupby(arr).<agg>():
  * replaces sdc_pandas_dataframe_groupby (sdc/datatypes/hpat_pandas_dataframe_functions.py:2993-3106),
  * merge_groupby_dicts_inplace and the per-group take + reduce loop
  * (sdc/datatypes/hpat_pandas_groupby_functions.py:58-73, 194-283) with one hash aggregate.
@@ -126,7 +126,7 @@ int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t
  *   sort             1: result ordered by key (stable argsort, groupby_functions.py:209-210);
  *                    0: first-appearance order (the merged dict's order, :58-73)
  *   expected_groups  hint (<= 0: unknown) used to size the hash table / pick the shared-memory path
- * Result values are float64 except: count -> int64; sum/min/max of an int64 column -> int64.
+ * Result values are float64 except: count -> int64; sum/min/max/prod of an int64 column -> int64.
  * The result lives in a handle; copy keys / values out (device or host destination) and free it.  */
 #define SDCB200_AGG_SUM   1u
 #define SDCB200_AGG_MEAN  2u
@@ -135,6 +135,8 @@ int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t
 #define SDCB200_AGG_COUNT 16u
 #define SDCB200_AGG_VAR   32u
 #define SDCB200_AGG_STD   64u
+#define SDCB200_AGG_PROD  128u   /* nanprod: NaN skipped, all-NaN group -> 1; int64 columns multiply with wrap-around */
+#define SDCB200_AGG_MEDIAN 256u  /* nanmedian of the group; always float64 */
 int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
                         const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
                         int64_t expected_groups, void* stream, int64_t* handle_out, int64_t* ngroups_out);

@@ -9,7 +9,8 @@ Restates the reference's index-list groupby:
     group `take` + Series.<agg>() ......... sdc/datatypes/hpat_pandas_groupby_functions.py:194-243
   * reducers (skipna): nansum functions/numpy_like.py:504-532, nanmean :775-792, nanmin/nanmax
     :636-676, nanvar :850-872, Series.var/std hpat_pandas_series_functions.py:1605-1620, :1322-1324,
-    Series.count :3635-3658 (integer columns: len)
+    Series.count :3635-3658 (integer columns: len), nanprod numpy_like.py:683-705 (all-NaN -> 1, integer
+    columns accumulate in intp), Series.median -> numpy.nanmedian hpat_pandas_series_functions.py:3721-3730
 Pinned by tests/test_oracle_groupby.py against the literal outputs of
 examples/dataframe/groupby/*.py, examples/series/series_groupby.py and pandas on the inputs of
 sdc/tests/test_groupby.py.
@@ -21,7 +22,7 @@ from numba.typed import Dict, List
 
 from .prange_utils import chunk_bounds
 
-AGGS = ("sum", "mean", "min", "max", "count", "var", "std")
+AGGS = ("sum", "mean", "min", "max", "count", "var", "std", "prod", "median")
 
 
 _ROWS_T = types.ListType(types.int64)
@@ -101,12 +102,34 @@ def group_rows(keys, nchunks=None):
 
 @numba.njit(cache=True)
 def _reduce_f64(vals, offs, rows, order, op, ddof):
-    """op: 0 sum 1 mean 2 min 3 max 4 count 5 var 6 std -- per group in `order`, NaN skipped."""
+    """op: 0 sum 1 mean 2 min 3 max 4 count 5 var 6 std 7 prod 8 median -- per group in `order`, NaN skipped."""
     ng = len(order)
     out = np.empty(ng, dtype=np.float64)
     for jj in range(ng):
         g = order[jj]
         lo, hi = offs[g], offs[g + 1]
+        if op == 7:
+            pr = 1.0
+            for p in range(lo, hi):
+                v = vals[rows[p]]
+                if not np.isnan(v):
+                    pr *= v
+            out[jj] = pr
+            continue
+        if op == 8:
+            tmp = np.empty(hi - lo, dtype=np.float64)
+            m = 0
+            for p in range(lo, hi):
+                v = vals[rows[p]]
+                if not np.isnan(v):
+                    tmp[m] = v
+                    m += 1
+            if m == 0:
+                out[jj] = np.nan
+            else:
+                srt = np.sort(tmp[:m])
+                out[jj] = (srt[(m - 1) // 2] + srt[m // 2]) / 2.0
+            continue
         s = 0.0
         cnt = 0
         mn = np.inf
@@ -145,12 +168,18 @@ def _reduce_f64(vals, offs, rows, order, op, ddof):
 
 @numba.njit(cache=True)
 def _reduce_i64(vals, offs, rows, order, op):
-    """integer column: 0 sum 2 min 3 max 4 count (exact int64)."""
+    """integer column: 0 sum 2 min 3 max 4 count 7 prod (exact int64, wrap-around)."""
     ng = len(order)
     out = np.empty(ng, dtype=np.int64)
     for jj in range(ng):
         g = order[jj]
         lo, hi = offs[g], offs[g + 1]
+        if op == 7:
+            pr = np.int64(1)
+            for p in range(lo, hi):
+                pr = pr * vals[rows[p]]
+            out[jj] = pr
+            continue
         s = 0
         mn = vals[rows[lo]]
         mx = mn
@@ -184,7 +213,7 @@ def groupby_agg(keys, columns, agg, sort=True, ddof=1, nchunks=None):
     """-> (result_keys, {name: result array}).  `columns` maps name -> 1-D numeric ndarray.
 
     Result dtypes follow pandas (SURVEY 8a G7): float columns -> float64 (count -> int64);
-    integer columns: sum / min / max / count -> int64, mean / var / std -> float64.
+    integer columns: sum / min / max / count / prod -> int64, mean / var / std / median -> float64.
     """
     assert agg in AGGS
     gkeys, offs, rows = group_rows(keys, nchunks)
@@ -193,7 +222,7 @@ def groupby_agg(keys, columns, agg, sort=True, ddof=1, nchunks=None):
     out = {}
     for name, col in columns.items():
         col = np.ascontiguousarray(col)
-        if col.dtype.kind in "iub" and agg in ("sum", "min", "max", "count"):
+        if col.dtype.kind in "iub" and agg in ("sum", "min", "max", "count", "prod"):
             out[name] = _reduce_i64(col.astype(np.int64), offs, rows, order, opc)
         else:
             r = _reduce_f64(col.astype(np.float64), offs, rows, order, opc, ddof)

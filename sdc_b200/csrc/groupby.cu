@@ -41,8 +41,9 @@ __host__ __device__ constexpr unsigned long long kEmptyKey() { return 0x7ff8dead
 constexpr int kMaxCols = 32;
 constexpr int kGbThreads = 256;
 
-enum : unsigned { AGG_SUM = 1, AGG_MEAN = 2, AGG_MIN = 4, AGG_MAX = 8, AGG_COUNT = 16, AGG_VAR = 32, AGG_STD = 64 };
-enum { NEED_SUM = 1, NEED_CNT = 2, NEED_MIN = 4, NEED_MAX = 8, NEED_FIRST = 16 };
+enum : unsigned { AGG_SUM = 1, AGG_MEAN = 2, AGG_MIN = 4, AGG_MAX = 8, AGG_COUNT = 16, AGG_VAR = 32, AGG_STD = 64,
+                  AGG_PROD = 128, AGG_MEDIAN = 256, AGG_LAST = AGG_MEDIAN };
+enum { NEED_SUM = 1, NEED_CNT = 2, NEED_MIN = 4, NEED_MAX = 8, NEED_FIRST = 16, NEED_PROD = 32 };
 
 __host__ __device__ inline unsigned long long mix64(unsigned long long x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
@@ -76,6 +77,9 @@ struct Table {
     unsigned long long* mn[kMaxCols];   // ordered u64
     unsigned long long* mx[kMaxCols];
     double* ssd[kMaxCols];          // second pass: sum of squared deviations (replica 0 only)
+    void* prod[kMaxCols];           // sort-and-segment path only: product of the non-NaN values (double or long long)
+    double* med[kMaxCols];          // sort-and-segment path only: median of the non-NaN values
+    unsigned long long* start;      // sort-and-segment path only: first sorted position of the group
     unsigned long long cap;         // power of two
     unsigned long long limit;       // max occupied slots before "overflow"
     unsigned long long* occupied;   // device counter
@@ -337,6 +341,10 @@ __device__ __forceinline__ unsigned long long agg_value(const Table& t, bool f, 
         }
         case AGG_COUNT:
             return cn;
+        case AGG_PROD:
+            return reinterpret_cast<const unsigned long long*>(t.prod[c])[slot];
+        case AGG_MEDIAN:
+            return (unsigned long long)__double_as_longlong(t.med[c][slot]);
         case AGG_VAR:
         case AGG_STD: {
             if ((long long)cn <= ddof) return nanb;
@@ -354,7 +362,7 @@ __device__ __forceinline__ void write_group(const Table& t, int ncols, unsigned 
                                             unsigned long long* out_keys, unsigned long long* out_vals) {
     out_keys[j] = slot == t.cap ? kEmptyKey() : t.keys[slot];
     int rank = 0;
-    for (unsigned bit = 1; bit <= AGG_STD; bit <<= 1) {
+    for (unsigned bit = 1; bit <= AGG_LAST; bit <<= 1) {
         if (!(agg_mask & bit)) continue;
         for (int c = 0; c < ncols; ++c)
             out_vals[((int64_t)rank * ncols + c) * ngcap + j] = agg_value(t, (is_f64_mask >> c) & 1u, c, bit, ddof, slot);
@@ -868,6 +876,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
             if ((heads >> e) & 1u) {
                 ++g;
                 t.keys[g] = k[e];
+                if (t.start) t.start[g] = (unsigned long long)(i0 + e);
                 if (!VALPAY && (need & NEED_FIRST)) t.first[g] = (unsigned long long)r[e];
             }
         }
@@ -881,14 +890,25 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
             bits[e] = (valid >> e) & 1u ? (VALPAY ? (unsigned long long)r[e] : __ldg(col + r[e])) : 0ull;
         unsigned long long g = gid;
         // open run: folded in registers, flushed with atomics when the next head (or the thread's end) comes
-        double fs = 0.0;
-        long long is = 0;
+        double fs = 0.0, fp = 1.0;
+        long long is = 0, ip = 1;
         unsigned long long cn = 0, mn = ~0ull, mx = 0ull;
         bool open = false;
         auto flush = [&]() {
             if (!open) return;
             if (pass == 1) { if (cn) atomicAdd(&t.ssd[c][g], fs); }
             else {
+                if ((need & NEED_PROD) && cn) {
+                    // no native atomic multiply: CAS loop (runs rarely meet: only at thread / tile borders)
+                    unsigned long long* p = reinterpret_cast<unsigned long long*>(t.prod[c]) + g;
+                    unsigned long long old = *p, assumed;
+                    do {
+                        assumed = old;
+                        const unsigned long long nv = f ? (unsigned long long)__double_as_longlong(__longlong_as_double((long long)assumed) * fp)
+                                                        : (unsigned long long)((long long)assumed * ip);
+                        old = atomicCAS(p, assumed, nv);
+                    } while (old != assumed);
+                }
                 if (need & NEED_SUM) {
                     if (f) { if (cn) atomicAdd(reinterpret_cast<double*>(t.sum[c]) + g, fs); }
                     else atomicAdd(reinterpret_cast<unsigned long long*>(t.sum[c]) + g, (unsigned long long)is);
@@ -897,7 +917,7 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
                 if ((need & NEED_MIN) && cn) atomicMin(&t.mn[c][g], mn);
                 if ((need & NEED_MAX) && cn) atomicMax(&t.mx[c][g], mx);
             }
-            fs = 0.0; is = 0; cn = 0; mn = ~0ull; mx = 0ull;
+            fs = 0.0; is = 0; cn = 0; mn = ~0ull; mx = 0ull; fp = 1.0; ip = 1;
         };
 #pragma unroll
         for (int e = 0; e < kSegItems; ++e) {
@@ -922,12 +942,14 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
                 const double v = __longlong_as_double((long long)bits[e]);
                 if (v != v) continue;                                    // skipna
                 fs += v;
+                fp *= v;
                 ++cn;
                 const unsigned long long o = f64_to_ordered(v);
                 mn = o < mn ? o : mn;
                 mx = o > mx ? o : mx;
             } else {
                 is += (long long)bits[e];
+                ip = (long long)((unsigned long long)ip * bits[e]);      // wraps like numpy's int64 product
                 ++cn;
                 const unsigned long long o = i64_to_ordered((long long)bits[e]);
                 mn = o < mn ? o : mn;
@@ -975,6 +997,32 @@ __global__ void gb_finalize_kernel(Table t, int ncols, unsigned is_f64_mask, uns
         write_group(t, ncols, is_f64_mask, agg_mask, ddof, slots[order[j]], j, ng, out_keys, out_vals);
 }
 
+// ---- median (sort-and-segment path): rows ordered by (key, value), NaN values last inside every group ----
+__global__ void gb_gather_u32_kernel(const unsigned long long* __restrict__ src, const uint32_t* __restrict__ idx,
+                                     unsigned long long* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[idx[i]];
+}
+
+// numpy.nanmedian per group (Series.median, sdc/datatypes/hpat_pandas_series_functions.py:3721-3730): the mean of the
+// two middle non-NaN values (the same value twice for an odd count); NaN for a group without one
+__global__ void gb_median_kernel(Table t, int c, int is_f64, const unsigned long long* __restrict__ col,
+                                 const uint32_t* __restrict__ rows_kv, int64_t ng) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long m = t.cnt[c][g];
+        double r = nan;
+        if (m) {
+            const unsigned long long s0 = t.start[g];
+            const unsigned long long a = col[rows_kv[s0 + (m - 1) / 2]], b = col[rows_kv[s0 + m / 2]];
+            const double x = is_f64 ? __longlong_as_double((long long)a) : (double)(long long)a;
+            const double y = is_f64 ? __longlong_as_double((long long)b) : (double)(long long)b;
+            r = (x + y) / 2.0;
+        }
+        t.med[c][g] = r;
+    }
+}
+
 // segment path: the group arrays are already dense (group j at index j, in key order); `order` (sort=False)
 // permutes them into first-appearance order
 __global__ void gb_finalize_seg_kernel(Table t, int ncols, unsigned is_f64_mask, unsigned agg_mask, long long ddof,
@@ -1009,7 +1057,8 @@ void free_result(GroupbyResult* r) {
 int need_for(unsigned agg_mask, bool sort) {
     int need = 0;
     if (agg_mask & (AGG_SUM | AGG_MEAN | AGG_VAR | AGG_STD)) need |= NEED_SUM;
-    if (agg_mask & (AGG_MEAN | AGG_MIN | AGG_MAX | AGG_COUNT | AGG_VAR | AGG_STD)) need |= NEED_CNT;
+    if (agg_mask & (AGG_MEAN | AGG_MIN | AGG_MAX | AGG_COUNT | AGG_VAR | AGG_STD | AGG_MEDIAN)) need |= NEED_CNT;
+    if (agg_mask & AGG_PROD) need |= NEED_PROD;
     if (agg_mask & AGG_MIN) need |= NEED_MIN;
     if (agg_mask & AGG_MAX) need |= NEED_MAX;
     if (!sort) need |= NEED_FIRST;
@@ -1089,6 +1138,8 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     const int skip_neg = key_mode == KEYS_GID ? 1 : 0;
     const int need = need_for(agg_mask, sort);
     const bool need_ssd = (agg_mask & (AGG_VAR | AGG_STD)) != 0;
+    const bool need_med = (agg_mask & AGG_MEDIAN) != 0;
+    if (need_med && n > 0xffffffffll) { set_error("groupby: median needs fewer than 2^32 rows"); return SDCB200_ERR_ARG; }
     const int sms = sm_count();
     const int nagg = __builtin_popcount(agg_mask);
     unsigned is_f64_mask = 0;
@@ -1129,9 +1180,9 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     InitPlan ip;
     ip.count = 0;
     {
-        int narr = 1 + ((need & NEED_FIRST) ? 1 : 0);
+        int narr = 1 + ((need & NEED_FIRST) ? 1 : 0) + (need_med ? 1 : 0);
         narr += cols.ncols * (((need & NEED_SUM) ? 1 : 0) + ((need & NEED_CNT) ? 1 : 0) + ((need & NEED_MIN) ? 1 : 0) +
-                              ((need & NEED_MAX) ? 1 : 0) + (need_ssd ? 1 : 0));
+                              ((need & NEED_MAX) ? 1 : 0) + (need_ssd ? 1 : 0) + ((need & NEED_PROD) ? 1 : 0) + (need_med ? 1 : 0));
         SDC_TRY(mem.reserve((size_t)narr * (((size_t)ng * 8 + 255) & ~size_t(255)) + 256, s));
     }
     void* p;
@@ -1147,12 +1198,15 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     };
     SDC_TRY(add(reinterpret_cast<void**>(&t.keys), 0ull, false));                 // every entry is written by its head
     if (need & NEED_FIRST) SDC_TRY(add(reinterpret_cast<void**>(&t.first), 0ull, false));
+    if (need_med) SDC_TRY(add(reinterpret_cast<void**>(&t.start), 0ull, false));
     for (int c = 0; c < cols.ncols; ++c) {
         if (need & NEED_SUM) SDC_TRY(add(&t.sum[c], 0ull, true));
         if (need & NEED_CNT) SDC_TRY(add(reinterpret_cast<void**>(&t.cnt[c]), 0ull, true));
         if (need & NEED_MIN) SDC_TRY(add(reinterpret_cast<void**>(&t.mn[c]), ~0ull, true));
         if (need & NEED_MAX) SDC_TRY(add(reinterpret_cast<void**>(&t.mx[c]), 0ull, true));
         if (need_ssd) SDC_TRY(add(reinterpret_cast<void**>(&t.ssd[c]), 0ull, true));
+        if (need & NEED_PROD) SDC_TRY(add(&t.prod[c], cols.is_f64[c] ? 0x3ff0000000000000ull : 1ull, true));   // 1.0 / 1
+        if (need_med) SDC_TRY(add(reinterpret_cast<void**>(&t.med[c]), 0ull, false));
     }
     if (ip.count) {
         unsigned gx = (unsigned)(ceil_div(ng, 1024) < (int64_t)sms * 4 ? ceil_div(ng, 1024) : (int64_t)sms * 4);
@@ -1171,6 +1225,35 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
             gb_seg_kernel<KEY_F64, unsigned long long, false><<<(unsigned)nt, kGbThreads, 0, s>>>(
                 sk, reinterpret_cast<const unsigned long long*>(rp), n, cols, t, need, pass, skip_neg, tcnt.as<unsigned long long>());
         SDC_CHECK_LAUNCH();
+    }
+    if (need_med) {
+        // rows ordered by (key, value): stable sort by value, then stable sort of the permuted keys carrying the rows.
+        // The key order is the same as in the main sort, so its group starts and counts apply unchanged.
+        Scratch va, vb, r1a, r1b, kp, k2a, k2b, r2a, r2b;
+        SDC_TRY(va.alloc((size_t)n * 8, s));
+        SDC_TRY(vb.alloc((size_t)n * 8, s));
+        SDC_TRY(r1a.alloc((size_t)n * 4, s));
+        SDC_TRY(r1b.alloc((size_t)n * 4, s));
+        SDC_TRY(kp.alloc((size_t)n * 8, s));
+        SDC_TRY(k2a.alloc((size_t)n * 8, s));
+        SDC_TRY(k2b.alloc((size_t)n * 8, s));
+        SDC_TRY(r2a.alloc((size_t)n * 4, s));
+        SDC_TRY(r2b.alloc((size_t)n * 4, s));
+        const int ggrid = (int)(ceil_div(n, 256) < (int64_t)sms * 8 ? ceil_div(n, 256) : (int64_t)sms * 8);
+        const int mgrid = (int)(ceil_div(ng, 256) < (int64_t)sms * 8 ? ceil_div(ng, 256) : (int64_t)sms * 8);
+        for (int c = 0; c < cols.ncols; ++c) {
+            const void *vk, *vr, *k2, *r2;
+            SDC_TRY(radix_sort_core(cols.is_f64[c] ? SDCB200_F64 : SDCB200_I64, cols.data[c], va.p, vb.p, 4, nullptr, r1a.p, r1b.p, n,
+                                    true, false, &vk, &vr, s));
+            gb_gather_u32_kernel<<<ggrid, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(keys),
+                                                       reinterpret_cast<const uint32_t*>(vr), kp.as<unsigned long long>(), n);
+            SDC_CHECK_LAUNCH();
+            SDC_TRY(radix_sort_core(key_dtype, kp.p, k2a.p, k2b.p, 4, vr, r2a.p, r2b.p, n, false, false, &k2, &r2, s));
+            gb_median_kernel<<<mgrid, 256, 0, s>>>(t, c, cols.is_f64[c], reinterpret_cast<const unsigned long long*>(cols.data[c]),
+                                                   reinterpret_cast<const uint32_t*>(r2), ng);
+            SDC_CHECK_LAUNCH();
+        }
+        SDC_CUDA_TRY(cudaStreamSynchronize(s));       // the scratch above goes out of scope
     }
     Scratch order;
     if (!sort) {
@@ -1203,6 +1286,8 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     // overflow) the sort-and-segment path, whose cost does not depend on the number of groups
     const unsigned long long worst = pow2_at_least(2ull * (unsigned long long)n, 64);
     const bool big = n >= sort_path_rows();
+    if (agg_mask & (AGG_PROD | AGG_MEDIAN))      // only the sort-and-segment path computes these
+        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     if (big && expected_groups > sort_path_groups())
         return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     Attempt plan[3];
@@ -1420,7 +1505,7 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
         key_dtype = SDCB200_I64;
     }
     SDC_ARG_CHECK(n >= 0 && ncols >= 0 && ncols <= kMaxCols, "n / ncols");
-    SDC_ARG_CHECK(agg_mask != 0 && (agg_mask & ~0x7fu) == 0, "agg mask");
+    SDC_ARG_CHECK(agg_mask != 0 && (agg_mask & ~0x1ffu) == 0, "agg mask");
     SDC_ARG_CHECK(handle_out != nullptr && ngroups_out != nullptr, "null out pointer");
     SDC_ARG_CHECK(n == 0 || keys != nullptr, "null keys");
     Cols c;

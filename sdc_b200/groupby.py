@@ -5,7 +5,7 @@ Host-side mirror of the reference's groupby interface:
   * Series.groupby(by)    -- `by` a 1-D array of equal length . sdc/datatypes/hpat_pandas_series_functions.py:4720-4811
   * gb['B'] -> SeriesGroupBy, gb['B','C'] -> column subset, a second [] raises IndexError
                                                                sdc/datatypes/hpat_pandas_groupby_functions.py:144-191
-  * count / max / mean / min / std(ddof) / sum / var(ddof) ... groupby_functions.py:361-480, 483-600
+  * count / max / mean / median / min / prod / std(ddof) / sum / var(ddof) ... groupby_functions.py:361-480, 483-600
 The aggregation runs in libsdc_b200.so (csrc/groupby.cu: one hash-aggregate pass); nothing here
 touches a row.  torch only holds device buffers.
 """
@@ -15,7 +15,7 @@ import numpy as np
 
 from . import native
 
-AGGS = ("sum", "mean", "min", "max", "count", "var", "std")
+AGGS = ("sum", "mean", "min", "max", "count", "var", "std", "prod", "median")
 
 
 def _torch():
@@ -95,7 +95,7 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, gid_r
 
 
 def _out_dtype(torch, agg, col):
-    is_int = agg == "count" or (col.dtype == torch.int64 and agg in ("sum", "min", "max"))
+    is_int = agg == "count" or (col.dtype == torch.int64 and agg in ("sum", "min", "max", "prod"))
     return torch.int64 if is_int else torch.float64
 
 
@@ -172,8 +172,14 @@ class _GroupByBase:
     def mean(self, *args):
         return self._apply("mean")
 
+    def median(self):
+        return self._apply("median")
+
     def min(self):
         return self._apply("min")
+
+    def prod(self):
+        return self._apply("prod")
 
     def sum(self):
         return self._apply("sum")

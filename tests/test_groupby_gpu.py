@@ -226,6 +226,11 @@ def test_dataframe_and_series_api():
     pd.testing.assert_frame_equal(groupby(df, "A", sort=False).sum()[["B", "C", "D"]],
                                   df.groupby("A", sort=False).sum()[["B", "C", "D"]])
     pd.testing.assert_frame_equal(groupby(df, "A").std()[["B", "C", "D"]], df.groupby("A").std()[["B", "C", "D"]])
+    # sdc/tests/test_groupby.py:244-300, 446-498: median / prod (DataFrame and Series forms)
+    pd.testing.assert_frame_equal(groupby(df, "A").median()[["B", "C", "D"]], df.groupby("A").median()[["B", "C", "D"]])
+    pd.testing.assert_frame_equal(groupby(df, "A").prod()[["B", "C", "D"]], df.groupby("A").prod()[["B", "C", "D"]])
+    pd.testing.assert_series_equal(groupby(df, "A")["B"].median(), df.groupby("A")["B"].median())
+    pd.testing.assert_series_equal(groupby(df, "A")["B"].prod(), df.groupby("A")["B"].prod())
     s = pd.Series([390., 350., 30., 20.], name="S")
     pd.testing.assert_series_equal(groupby(s, [0, 1, 0, 1]).mean(), s.groupby(np.array([0, 1, 0, 1])).mean())
     with pytest.raises(IndexError):
