@@ -150,16 +150,21 @@ int32_t sdcb200_groupby_result(int64_t handle, void** keys, void** vals, int64_t
 int32_t sdcb200_groupby_free(int64_t handle);
 
 /* ------------------------------------------------------------------ join
- * pd.merge(left, right, on=key, how='inner' | 'left') on one int64 / float64 key column.  The
+ * pd.merge(left, right, on=key, how='inner' | 'left' | 'right' | 'outer') on one int64 / float64 key column.  The
  * reference snapshot has no merge overload (sdc/hiframes/join.py:34-43 is a stub; every test of
  * sdc/tests/test_join.py:51-394 is skipped): behaviour follows pandas.merge, the artefact follows
  * the reference's live indexer convention (_sdc_internal_join,
  * sdc/datatypes/common_functions.py:225-455): two int64 row-position arrays, -1 = no partner
- * (how='left'), duplicate keys give the cross product.  Pairs come out in left-row order; the order
- * of several right matches of one left row is unspecified.  Float keys: NaN == NaN, -0.0 == +0.0
- * (pandas).  Build (right) side < 2^32 - 1 rows.  The result lives in a handle.                   */
+ * (how='left' / 'right' / 'outer'), duplicate keys give the cross product.  inner / left: pairs come out
+ * in left-row order; right: in right-row order; outer: the left join's pairs, then the unmatched right rows
+ * in right-row order; the order of several matches of one row is unspecified.  Float keys: NaN == NaN,
+ * -0.0 == +0.0 (pandas).  Build side (right; left for how='right') < 2^32 - 1 rows.  The result lives in a
+ * handle.                                                                                           */
 #define SDCB200_JOIN_INNER 0
 #define SDCB200_JOIN_LEFT  1
+#define SDCB200_JOIN_RIGHT 2   /* every right row: a left join with the sides swapped */
+#define SDCB200_JOIN_OUTER 3   /* the left join's pairs, then the unmatched right rows as (-1, row): the row set of
+                                  _sdc_internal_join (sdc/datatypes/common_functions.py:225-455) */
 int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                      void* stream, int64_t* handle_out, int64_t* n_out);
 int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_idx, int32_t dst_is_host, void* stream);

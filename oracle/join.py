@@ -83,9 +83,10 @@ def outer_indexers(left_keys, right_keys, nan_equal=True):
 
 def join_indexers(left_keys, right_keys, how="inner"):
     """-> (lidx, ridx) int64 in canonical order (sorted by left row, then right row)."""
-    assert how in ("inner", "left")
+    assert how in ("inner", "left", "right", "outer")
     lidx, ridx = outer_indexers(left_keys, right_keys, True)
-    keep = (lidx >= 0) & (ridx >= 0) if how == "inner" else (lidx >= 0)
+    keep = {"inner": (lidx >= 0) & (ridx >= 0), "left": lidx >= 0, "right": ridx >= 0,
+            "outer": np.ones(len(lidx), dtype=bool)}[how]
     lidx, ridx = lidx[keep], ridx[keep]
     order = np.lexsort((ridx, lidx))
     return lidx[order], ridx[order]

@@ -508,7 +508,7 @@ int64_t g_next_join = 1;
 
 template <bool KEY_F64, bool LEFT>
 int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long long* r, int64_t nr, cudaStream_t s,
-                 JoinResult* res) {
+                 JoinResult* res, int64_t extra = 0 /* rows of spare capacity behind the pairs (how='outer') */) {
     const int sms = sm_count();
     const int wide = sms * 8;
     // ---- build ----
@@ -594,9 +594,9 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     void* p = nullptr;
     if (unique) {
         // every left row has at most one partner: one kernel, n_out <= nl
-        SDC_TRY(dev_alloc(&p, (size_t)nl * 8, s));
+        SDC_TRY(dev_alloc(&p, (size_t)(nl + extra) * 8, s));
         res->lidx = reinterpret_cast<int64_t*>(p);
-        SDC_TRY(dev_alloc(&p, (size_t)nl * 8, s));
+        SDC_TRY(dev_alloc(&p, (size_t)(nl + extra) * 8, s));
         res->ridx = reinterpret_cast<int64_t*>(p);
         const int vec = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
         if (LEFT) {
@@ -643,13 +643,61 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     SDC_CUDA_TRY(cudaStreamSynchronize(s));
     res->n_out = (int64_t)total;
     if (total == 0) return SDCB200_OK;
-    SDC_TRY(dev_alloc(&p, (size_t)total * 8, s));
+    SDC_TRY(dev_alloc(&p, (size_t)(total + extra) * 8, s));
     res->lidx = reinterpret_cast<int64_t*>(p);
-    SDC_TRY(dev_alloc(&p, (size_t)total * 8, s));
+    SDC_TRY(dev_alloc(&p, (size_t)(total + extra) * 8, s));
     res->ridx = reinterpret_cast<int64_t*>(p);
     probe_emit_kernel<LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(pval.as<unsigned long long>(), nl, tile_counts,
                                                                   rid.as<uint32_t>(), res->lidx, res->ridx);
     SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+// ---- how='outer': the left join's pairs, then every right row nobody matched as (-1, row), in right-row order
+__global__ void mark_matched_kernel(const int64_t* __restrict__ ridx, int64_t n, uint8_t* __restrict__ matched) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = ridx[i];
+        if (r >= 0) matched[r] = 1;            // every writer stores the same value
+    }
+}
+struct UnmatchedLoad {
+    const uint8_t* matched;
+    __device__ unsigned long long operator()(int64_t i) const { return matched[i] ? 0ull : 1ull; }
+};
+struct UnmatchedStore {
+    int64_t* lidx;
+    int64_t* ridx;
+    __device__ void operator()(int64_t i, unsigned long long excl, unsigned long long v) const {
+        if (v) { lidx[excl] = -1; ridx[excl] = i; }
+    }
+};
+
+int32_t append_unmatched_right(JoinResult* res, int64_t nr, cudaStream_t s) {
+    if (nr == 0) return SDCB200_OK;
+    void* p = nullptr;
+    if (!res->lidx) {                          // the left join produced nothing (empty left side): room for the right rows
+        SDC_TRY(dev_alloc(&p, (size_t)nr * 8, s));
+        res->lidx = reinterpret_cast<int64_t*>(p);
+        SDC_TRY(dev_alloc(&p, (size_t)nr * 8, s));
+        res->ridx = reinterpret_cast<int64_t*>(p);
+    }
+    Scratch matched, tsum;
+    SDC_TRY(matched.alloc((size_t)nr, s));
+    SDC_CUDA_TRY(cudaMemsetAsync(matched.p, 0, (size_t)nr, s));
+    const int64_t nt = ceil_div(nr, kTile);
+    SDC_TRY(tsum.alloc((size_t)(nt + 1) * 8, s));
+    if (res->n_out > 0) {
+        const int grid = (int)(ceil_div(res->n_out, 256) < (int64_t)sm_count() * 8 ? ceil_div(res->n_out, 256) : (int64_t)sm_count() * 8);
+        mark_matched_kernel<<<grid, 256, 0, s>>>(res->ridx, res->n_out, matched.as<uint8_t>());
+        SDC_CHECK_LAUNCH();
+    }
+    SDC_TRY(device_exclusive_scan(UnmatchedLoad{matched.as<uint8_t>()},
+                                  UnmatchedStore{res->lidx + res->n_out, res->ridx + res->n_out}, nr,
+                                  tsum.as<unsigned long long>(), s));
+    unsigned long long m = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&m, tsum.as<unsigned long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    res->n_out += (int64_t)m;
     return SDCB200_OK;
 }
 
@@ -670,18 +718,29 @@ extern "C" {
 int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                      void* stream, int64_t* handle_out, int64_t* n_out) {
     cudaStream_t s = (cudaStream_t)stream;
-    SDC_ARG_CHECK(how == SDCB200_JOIN_INNER || how == SDCB200_JOIN_LEFT, "how must be INNER or LEFT");
+    SDC_ARG_CHECK(how >= SDCB200_JOIN_INNER && how <= SDCB200_JOIN_OUTER, "how must be INNER, LEFT, RIGHT or OUTER");
     SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
-    SDC_ARG_CHECK(nl >= 0 && nr >= 0 && nr < 0xffffffffll, "row counts (build side < 2^32 - 1 rows)");
+    SDC_ARG_CHECK(nl >= 0 && nr >= 0, "row counts");
+    SDC_ARG_CHECK((how == SDCB200_JOIN_RIGHT ? nl : nr) < 0xffffffffll, "build side must have fewer than 2^32 - 1 rows");
     SDC_ARG_CHECK((nl == 0 || left_keys) && (nr == 0 || right_keys), "null key column");
     SDC_ARG_CHECK(handle_out && n_out, "null out pointer");
     JoinResult* res = new JoinResult();
     const unsigned long long* l = reinterpret_cast<const unsigned long long*>(left_keys);
     const unsigned long long* r = reinterpret_cast<const unsigned long long*>(right_keys);
     int32_t rc;
-    const bool f = key_dtype == SDCB200_F64, left = how == SDCB200_JOIN_LEFT;
-    if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res) : run_join<true, false>(l, nl, r, nr, s, res);
-    else rc = left ? run_join<false, true>(l, nl, r, nr, s, res) : run_join<false, false>(l, nl, r, nr, s, res);
+    const bool f = key_dtype == SDCB200_F64;
+    if (how == SDCB200_JOIN_RIGHT) {
+        // a left join with the sides swapped: every right row once per partner (or once with -1)
+        rc = f ? run_join<true, true>(r, nr, l, nl, s, res) : run_join<false, true>(r, nr, l, nl, s, res);
+        int64_t* t = res->lidx; res->lidx = res->ridx; res->ridx = t;
+    } else if (how == SDCB200_JOIN_OUTER) {
+        rc = f ? run_join<true, true>(l, nl, r, nr, s, res, nr) : run_join<false, true>(l, nl, r, nr, s, res, nr);
+        if (rc == SDCB200_OK) rc = append_unmatched_right(res, nr, s);
+    } else {
+        const bool left = how == SDCB200_JOIN_LEFT;
+        if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res) : run_join<true, false>(l, nl, r, nr, s, res);
+        else rc = left ? run_join<false, true>(l, nl, r, nr, s, res) : run_join<false, false>(l, nl, r, nr, s, res);
+    }
     if (rc != SDCB200_OK) {
         free_join(res, s);
         return rc;

@@ -28,7 +28,7 @@ def join_device(left_keys, right_keys, how="inner"):
     torch = _torch()
     lib = native.load()
     if how not in native.JOIN_HOW:
-        raise ValueError("merge: how=%r is not supported (inner / left)" % (how,))
+        raise ValueError("merge: how=%r is not supported (inner / left / right / outer)" % (how,))
     assert left_keys.is_cuda and right_keys.is_cuda and left_keys.dim() == 1 and right_keys.dim() == 1
     assert left_keys.is_contiguous() and right_keys.is_contiguous()
     if left_keys.dtype != right_keys.dtype:
@@ -117,11 +117,12 @@ def _gather_column(values, idx_dev, nullable):
 
 
 def merge(left, right, how="inner", on=None, left_on=None, right_on=None):
-    """pandas.merge for one key column, how in {'inner', 'left'} (see module docstring)."""
+    """pandas.merge for one key column, how in {'inner', 'left', 'right', 'outer'} (see module docstring).
+    Row order: the kernel's (left-row order, unmatched right rows last); pandas sorts 'outer' results by key."""
     import pandas as pd
     torch = _torch()
     if how not in native.JOIN_HOW:
-        raise ValueError("merge: how=%r is not supported (inner / left)" % (how,))
+        raise ValueError("merge: how=%r is not supported (inner / left / right / outer)" % (how,))
     if on is not None:
         if left_on is not None or right_on is not None:
             raise ValueError('Can only pass argument "on" OR "left_on" and "right_on", not a combination of both.')
@@ -137,17 +138,27 @@ def merge(left, right, how="inner", on=None, left_on=None, right_on=None):
     if lk.dtype != rk.dtype:
         lk, rk = lk.astype(np.float64), rk.astype(np.float64)
     li, ri = join_device(torch.from_numpy(lk).cuda(), torch.from_numpy(rk).cuda(), how)
-    any_missing = how == "left" and bool((ri < 0).any().item())
+    right_missing = how in ("left", "outer") and bool((ri < 0).any().item())
+    left_missing = how in ("right", "outer") and bool((li < 0).any().item())
     shared_key = left_on == right_on
     data = {}
     for c in left.columns:
         name = c
         if c in right.columns and not (shared_key and c == left_on):
             name = "%s_x" % c
-        data[name] = _gather_column(left[c].to_numpy(), li, False)
+        if shared_key and c == left_on and left_missing:
+            # the key of a row without a left partner comes from the right side (pandas coalesces the key column)
+            lv = _gather_column(left[c].to_numpy(), li, True)
+            rv = _gather_column(right[c].to_numpy(), ri, right_missing)
+            miss = li.cpu().numpy() < 0
+            kv = np.where(miss, rv, lv)
+            both_int = left[c].to_numpy().dtype.kind in "iu" and right[c].to_numpy().dtype.kind in "iu"
+            data[name] = kv.astype(np.int64) if both_int else kv
+            continue
+        data[name] = _gather_column(left[c].to_numpy(), li, left_missing)
     for c in right.columns:
         if shared_key and c == right_on:
             continue
         name = "%s_y" % c if c in left.columns else c
-        data[name] = _gather_column(right[c].to_numpy(), ri, any_missing)
+        data[name] = _gather_column(right[c].to_numpy(), ri, right_missing)
     return pd.DataFrame(data)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsdc_b200.so")
 
 OK = 0
-JOIN_HOW = {"inner": 0, "left": 1}
+JOIN_HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}
 AGG_BITS = {"sum": 1, "mean": 2, "min": 4, "max": 8, "count": 16, "var": 32, "std": 64, "prod": 128, "median": 256}
 ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,

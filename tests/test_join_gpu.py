@@ -13,8 +13,17 @@ def _device_pairs(l, r, how):
     from sdc_b200.join import join_device
     li, ri = join_device(torch.from_numpy(np.ascontiguousarray(l)).cuda(), torch.from_numpy(np.ascontiguousarray(r)).cuda(), how)
     li, ri = li.cpu().numpy(), ri.cpu().numpy()
-    # pairs must come out in left-row order (how='left' keeps the left order like pandas)
-    assert np.all(np.diff(li) >= 0)
+    # inner / left: pairs come out in left-row order (how='left' keeps the left order like pandas); right: in
+    # right-row order; outer: the left join's pairs in left-row order, then the unmatched right rows in row order
+    if how in ("inner", "left"):
+        assert np.all(np.diff(li) >= 0)
+    elif how == "right":
+        assert np.all(np.diff(ri) >= 0)
+    else:
+        tail = int((li < 0).sum())
+        head = len(li) - tail
+        assert np.all(li[:head] >= 0) and np.all(np.diff(li[:head]) >= 0)
+        assert np.all(li[head:] == -1) and np.all(np.diff(ri[head:]) > 0)
     return ojoin.canonical(li, ri)
 
 
@@ -25,7 +34,7 @@ def _check(l, r, how):
     np.testing.assert_array_equal(got[1], want[1])
 
 
-@pytest.mark.parametrize("how", ["inner", "left"])
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
 def test_small_cases(how):
     i64 = np.int64
     sentinel = np.array([0x7ff8dead0000beef], dtype=np.uint64).view(np.int64)[0]
@@ -42,7 +51,7 @@ def test_small_cases(how):
         _check(l, r, how)
 
 
-@pytest.mark.parametrize("how", ["inner", "left"])
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
 @pytest.mark.parametrize("nl,nr,hi", [(1, 1, 2), (2047, 100, 50), (2048, 2049, 4000), (100_000, 10_000, 10_000),
                                       (300_000, 300_000, 50_000), (50_000, 500_000, 2_000_000), (200_000, 1000, 10)])
 def test_random_sizes(nl, nr, hi, how):
@@ -67,7 +76,7 @@ def test_float_keys_random():
     r[rng.integers(0, len(r), 3)] = np.nan
     l[::1000] = -0.0
     r[5] = 0.0
-    for how in ("inner", "left"):
+    for how in ("inner", "left", "right", "outer"):
         _check(l, r, how)
 
 
@@ -76,7 +85,7 @@ def test_merge_frames_like_reference_tests():
     from sdc_b200.join import merge
     df1 = pd.DataFrame({"key1": [2, 3, 5, 1, 2, 8], "A": np.array([4, 6, 3, 9, 9, -1], np.float64)})
     df2 = pd.DataFrame({"key1": [1, 2, 9, 3, 2], "B": np.array([1, 7, 2, 6, 5], np.float64)})
-    for how in ("inner", "left"):
+    for how in ("inner", "left", "right", "outer"):      # right / outer: sdc/tests/test_join.py:262-335
         got = merge(df1, df2, how=how, on="key1")
         want = df1.merge(df2, how=how, on="key1")
         key = ["key1", "A", "B"]
@@ -93,7 +102,7 @@ def test_merge_frames_like_reference_tests():
     pd.testing.assert_frame_equal(got[cols].sort_values(cols).reset_index(drop=True),
                                   want.sort_values(cols).reset_index(drop=True))
     with pytest.raises(ValueError):
-        merge(df1, df2, how="outer", on="key1")
+        merge(df1, df2, how="cross", on="key1")
 
 
 def test_c3_shape_row_count_and_properties():

@@ -10,7 +10,7 @@ def _pandas_pairs(l, r, how):
     L = pd.DataFrame({"k": l, "li": np.arange(len(l), dtype=np.int64)})
     R = pd.DataFrame({"k": r, "ri": np.arange(len(r), dtype=np.int64)})
     m = L.merge(R, on="k", how=how)
-    return ojoin.canonical(m["li"].to_numpy(), m["ri"].fillna(-1).to_numpy().astype(np.int64))
+    return ojoin.canonical(m["li"].fillna(-1).to_numpy().astype(np.int64), m["ri"].fillna(-1).to_numpy().astype(np.int64))
 
 
 CASES = {
@@ -23,7 +23,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("how", ["inner", "left"])
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_small_cases_match_pandas(case, how):
     l, r = CASES[case]
@@ -33,7 +33,7 @@ def test_small_cases_match_pandas(case, how):
     np.testing.assert_array_equal(got[1], want[1])
 
 
-@pytest.mark.parametrize("how", ["inner", "left"])
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
 def test_random_match_pandas(how):
     rng = np.random.default_rng(11)
     for nl, nr, hi in ((5000, 700, 1000), (20000, 20000, 3000), (1000, 5000, 100000)):
