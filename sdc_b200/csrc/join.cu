@@ -314,32 +314,34 @@ __device__ __forceinline__ uint32_t lookup_row1(const JTable& t, const uint32_t*
 //   w0 + j * 64 + 2 L + {0, 1},  j = 0 .. 3   (items e = 2 j, 2 j + 1)
 // so every 128-bit access of a warp covers 512 contiguous bytes (whole sectors, whole lines), both for the
 // key loads and for the (left row, right row) stores of how='left'.
+template <int ITEMS = kItems>
 __device__ __forceinline__ int64_t probe_row(int64_t tile0, int warp, int lane, int e) {
-    return tile0 + warp * 256 + (e >> 1) * 64 + 2 * lane + (e & 1);
+    return tile0 + warp * (32 * ITEMS) + (e >> 1) * 64 + 2 * lane + (e & 1);
 }
 
-template <bool KEY_F64>
+template <bool KEY_F64, int ITEMS = kItems>
 __device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t tile0, int warp, int lane,
-                                                int64_t n, bool vec, uint64_t stream_pol, unsigned long long k[kItems]) {
-    if (vec && tile0 + kTile <= n) {
+                                                int64_t n, bool vec, uint64_t stream_pol, unsigned long long* k) {
+    if (vec && tile0 + kJoinThreads * ITEMS <= n) {
 #pragma unroll
-        for (int e = 0; e < kItems; e += 2) {
-            const ulonglong2 kk = ld_hint_v2u64(keys + probe_row(tile0, warp, lane, e), stream_pol);
+        for (int e = 0; e < ITEMS; e += 2) {
+            const ulonglong2 kk = ld_hint_v2u64(keys + probe_row<ITEMS>(tile0, warp, lane, e), stream_pol);
             k[e] = canon_key<KEY_F64>(kk.x);
             k[e + 1] = canon_key<KEY_F64>(kk.y);
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < kItems; ++e) {
-            const int64_t r = probe_row(tile0, warp, lane, e);
+        for (int e = 0; e < ITEMS; ++e) {
+            const int64_t r = probe_row<ITEMS>(tile0, warp, lane, e);
             k[e] = r < n ? canon_key<KEY_F64>(keys[r]) : 0ull;
         }
     }
 }
 
 // meta[0] ticket, meta[1] n_out.  status[tile] = flag << 62 | value; flag 1: tile aggregate, 2: inclusive prefix
-template <bool KEY_F64>
-__global__ void __launch_bounds__(kJoinThreads, 5) probe_unique_inner_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+// ITEMS rows per thread: 8 (2048-row tiles, 5 CTAs per SM) or 16 (4096-row tiles: half as many look-backs per row)
+template <bool KEY_F64, int ITEMS>
+__global__ void __launch_bounds__(kJoinThreads, ITEMS == 8 ? 5 : 3) probe_unique_inner_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                           JTable t, const uint32_t* __restrict__ rid,
                                                                           unsigned long long* __restrict__ status,
                                                                           unsigned long long* __restrict__ meta, int64_t ntiles,
@@ -348,27 +350,29 @@ __global__ void __launch_bounds__(kJoinThreads, 5) probe_unique_inner_kernel(con
     constexpr int kWarps = kJoinThreads / 32;
     __shared__ unsigned wcnt[kWarps];
     __shared__ unsigned long long s_base;
-    __shared__ int64_t sl[kTile];
-    __shared__ int64_t sr[kTile];
+    constexpr int kPTile = kJoinThreads * ITEMS;
+    extern __shared__ __align__(16) int64_t sdyn[];
+    int64_t* sl = sdyn;                 // [kPTile]
+    int64_t* sr = sdyn + kPTile;        // [kPTile]
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     // tile = blockIdx.x: CTAs are dispatched in blockIdx order, so a tile's predecessors are resident or done
     // (the forward-progress assumption every single-pass chained scan makes); no ticket, no start-up barrier
     const int64_t tile = (int64_t)blockIdx.x;
-    const int64_t tile0 = tile * kTile;
-    unsigned long long k[kItems];
-    uint32_t row1[kItems];
-    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
+    const int64_t tile0 = tile * kPTile;
+    unsigned long long k[ITEMS];
+    uint32_t row1[ITEMS];
+    load_probe_keys<KEY_F64, ITEMS>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
 #pragma unroll
-    for (int e = 0; e < kItems; ++e) {
-        row1[e] = (probe_row(tile0, warp, lane, e) < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
+    for (int e = 0; e < ITEMS; ++e) {
+        row1[e] = (probe_row<ITEMS>(tile0, warp, lane, e) < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
         __syncwarp();                                  // hash probes end at different times per lane
     }
-    // rank of every hit inside the warp's 256 rows, in row order: segment j = 64 rows, lane L holds 2 of them
-    unsigned rank[kItems], wtot = 0;
+    // rank of every hit inside the warp's 32 * ITEMS rows, in row order: segment j = 64 rows, lane L holds 2 of them
+    unsigned rank[ITEMS], wtot = 0;
 #pragma unroll
-    for (int j = 0; j < kItems / 2; ++j) {
+    for (int j = 0; j < ITEMS / 2; ++j) {
         const unsigned ba = __ballot_sync(0xffffffffu, row1[2 * j] != 0u);
         const unsigned bb = __ballot_sync(0xffffffffu, row1[2 * j + 1] != 0u);
         rank[2 * j] = wtot + __popc(ba & lt_mask) + __popc(bb & lt_mask);
@@ -431,10 +435,10 @@ __global__ void __launch_bounds__(kJoinThreads, 5) probe_unique_inner_kernel(con
     }
     // stage the tile's pairs (consecutive hits -> consecutive words: conflict-free), then coalesced streaming stores
 #pragma unroll
-    for (int e = 0; e < kItems; ++e) {
+    for (int e = 0; e < ITEMS; ++e) {
         if (row1[e]) {
             const unsigned p = wbase + rank[e];
-            sl[p] = probe_row(tile0, warp, lane, e);
+            sl[p] = probe_row<ITEMS>(tile0, warp, lane, e);
             sr[p] = (int64_t)row1[e] - 1;
         }
     }
@@ -603,12 +607,24 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
             probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx, vec);
             SDC_CHECK_LAUNCH();
         } else {
+            // 4096-row tiles halve the number of look-backs per row (1.31 -> 1.26 ms on C3); the hashed table's probe
+            // loops run better with the smaller tile (5.8 vs 5.4 ms), so only the dense table takes the big one
+            const int items = t.dense32 ? 16 : 8;
+            const int64_t ptile = (int64_t)kJoinThreads * items;
+            const int64_t pnt = ceil_div(nl, ptile);
             Scratch status;
-            SDC_TRY(status.alloc((size_t)nt * 8, s));
-            SDC_CUDA_TRY(cudaMemsetAsync(status.p, 0, (size_t)nt * 8, s));
-            probe_unique_inner_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(),
-                                                                                    status.as<unsigned long long>(), dmeta, nt,
-                                                                                    res->lidx, res->ridx, vec);
+            SDC_TRY(status.alloc((size_t)pnt * 8, s));
+            SDC_CUDA_TRY(cudaMemsetAsync(status.p, 0, (size_t)pnt * 8, s));
+            const size_t smem = (size_t)ptile * 16;
+            if (items == 8) {
+                probe_unique_inner_kernel<KEY_F64, 8><<<(unsigned)pnt, kJoinThreads, smem, s>>>(
+                    l, nl, t, rid.as<uint32_t>(), status.as<unsigned long long>(), dmeta, pnt, res->lidx, res->ridx, vec);
+            } else {
+                auto kern = probe_unique_inner_kernel<KEY_F64, 16>;
+                SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(unsigned)pnt, kJoinThreads, smem, s>>>(l, nl, t, rid.as<uint32_t>(), status.as<unsigned long long>(), dmeta, pnt,
+                                                               res->lidx, res->ridx, vec);
+            }
             SDC_CHECK_LAUNCH();
         }
         if (LEFT) {
