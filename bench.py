@@ -136,7 +136,7 @@ def run_reference(args):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rolling kernel, from the committed
     `ncu --set full` summary (profiles/); None when no capture of the current kernel is on file."""
-    p = os.path.join(ROOT, "profiles", "r1_rolling_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", "r1_rolling_mean_ncu_summary.json")
     try:
         with open(p) as f:
             d = json.load(f)

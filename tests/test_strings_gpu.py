@@ -177,3 +177,43 @@ def test_c4_shape_scaled_properties():
     rows = np.flatnonzero((pool[which] == np.frombuffer(g0, dtype=np.uint8)).all(axis=1))
     assert int(res["count"][0][0].item()) == len(rows)
     np.testing.assert_allclose(float(res["min"][0][0].item()), val.cpu().numpy()[rows].min(), rtol=0)
+
+
+def test_c4_full_size_properties():
+    """BASELINE config C4 at its full 200 M rows (8-char string keys, G = 1 K; built on the device like
+    tools/bench_ops.py): sortedness + stability of the argsort, and the multi-aggregate checked through totals."""
+    import torch
+    from sdc_b200.str_arr import StringArray, groupby_str_device
+    n, G = 200_000_000, 1000
+    rng = np.random.default_rng(4)
+    al = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789", dtype=np.uint8)
+    pool = al[rng.integers(0, len(al), (G, 8))]
+    dic = torch.from_numpy(pool).cuda()
+    ids = torch.randint(0, G, (n,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(4))
+    chars = dic[ids].reshape(-1).contiguous()
+    offsets = (torch.arange(n + 1, device="cuda", dtype=torch.int64) * 8).to(torch.int32)
+    bitmap = torch.full(((n + 7) // 8,), 0xFF, dtype=torch.uint8, device="cuda")
+    sa = StringArray(offsets, chars, bitmap, n)
+    # big-endian value of the 8 bytes = byte-lexicographic order; computed per dictionary entry, looked up per row
+    be = torch.from_numpy(pool.copy().view(">u8").astype(np.uint64).reshape(-1).view(np.int64)).cuda()
+    flip = torch.tensor(-2**63, dtype=torch.int64, device="cuda")
+    order = sa.argsort(True)
+    sk = (be[ids[order]] ^ flip)
+    assert bool((sk[1:] >= sk[:-1]).all())
+    same = sk[1:] == sk[:-1]
+    assert bool((order[1:][same] > order[:-1][same]).all())          # stable
+    del sk, same, order
+    val = torch.rand(n, device="cuda", dtype=torch.float64)
+    rk, res = groupby_str_device(sa, [val], ("sum", "mean", "min", "max", "count"), True, 1, G)
+    present = torch.unique(ids)
+    assert rk.n == int(present.shape[0])
+    assert int(res["count"][0].sum().item()) == n
+    np.testing.assert_allclose(float(res["sum"][0].sum().item()), float(val.sum().item()), rtol=1e-9)
+    got_keys = rk.to_pylist()
+    assert got_keys == sorted(got_keys, key=lambda s_: s_.encode())
+    # the counts per key against a device bincount over the dictionary ids, in string order
+    cnt = torch.bincount(ids, minlength=G)[present]
+    key_order = np.argsort(pool[present.cpu().numpy()].copy().view(">u8").reshape(-1), kind="stable")
+    np.testing.assert_array_equal(res["count"][0].cpu().numpy(), cnt.cpu().numpy()[key_order])
+    assert float(res["min"][0].min().item()) == float(val.min().item())
+    assert float(res["max"][0].max().item()) == float(val.max().item())
