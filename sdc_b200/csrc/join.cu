@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
         if (j < n) {
             const unsigned long long k = canon_key<KEY_F64>(keys[j]);
             s = jt_upsert(t, k);
-            rank = atomicAdd(&t.slots[s].y, 1ull);
+            // one add carries the count (low word) AND the row (high word): with unique build keys the slot then
+            // already reads row << 32 | 1 -- no scan, no scatter, and the probe needs no row-id indirection.  With
+            // duplicates the high words are garbage; the scan below rebuilds them from the counts.
+            rank = atomicAdd(&t.slots[s].y, ((unsigned long long)j << 32) | 1ull) & 0xffffffffull;
             if (rank) *dup_flag = 1ull;
         }
         __syncwarp();
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(kJoinThreads) dense_scatter_kernel(const uint3
 
 struct SlotCountLoad {
     const ulonglong2* slots;
-    __device__ unsigned long long operator()(int64_t i) const { return slots[i].y; }
+    __device__ unsigned long long operator()(int64_t i) const { return slots[i].y & 0xffffffffull; }   // the count
 };
 struct SlotStartStore {          // val = start << 32 | count
     ulonglong2* slots;
@@ -306,8 +309,8 @@ __device__ __forceinline__ uint32_t lookup_row1(const JTable& t, const uint32_t*
         const unsigned long long d = key - t.dlo;
         return d < t.drange ? ld_hint_u32(t.dense32 + d, keep) : 0u;
     }
-    const unsigned long long v = jt_lookup(t, key);
-    return (unsigned)v ? rid[v >> 32] + 1u : 0u;
+    const unsigned long long v = jt_lookup(t, key);      // unique build keys: row << 32 | 1 straight from the insert
+    return (unsigned)v ? (uint32_t)(v >> 32) + 1u : 0u;
 }
 
 // Probe tiles are WARP-STRIPED: a warp owns 256 consecutive rows and lane L holds rows
@@ -583,12 +586,15 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         if (nr > 0) {
             jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(r, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2);
             SDC_CHECK_LAUNCH();
-            SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
-                                          tsum_b.as<unsigned long long>(), s));
-            jt_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
-            SDC_CHECK_LAUNCH();
             SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            if (hdup != 0) {
+                // duplicate build keys: counts -> starts, right rows grouped by key
+                SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
+                                              tsum_b.as<unsigned long long>(), s));
+                jt_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
+                SDC_CHECK_LAUNCH();
+            }
             unique = hdup == 0;
         }
     }

@@ -71,6 +71,13 @@ elif what == "join_left":
     l = torch.from_numpy(np.random.default_rng(3).integers(0, 10_000_000, 100_000_000, dtype=np.int64)).cuda()
     for _ in range(reps):
         join_device(l, r, "left")
+elif what == "join_sparse":
+    from sdc_b200.join import join_device
+    r = torch.from_numpy(np.random.default_rng(2).permutation(10_000_000).astype(np.int64)).cuda() * 1000003
+    l = torch.from_numpy(np.random.default_rng(3).integers(0, 10_000_000, 100_000_000, dtype=np.int64)).cuda() * 1000003
+    for _ in range(reps):
+        join_device(l, r, "left")
+        join_device(l, r, "inner")
 elif what == "join":
     from sdc_b200.join import join_device
     r = torch.from_numpy(np.random.default_rng(2).permutation(10_000_000).astype(np.int64)).cuda()
