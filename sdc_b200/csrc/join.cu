@@ -250,12 +250,21 @@ __global__ void __launch_bounds__(kJoinThreads) probe_count_kernel(const unsigne
 }
 
 // ---- probe pass B: emit (left row, right row) pairs in left-row order ----
+// Every warp expands its own 256 rows cooperatively: the rows' output offsets (exclusive prefix of the pair counts)
+// go to shared memory, then lane L produces outputs L, L + 32, ... of the warp -- a binary search over the 256
+// offsets finds the row an output belongs to -- so consecutive lanes write consecutive pairs (coalesced) however
+// the duplicates are distributed.
 template <bool LEFT>
 __global__ void __launch_bounds__(kJoinThreads) probe_emit_kernel(const unsigned long long* __restrict__ pval, int64_t n,
                                                                   const unsigned long long* __restrict__ tile_offs,
                                                                   const uint32_t* __restrict__ rid,
                                                                   int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
-    __shared__ unsigned long long wsum[kJoinThreads / 32];
+    constexpr int kWarps = kJoinThreads / 32;
+    constexpr int kWRows = 32 * kItems;                       // 256 rows per warp
+    __shared__ unsigned long long wsum[kWarps];
+    __shared__ unsigned woff[kWarps][kWRows + 1];
+    __shared__ unsigned long long wval[kWarps][kWRows];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
     unsigned long long v[kItems];
     if (i0 + kItems <= n) {
@@ -269,35 +278,50 @@ __global__ void __launch_bounds__(kJoinThreads) probe_emit_kernel(const unsigned
 #pragma unroll
         for (int e = 0; e < kItems; ++e) v[e] = (i0 + e < n) ? pval[i0 + e] : 0ull;
     }
-    unsigned long long c = 0;
+    unsigned c = 0;
+    unsigned ce[kItems];
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
-        const unsigned long long cnt = v[e] & 0xffffffffull;
-        if (i0 + e < n) c += LEFT ? (cnt ? cnt : 1ull) : cnt;
+        const unsigned cnt = (unsigned)(v[e] & 0xffffffffull);
+        ce[e] = (i0 + e < n) ? (LEFT ? (cnt ? cnt : 1u) : cnt) : 0u;
+        c += ce[e];
     }
-    unsigned long long tot;
-    unsigned long long pos = tile_offs[blockIdx.x] + block_excl_scan_u64(c, &tot, wsum);
+    // exclusive offsets inside the warp
+    unsigned incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const unsigned wtot = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned run = incl - c;
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
-        if (i0 + e >= n) break;
-        const unsigned long long cnt = v[e] & 0xffffffffull, start = v[e] >> 32;
-        if (cnt == 1) {
-            lidx[pos] = i0 + e;
-            ridx[pos] = (int64_t)rid[start];
-            ++pos;
-        } else if (cnt == 0) {
-            if (LEFT) {
-                lidx[pos] = i0 + e;
-                ridx[pos] = -1;
-                ++pos;
-            }
-        } else {
-            for (unsigned long long m = 0; m < cnt; ++m) {
-                lidx[pos + m] = i0 + e;
-                ridx[pos + m] = (int64_t)rid[start + m];
-            }
-            pos += cnt;
+        woff[warp][lane * kItems + e] = run;
+        wval[warp][lane * kItems + e] = v[e];
+        run += ce[e];
+    }
+    if (lane == 31) { woff[warp][kWRows] = wtot; wsum[warp] = wtot; }
+    __syncthreads();
+    unsigned long long wbase = tile_offs[blockIdx.x];
+    for (int w = 0; w < warp; ++w) wbase += wsum[w];
+    const int64_t wrow0 = (int64_t)blockIdx.x * kTile + (int64_t)warp * kWRows;
+    const unsigned* off = woff[warp];
+    for (unsigned o = lane; o < wtot; o += 32) {
+        // largest i with off[i] <= o  (rows with no pairs share their successor's offset and are skipped)
+        int lo = 0, hi = kWRows;
+#pragma unroll
+        for (int step = 0; step < 8; ++step) {
+            const int mid = (lo + hi) >> 1;
+            if (off[mid] <= o) lo = mid; else hi = mid;
         }
+        // lo is the LAST row whose offset is <= o: rows after it start beyond o, rows before it that share its
+        // offset are empty
+        const unsigned long long val = wval[warp][lo];
+        const unsigned cnt = (unsigned)(val & 0xffffffffull);
+        const unsigned m = o - off[lo];
+        lidx[wbase + o] = wrow0 + lo;
+        ridx[wbase + o] = cnt ? (int64_t)rid[(val >> 32) + m] : -1;
     }
 }
 

@@ -97,6 +97,17 @@ def bench_join(reps):
             emit("join_%s_%s probe=%d build=%d" % (how, name, npr, nb), npr, 8 * (npr + nb) + 16 * n_out, med, best,
                  n_out=n_out)
         del l
+    # build keys duplicated x4 (SURVEY 8d C3 variant): 25 M probe rows x 10 M build rows -> 100 M pairs
+    rd = torch.from_numpy(np.tile(np.random.default_rng(2).permutation(nb // 4), 4).astype(np.int64)).cuda()
+    ld = torch.from_numpy(np.random.default_rng(3).integers(0, nb // 4, npr // 4, dtype=np.int64)).cuda()
+    for how in ("inner", "left"):
+        out = {}
+
+        def run_dup():
+            out["r"] = join_device(ld, rd, how)
+        med, best = timeit(run_dup, reps)
+        n_out = out["r"][0].shape[0]
+        emit("join_%s_dup4 probe=%d build=%d" % (how, npr // 4, nb), npr // 4, 8 * (npr // 4 + nb) + 16 * n_out, med, best, n_out=n_out)
 
 
 def bench_rolling(reps, n=100_000_000):
