@@ -208,41 +208,64 @@ __global__ void __launch_bounds__(kJoinThreads) jt_scatter_kernel(const uint32_t
     }
 }
 
+// Probe tiles are WARP-STRIPED: a warp owns 256 consecutive rows and lane L holds rows
+//   w0 + j * 64 + 2 L + {0, 1},  j = 0 .. 3   (items e = 2 j, 2 j + 1)
+// so every 128-bit access of a warp covers 512 contiguous bytes (whole sectors, whole lines), both for the
+// key loads and for the (left row, right row) stores of how='left'.
+template <int ITEMS = kItems>
+__device__ __forceinline__ int64_t probe_row(int64_t tile0, int warp, int lane, int e) {
+    return tile0 + warp * (32 * ITEMS) + (e >> 1) * 64 + 2 * lane + (e & 1);
+}
+
+template <bool KEY_F64, int ITEMS = kItems>
+__device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t tile0, int warp, int lane,
+                                                int64_t n, bool vec, uint64_t stream_pol, unsigned long long* k) {
+    if (vec && tile0 + kJoinThreads * ITEMS <= n) {
+#pragma unroll
+        for (int e = 0; e < ITEMS; e += 2) {
+            const ulonglong2 kk = ld_hint_v2u64(keys + probe_row<ITEMS>(tile0, warp, lane, e), stream_pol);
+            k[e] = canon_key<KEY_F64>(kk.x);
+            k[e + 1] = canon_key<KEY_F64>(kk.y);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < ITEMS; ++e) {
+            const int64_t r = probe_row<ITEMS>(tile0, warp, lane, e);
+            k[e] = r < n ? canon_key<KEY_F64>(keys[r]) : 0ull;
+        }
+    }
+}
+
 // ---- probe pass A: per-row val, per-tile output count ----
 template <bool KEY_F64, bool LEFT>
 __global__ void __launch_bounds__(kJoinThreads) probe_count_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                    JTable t, unsigned long long* __restrict__ pval,
-                                                                   unsigned long long* __restrict__ tile_counts) {
+                                                                   unsigned long long* __restrict__ tile_counts, int vec) {
     __shared__ unsigned long long wsum[kJoinThreads / 32];
-    const int64_t i0 = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kItems;
+    const uint64_t stream_pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
     unsigned long long k[kItems], v[kItems];
-    if (i0 + kItems <= n) {
-#pragma unroll
-        for (int e = 0; e < kItems; e += 2) {
-            const ulonglong2 kk = __ldg(reinterpret_cast<const ulonglong2*>(keys + i0 + e));
-            k[e] = kk.x;
-            k[e + 1] = kk.y;
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < kItems; ++e) k[e] = (i0 + e < n) ? keys[i0 + e] : 0ull;
-    }
+    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);     // warp-striped: whole sectors
     unsigned long long c = 0;
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
-        v[e] = (i0 + e < n) ? jt_lookup(t, canon_key<KEY_F64>(k[e])) : 0ull;
+        const bool in = probe_row(tile0, warp, lane, e) < n;
+        v[e] = in ? jt_lookup(t, k[e]) : 0ull;
         __syncwarp();                                  // hash probes end at different times per lane
         const unsigned long long cnt = v[e] & 0xffffffffull;
-        if (i0 + e < n) c += LEFT ? (cnt ? cnt : 1ull) : cnt;
+        if (in) c += LEFT ? (cnt ? cnt : 1ull) : cnt;
     }
-    if (i0 + kItems <= n) {
+    if (tile0 + kTile <= n) {
 #pragma unroll
         for (int e = 0; e < kItems; e += 2)
-            *reinterpret_cast<ulonglong2*>(pval + i0 + e) = make_ulonglong2(v[e], v[e + 1]);
+            *reinterpret_cast<ulonglong2*>(pval + probe_row(tile0, warp, lane, e)) = make_ulonglong2(v[e], v[e + 1]);
     } else {
 #pragma unroll
-        for (int e = 0; e < kItems; ++e)
-            if (i0 + e < n) pval[i0 + e] = v[e];
+        for (int e = 0; e < kItems; ++e) {
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            if (r < n) pval[r] = v[e];
+        }
     }
     unsigned long long tot;
     block_excl_scan_u64(c, &tot, wsum);
@@ -335,34 +358,6 @@ __device__ __forceinline__ uint32_t lookup_row1(const JTable& t, const uint32_t*
     }
     const unsigned long long v = jt_lookup(t, key);      // unique build keys: row << 32 | 1 straight from the insert
     return (unsigned)v ? (uint32_t)(v >> 32) + 1u : 0u;
-}
-
-// Probe tiles are WARP-STRIPED: a warp owns 256 consecutive rows and lane L holds rows
-//   w0 + j * 64 + 2 L + {0, 1},  j = 0 .. 3   (items e = 2 j, 2 j + 1)
-// so every 128-bit access of a warp covers 512 contiguous bytes (whole sectors, whole lines), both for the
-// key loads and for the (left row, right row) stores of how='left'.
-template <int ITEMS = kItems>
-__device__ __forceinline__ int64_t probe_row(int64_t tile0, int warp, int lane, int e) {
-    return tile0 + warp * (32 * ITEMS) + (e >> 1) * 64 + 2 * lane + (e & 1);
-}
-
-template <bool KEY_F64, int ITEMS = kItems>
-__device__ __forceinline__ void load_probe_keys(const unsigned long long* __restrict__ keys, int64_t tile0, int warp, int lane,
-                                                int64_t n, bool vec, uint64_t stream_pol, unsigned long long* k) {
-    if (vec && tile0 + kJoinThreads * ITEMS <= n) {
-#pragma unroll
-        for (int e = 0; e < ITEMS; e += 2) {
-            const ulonglong2 kk = ld_hint_v2u64(keys + probe_row<ITEMS>(tile0, warp, lane, e), stream_pol);
-            k[e] = canon_key<KEY_F64>(kk.x);
-            k[e + 1] = canon_key<KEY_F64>(kk.y);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < ITEMS; ++e) {
-            const int64_t r = probe_row<ITEMS>(tile0, warp, lane, e);
-            k[e] = r < n ? canon_key<KEY_F64>(keys[r]) : 0ull;
-        }
-    }
 }
 
 // meta[0] ticket, meta[1] n_out.  status[tile] = flag << 62 | value; flag 1: tile aggregate, 2: inclusive prefix
@@ -673,7 +668,8 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
     unsigned long long* tile_counts = tcnt.as<unsigned long long>();
     unsigned long long* tsum_p = tile_counts + nt + 1;
-    probe_count_kernel<KEY_F64, LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, pval.as<unsigned long long>(), tile_counts);
+    probe_count_kernel<KEY_F64, LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, pval.as<unsigned long long>(), tile_counts,
+                                                                            (reinterpret_cast<uintptr_t>(l) & 15) == 0);
     SDC_CHECK_LAUNCH();
     // exclusive scan of the tile counts in place; total lands in tile_counts[nt]
     if (nt <= 256 * 1024) {
