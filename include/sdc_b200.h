@@ -98,6 +98,18 @@ int32_t sdcb200_rolling(int32_t op, int32_t dtype, const void* in, double* out, 
 int32_t sdcb200_host_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
                              int64_t win, int64_t minp, int64_t ddof);
 
+/* Series.rolling(win, minp).skew() / .kurt() / .cov(other, ddof) / .corr(other) on float64 DEVICE columns
+ * (sdc/datatypes/hpat_pandas_series_rolling_functions.py: skew :408-431, :548-556; kurt :303-331, :520-536;
+ * cov :261-300, :509-517, :925-992; corr :207-236, :487-506, :824-879).  A row takes part only when it is
+ * finite in both series; `y` NULL means other = self.  Series of different lengths: the output has
+ * max(n_x, n_y) rows, only rows below min(n_x, n_y) enter a window.  win <= 4097.                       */
+#define SDCB200_ROLL_SKEW 7
+#define SDCB200_ROLL_KURT 8
+#define SDCB200_ROLL_COV 9
+#define SDCB200_ROLL_CORR 10
+int32_t sdcb200_rolling_moments(int32_t op, const double* x, int64_t n_x, const double* y, int64_t n_y,
+                                double* out, int64_t win, int64_t minp, int64_t ddof, void* stream);
+
 /* ------------------------------------------------------------------ sort / argsort / gather
  * In-place ascending sort with NaN last: replaces parallel_sort_<t> / parallel_stable_sort_<t>
  * (sdc/native/sort.cpp:119-121, sdc/native/stable_sort.cpp:308-310; exported at

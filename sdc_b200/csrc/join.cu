@@ -477,6 +477,115 @@ __global__ void __launch_bounds__(kJoinThreads, ITEMS == 8 ? 5 : 3) probe_unique
     }
 }
 
+// Two-pass variant of the kernel above (the default; SDCB200_JOIN_INNER=chained restores the chained scan).
+// The chained scan moves its prefix forward 32 tiles per L2 round trip, and the CTAs of a wave publish their
+// totals together, so every wave pays a serial look-back chain: 1.06 ms against the 0.63 ms of the scan-free
+// left probe on C3, with neither L1 nor L2 nor DRAM busy.  Here pass 1 is the left probe writing `right row + 1`
+// as ONE 32-bit word per left row plus the tile's hit count, a one-CTA scan turns the counts into offsets, and
+// pass 2 reads the words back (4 bytes per row) and stores the pairs straight from registers: within a 64-row
+// segment lane L's two rows land on adjacent output positions, so a fully matched segment on an even offset
+// leaves as 16-byte stores covering 512 contiguous bytes, anything else as 8-byte stores inside one 512-byte
+// window.  No look-back, no spinning: 8 bytes per row of extra traffic buy two streaming kernels.
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kJoinThreads) probe_unique_row1_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                         JTable t, const uint32_t* __restrict__ rid,
+                                                                         uint32_t* __restrict__ row1_out,
+                                                                         unsigned long long* __restrict__ tile_counts, int vec) {
+    __shared__ unsigned wcnt[kJoinThreads / 32];
+    const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+    unsigned long long k[kItems];
+    uint32_t row1[kItems];
+    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) {
+        row1[e] = (probe_row(tile0, warp, lane, e) < n) ? lookup_row1(t, rid, k[e], keep_pol) : 0u;
+        if (!t.dense32) __syncwarp();                  // hash probes end at different times per lane
+    }
+    unsigned hits = 0;
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) hits += __popc(__ballot_sync(0xffffffffu, row1[e] != 0u));
+    if (tile0 + kTile <= n) {
+#pragma unroll
+        for (int e = 0; e < kItems; e += 2)
+            *reinterpret_cast<uint2*>(row1_out + probe_row(tile0, warp, lane, e)) = make_uint2(row1[e], row1[e + 1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < kItems; ++e) {
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            if (r < n) row1_out[r] = row1[e];
+        }
+    }
+    if (lane == 0) wcnt[warp] = hits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < kJoinThreads / 32; ++w) tot += wcnt[w];
+        tile_counts[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(const uint32_t* __restrict__ row1_in, int64_t n,
+                                                                            const unsigned long long* __restrict__ tile_offs,
+                                                                            int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+    constexpr int kWarps = kJoinThreads / 32;
+    __shared__ unsigned wcnt[kWarps];
+    const uint64_t stream_pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+    uint32_t row1[kItems];
+    if (tile0 + kTile <= n) {
+#pragma unroll
+        for (int e = 0; e < kItems; e += 2) {
+            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(row1_in + probe_row(tile0, warp, lane, e)));
+            row1[e] = v.x;
+            row1[e + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < kItems; ++e) {
+            const int64_t r = probe_row(tile0, warp, lane, e);
+            row1[e] = r < n ? row1_in[r] : 0u;
+        }
+    }
+    unsigned rank[kItems], wtot = 0, fullmask = 0;
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const unsigned ba = __ballot_sync(0xffffffffu, row1[2 * j] != 0u);
+        const unsigned bb = __ballot_sync(0xffffffffu, row1[2 * j + 1] != 0u);
+        rank[2 * j] = wtot + __popc(ba & lt_mask) + __popc(bb & lt_mask);
+        rank[2 * j + 1] = rank[2 * j] + (row1[2 * j] != 0u ? 1u : 0u);
+        if ((ba & bb) == 0xffffffffu && !(wtot & 1u)) fullmask |= 1u << j;
+        wtot += __popc(ba) + __popc(bb);
+    }
+    if (lane == 0) wcnt[warp] = wtot;
+    __syncthreads();
+    unsigned long long base = tile_offs[blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if (w < warp) base += wcnt[w];
+    const bool even = !(base & 1ull);
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const int64_t r = probe_row(tile0, warp, lane, 2 * j);
+        const unsigned long long p0 = base + rank[2 * j];
+        if (((fullmask >> j) & 1u) && even) {
+            st_hint_v2s64(lidx + p0, r, r + 1, stream_pol);
+            st_hint_v2s64(ridx + p0, (int64_t)row1[2 * j] - 1, (int64_t)row1[2 * j + 1] - 1, stream_pol);
+        } else {
+            if (row1[2 * j]) { lidx[p0] = r; ridx[p0] = (int64_t)row1[2 * j] - 1; }
+            if (row1[2 * j + 1]) {
+                const unsigned long long p1 = base + rank[2 * j + 1];
+                lidx[p1] = r + 1;
+                ridx[p1] = (int64_t)row1[2 * j + 1] - 1;
+            }
+        }
+    }
+}
+
 // how='left' with unique build keys: output row i = left row i, no scan
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const unsigned long long* __restrict__ keys, int64_t n,
@@ -634,6 +743,31 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         } else {
             // 4096-row tiles halve the number of look-backs per row (1.31 -> 1.26 ms on C3); the hashed table's probe
             // loops run better with the smaller tile (5.8 vs 5.4 ms), so only the dense table takes the big one
+            static const int two_pass = [] { const char* e = getenv("SDCB200_JOIN_INNER"); return !(e && !strcmp(e, "chained")); }();
+            if (two_pass) {
+                Scratch row1, tcnt;
+                SDC_TRY(row1.alloc((size_t)(nt * kTile) * 4, s));
+                SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
+                unsigned long long* tile_counts = tcnt.as<unsigned long long>();
+                unsigned long long* tsum_p = tile_counts + nt + 1;
+                probe_unique_row1_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), row1.as<uint32_t>(),
+                                                                                        tile_counts, vec);
+                SDC_CHECK_LAUNCH();
+                if (nt <= 256 * 1024) {
+                    scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tile_counts, nt);
+                    SDC_CHECK_LAUNCH();
+                } else {
+                    SDC_TRY(device_exclusive_scan(ArrayLoad{tile_counts}, ArrayStore{tile_counts}, nt, tsum_p, s));
+                    SDC_CUDA_TRY(cudaMemcpyAsync(tile_counts + nt, tsum_p + ceil_div(nt, kTile), 8, cudaMemcpyDeviceToDevice, s));
+                }
+                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx);
+                SDC_CHECK_LAUNCH();
+                unsigned long long total = 0;
+                SDC_CUDA_TRY(cudaMemcpyAsync(&total, tile_counts + nt, 8, cudaMemcpyDeviceToHost, s));
+                SDC_CUDA_TRY(cudaStreamSynchronize(s));
+                res->n_out = (int64_t)total;
+                return SDCB200_OK;
+            }
             const int items = t.dense32 ? 16 : 8;
             const int64_t ptile = (int64_t)kJoinThreads * items;
             const int64_t pnt = ceil_div(nl, ptile);

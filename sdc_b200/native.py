@@ -15,6 +15,7 @@ OK = 0
 JOIN_HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}
 AGG_BITS = {"sum": 1, "mean": 2, "min": 4, "max": 8, "count": 16, "var": 32, "std": 64, "prod": 128, "median": 256}
 ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
+ROLL_MOMENT_OPS = {"skew": 7, "kurt": 8, "cov": 9, "corr": 10}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
                "int64": 6, "uint64": 7, "float32": 8, "float64": 9}
 DTYPE_GID = 100     # SDCB200_GID: dense int64 group ids as a groupby key column
@@ -36,6 +37,7 @@ SIGNATURES = {
     "sdcb200_stream_sync": (_i32, [_vp]),
     "sdcb200_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "sdcb200_host_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64]),
+    "sdcb200_rolling_moments": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "sdcb200_sort": (_i32, [_i32, _vp, _i64, _vp]),
     "sdcb200_argsort": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp]),
     "sdcb200_gather": (_i32, [_i32, _vp, _vp, _i64, _vp, _vp]),

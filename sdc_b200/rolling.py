@@ -5,6 +5,7 @@ Host-side mirror of the reference's rolling interface:
   * Series methods ....................... sdc/datatypes/hpat_pandas_series_rolling_functions.py
         count :886-892, max :1022-1028, mean :1031-1037, min :1049-1055,
         std :1114-1123, sum :1126-1132, var :1135-1144
+        skew :1105-1111, kurt :1013-1019, cov :995-1003, corr :797-883
   * DataFrame = per-column Series rolling  sdc/datatypes/hpat_pandas_dataframe_rolling_functions.py:167-189
 The arithmetic runs in libsdc_b200.so (csrc/rolling.cu); nothing here computes a window.
 """
@@ -91,6 +92,31 @@ def rolling_device(col, op, window, minp, ddof=1, out=None, halo=None, row_offse
     return out
 
 
+def rolling_moments_device(col, op, window, minp, other=None, ddof=1):
+    """skew / kurt / cov / corr of 1-D contiguous float64 CUDA tensors (`other` None = the column itself);
+    float64[max(len)] on the same device.  Asynchronous on torch's current stream."""
+    import torch
+    lib = native.load()
+    assert col.is_cuda and col.dim() == 1 and col.is_contiguous() and col.dtype == torch.float64
+    if other is not None:
+        assert other.is_cuda and other.dim() == 1 and other.is_contiguous() and other.dtype == torch.float64
+    n_y = col.shape[0] if other is None else other.shape[0]
+    out = torch.empty(max(col.shape[0], n_y), dtype=torch.float64, device=col.device)
+    with torch.cuda.device(col.device):
+        native.check(lib.sdcb200_rolling_moments(
+            native.ROLL_MOMENT_OPS[op], col.data_ptr(), col.shape[0], None if other is None else other.data_ptr(), n_y,
+            out.data_ptr(), window, minp, ddof, native.current_stream_ptr()))
+    return out
+
+
+def rolling_moments_host(values, op, window, minp, other=None, ddof=1):
+    """NumPy in / NumPy out around `rolling_moments_device` (ints are read as numbers, like every rolling op)."""
+    import torch
+    x = torch.from_numpy(np.ascontiguousarray(values, dtype=np.float64)).cuda()
+    y = None if other is None else torch.from_numpy(np.ascontiguousarray(other, dtype=np.float64)).cuda()
+    return rolling_moments_device(x, op, window, minp, y, ddof).cpu().numpy()
+
+
 class Rolling:
     """`obj.rolling(window, min_periods)` for a pandas Series / DataFrame, NumPy array or CUDA tensor."""
 
@@ -145,6 +171,69 @@ class Rolling:
     def std(self, ddof=1):
         self._check_ddof("std", ddof)
         return self._apply("std", int(ddof))
+
+    # ---- skew / kurt / cov / corr (csrc/rolling_moments.cu)
+    def _moment_column(self, values, op, other=None, ddof=1):
+        try:
+            import torch
+            if isinstance(values, torch.Tensor):
+                return rolling_moments_device(values, op, self._window, self._minp, other, ddof)
+        except ImportError:
+            pass
+        return rolling_moments_host(values, op, self._window, self._minp, other, ddof)
+
+    def _apply_moment(self, op, other=None, ddof=1):
+        import pandas as pd
+        obj = self._obj
+        if isinstance(obj, pd.Series):
+            oth = None if other is None else pd.Series(other).to_numpy()
+            res = self._moment_column(obj.to_numpy(), op, oth, ddof)
+            if other is None:
+                return pd.Series(res, index=obj.index, name=obj.name)
+            return pd.Series(res)            # two series: the reference returns a default index (:881, :990)
+        if isinstance(obj, pd.DataFrame):
+            # per-column Series rolling against the same column of `other` (df_rolling_method_other_df_codegen,
+            # sdc/datatypes/hpat_pandas_dataframe_rolling_functions.py:83-135) or against the one `other` Series
+            cols = {}
+            for c in obj.columns:
+                oth = None
+                if isinstance(other, pd.DataFrame):
+                    if c not in other.columns:
+                        cols[c] = np.full(len(obj), np.nan)
+                        continue
+                    oth = other[c].to_numpy()
+                elif other is not None:
+                    oth = pd.Series(other).to_numpy()
+                cols[c] = self._moment_column(obj[c].to_numpy(), op, oth, ddof)
+            n = max(len(v) for v in cols.values()) if cols else 0
+            cols = {c: (v if len(v) == n else np.concatenate([v, np.full(n - len(v), np.nan)])) for c, v in cols.items()}
+            return pd.DataFrame(cols, columns=obj.columns)
+        return self._moment_column(obj, op, other, ddof)
+
+    def skew(self):
+        return self._apply_moment("skew")
+
+    def kurt(self):
+        return self._apply_moment("kurt")
+
+    def _check_other(self, name, other, pairwise):
+        import pandas as pd
+        ok = other is None or isinstance(other, (pd.Series, pd.DataFrame, np.ndarray)) or hasattr(other, "is_cuda")
+        if not ok:
+            raise TypeError('Method rolling.{}(). The object other\n given: {}\n expected: Series'.format(
+                name, type(other).__name__))
+        if pairwise is not None and not isinstance(pairwise, (bool, np.bool_)):
+            raise TypeError('Method rolling.{}(). The object pairwise\n given: {}\n expected: bool'.format(
+                name, type(pairwise).__name__))
+
+    def cov(self, other=None, pairwise=None, ddof=1):
+        self._check_other("cov", other, pairwise)
+        self._check_ddof("cov", ddof)
+        return self._apply_moment("cov", other, int(ddof))
+
+    def corr(self, other=None, pairwise=None):
+        self._check_other("corr", other, pairwise)
+        return self._apply_moment("corr", other)
 
 
 def rolling(obj, window, min_periods=None, center=False, win_type=None, on=None, axis=0, closed=None):

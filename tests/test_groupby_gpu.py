@@ -261,3 +261,38 @@ def test_c1_full_size_sum_and_multi():
             np.testing.assert_allclose(res[agg][0].cpu().numpy(), want[agg].to_numpy(), rtol=1e-9, atol=0)
         for agg in ("min", "max", "count"):
             np.testing.assert_array_equal(res[agg][0].cpu().numpy(), want[agg].to_numpy())
+
+
+@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide"])
+def test_single_f64_column_specialised_kernels(keys_kind):
+    """One float64 column with sum / mean / the five-aggregate set takes gb_smem_kernel's compile-time specialised
+    loops (SPEC 1 / 3 / 15): dense keys inside the sampled direct window, a hot key, hashed keys, float keys, keys
+    outside the sampled span (rerun with hashing), more groups than shared slots (global-table fallback)."""
+    rng = np.random.default_rng(23)
+    n = 300_000
+    if keys_kind == "dense":
+        a = rng.integers(0, 1000, n)
+    elif keys_kind == "skewed":
+        a = np.where(rng.random(n) < 0.8, 7, rng.integers(0, 1000, n))
+    elif keys_kind == "sparse":
+        a = rng.integers(0, 1000, n) * 1000003 - 5
+    elif keys_kind == "float":
+        a = rng.integers(0, 700, n).astype(np.float64) / 4
+        a[rng.integers(0, n, 50)] = np.nan
+    elif keys_kind == "outliers":
+        a = rng.integers(100, 600, n)
+        a[rng.integers(0, n, 5)] = 1300          # inside the table window, outside the sampled span
+        a[rng.integers(0, n, 5)] = 2
+    else:
+        a = rng.integers(0, 3000, n)
+    b = rng.standard_normal(n) * 50
+    b[rng.integers(0, n, n // 50)] = np.nan
+    b[rng.integers(0, n, 20)] = np.inf
+    cols = {"b": b}
+    from sdc_b200.groupby import groupby_host
+    for aggs in (("sum",), ("mean",), ("sum", "mean", "min", "max", "count"), ("min",)):
+        for hint in (1000, 0):
+            rk, res = groupby_host(a, cols, aggs, True, 1, hint)
+            for agg in aggs:
+                wk, want = ogroupby.groupby_agg(a, cols, agg)
+                _compare(rk, res[agg], wk, want, agg, "%s %s hint=%d" % (keys_kind, aggs, hint))

@@ -21,6 +21,14 @@ if what == "groupby":
     b = torch.from_numpy(rng.random(n)).cuda()
     for _ in range(reps):
         groupby_device(a, [b], ("sum",), True, 1, 1000)
+elif what in ("groupby_100m", "groupby_100m_5agg"):
+    from sdc_b200.groupby import groupby_device
+    n = 100_000_000
+    a = torch.from_numpy(rng.integers(0, 1000, n, dtype=np.int64)).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    aggs = ("sum",) if what == "groupby_100m" else ("sum", "mean", "min", "max", "count")
+    for _ in range(reps):
+        groupby_device(a, [b], aggs, True, 1, 1000)
 elif what == "groupby_small":
     from sdc_b200.groupby import groupby_device
     n = 200_000
