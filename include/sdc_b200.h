@@ -161,6 +161,13 @@ int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* 
 int32_t sdcb200_groupby_result(int64_t handle, void** keys, void** vals, int64_t* stride);
 int32_t sdcb200_groupby_free(int64_t handle);
 
+/* Composite ids for multi-key groupby / merge (the reference takes ONE `by` column,
+ * sdc/datatypes/hpat_pandas_dataframe_functions.py:3066-3067): out[i] = a[i] * nb + b[i], `invalid` where either
+ * id is negative.  The per-column ids are positions among the sorted distinct keys, so the composite id orders
+ * the key tuples lexicographically.  Device pointers.                                                      */
+int32_t sdcb200_combine_ids(const int64_t* a, const int64_t* b, int64_t nb, int64_t invalid, int64_t* out, int64_t n,
+                            void* stream);
+
 /* ------------------------------------------------------------------ join
  * pd.merge(left, right, on=key, how='inner' | 'left' | 'right' | 'outer') on one int64 / float64 key column.  The
  * reference snapshot has no merge overload (sdc/hiframes/join.py:34-43 is a stub; every test of
@@ -188,6 +195,11 @@ int32_t sdcb200_join_free(int64_t handle, void* stream);
  * (setitem_arr_nan, sdc/hiframes/join.py:34-43); src_dtype SDCB200_I64 or SDCB200_F64.            */
 int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int64_t* idx, int64_t n, double* dst,
                                   void* stream);
+/* pd.merge_asof(left, right, on=key) with the defaults direction='backward', allow_exact_matches=True (the shape of
+ * sdc/tests/test_join.py:237-262, skipped there -- SURVEY 8f item 3): right_idx[i] = the LAST right row whose key is
+ * <= left_keys[i], -1 when there is none.  Both key columns sorted ascending; device pointers.             */
+int32_t sdcb200_asof_backward(int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                              int64_t* right_idx, void* stream);
 
 /* ------------------------------------------------------------------ string columns (str_arr)
  * Layout = the reference's StringArray (sdc/str_arr_type.py:33-101, sdc/native/str_ext/sdc_str_arr.hpp:160-176):

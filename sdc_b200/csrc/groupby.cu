@@ -1033,6 +1033,16 @@ __global__ void gb_finalize_seg_kernel(Table t, int ncols, unsigned is_f64_mask,
 }
 
 // ------------------------------------------------------------------ host side
+// composite group ids of several key columns: out = a * nb + b, `invalid` where either id is negative
+__global__ void combine_ids_kernel(const long long* __restrict__ a, const long long* __restrict__ b, long long nb, long long invalid,
+                                   long long* __restrict__ out, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long x = a[i], y = b[i];
+        out[i] = (x < 0 || y < 0) ? invalid : x * nb + y;
+    }
+}
+
 struct GroupbyResult {
     int key_dtype = 0;
     int ncols = 0;
@@ -1592,3 +1602,17 @@ int32_t sdcb200_groupby_free(int64_t handle) {
 }
 
 }  // extern "C"
+
+extern "C" int32_t sdcb200_combine_ids(const int64_t* a, const int64_t* b, int64_t nb, int64_t invalid, int64_t* out, int64_t n,
+                                       void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(n >= 0 && nb >= 0, "n / nb");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(a != nullptr && b != nullptr && out != nullptr, "null column");
+    int64_t grid = ceil_div(n, 256 * 4);
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    combine_ids_kernel<<<(unsigned)grid, 256, 0, s>>>(reinterpret_cast<const long long*>(a), reinterpret_cast<const long long*>(b),
+                                                      (long long)nb, (long long)invalid, reinterpret_cast<long long*>(out), n);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}

@@ -877,6 +877,25 @@ int32_t append_unmatched_right(JoinResult* res, int64_t nr, cudaStream_t s) {
     return SDCB200_OK;
 }
 
+// ---- merge_asof (direction='backward', allow_exact_matches=True): for every left key the LAST right row whose key
+// is <= it, -1 when there is none.  Both key columns are sorted ascending (pandas requires it), so neighbouring
+// threads walk the same binary-search path and their loads coalesce / broadcast; the top of the search tree stays in
+// L1 / L2.  A NaN left key matches nothing.
+template <typename T>
+__global__ void __launch_bounds__(256) asof_backward_kernel(const T* __restrict__ left, int64_t nl, const T* __restrict__ right,
+                                                            int64_t nr, int64_t* __restrict__ ridx) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += stride) {
+        const T k = left[i];
+        int64_t lo = 0, hi = nr;                 // first j with right[j] > k (NaN right keys sort last: never <= k)
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(right + mid) <= k) lo = mid + 1; else hi = mid;
+        }
+        ridx[i] = (k == k) ? lo - 1 : -1;
+    }
+}
+
 void free_join(JoinResult* r, cudaStream_t s) {
     if (!r) return;
     if (r->lidx) dev_free(r->lidx, s);
@@ -979,6 +998,24 @@ int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int6
         take_nullable_kernel<double><<<grid, 256, 0, s>>>(reinterpret_cast<const double*>(src), idx, dst, n);
     else
         take_nullable_kernel<long long><<<grid, 256, 0, s>>>(reinterpret_cast<const long long*>(src), idx, dst, n);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_asof_backward(int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                              int64_t* right_idx, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
+    SDC_ARG_CHECK(nl >= 0 && nr >= 0, "row counts");
+    if (nl == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(left_keys != nullptr && right_idx != nullptr && (nr == 0 || right_keys != nullptr), "null column");
+    const int grid = (int)(ceil_div(nl, 256) < (int64_t)sm_count() * 16 ? ceil_div(nl, 256) : (int64_t)sm_count() * 16);
+    if (key_dtype == SDCB200_F64)
+        asof_backward_kernel<double><<<grid, 256, 0, s>>>(reinterpret_cast<const double*>(left_keys), nl,
+                                                          reinterpret_cast<const double*>(right_keys), nr, right_idx);
+    else
+        asof_backward_kernel<long long><<<grid, 256, 0, s>>>(reinterpret_cast<const long long*>(left_keys), nl,
+                                                             reinterpret_cast<const long long*>(right_keys), nr, right_idx);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

@@ -70,6 +70,59 @@ def _length(col):
     return col.n if _is_str(col) else col.shape[0]
 
 
+def _as_key(col):
+    """numeric key column as the kernels read it (int64 / float64, contiguous)"""
+    torch = _torch()
+    if _is_str(col):
+        raise TypeError("multi-key groupby / merge: key dtype str is not supported (int64 / float64)")
+    if col.dtype not in (torch.int64, torch.float64):
+        col = col.to(torch.float64 if col.dtype.is_floating_point else torch.int64)
+    return col.contiguous()
+
+
+def _dense_ids(col, domain=None):
+    """Order-preserving dense ids of a key column, from the library's own kernels: the sorted distinct keys of
+    `domain` (default: the column) come from a value-less groupby, a row's id is its key's position among them --
+    the right indexer of a left join against that unique list (-1: NaN key, or a key `domain` does not hold).
+    -> (distinct keys, int64 ids)"""
+    from .groupby import groupby_device
+    from .join import join_device
+    uniq, _ = groupby_device(col if domain is None else domain, [], ("count",), True)
+    _, ids = join_device(col, uniq, "left")
+    return uniq, ids
+
+
+def _combine_ids(a, b, nb, invalid=-1):
+    """a * nb + b per row, `invalid` where either id is negative (csrc/groupby.cu: sdcb200_combine_ids)"""
+    torch = _torch()
+    lib = native.load()
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        native.check(lib.sdcb200_combine_ids(a.data_ptr(), b.data_ptr(), int(nb), int(invalid), out.data_ptr(), a.shape[0],
+                                             native.current_stream_ptr()))
+    return out
+
+
+def _composite_ids(cols, domains=None, invalid=-1):
+    """Several key columns -> one int64 id column whose order is the lexicographic order of the key tuples.
+    -> (ids, [distinct keys per column])"""
+    uniqs, gid, total = [], None, 1
+    for j, c in enumerate(cols):
+        c = _as_key(c)
+        d = None if domains is None else _as_key(domains[j])
+        if d is not None and d.dtype != c.dtype:
+            torch = _torch()
+            c, d = c.to(torch.float64), d.to(torch.float64)
+        u, ids = _dense_ids(c, d)
+        nu = max(int(u.shape[0]), 1)
+        total *= nu
+        if total >= 1 << 62:
+            raise OverflowError("multi-key: the product of the distinct key counts does not fit an int64 id")
+        gid = _combine_ids(ids, ids, 0, invalid) if gid is None else _combine_ids(gid, ids, nu, invalid)
+        uniqs.append(u)
+    return gid, uniqs
+
+
 class DeviceSeries:
     def __init__(self, data, name=None):
         self.data, self.name = data, name
@@ -144,6 +197,37 @@ class _DeviceRolling:
     def var(self, ddof=1): return self._apply("var", int(ddof))
     def std(self, ddof=1): return self._apply("std", int(ddof))
 
+    def _apply_moment(self, op, other=None, ddof=1):
+        """skew / kurt / cov / corr (csrc/rolling_moments.cu); `other`: a DeviceSeries (every column against it), a
+        DeviceFrame (column by column, missing columns skipped) or None (each column against itself)."""
+        from .rolling import rolling_moments_device
+        torch = _torch()
+        out = {}
+        for name, col in self._cols.items():
+            if _is_str(col):
+                continue
+            oth = None
+            if isinstance(other, DeviceFrame):
+                if name not in other._cols:
+                    continue
+                oth = other._cols[name]
+            elif isinstance(other, DeviceSeries):
+                oth = other.data
+            elif other is not None:
+                oth = other
+            x = col.to(torch.float64).contiguous()
+            y = None if oth is None else oth.to(torch.float64).contiguous()
+            out[name] = rolling_moments_device(x, op, self._w, self._minp, y, ddof)
+        if self._series:
+            (name, data), = out.items()
+            return DeviceSeries(data, name)
+        return DeviceFrame(out)
+
+    def skew(self): return self._apply_moment("skew")
+    def kurt(self): return self._apply_moment("kurt")
+    def cov(self, other=None, pairwise=None, ddof=1): return self._apply_moment("cov", other, int(ddof))
+    def corr(self, other=None, pairwise=None): return self._apply_moment("corr", other)
+
 
 class _DeviceGroupBy:
     def __init__(self, cols, keys, key_name, sort):
@@ -186,6 +270,47 @@ class _DeviceGroupBy:
     def std(self, ddof=1): return self.agg("std", int(ddof))
 
 
+class _DeviceGroupByMulti(_DeviceGroupBy):
+    """groupby([k1, k2, ...]) (the reference accepts ONE key column,
+    hpat_pandas_dataframe_functions.py:3066-3067): the key tuples become one dense id column (`_composite_ids`),
+    the aggregate runs on the ids (SDCB200_GID while the id space fits a direct table, plain int64 keys beyond),
+    and the group ids are decoded back into one key column each.  sort=True orders the groups lexicographically,
+    rows with a NaN in any key are dropped (pandas dropna=True)."""
+    _GID_LIMIT = 1 << 24
+
+    def __init__(self, cols, key_cols, key_names, sort):
+        self._cols, self._key_cols, self._key_names, self._sort = cols, key_cols, list(key_names), bool(sort)
+
+    def agg(self, funcs, ddof=1):
+        from .groupby import groupby_device
+        torch = _torch()
+        funcs = (funcs,) if isinstance(funcs, str) else tuple(funcs)
+        names = [n for n, c in self._cols.items() if not _is_str(c)]
+        cols = [_as_key(self._cols[n]) for n in names]
+        gid, uniqs = _composite_ids(self._key_cols)
+        sizes = [max(int(u.shape[0]), 1) for u in uniqs]
+        total = 1
+        for x in sizes:
+            total *= x
+        if total <= self._GID_LIMIT:
+            rk, res = groupby_device(gid, cols, funcs, self._sort, ddof, gid_range=total)
+        else:
+            rk, res = groupby_device(gid, cols, funcs, self._sort, ddof)
+            keep = rk >= 0                                   # the rows with a NaN key collapsed into group -1
+            if not bool(keep.all()):
+                rk = rk[keep]
+                res = {a: [t[keep] for t in ts] for a, ts in res.items()}
+        out, rem = {}, rk
+        for name, u, size in reversed(list(zip(self._key_names, uniqs, sizes))):
+            out[name] = u[rem % size] if u.shape[0] else u
+            rem = rem // size
+        out = {n: out[n] for n in self._key_names}
+        for a in funcs:
+            for n, t in zip(names, res[a]):
+                out[n if len(funcs) == 1 else "%s_%s" % (n, a)] = t
+        return DeviceFrame(out, index=list(self._key_names))
+
+
 class DeviceFrame:
     """Ordered mapping name -> device column.  `index`: the column to_pandas() turns into the index (groupby results)."""
 
@@ -222,6 +347,13 @@ class DeviceFrame:
 
     # ---- operators ----
     def groupby(self, by, sort=True):
+        if isinstance(by, (list, tuple)) and len(by) == 1:
+            by = by[0]
+        if isinstance(by, (list, tuple)):
+            for b in by:
+                if not isinstance(b, str) or b not in self._cols:
+                    raise KeyError(b)
+            return _DeviceGroupByMulti({n: c for n, c in self._cols.items() if n not in by}, [self._cols[b] for b in by], by, sort)
         if not isinstance(by, str) or by not in self._cols:
             raise TypeError("Method groupby(). The object by\n expected: one column name")
         return _DeviceGroupBy({n: c for n, c in self._cols.items() if n != by}, self._cols[by], by, sort)
@@ -239,8 +371,8 @@ class DeviceFrame:
         return self.take(_sort_indexer(self._cols[by], ascending, na_position))
 
     def merge(self, right, how="inner", on=None, left_on=None, right_on=None):
-        """pandas.merge on one numeric key column; payload columns gathered on the device, `_x` / `_y` suffixes for
-        overlapping names, the key column coalesced for rows without a left partner."""
+        """pandas.merge on numeric key columns (one, or a list through composite ids); payload columns gathered on the
+        device, `_x` / `_y` suffixes for overlapping names, key columns coalesced for rows without a left partner."""
         from .join import join_device
         torch = _torch()
         if how not in native.JOIN_HOW:
@@ -254,28 +386,64 @@ class DeviceFrame:
             if len(common) != 1:
                 raise ValueError("merge: exactly one key column is supported")
             left_on = right_on = common[0]
-        lk, rk = self._cols[left_on], right._cols[right_on]
-        if _is_str(lk) or _is_str(rk):
-            raise TypeError("merge: key dtype str is not supported (int64 / float64)")
-        if lk.dtype != rk.dtype or lk.dtype not in (torch.int64, torch.float64):
-            both_int = not lk.dtype.is_floating_point and not rk.dtype.is_floating_point
-            lk, rk = lk.to(torch.int64 if both_int else torch.float64), rk.to(torch.int64 if both_int else torch.float64)
-        li, ri = join_device(lk.contiguous(), rk.contiguous(), how)
+        lkeys = [left_on] if isinstance(left_on, str) else list(left_on)
+        rkeys = [right_on] if isinstance(right_on, str) else list(right_on)
+        if len(lkeys) != len(rkeys) or not lkeys:
+            raise ValueError("len(right_on) must equal len(left_on)")
+        if len(lkeys) == 1:
+            lk, rk = self._cols[lkeys[0]], right._cols[rkeys[0]]
+            if _is_str(lk) or _is_str(rk):
+                raise TypeError("merge: key dtype str is not supported (int64 / float64)")
+            if lk.dtype != rk.dtype or lk.dtype not in (torch.int64, torch.float64):
+                both_int = not lk.dtype.is_floating_point and not rk.dtype.is_floating_point
+                lk, rk = lk.to(torch.int64 if both_int else torch.float64), rk.to(torch.int64 if both_int else torch.float64)
+            li, ri = join_device(lk.contiguous(), rk.contiguous(), how)
+        else:
+            # several key columns: both sides get ids over the RIGHT side's distinct keys, column
+            # by column; a left key tuple the right side does not hold (or a NaN on either side) gets an id that
+            # matches nothing (-1 left, -2 right), then the single-key hash join runs on the composite ids
+            rcols = [right._cols[k] for k in rkeys]
+            rgid, _ = _composite_ids(rcols, invalid=-2)
+            lgid, _ = _composite_ids([self._cols[k] for k in lkeys], domains=rcols, invalid=-1)
+            li, ri = join_device(lgid, rgid, how)
         left_null, right_null = how in ("right", "outer"), how in ("left", "outer")
-        shared = left_on == right_on
+        shared = {l for l, r in zip(lkeys, rkeys) if l == r}           # key columns that appear once in the result
         out = {}
         for n, c in self._cols.items():
-            name = "%s_x" % n if (n in right._cols and not (shared and n == left_on)) else n
-            if shared and n == left_on and left_null:
+            name = "%s_x" % n if (n in right._cols and n not in shared) else n
+            if n in shared and left_null:
                 # the key of a row without a left partner comes from the right side
-                lv = _take(c.to(rk.dtype) if c.dtype != rk.dtype else c, li.clamp(min=0))
-                rv = _take(right._cols[right_on].to(rk.dtype) if right._cols[right_on].dtype != rk.dtype else right._cols[right_on],
-                           ri.clamp(min=0))
+                rc = right._cols[n]
+                kd = torch.int64 if (c.dtype == torch.int64 and rc.dtype == torch.int64) else torch.float64
+                lv = _take(c.to(kd) if c.dtype != kd else c, li.clamp(min=0))
+                rv = _take(rc.to(kd) if rc.dtype != kd else rc, ri.clamp(min=0))
                 out[name] = torch.where(li < 0, rv, lv)          # plumbing: picks between two gathered columns
                 continue
             out[name] = _take(c, li, left_null)
         for n, c in right._cols.items():
-            if shared and n == right_on:
+            if n in shared:
                 continue
             out["%s_y" % n if n in self._cols else n] = _take(c, ri, right_null)
+        return DeviceFrame(out)
+
+    def merge_asof(self, right, on):
+        """pd.merge_asof(left, right, on=key) with the defaults (direction='backward', exact matches allowed): every
+        left row keeps its place and gets the last right row whose key is <= its own (NaN payload when there is none).
+        Both frames must be sorted by the key, as pandas requires."""
+        from .join import asof_backward_device
+        torch = _torch()
+        lk, rk = _as_key(self._cols[on]), _as_key(right._cols[on])
+        if lk.dtype != rk.dtype:
+            lk, rk = lk.to(torch.float64), rk.to(torch.float64)
+        if lk.shape[0] > 1 and not bool((lk[1:] >= lk[:-1]).all()):
+            raise ValueError("left keys must be sorted")
+        if rk.shape[0] > 1 and not bool((rk[1:] >= rk[:-1]).all()):
+            raise ValueError("right keys must be sorted")
+        ri = asof_backward_device(lk, rk)
+        out = {}
+        for n, c in self._cols.items():
+            out["%s_x" % n if (n in right._cols and n != on) else n] = c
+        for n, c in right._cols.items():
+            if n != on:
+                out["%s_y" % n if n in self._cols else n] = _take(c, ri, True)
         return DeviceFrame(out)

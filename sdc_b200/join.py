@@ -88,6 +88,25 @@ def take_nullable_device(col, idx):
     return out
 
 
+def asof_backward_device(left_keys, right_keys):
+    """merge_asof indexer (direction='backward'): int64 CUDA tensor, for every left key the last right row whose key
+    is <= it, -1 when there is none.  Both key columns must be sorted ascending."""
+    torch = _torch()
+    lib = native.load()
+    assert left_keys.is_cuda and right_keys.is_cuda and left_keys.is_contiguous() and right_keys.is_contiguous()
+    if left_keys.dtype != right_keys.dtype:
+        raise TypeError("merge_asof: key dtypes differ (%s vs %s)" % (left_keys.dtype, right_keys.dtype))
+    name = str(left_keys.dtype).replace("torch.", "")
+    if name not in ("int64", "float64"):
+        raise TypeError("merge_asof: key dtype %s is not supported (int64 / float64)" % name)
+    out = torch.empty(left_keys.shape[0], dtype=torch.int64, device=left_keys.device)
+    with torch.cuda.device(left_keys.device):
+        native.check(lib.sdcb200_asof_backward(native.DTYPE_CODES[name], left_keys.data_ptr(), left_keys.shape[0],
+                                               right_keys.data_ptr(), right_keys.shape[0], out.data_ptr(),
+                                               native.current_stream_ptr()))
+    return out
+
+
 def _key_column(values):
     a = np.ascontiguousarray(values)
     if a.dtype.kind in "iub":

@@ -50,11 +50,13 @@ SIGNATURES = {
     "sdcb200_groupby_values": (_i32, [_i64, _i32, ct.c_uint32, _vp, _i32, _vp]),
     "sdcb200_groupby_result": (_i32, [_i64, ct.POINTER(_vp), ct.POINTER(_vp), ct.POINTER(_i64)]),
     "sdcb200_groupby_free": (_i32, [_i64]),
+    "sdcb200_combine_ids": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "sdcb200_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
     "sdcb200_join_indexers": (_i32, [_i64, _vp, _vp, _i32, _vp]),
     "sdcb200_join_result": (_i32, [_i64, ct.POINTER(_vp), ct.POINTER(_vp)]),
     "sdcb200_join_free": (_i32, [_i64, _vp]),
     "sdcb200_take_nullable_f64": (_i32, [_i32, _vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_asof_backward": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _vp]),
     "sdcb200_str_argsort": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "sdcb200_str_factorize": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64),
                                      ct.POINTER(_i64), _vp]),

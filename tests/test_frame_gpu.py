@@ -89,3 +89,83 @@ def test_rolling():
     pd.testing.assert_series_equal(got, df["x"].rolling(7, min_periods=2).std(), rtol=1e-9, atol=1e-9)
     with pytest.raises(ValueError):
         dev.rolling(3, center=True)
+
+
+@pytest.mark.parametrize("sort", [True, False])
+def test_groupby_several_keys(sort, monkeypatch):
+    """groupby([k1, k2]) -- the shape of sdc/tests/test_groupby.py:526-558 (skipped there: one `by` column only)."""
+    from sdc_b200 import frame
+    from sdc_b200.frame import DeviceFrame
+    rng = np.random.default_rng(12)
+    n = 40_000
+    df = pd.DataFrame({"a": rng.integers(-5, 20, n), "b": rng.integers(0, 7, n).astype(np.float64) / 2,
+                       "c": rng.integers(100, 103, n), "x": rng.standard_normal(n), "i": rng.integers(-9, 9, n)})
+    df.loc[rng.integers(0, n, 300), "b"] = np.nan          # NaN keys drop the row (pandas dropna=True)
+    df.loc[rng.integers(0, n, 300), "x"] = np.nan
+    dev = DeviceFrame.from_pandas(df)
+    for keys in (["a", "b"], ["c", "a", "b"]):
+        for agg in ("sum", "mean", "min", "count"):
+            got = getattr(dev.groupby(keys, sort=sort), agg)().to_pandas()
+            want = getattr(df.groupby(keys, sort=sort), agg)()
+            if not sort:
+                got, want = got.sort_index(), want.sort_index()
+            pd.testing.assert_frame_equal(got, want, check_dtype=False, rtol=1e-9, check_index_type=False)
+    if sort:
+        # beyond the direct-table limit the composite ids are aggregated as plain int64 keys
+        monkeypatch.setattr(frame._DeviceGroupByMulti, "_GID_LIMIT", 16)
+        got = dev.groupby(["a", "b"]).sum().to_pandas()
+        pd.testing.assert_frame_equal(got, df.groupby(["a", "b"]).sum(), check_dtype=False, rtol=1e-9, check_index_type=False)
+        first = dev.groupby(["a", "b"], sort=False).agg(["sum", "max"]).to_pandas()
+        assert list(first.columns) == ["c_sum", "x_sum", "i_sum", "c_max", "x_max", "i_max"]
+
+
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
+def test_merge_on_several_keys(how):
+    """merge(on=[k1, k2]) -- the shape of sdc/tests/test_join.py:106-160 (skipped there)."""
+    from sdc_b200.frame import DeviceFrame
+    rng = np.random.default_rng(31)
+    n, m = 30_000, 500
+    left = pd.DataFrame({"k1": rng.integers(0, 30, n), "k2": rng.integers(0, 25, n), "x": rng.standard_normal(n)})
+    pairs = rng.permutation(40 * 30)[:m]                   # unique (k1, k2) pairs, some absent on the left
+    right = pd.DataFrame({"k1": pairs // 30, "k2": pairs % 30, "w": rng.random(m)})
+    got = DeviceFrame.from_pandas(left).merge(DeviceFrame.from_pandas(right), how=how, on=["k1", "k2"]).to_pandas()
+    want = left.merge(right, how=how, on=["k1", "k2"])
+    cols = list(want.columns)
+    assert list(got.columns) == cols
+    pd.testing.assert_frame_equal(got.sort_values(cols).reset_index(drop=True), want.sort_values(cols).reset_index(drop=True),
+                                  check_dtype=False)
+    # duplicate pairs on the build side: cross product per pair
+    right2 = pd.concat([right, right.assign(w=right["w"] + 1)], ignore_index=True)
+    got = DeviceFrame.from_pandas(left).merge(DeviceFrame.from_pandas(right2), how=how, left_on=["k1", "k2"],
+                                              right_on=["k1", "k2"]).to_pandas()
+    want = left.merge(right2, how=how, on=["k1", "k2"])
+    pd.testing.assert_frame_equal(got.sort_values(cols).reset_index(drop=True), want.sort_values(cols).reset_index(drop=True),
+                                  check_dtype=False)
+
+
+def test_rolling_moments_on_device_frames():
+    df, dev = _frames()
+    got = dev[["x"]].rolling(30, 10).skew().to_pandas()
+    pd.testing.assert_frame_equal(got, df[["x"]].rolling(30, 10).skew(), rtol=1e-7, atol=1e-9)
+    other = dev["i"]
+    got = dev["x"].rolling(50).corr(other).to_pandas()
+    want = df["x"].rolling(50).corr(df["i"])
+    np.testing.assert_allclose(got.to_numpy(), want.to_numpy(), rtol=1e-7, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("kind", ["int", "float"])
+def test_merge_asof(kind):
+    """pd.merge_asof(df1, df2, on='time') -- sdc/tests/test_join.py:237-262 (skipped there)."""
+    from sdc_b200.frame import DeviceFrame
+    rng = np.random.default_rng(17)
+    t1 = np.sort(rng.integers(0, 10_000, 20_000))
+    t2 = np.sort(rng.integers(500, 9_000, 3_000))
+    if kind == "float":
+        t1, t2 = t1 / 4.0, t2 / 4.0
+    left = pd.DataFrame({"time": t1, "a": rng.standard_normal(len(t1))})
+    right = pd.DataFrame({"time": t2, "b": rng.standard_normal(len(t2)), "a": rng.integers(0, 9, len(t2))})
+    got = DeviceFrame.from_pandas(left).merge_asof(DeviceFrame.from_pandas(right), on="time").to_pandas()
+    want = pd.merge_asof(left, right, on="time")
+    pd.testing.assert_frame_equal(got, want, check_dtype=False)
+    with pytest.raises(ValueError):
+        DeviceFrame.from_pandas(left.iloc[::-1].reset_index(drop=True)).merge_asof(DeviceFrame.from_pandas(right), on="time")

@@ -2,9 +2,10 @@
 
 Tolerance.  Both sides evaluate the reference's formulas on sums of powers; they differ in where the sliding
 sums are restarted (every 15 / 31 outputs on the GPU, at chunk starts in the oracle), so the results agree up to
-the cancellation of those formulas: rtol 1e-7 on standard-normal data (observed ~1e-11), NaN pattern exact
-wherever the variance of the window is not within rounding of zero (the reference's `m2 == 0` /
-`_almost_equal(var, 0)` decisions are rounding-dependent by construction)."""
+the cancellation of those formulas: rtol 1e-7 on standard-normal data wherever the window's variance exceeds 1e-3
+(m3 / m2^1.5 and m4 / m2^2 amplify the rounding of the sums by 1 / m2^1.5 and 1 / m2^2: a 3-row window with variance
+1e-7 differs by 5e-6 between the two summation orders), NaN pattern exact on the same windows (the reference's
+`m2 == 0` / `_almost_equal(var, 0)` decisions are rounding-dependent by construction)."""
 import numpy as np
 import pandas as pd
 import pytest
@@ -32,7 +33,7 @@ def _cond_mask(x, win, other=None):
         both = np.isfinite(a) & np.isfinite(b)
         for col in (a, b):
             v = pd.Series(np.where(both, col, np.nan)).rolling(win, min_periods=1).var(ddof=0).to_numpy()
-            m[:nmin] &= ~(v <= 1e-9)
+            m[:nmin] &= ~(v <= 1e-3)
     return m
 
 

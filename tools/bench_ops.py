@@ -118,6 +118,13 @@ def bench_rolling(reps, n=100_000_000):
     for op in ("sum", "mean", "std", "var", "count", "min", "max"):
         med, best = timeit(lambda: rolling_device(x, op, 100, 100, 1, out=out), reps)
         emit("rolling_%s w=100 n=%d" % (op, n), n, 16 * n, med, best)
+    from sdc_b200.rolling import rolling_moments_device
+    y = torch.from_numpy(np.random.default_rng(2).random(n)).cuda()
+    for op in ("skew", "kurt", "cov", "corr"):
+        other = y if op in ("cov", "corr") else None
+        med, best = timeit(lambda: rolling_moments_device(x, op, 100, 100, other), reps)
+        emit("rolling_%s w=100 n=%d" % (op, n), n, (24 if other is not None else 16) * n, med, best)
+    del y
     x[::1000] = float("nan")
     x[7::100_000] = float("inf")
     for op in ("mean", "std", "min"):
