@@ -330,6 +330,63 @@ class DeviceFrame:
         df = pd.DataFrame({n: _to_host(c) for n, c in self._cols.items()})
         return df.set_index(self._index) if self._index is not None else df
 
+    # ---- columnar I/O: Arrow tables become device columns without a pandas detour ----
+    @classmethod
+    def from_arrow(cls, table):
+        """pyarrow.Table -> device columns.  Numeric columns are copied from their Arrow buffers (nulls become NaN,
+        which makes an integer column float64 -- pandas' rule); string columns keep Arrow's offsets / data / validity
+        buffers, which ARE the str_arr layout (`StringArray.from_arrow`); bool columns become int64.  The reference
+        reads CSV through Arrow as well (sdc/native/arrow_reader.cpp, sdc/io/csv_ext.py) but boxes every column into
+        pandas / NumPy first."""
+        import pyarrow as pa
+        from .str_arr import StringArray
+        torch = _torch()
+        cols = {}
+        for name, col in zip(table.column_names, table.columns):
+            t = col.type
+            if pa.types.is_dictionary(t):
+                col = col.cast(t.value_type)
+                t = col.type
+            if pa.types.is_string(t) or pa.types.is_large_string(t):
+                cols[name] = StringArray.from_arrow(col).cuda()
+                continue
+            if pa.types.is_boolean(t):
+                col, t = col.cast(pa.int64()), pa.int64()
+            if not (pa.types.is_integer(t) or pa.types.is_floating(t)):
+                raise TypeError("DeviceFrame.from_arrow: unsupported column type %s (%s)" % (t, name))
+            if col.null_count:
+                col = col.cast(pa.float64())
+                a = col.to_numpy(zero_copy_only=False) if not isinstance(col, pa.ChunkedArray) else col.combine_chunks().to_numpy(zero_copy_only=False)
+            else:
+                a = (col.combine_chunks() if isinstance(col, pa.ChunkedArray) else col).to_numpy(zero_copy_only=False)
+            a = np.ascontiguousarray(a)
+            if a.dtype.kind in "iu" and a.dtype != np.int64:
+                a = a.astype(np.int64)
+            elif a.dtype.kind == "f" and a.dtype != np.float64:
+                a = a.astype(np.float64)
+            cols[name] = torch.from_numpy(a.copy() if not a.flags.writeable else a).cuda()
+        return cls(cols)
+
+    def to_arrow(self):
+        import pyarrow as pa
+        arrays, names = [], []
+        for n, c in self._cols.items():
+            arrays.append(c.to_arrow() if _is_str(c) else pa.array(c.cpu().numpy()))
+            names.append(n)
+        return pa.table(arrays, names=names)
+
+    @classmethod
+    def read_csv(cls, path, **read_options):
+        """CSV file -> device columns through Arrow's multithreaded reader (what `pd.read_csv` is lowered to in the
+        reference: sdc/io/csv_ext.py + native/arrow_reader.cpp; census_benchmark.py:84-85 starts this way)."""
+        import pyarrow.csv as pacsv
+        return cls.from_arrow(pacsv.read_csv(path, **read_options))
+
+    @classmethod
+    def read_parquet(cls, path, columns=None):
+        import pyarrow.parquet as pq
+        return cls.from_arrow(pq.read_table(path, columns=columns))
+
     @property
     def columns(self):
         return list(self._cols)

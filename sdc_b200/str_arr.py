@@ -44,6 +44,53 @@ class StringArray:
         return cls(offsets, chars, bitmap, n)
 
     @classmethod
+    def from_arrow(cls, arr):
+        """pyarrow string / large_string array (or chunked array) -> str_arr WITHOUT touching Python strings: Arrow's
+        layout is the reference's (offsets + UTF-8 data + validity bitmap, LSB-first, 1 = valid --
+        sdc/str_arr_type.py:69-70), so the buffers are viewed, rebased to offset 0 and narrowed to uint32.  The
+        reference's own CSV path hands Arrow string columns over the same way (sdc/native/arrow_reader.cpp)."""
+        import pyarrow as pa
+        if isinstance(arr, pa.ChunkedArray):
+            arr = arr.combine_chunks() if arr.num_chunks != 1 else arr.chunk(0)
+        if pa.types.is_dictionary(arr.type):
+            arr = arr.dictionary_decode()
+        if not (pa.types.is_string(arr.type) or pa.types.is_large_string(arr.type)):
+            raise TypeError("StringArray.from_arrow: expected a string array, got %s" % arr.type)
+        n = len(arr)
+        wide = pa.types.is_large_string(arr.type)
+        vbuf, obuf, dbuf = arr.buffers()
+        odt = np.int64 if wide else np.int32
+        offs = np.frombuffer(obuf, dtype=odt, count=arr.offset + n + 1)[arr.offset:] if n else np.zeros(1, dtype=odt)
+        lo, hi = int(offs[0]), int(offs[-1])
+        if hi - lo >= 2**32:
+            raise ValueError("string array exceeds the uint32 offset range")          # sdc_str_arr.hpp:206
+        offsets = (offs - lo).astype(np.uint32)
+        chars = np.frombuffer(dbuf, dtype=np.uint8, count=hi)[lo:hi].copy() if (dbuf is not None and hi > lo) else np.zeros(0, dtype=np.uint8)
+        if vbuf is None or arr.null_count == 0:
+            bitmap = np.packbits(np.ones(n, dtype=np.uint8), bitorder="little") if n else np.zeros(0, dtype=np.uint8)
+        else:
+            bits = np.unpackbits(np.frombuffer(vbuf, dtype=np.uint8), bitorder="little")[arr.offset:arr.offset + n]
+            bitmap = np.packbits(bits, bitorder="little")
+            if bits.size and not bits.all():
+                # NA strings are stored empty (sdc_str_arr.hpp:389-393); Arrow may keep bytes under a null slot
+                lens = np.diff(offsets.astype(np.int64))
+                if (lens[bits == 0] != 0).any():
+                    keep = np.repeat(bits.astype(bool), lens)
+                    chars = chars[keep]
+                    lens = np.where(bits.astype(bool), lens, 0)
+                    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+        return cls(offsets, chars, bitmap, n)
+
+    def to_arrow(self):
+        """-> pyarrow.StringArray sharing the layout (one copy of each buffer to the host)."""
+        import pyarrow as pa
+        h = self.cpu()
+        valid = h.valid_mask()
+        vb = None if valid.all() else pa.py_buffer(np.packbits(valid, bitorder="little").tobytes())
+        return pa.StringArray.from_buffers(h.n, pa.py_buffer(h.offsets.astype(np.int32).tobytes()), pa.py_buffer(h.chars.tobytes()),
+                                           vb, -1 if vb is not None else 0)
+
+    @classmethod
     def from_fixed_width(cls, codes_u8):
         """n x w uint8 matrix of characters -> str_arr without touching Python strings (benchmarks)."""
         n, w = codes_u8.shape

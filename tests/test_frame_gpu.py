@@ -169,3 +169,29 @@ def test_merge_asof(kind):
     pd.testing.assert_frame_equal(got, want, check_dtype=False)
     with pytest.raises(ValueError):
         DeviceFrame.from_pandas(left.iloc[::-1].reset_index(drop=True)).merge_asof(DeviceFrame.from_pandas(right), on="time")
+
+
+def test_arrow_csv_parquet_ingest(tmp_path):
+    """CSV / Parquet -> Arrow -> device columns, then the kernels, then back."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from sdc_b200.frame import DeviceFrame
+    rng = np.random.default_rng(4)
+    n = 5000
+    df = pd.DataFrame({"k": rng.integers(0, 50, n), "s": np.array(["aa", "b", "ccc", "dddd"], dtype=object)[rng.integers(0, 4, n)],
+                       "x": rng.standard_normal(n), "flag": rng.integers(0, 2, n).astype(bool)})
+    df.loc[rng.integers(0, n, 60), "x"] = np.nan
+    df.loc[rng.integers(0, n, 40), "s"] = None
+    csv, parquet = tmp_path / "t.csv", tmp_path / "t.parquet"
+    df.to_csv(csv, index=False)
+    pq.write_table(pa.Table.from_pandas(df, preserve_index=False), parquet)
+    for dev in (DeviceFrame.read_csv(str(csv)), DeviceFrame.read_parquet(str(parquet))):
+        assert dev.columns == ["k", "s", "x", "flag"] and len(dev) == n
+        back = dev.to_pandas()
+        np.testing.assert_array_equal(back["k"].to_numpy(), df["k"].to_numpy())
+        np.testing.assert_allclose(back["x"].to_numpy(), df["x"].to_numpy(), rtol=1e-15, equal_nan=True)
+        assert [None if pd.isna(v) else v for v in back["s"]] == [None if pd.isna(v) else v for v in df["s"]]
+        got = dev[["s", "x"]].groupby("s").sum().to_pandas()
+        pd.testing.assert_frame_equal(got, df[["s", "x"]].groupby("s").sum(), check_dtype=False, rtol=1e-9)
+        tab = dev.to_arrow()
+        assert tab.column("s").to_pylist() == [None if pd.isna(v) else v for v in df["s"]]
