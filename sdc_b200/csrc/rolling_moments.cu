@@ -62,38 +62,65 @@ __device__ __forceinline__ void mom_update(MomState& st, double x, double y, dou
     }
 }
 
+// Everything in the result formulas that depends on the row count alone, cached while the count stays the same
+// (consecutive windows almost always hold the same number of finite rows): the divisions by n become
+// multiplications by 1/n, which leaves one division (and one square root) per output.
+struct MomConsts {
+    int n;              // the count the constants belong to (-1: none yet)
+    double rn;          // 1 / n
+    double c0, c1, c2;  // skew: sqrt((n-1) n) / (n-2);  kurt: 1 / ((n-2)(n-3)), n^2 - 1, 3 (n-1)^2;  cov: n / (n - ddof)
+};
+
 template <int OP>
-__device__ __forceinline__ double mom_emit(const MomState& st, int minp, int ddof) {
+__device__ __forceinline__ void mom_consts_for(MomConsts& c, int ni, int ddof) {
+    if (ni == c.n) return;
+    c.n = ni;
+    const double n = (double)ni;
+    c.rn = ni != 0 ? 1.0 / n : 0.0;
+    if (OP == OP_SKEW) c.c0 = ni > 2 ? sqrt((n - 1.0) * n) / (n - 2.0) : 0.0;
+    if (OP == OP_KURT) {
+        c.c0 = ni > 3 ? 1.0 / (n - 2.0) / (n - 3.0) : 0.0;
+        c.c1 = n * n - 1.0;
+        c.c2 = 3.0 * (n - 1.0) * (n - 1.0);
+    }
+    if (OP == OP_COV) c.c0 = (ni - ddof) >= 1 ? n / (double)(ni - ddof) : 0.0;
+}
+
+// skew_result_or_nan / kurt_result_or_nan / cov_result_or_nan / corr_result_or_nan (reference :487-556)
+template <int OP>
+__device__ __forceinline__ double mom_emit(const MomState& st, int minp, int ddof, MomConsts& c) {
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     const int ni = st.n;
-    const double n = (double)ni;
     if (OP == OP_SKEW) {
         if (ni < (minp > 3 ? minp : 3)) return nan;
-        const double m2 = (st.s1 - st.s0 * st.s0 / n) / n;
-        const double m3 = (st.s2 - 3.0 * st.s0 * st.s1 / n + 2.0 * st.s0 * st.s0 * st.s0 / n / n) / n;
+        mom_consts_for<OP>(c, ni, ddof);
+        const double a = st.s0 * c.rn;                                  // mean
+        const double m2 = (st.s1 - st.s0 * a) * c.rn;
+        const double m3 = (st.s2 - 3.0 * a * st.s1 + 2.0 * a * a * st.s0) * c.rn;
         if (!(m2 > 0.0)) return m2 == 0.0 ? nan : m3 / (m2 * sqrt(m2));     // m2 < 0 (rounding): pow gives NaN
-        return sqrt((n - 1.0) * n) / (n - 2.0) * m3 / (m2 * sqrt(m2));
+        return c.c0 * m3 / (m2 * sqrt(m2));
     }
     if (OP == OP_KURT) {
         if (ni < (minp > 4 ? minp : 4)) return nan;
-        const double m2 = (st.s1 - st.s0 * st.s0 / n) / n;
-        const double m4 = (st.s3 - 4.0 * st.s0 * st.s2 / n + 6.0 * st.s0 * st.s0 * st.s1 / n / n -
-                           3.0 * st.s0 * st.s0 * st.s0 * st.s0 / n / n / n) / n;
+        mom_consts_for<OP>(c, ni, ddof);
+        const double a = st.s0 * c.rn;
+        const double m2 = (st.s1 - st.s0 * a) * c.rn;
+        const double m4 = (st.s3 - 4.0 * a * st.s2 + 6.0 * a * a * st.s1 - 3.0 * a * a * a * st.s0) * c.rn;
         if (!(m2 > 0.0)) return m2 == 0.0 ? 0.0 : m4 / (m2 * m2);
-        return 1.0 / (n - 2.0) / (n - 3.0) * ((n * n - 1.0) * m4 / (m2 * m2) - 3.0 * (n - 1.0) * (n - 1.0));
+        return c.c0 * (c.c1 * m4 / (m2 * m2) - c.c2);
     }
     if (ni < (minp > 1 ? minp : 1)) return nan;
+    mom_consts_for<OP>(c, ni, ddof);
     if (OP == OP_COV) {
-        const double res = (st.s2 - st.s0 * st.s1 / n) / n;
         if (ni - ddof < 1) return nan;
-        return res * n / (double)(ni - ddof);
+        return (st.s2 - st.s0 * st.s1 * c.rn) * c.rn * c.c0;
     }
     const double eps = 2.220446049250313e-16;
-    const double var_x = st.s3 - st.s0 * st.s0 / n;
+    const double var_x = st.s3 - st.s0 * st.s0 * c.rn;
     if (fabs(var_x) <= eps) return nan;
-    const double var_y = st.s4 - st.s1 * st.s1 / n;
+    const double var_y = st.s4 - st.s1 * st.s1 * c.rn;
     if (fabs(var_y) <= eps) return nan;
-    const double cov_xy = st.s2 - st.s0 * st.s1 / n;
+    const double cov_xy = st.s2 - st.s0 * st.s1 * c.rn;
     return cov_xy / sqrt(var_x * var_y);
 }
 
@@ -122,13 +149,19 @@ __global__ void __launch_bounds__(kMThreads) rolling_moments_kernel(MomArgs a) {
         const int o0 = tid * R;
         if (tile0 + o0 < a.n_out) {
             MomState st = {0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            for (int j = o0; j <= o0 + hp; ++j) mom_update<OP>(st, X[j], Y[j], 1.0, 1);
-            O[o0] = mom_emit<OP>(st, a.minp, a.ddof);
+            MomConsts mc;
+            mc.n = -1;
+            auto row = [&](int j, double sign, int dn) {
+                const double xv = X[j];
+                mom_update<OP>(st, xv, kTwo ? Y[j] : xv, sign, dn);
+            };
+            for (int j = o0; j <= o0 + hp; ++j) row(j, 1.0, 1);
+            O[o0] = mom_emit<OP>(st, a.minp, a.ddof, mc);
 #pragma unroll 4
             for (int k = 1; k < R; ++k) {
-                mom_update<OP>(st, X[o0 + hp + k], Y[o0 + hp + k], 1.0, 1);
-                mom_update<OP>(st, X[o0 + k - 1], Y[o0 + k - 1], -1.0, -1);
-                O[o0 + k] = mom_emit<OP>(st, a.minp, a.ddof);
+                row(o0 + hp + k, 1.0, 1);
+                row(o0 + k - 1, -1.0, -1);
+                O[o0 + k] = mom_emit<OP>(st, a.minp, a.ddof, mc);
             }
         }
         __syncthreads();
