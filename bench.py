@@ -201,6 +201,32 @@ def bench_other_ops(dev, peak, cpu_legs=True):
         gb["cpu_baseline"] = {"value": ns / dt, "unit": "rows/s", "cores": numba.config.NUMBA_NUM_THREADS, "kind": "port",
                               "sample": "first 2M rows of the workload, one call after a compile call",
                               "pandas_rows_per_s": n / dtp}
+    # end to end through the C ABI with HOST buffers (pinned): H2D of both columns, aggregate, D2H of keys + sums
+    import ctypes as ct
+    from sdc_b200 import native
+    lib = native.load()
+    a_p, b_p = torch.from_numpy(a_h).pin_memory(), torch.from_numpy(b_h).pin_memory()
+    ptrs = (ct.c_void_p * 1)(b_p.data_ptr())
+    dts = (ct.c_int32 * 1)(native.DTYPE_CODES["float64"])
+    rk, rv = np.empty(4096, np.int64), np.empty(4096, np.float64)
+
+    def host_call():
+        h, ng = ct.c_int64(0), ct.c_int64(0)
+        native.check(lib.sdcb200_host_groupby(native.DTYPE_CODES["int64"], a_p.data_ptr(), n, 1, ptrs, dts, native.AGG_BITS["sum"],
+                                              1, 1, 1000, ct.byref(h), ct.byref(ng)))
+        native.check(lib.sdcb200_groupby_keys(h.value, rk.ctypes.data, 1, None))
+        native.check(lib.sdcb200_groupby_values(h.value, 0, native.AGG_BITS["sum"], rv.ctypes.data, 1, None))
+        lib.sdcb200_groupby_free(h.value)
+        return ng.value
+    host_call()
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        ng = host_call()
+        ts.append(time.perf_counter() - t0)
+    gb["e2e"] = {"value": n / float(np.median(ts)), "unit": "rows/s", "h2d_bytes_per_step": 16 * n, "d2h_bytes_per_step": 16 * ng,
+                 "api": "sdcb200_host_groupby + sdcb200_groupby_keys / _values (pinned host buffers)", "ms_median": float(np.median(ts)) * 1e3}
+    del a_p, b_p
     out["groupby_sum_c1"] = gb
     del a, b
 
@@ -229,6 +255,26 @@ def bench_other_ops(dev, peak, cpu_legs=True):
         dt = time.perf_counter() - t0
         jn["cpu_baseline"] = {"value": ns / dt, "unit": "probe rows/s", "cores": 1, "kind": "pandas.merge (the reference ships no merge)",
                               "sample": "first 10M probe rows x the full 10M-row build side"}
+    l_p, r_p = torch.from_numpy(l_h).pin_memory(), torch.from_numpy(r_h).pin_memory()
+    li_p = torch.empty(npr, dtype=torch.int64).pin_memory()
+    ri_p = torch.empty(npr, dtype=torch.int64).pin_memory()
+
+    def host_join():
+        h, no = ct.c_int64(0), ct.c_int64(0)
+        native.check(lib.sdcb200_host_join(native.JOIN_HOW["inner"], native.DTYPE_CODES["int64"], l_p.data_ptr(), npr, r_p.data_ptr(), nb,
+                                           ct.byref(h), ct.byref(no)))
+        native.check(lib.sdcb200_join_indexers(h.value, li_p.data_ptr(), ri_p.data_ptr(), 1, None))
+        lib.sdcb200_join_free(h.value, None)
+        return no.value
+    host_join()
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        no = host_join()
+        ts.append(time.perf_counter() - t0)
+    jn["e2e"] = {"value": npr / float(np.median(ts)), "unit": "probe rows/s", "h2d_bytes_per_step": 8 * (npr + nb),
+                 "d2h_bytes_per_step": 16 * no, "api": "sdcb200_host_join + sdcb200_join_indexers (pinned host buffers)",
+                 "ms_median": float(np.median(ts)) * 1e3}
     out["join_inner_c3"] = jn
     return out
 

@@ -160,6 +160,12 @@ int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* 
  * the requested ones in ascending bit order).                                                       */
 int32_t sdcb200_groupby_result(int64_t handle, void** keys, void** vals, int64_t* stride);
 int32_t sdcb200_groupby_free(int64_t handle);
+/* host-buffer form of sdcb200_groupby (the NumPy / NRT buffers a jitted SDC function holds, as every native of the
+ * reference receives them): columns are copied in on two streams, the aggregate runs, the inputs are released; read
+ * the result with sdcb200_groupby_keys / sdcb200_groupby_values(dst_is_host = 1), then sdcb200_groupby_free.      */
+int32_t sdcb200_host_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
+                             const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
+                             int64_t expected_groups, int64_t* handle_out, int64_t* ngroups_out);
 
 /* Composite ids for multi-key groupby / merge (the reference takes ONE `by` column,
  * sdc/datatypes/hpat_pandas_dataframe_functions.py:3066-3067): out[i] = a[i] * nb + b[i], `invalid` where either
@@ -191,6 +197,9 @@ int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_
  * sdcb200_join_free                                                                                  */
 int32_t sdcb200_join_result(int64_t handle, int64_t** left_idx, int64_t** right_idx);
 int32_t sdcb200_join_free(int64_t handle, void* stream);
+/* host-buffer form of sdcb200_join; read the indexers with sdcb200_join_indexers(dst_is_host = 1). */
+int32_t sdcb200_host_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                          int64_t* handle_out, int64_t* n_out);
 /* dst[i] = idx[i] < 0 ? NaN : (double)src[idx[i]] -- payload gather of a left join
  * (setitem_arr_nan, sdc/hiframes/join.py:34-43); src_dtype SDCB200_I64 or SDCB200_F64.            */
 int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int64_t* idx, int64_t n, double* dst,

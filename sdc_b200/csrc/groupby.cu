@@ -1616,3 +1616,45 @@ extern "C" int32_t sdcb200_combine_ids(const int64_t* a, const int64_t* b, int64
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }
+
+// Host-buffer form (what a jitted SDC function holds: NumPy / NRT memory): the key and value columns go to the
+// device on two copy streams, the aggregate runs, the inputs are released; the result stays in the handle and is
+// read with sdcb200_groupby_keys / _values (dst_is_host = 1).  The copies dominate (16 B per row over PCIe).
+extern "C" int32_t sdcb200_host_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
+                                        const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
+                                        int64_t expected_groups, int64_t* handle_out, int64_t* ngroups_out) {
+    SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
+    SDC_ARG_CHECK(n >= 0 && ncols >= 0 && ncols <= kMaxCols, "n / ncols");
+    SDC_ARG_CHECK(n == 0 || keys != nullptr, "null keys");
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    void* dkeys = nullptr;
+    void* dcols[kMaxCols];
+    for (int i = 0; i < kMaxCols; ++i) dcols[i] = nullptr;
+    auto body = [&]() -> int32_t {
+        for (int i = 0; i < 2; ++i) SDC_CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        SDC_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        const size_t bytes = (size_t)(n > 0 ? n : 1) * 8;
+        SDC_TRY(dev_alloc(&dkeys, bytes, st[0]));
+        if (n > 0) SDC_CUDA_TRY(cudaMemcpyAsync(dkeys, keys, (size_t)n * 8, cudaMemcpyHostToDevice, st[0]));
+        for (int i = 0; i < ncols; ++i) {
+            SDC_ARG_CHECK(n == 0 || cols[i] != nullptr, "null column");
+            cudaStream_t cs = st[(i + 1) & 1];
+            SDC_TRY(dev_alloc(&dcols[i], bytes, cs));
+            if (n > 0) SDC_CUDA_TRY(cudaMemcpyAsync(dcols[i], cols[i], (size_t)n * 8, cudaMemcpyHostToDevice, cs));
+        }
+        SDC_CUDA_TRY(cudaEventRecord(ev, st[1]));
+        SDC_CUDA_TRY(cudaStreamWaitEvent(st[0], ev, 0));
+        SDC_TRY(sdcb200_groupby(key_dtype, dkeys, n, ncols, dcols, col_dtypes, agg_mask, sort, ddof, expected_groups, st[0],
+                                handle_out, ngroups_out));
+        return SDCB200_OK;
+    };
+    const int32_t rc = body();
+    if (dkeys) dev_free(dkeys, st[0]);
+    for (int i = 0; i < ncols; ++i)
+        if (dcols[i]) dev_free(dcols[i], st[0]);
+    for (int i = 0; i < 2; ++i)
+        if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+    if (ev) cudaEventDestroy(ev);
+    return rc;
+}

@@ -1002,6 +1002,36 @@ int32_t sdcb200_take_nullable_f64(int32_t src_dtype, const void* src, const int6
     return SDCB200_OK;
 }
 
+// Host-buffer form: both key columns go to the device, the join runs, the inputs are released; the indexers stay in the
+// handle and are read with sdcb200_join_indexers (dst_is_host = 1).
+int32_t sdcb200_host_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                          int64_t* handle_out, int64_t* n_out) {
+    SDC_ARG_CHECK(nl >= 0 && nr >= 0, "row counts");
+    SDC_ARG_CHECK((nl == 0 || left_keys != nullptr) && (nr == 0 || right_keys != nullptr), "null keys");
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ev = nullptr;
+    void *dl = nullptr, *dr = nullptr;
+    auto body = [&]() -> int32_t {
+        for (int i = 0; i < 2; ++i) SDC_CUDA_TRY(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+        SDC_CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        SDC_TRY(dev_alloc(&dl, (size_t)(nl > 0 ? nl : 1) * 8, st[0]));
+        SDC_TRY(dev_alloc(&dr, (size_t)(nr > 0 ? nr : 1) * 8, st[1]));
+        if (nl > 0) SDC_CUDA_TRY(cudaMemcpyAsync(dl, left_keys, (size_t)nl * 8, cudaMemcpyHostToDevice, st[0]));
+        if (nr > 0) SDC_CUDA_TRY(cudaMemcpyAsync(dr, right_keys, (size_t)nr * 8, cudaMemcpyHostToDevice, st[1]));
+        SDC_CUDA_TRY(cudaEventRecord(ev, st[1]));
+        SDC_CUDA_TRY(cudaStreamWaitEvent(st[0], ev, 0));
+        SDC_TRY(sdcb200_join(how, key_dtype, dl, nl, dr, nr, st[0], handle_out, n_out));
+        return SDCB200_OK;
+    };
+    const int32_t rc = body();
+    if (dl) dev_free(dl, st[0]);
+    if (dr) dev_free(dr, st[0]);
+    for (int i = 0; i < 2; ++i)
+        if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+    if (ev) cudaEventDestroy(ev);
+    return rc;
+}
+
 int32_t sdcb200_asof_backward(int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                               int64_t* right_idx, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;

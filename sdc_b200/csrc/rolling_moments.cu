@@ -197,8 +197,10 @@ int32_t launch_moments(const MomArgs& a, cudaStream_t s) {
 
 template <int OP>
 int32_t dispatch_moments(const MomArgs& a, cudaStream_t s) {
-    // long runs amortise the from-scratch window sum; short ones keep more CTAs per SM when the window is small
-    if (a.win >= 48) return launch_moments<OP, 31>(a, s);
+    // long runs amortise the from-scratch window sum; short ones keep more CTAs per SM when the window is small or
+    // two series are staged (R = 31 with two series needs 192 KB: one CTA per SM, 2.3 ms per 100 M rows for cov)
+    constexpr bool kTwo = (OP == OP_COV || OP == OP_CORR);
+    if (a.win >= (kTwo ? 512 : 48)) return launch_moments<OP, 31>(a, s);
     return launch_moments<OP, 15>(a, s);
 }
 

@@ -376,11 +376,15 @@ class DeviceFrame:
         return pa.table(arrays, names=names)
 
     @classmethod
-    def read_csv(cls, path, **read_options):
+    def read_csv(cls, path, read_options=None, parse_options=None, convert_options=None):
         """CSV file -> device columns through Arrow's multithreaded reader (what `pd.read_csv` is lowered to in the
-        reference: sdc/io/csv_ext.py + native/arrow_reader.cpp; census_benchmark.py:84-85 starts this way)."""
+        reference: sdc/io/csv_ext.py + native/arrow_reader.cpp; census_benchmark.py:84-85 starts this way).  Like
+        pandas, an empty field of a string column is a missing value unless `convert_options` says otherwise."""
         import pyarrow.csv as pacsv
-        return cls.from_arrow(pacsv.read_csv(path, **read_options))
+        if convert_options is None:
+            convert_options = pacsv.ConvertOptions(strings_can_be_null=True)
+        return cls.from_arrow(pacsv.read_csv(path, read_options=read_options, parse_options=parse_options,
+                                             convert_options=convert_options))
 
     @classmethod
     def read_parquet(cls, path, columns=None):

@@ -50,6 +50,9 @@ SIGNATURES = {
     "sdcb200_groupby_values": (_i32, [_i64, _i32, ct.c_uint32, _vp, _i32, _vp]),
     "sdcb200_groupby_result": (_i32, [_i64, ct.POINTER(_vp), ct.POINTER(_vp), ct.POINTER(_i64)]),
     "sdcb200_groupby_free": (_i32, [_i64]),
+    "sdcb200_host_groupby": (_i32, [_i32, _vp, _i64, _i32, ct.POINTER(_vp), ct.POINTER(_i32), ct.c_uint32, _i32, _i64,
+                                    _i64, ct.POINTER(_i64), ct.POINTER(_i64)]),
+    "sdcb200_host_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, ct.POINTER(_i64), ct.POINTER(_i64)]),
     "sdcb200_combine_ids": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "sdcb200_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
     "sdcb200_join_indexers": (_i32, [_i64, _vp, _vp, _i32, _vp]),

@@ -25,6 +25,19 @@ def test_nopython_binding_raises_without_a_device():
         f(np.arange(10.0))
     with pytest.raises(RuntimeError, match="libsdc_b200"):
         g(np.arange(10.0))
+    # groupby / merge on host arrays type and compile the same way, and fail loudly without a device
+    @numba.njit
+    def h(k, v):
+        return nx.groupby_sum(k, v)
+
+    @numba.njit
+    def m(l, r):
+        return nx.merge_indexers(l, r, "left")
+
+    with pytest.raises(RuntimeError, match="libsdc_b200"):
+        h(np.arange(10), np.arange(10.0))
+    with pytest.raises(RuntimeError, match="libsdc_b200"):
+        m(np.arange(10), np.arange(10))
     # argument errors are raised in the jitted code before the native call, with the reference's messages
     @numba.njit
     def bad(x):

@@ -64,6 +64,11 @@ elif what in ("rolling_std", "rolling_min", "rolling_mean_nan"):
     out = torch.empty_like(x)
     for _ in range(reps):
         rolling_device(x, {"rolling_std": "std", "rolling_min": "min", "rolling_mean_nan": "mean"}[what], 100, 100, 1, out=out)
+elif what == "rolling_skew":
+    from sdc_b200.rolling import rolling_moments_device
+    x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
+    for _ in range(reps):
+        rolling_moments_device(x, "skew", 100, 100)
 elif what == "strings":
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_ops
