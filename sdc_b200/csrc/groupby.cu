@@ -412,9 +412,27 @@ struct SmallFin {
 
 // SPEC >= 0: compile-time `need` mask for ONE float64 value column (the common df.groupby(k).agg() shapes get a
 // tight loop); SPEC < 0: any columns / aggregates, decided at run time.
-template <bool KEY_F64, int SPEC>
+// ---- LEAN instantiations of gb_smem_kernel (one float64 column, direct-addressed slots): the per-row work of the
+// generic loop is 92 instructions of which a quarter is the float64 add itself (ncu, profiles/r1_groupby_100m_*) and
+// the kernel is issue-bound (62 % issue slots busy).  The lean loop drops everything a direct window does not need
+// (probe loop, global-table fallback, slot arrays, overflow polling) and addresses shared memory through explicit
+// 32-bit shared addresses: with generic pointers the compiler rebuilt the shared window base (five uniform
+// instructions) in front of every access.  `red.shared.add.f64` expands to the same load / add / CAS-spin loop as
+// atomicAdd(double*).
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {      // keeps an address in a register instead of
+    asm volatile("" : "+r"(x));                                   // letting the compiler rematerialise it
+    return x;
+}
+__device__ __forceinline__ void reds_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void reds_inc_u32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void reds_min_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void reds_max_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void sts_zero_u32(uint32_t a) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory"); }
+
+template <bool KEY_F64, int SPEC, bool LEAN = false>
 __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __restrict__ keys, int64_t n, Cols cols_rt, Table t,
                                                                 int need_rt, SmemLayout lay, SmallFin fin) {
+    static_assert(!LEAN || (SPEC >= 0 && !KEY_F64), "lean loop: one float64 column, int64 keys / group ids");
     const int need = SPEC >= 0 ? SPEC : need_rt;
     struct ColsView {
         const Cols& c;
@@ -471,7 +489,54 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     __syncthreads();
     const unsigned long long dlo = s_dlo, drange = s_drange;
 
-    // ---- 2. aggregate
+    // ---- 2 (LEAN). aggregate, direct-addressed slots only
+    if (LEAN && drange) {
+        const uint32_t keys_a = opaque_u32(smem_u32(skeys));
+        const uint32_t sum_a = opaque_u32(smem_u32(sm + lay.off_sum[0]));
+        const uint32_t cnt_a = opaque_u32(smem_u32(sm + lay.off_cnt[0]));
+        const uint32_t mn_a = opaque_u32(smem_u32(sm + lay.off_mn[0]));
+        const uint32_t mx_a = opaque_u32(smem_u32(sm + lay.off_mx[0]));
+        auto row = [&](unsigned long long k, unsigned long long vbits) {
+            const unsigned long long d = k - dlo;
+            if (d < drange && k != kEmptyKey()) {
+                const uint32_t o8 = (uint32_t)d * 8u;
+                sts_zero_u32(keys_a + o8 + 4u);             // presence: the high word of the slot's key leaves the empty pattern
+                const double v = __longlong_as_double((long long)vbits);
+                if (v == v) {
+                    if (need & NEED_SUM) reds_add_f64(sum_a + o8, v);
+                    if (need & NEED_CNT) reds_inc_u32(cnt_a + (uint32_t)d * 4u);
+                    if (need & (NEED_MIN | NEED_MAX)) {
+                        const unsigned long long o = f64_to_ordered(v);
+                        if (need & NEED_MIN) reds_min_u64(mn_a + o8, o);
+                        if (need & NEED_MAX) reds_max_u64(mx_a + o8, o);
+                    }
+                }
+            } else if (!(skip_neg && (long long)k < 0)) {
+                *(volatile int*)t.overflow = 2;             // outside the sampled window: rerun with hashing
+            }
+        };
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t base = tile * kSmTile;
+            unsigned long long kb[kRows], v0[kRows];
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) { kb[e] = kbn[e]; v0[e] = v0n[e]; }
+            if (tile + gridDim.x < ntiles) {
+                const int64_t nbase = (tile + gridDim.x) * kSmTile;
+                load4<kSmThreads>(keys, nbase, n, tid, cols.vec_ok, kbn);
+                load4<kSmThreads>(cols.data[0], nbase, n, tid, cols.vec_ok, v0n);
+            }
+            if (base + kSmTile <= n) {
+#pragma unroll
+                for (int e = 0; e < kRows; ++e) row(kb[e], v0[e]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < kRows; ++e)
+                    if (tile_row<kSmThreads>(base, tid, e) < n) row(kb[e], v0[e]);
+            }
+        }
+    } else
+    // ---- 2. aggregate (generic: hashed or direct slots, any columns; a LEAN instantiation lands here when the
+    //      sampled keys do not fit a direct window)
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncwarp();
         const int64_t base = tile * kSmTile;
@@ -1064,6 +1129,15 @@ void free_result(GroupbyResult* r) {
     delete r;
 }
 
+// SDCB200_GB_LEAN=0 keeps the generic loop of gb_smem_kernel for dense keys too (A/B measurements)
+bool gb_lean_enabled() {
+    static const int on = [] {
+        const char* e = getenv("SDCB200_GB_LEAN");
+        return (e && *e) ? atoi(e) : 1;
+    }();
+    return on != 0;
+}
+
 int need_for(unsigned agg_mask, bool sort) {
     int need = 0;
     if (agg_mask & (AGG_SUM | AGG_MEAN | AGG_VAR | AGG_STD)) need |= NEED_SUM;
@@ -1383,6 +1457,16 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             else if (spec == 2) kern = gb_smem_kernel<KEY_F64, 2>;
             else if (spec == 3) kern = gb_smem_kernel<KEY_F64, 3>;
             else if (spec == 15) kern = gb_smem_kernel<KEY_F64, 15>;
+            // int64 keys / group ids: the instantiation with the lean loop for a direct window (it carries the generic
+            // loop as well, for sampled keys that do not fit one)
+            if constexpr (!KEY_F64) {
+                if (spec >= 0 && allow_direct && gb_lean_enabled()) {
+                    if (spec == 1) kern = gb_smem_kernel<false, 1, true>;
+                    else if (spec == 2) kern = gb_smem_kernel<false, 2, true>;
+                    else if (spec == 3) kern = gb_smem_kernel<false, 3, true>;
+                    else if (spec == 15) kern = gb_smem_kernel<false, 15, true>;
+                }
+            }
             SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
             const int64_t ntiles = ceil_div(n, (int64_t)kSmThreads * kRows);
             int64_t grid = (int64_t)sms * 2;

@@ -40,6 +40,7 @@ namespace {
 
 constexpr unsigned long long kEmptyKey = 0x7ff8dead0000beefull;   // never a canonical float key; an int64 key
                                                                   // equal to it lives in the spare slot [cap]
+constexpr int64_t kOneCtaScanMax = 256 * 1024;     // tile counts up to this many are scanned by one CTA (one launch)
 constexpr int kJoinThreads = kScanThreads;         // 256
 constexpr int kItems = kScanItems;                 // 8 rows per thread in the probe tiles
 constexpr int kTile = kScanTile;                   // 2048 rows per CTA
@@ -753,7 +754,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                 probe_unique_row1_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), row1.as<uint32_t>(),
                                                                                         tile_counts, vec);
                 SDC_CHECK_LAUNCH();
-                if (nt <= 256 * 1024) {
+                if (nt <= kOneCtaScanMax) {
                     scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tile_counts, nt);
                     SDC_CHECK_LAUNCH();
                 } else {
@@ -806,7 +807,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                                                                             (reinterpret_cast<uintptr_t>(l) & 15) == 0);
     SDC_CHECK_LAUNCH();
     // exclusive scan of the tile counts in place; total lands in tile_counts[nt]
-    if (nt <= 256 * 1024) {
+    if (nt <= kOneCtaScanMax) {
         scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tile_counts, nt);
         SDC_CHECK_LAUNCH();
     } else {
