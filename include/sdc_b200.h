@@ -220,15 +220,17 @@ int32_t sdcb200_asof_backward(int32_t key_dtype, const void* left_keys, int64_t 
  * writes uint64 row positions like the reference.                                                   */
 int32_t sdcb200_str_argsort(const uint8_t* chars, const uint32_t* offsets, int64_t n, int32_t ascending, uint64_t* index_out,
                             void* stream);
-/* String keys -> exact dense group ids (gid_out[i] = id of row i's string, -1 for NA rows, which groupby
- * skips: sdc/datatypes/hpat_pandas_dataframe_functions.py:3088-3089).  The ids feed sdcb200_groupby as an
- * int64 key column; sdcb200_str_group_rows maps result ids back to one representative input row each
- * (to materialise the key strings with sdcb200_str_gather_*); the table is released with
+/* String keys -> exact dense group ids in [0, *ngroups_out), numbered in order of insertion (gid_out[i] = id
+ * of row i's string, -1 for NA rows, which groupby skips: sdc/datatypes/hpat_pandas_dataframe_functions.py:3088-3089).
+ * The ids feed sdcb200_groupby as a SDCB200_GID key column with expected_groups = *ngroups_out;
+ * sdcb200_str_group_rows maps result ids back to one representative input row each (to materialise the key
+ * strings with sdcb200_str_gather_*; table_cap = *table_cap_out); the table is released with
  * sdcb200_str_table_free.                                                                           */
 int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n,
                               int64_t expected_groups, int64_t* gid_out, int64_t* ngroups_out, int64_t* table_handle_out,
                               int64_t* table_cap_out, void* stream);
-int32_t sdcb200_str_group_rows(int64_t table_handle, const int64_t* gids, int64_t ng, int64_t* rows_out, void* stream);
+int32_t sdcb200_str_group_rows(int64_t table_handle, int64_t table_cap, const int64_t* gids, int64_t ng, int64_t* rows_out,
+                               void* stream);
 int32_t sdcb200_str_table_free(int64_t table_handle, void* stream);
 /* take() on a str_arr (sdc/functions/numpy_like.py:1359-1388 for strings; convert_len_arr_to_offset,
  * sdc_str_arr.hpp:242-252): step 1 writes out_offsets[m + 1] and returns the char total, step 2 copies

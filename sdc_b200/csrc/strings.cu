@@ -86,13 +86,17 @@ inline int grid_for(int64_t n, int threads, int per_sm) {
 }
 
 // ---- factorize ----
-// Table of 16-byte slots {key word, len << 32 | representative row}, linear probing, the key word claimed
-// with one 64-bit atomicCAS; the second word is published right after and readers wait for it.
+// Table of 16-byte slots {key word, len << 32 | group id}, linear probing, the key word claimed with one 64-bit
+// atomicCAS; the second word is published right after and readers wait for it.  Group ids are DENSE, in order of
+// insertion (the claimer's ticket from the group counter), so the aggregate that follows runs on ids in
+// [0, ngroups) -- a direct-addressed table exactly as large as the result -- whatever the capacity of this table,
+// which can therefore be roomy (load factor <= 1/8 for small group counts: a warp's 32 probe loops end after one
+// or two steps instead of six to eight, and the kernel is issue-bound).  rep[id] = the inserting row.
 //   len <= 8 : key word = the string's bytes (little-endian, zero padded) -- together with the length in
 //              the second word that IS the string, so a match needs no look at the representative row:
 //              one 16-byte slot load per probe, no dependent random reads (C4's 8-character keys)
 //   len  > 8 : key word = 64-bit hash of the bytes; a (word, length) match is confirmed by comparing the bytes
-//              with the representative row, so ids are exact
+//              with the representative row rep[id], so ids are exact
 // A key word equal to the empty marker lives in the spare slot [cap].
 constexpr uint64_t kStrEmpty = ~0ull;
 constexpr uint64_t kStrPending = ~0ull;
@@ -132,12 +136,22 @@ __global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_
                                                                     const uint32_t* __restrict__ offsets,
                                                                     const uint8_t* __restrict__ bitmap, int64_t n,
                                                                     ulonglong2* __restrict__ table, uint64_t cap,
+                                                                    uint32_t* __restrict__ rep /* [limit + 2] */,
                                                                     int64_t* __restrict__ gid,
                                                                     unsigned long long* __restrict__ counters /* [0] groups, [1] overflow */,
                                                                     uint64_t limit) {
     const uint64_t total = offsets[n];
     const uint64_t stream_pol = l2_policy_evict_first();
     const int lane = threadIdx.x & 31;
+    // the claimer of a slot: ticket from the group counter, representative row, then the slot's second word
+    auto publish = [&](unsigned long long* second, uint32_t len, uint32_t row) -> int64_t {
+        const unsigned long long id = atomicAdd(&counters[0], 1ull);
+        if (id + 1 > limit) atomicExch(&counters[1], 1ull);
+        if (id <= limit) rep[id] = row;
+        __threadfence();                                   // rep[id] is visible before the id is
+        *reinterpret_cast<volatile unsigned long long*>(second) = ((uint64_t)len << 32) | (uint64_t)(uint32_t)id;
+        return (int64_t)id;
+    };
     // warp-uniform loop (a warp owns 32 consecutive rows per step) and an explicit reconvergence before the
     // coalesced accesses: the probe loop's trip count differs per lane, and a warp that stays split issues its
     // loads and stores as several partial requests
@@ -151,13 +165,17 @@ __global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_
         uint64_t kw = 0;
         if (valid) kw = len <= 8 ? load_word(chars, beg, len, total) : str_hash(chars, beg, len, total);
         if (len > 8 && kw == kStrEmpty) kw = kStrEmpty - 1;      // only the 8-byte string of 0xFF uses the spare slot
-        const uint64_t mine2 = ((uint64_t)len << 32) | (uint64_t)(uint32_t)i;
         int64_t out = valid ? -2 : -1;
         if (valid && kw == kStrEmpty) {
-            // the spare slot holds this one key; it is claimed through its second word
-            const unsigned long long old = atomicCAS(&table[cap].y, kStrPending, mine2);
-            if (old == kStrPending) atomicAdd(&counters[0], 1ull);
-            out = (int64_t)cap;
+            // the spare slot holds this one key; its first word is the claim flag (empty -> 0)
+            const unsigned long long old = atomicCAS(&table[cap].x, kStrEmpty, 0ull);
+            if (old == kStrEmpty) {
+                out = publish(&table[cap].y, len, (uint32_t)i);
+            } else {
+                unsigned long long y;
+                do { y = *reinterpret_cast<volatile unsigned long long*>(&table[cap].y); } while (y == kStrPending);
+                out = (int64_t)(uint32_t)y;
+            }
         } else if (valid) {
             uint64_t s = smix64(kw ^ ((uint64_t)len << 56)) & (cap - 1);
             for (uint64_t probes = 0; probes <= cap; ++probes) {
@@ -168,9 +186,7 @@ __global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_
                     if (*reinterpret_cast<volatile unsigned long long*>(&counters[1])) break;
                     const unsigned long long old = atomicCAS(&table[s].x, kStrEmpty, kw);
                     if (old == kStrEmpty) {
-                        *reinterpret_cast<volatile unsigned long long*>(&table[s].y) = mine2;
-                        if (atomicAdd(&counters[0], 1ull) + 1 > limit) atomicExch(&counters[1], 1ull);
-                        out = (int64_t)s;
+                        out = publish(&table[s].y, len, (uint32_t)i);
                         break;
                     }
                     sl.x = old;
@@ -179,9 +195,10 @@ __global__ void __launch_bounds__(kStrThreads) str_factorize_kernel(const uint8_
                 if (sl.x == kw) {
                     while (sl.y == kStrPending) sl.y = *reinterpret_cast<volatile unsigned long long*>(&table[s].y);
                     if ((uint32_t)(sl.y >> 32) == len) {
-                        if (len <= 8) { out = (int64_t)s; break; }
-                        const uint32_t rep = (uint32_t)sl.y;
-                        if (str_equal(chars, offsets[rep], beg, len, total)) { out = (int64_t)s; break; }
+                        if (len <= 8) { out = (int64_t)(uint32_t)sl.y; break; }
+                        const uint32_t id = (uint32_t)sl.y;
+                        const uint32_t r = id <= limit ? *reinterpret_cast<volatile uint32_t*>(&rep[id]) : 0u;
+                        if (id <= limit && str_equal(chars, offsets[r], beg, len, total)) { out = (int64_t)id; break; }
                     }
                 }
                 s = (s + 1) & (cap - 1);
@@ -198,11 +215,11 @@ __global__ void fill_slots_kernel(ulonglong2* p, uint64_t n) {
 }
 
 // representative row of each group id (for the result's key strings)
-__global__ void str_group_rows_kernel(const ulonglong2* __restrict__ table, const int64_t* __restrict__ gids,
+__global__ void str_group_rows_kernel(const uint32_t* __restrict__ rep, const int64_t* __restrict__ gids,
                                       int64_t ng, int64_t* __restrict__ rows) {
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x) {
         const int64_t g = gids[j];
-        rows[j] = g < 0 ? -1 : (int64_t)(uint32_t)table[g].y;
+        rows[j] = g < 0 ? -1 : (int64_t)rep[g];
     }
 }
 
@@ -327,19 +344,29 @@ int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, con
     SDC_ARG_CHECK(offsets && gid_out, "null pointer");
     uint64_t worst = 64;
     while (worst < 2ull * (uint64_t)n) worst <<= 1;
+    // capacity: room for twice the expected groups, eight times while the table stays small (<= 64 K slots = 1 MB)
     uint64_t cap = 1ull << 16;
-    if (expected_groups > 0) { cap = 1024; while (cap < 2ull * (uint64_t)expected_groups) cap <<= 1; }
+    if (expected_groups > 0) {
+        uint64_t want = 2ull * (uint64_t)expected_groups;
+        const uint64_t roomy = 8ull * (uint64_t)expected_groups < (1ull << 16) ? 8ull * (uint64_t)expected_groups : (1ull << 16);
+        if (roomy > want) want = roomy;
+        cap = 1024;
+        while (cap < want) cap <<= 1;
+    }
     if (cap > worst) cap = worst;
     for (;;) {
+        // one allocation: slots [cap + 1] | counters [2] | rep [limit + 2] (limit = cap / 2 + 1 groups at most)
+        const uint64_t limit = cap / 2 + 1;
         void* table = nullptr;
-        SDC_TRY(dev_alloc(&table, (size_t)(cap + 1) * 16 + 16, s));
+        SDC_TRY(dev_alloc(&table, (size_t)(cap + 1) * 16 + 16 + (size_t)(limit + 2) * 4, s));
         unsigned long long* counters = reinterpret_cast<unsigned long long*>(reinterpret_cast<ulonglong2*>(table) + cap + 1);
+        uint32_t* rep = reinterpret_cast<uint32_t*>(counters + 2);
         fill_slots_kernel<<<grid_for((int64_t)cap + 1, 256, 8), 256, 0, s>>>(reinterpret_cast<ulonglong2*>(table), cap + 1);
         SDC_CHECK_LAUNCH();
         SDC_CUDA_TRY(cudaMemsetAsync(counters, 0, 16, s));
         str_factorize_kernel<<<grid_for(n, kStrThreads, 8), kStrThreads, 0, s>>>(chars, offsets, bitmap, n,
-                                                                                reinterpret_cast<ulonglong2*>(table), cap,
-                                                                                gid_out, counters, cap / 2 + 1);
+                                                                                reinterpret_cast<ulonglong2*>(table), cap, rep,
+                                                                                gid_out, counters, limit);
         SDC_CHECK_LAUNCH();
         unsigned long long h[2];
         SDC_CUDA_TRY(cudaMemcpyAsync(h, counters, 16, cudaMemcpyDeviceToHost, s));
@@ -356,12 +383,15 @@ int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, con
     }
 }
 
-int32_t sdcb200_str_group_rows(int64_t table_handle_words, const int64_t* gids, int64_t ng, int64_t* rows_out, void* stream) {
-    SDC_ARG_CHECK(ng >= 0, "ng");
+int32_t sdcb200_str_group_rows(int64_t table_handle_words, int64_t table_cap, const int64_t* gids, int64_t ng, int64_t* rows_out,
+                               void* stream) {
+    SDC_ARG_CHECK(ng >= 0 && table_cap > 0, "ng / table capacity");
     if (ng == 0) return SDCB200_OK;
     SDC_ARG_CHECK(table_handle_words && gids && rows_out, "null pointer");
-    str_group_rows_kernel<<<grid_for(ng, 256, 4), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const ulonglong2*>((uintptr_t)table_handle_words), gids, ng, rows_out);
+    // rep[] follows the slots and the two counters in the table's allocation (sdcb200_str_factorize)
+    const ulonglong2* slots = reinterpret_cast<const ulonglong2*>((uintptr_t)table_handle_words);
+    const uint32_t* rep = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned long long*>(slots + table_cap + 1) + 2);
+    str_group_rows_kernel<<<grid_for(ng, 256, 4), 256, 0, (cudaStream_t)stream>>>(rep, gids, ng, rows_out);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

@@ -63,7 +63,7 @@ SIGNATURES = {
     "sdcb200_str_argsort": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "sdcb200_str_factorize": (_i32, [_vp, _vp, _vp, _i64, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64),
                                      ct.POINTER(_i64), _vp]),
-    "sdcb200_str_group_rows": (_i32, [_i64, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_group_rows": (_i32, [_i64, _i64, _vp, _i64, _vp, _vp]),
     "sdcb200_str_table_free": (_i32, [_i64, _vp]),
     "sdcb200_str_gather_sizes": (_i32, [_vp, _vp, _i64, _vp, ct.POINTER(_i64), _vp]),
     "sdcb200_str_gather_chars": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),

@@ -183,14 +183,14 @@ def groupby_str_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
     dev = d.offsets.device
     gid, ng, handle, cap = d.factorize(expected_groups)
     try:
-        # ids are table slots in [0, cap]; NA rows carry -1 and are skipped by the aggregate (SDCB200_GID keys:
-        # direct-addressed table).
+        # ids are dense, in [0, ng); NA rows carry -1 and are skipped by the aggregate (SDCB200_GID keys: a
+        # direct-addressed table exactly as large as the result).
         # sort=True reorders by string order below, so the id order of the aggregate is as good as any (and cheaper
         # than tracking first rows); sort=False needs the first-appearance order from the aggregate itself
-        gk, res = groupby_device(gid, cols, aggs, bool(sort), ddof, gid_range=cap + 1)
+        gk, res = groupby_device(gid, cols, aggs, bool(sort), ddof, gid_range=max(ng, 1))
         rows = torch.empty(gk.shape[0], dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
-            native.check(lib.sdcb200_str_group_rows(handle, gk.data_ptr(), gk.shape[0], rows.data_ptr(),
+            native.check(lib.sdcb200_str_group_rows(handle, cap, gk.data_ptr(), gk.shape[0], rows.data_ptr(),
                                                     native.current_stream_ptr()))
     finally:
         with torch.cuda.device(dev):

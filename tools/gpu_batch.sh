@@ -1,3 +1,5 @@
-python -m pytest tests/test_groupby_gpu.py tests/test_strings_gpu.py tests/test_frame_gpu.py tests/test_numba_ext_gpu.py -q > gpurun_out/s5_pytest9.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/s5_pytest9.log | cut -c1-220
-python tools/ab_r1.py groupby > gpurun_out/s5_ab_gb6.jsonl 2> gpurun_out/s5_ab_gb6.err; echo "gb lean rc=$?"
-SDCB200_GB_LEAN=0 python tools/ab_r1.py groupby > gpurun_out/s5_ab_gb6_off.jsonl 2> gpurun_out/s5_ab_gb6_off.err; echo "gb generic rc=$?"
+python -m pytest tests/test_strings_gpu.py tests/test_frame_gpu.py tests/test_groupby_gpu.py -q > gpurun_out/s5_pytest12.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/s5_pytest12.log | cut -c1-220
+python tools/bench_ops.py strings --reps 5 2>gpurun_out/s5_str.err | python -c "
+import json,sys
+for l in sys.stdin:
+    j=json.loads(l); print(j['case'], round(j['ms_median'],3), round(j['frac_of_measured_peak'],3))"
