@@ -271,11 +271,26 @@ __global__ void __launch_bounds__(kStrThreads) str_copy_kernel(const uint8_t* __
     }
 }
 
+// ---- low-cardinality argsort: rank of every distinct string, then a stable radix sort of the ranks ----
+__global__ void iota_i64_kernel(int64_t* out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = i;
+}
+// rank[order[j]] = j: order = the sorted position -> group id permutation of the distinct strings
+__global__ void rank_of_order_kernel(const uint64_t* __restrict__ order, int64_t ng, uint32_t* __restrict__ rank) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < ng; j += (int64_t)gridDim.x * blockDim.x)
+        rank[order[j]] = (uint32_t)j;
+}
+__global__ void rank_keys_kernel(const int64_t* __restrict__ gid, const uint32_t* __restrict__ rank, int64_t n,
+                                 uint32_t* __restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        keys[i] = rank[gid[i]];
+}
+
 }  // namespace
 
 // stable argsort of a device str_arr -> uint32 rows in *rows_out (a scratch-owned buffer pointer is returned
 // through the ping-pong arguments, so the caller passes its own buffers)
-static int32_t str_argsort_device(const uint8_t* chars, const uint32_t* offsets, int64_t n, bool ascending, uint64_t* index_out,
+static int32_t str_argsort_lsd(const uint8_t* chars, const uint32_t* offsets, int64_t n, bool ascending, uint64_t* index_out,
                                   cudaStream_t s) {
     if (n == 0) return SDCB200_OK;
     SDC_ARG_CHECK(n < 0xffffffffll, "str_argsort: fewer than 2^32 - 1 rows");
@@ -324,11 +339,92 @@ using namespace sdcb200;
 
 extern "C" {
 
+int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n,
+                              int64_t expected_groups, int64_t* gid_out, int64_t* ngroups_out, int64_t* table_handle_words,
+                              int64_t* table_cap_out, void* stream);
+int32_t sdcb200_str_group_rows(int64_t table_handle_words, int64_t table_cap, const int64_t* gids, int64_t ng, int64_t* rows_out,
+                               void* stream);
+int32_t sdcb200_str_table_free(int64_t table_handle_words, void* stream);
+int32_t sdcb200_str_gather_sizes(const uint32_t* offsets, const int64_t* rows, int64_t m, uint32_t* out_offsets, int64_t* total_chars,
+                                 void* stream);
+int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, const int64_t* rows, int64_t m,
+                                 const uint32_t* out_offsets, uint8_t* out_chars, uint8_t* out_bitmap, void* stream);
+}
+
+// Few distinct strings among many rows (C4's 1 K keys over 200 M rows): the LSD sort above moves every row once per
+// varying byte (8 passes of 16-byte rows for 8-character keys); instead the rows are factorized (one pass, ids in
+// [0, G)), the G distinct strings are sorted by the LSD sort, and the rows are ordered by a stable radix sort of their
+// strings' 32-bit RANKS, whose constant high digits cost nothing (2 passes of 8-byte rows for G = 1 K).  Taken when a
+// sample of the first rows holds at most 1/16 distinct strings; *used = 0 leaves the job to the LSD sort.
+static int32_t str_argsort_by_rank(const uint8_t* chars, const uint32_t* offsets, int64_t n, bool ascending, uint64_t* index_out,
+                                   cudaStream_t s, int32_t* used) {
+    *used = 0;
+    constexpr int64_t kMinRows = 1 << 20, kSample = 1 << 18;
+    if (n < kMinRows || n >= 0xffffffffll) return SDCB200_OK;
+    Scratch gid;
+    int64_t ng = 0, handle = 0, cap = 0;
+    {
+        Scratch sample_gid;
+        SDC_TRY(sample_gid.alloc((size_t)kSample * 8, s));
+        SDC_TRY(sdcb200_str_factorize(chars, offsets, nullptr, kSample, 0, sample_gid.as<int64_t>(), &ng, &handle, &cap, s));
+        SDC_TRY(sdcb200_str_table_free(handle, s));
+        if (ng * 16 > kSample) return SDCB200_OK;
+    }
+    SDC_TRY(gid.alloc((size_t)n * 8, s));
+    SDC_TRY(sdcb200_str_factorize(chars, offsets, nullptr, n, ng * 2, gid.as<int64_t>(), &ng, &handle, &cap, s));
+    int32_t rc = SDCB200_OK;
+    Scratch ids, rows, soff, schars, order, rank, keys, kA, kB, pA, pB;
+    auto body = [&]() -> int32_t {
+        if (ng * 16 > n) return SDCB200_OK;                          // the sample lied: many distinct strings after all
+        // the distinct strings (one representative row each), gathered into a small str_arr and sorted
+        SDC_TRY(ids.alloc((size_t)ng * 8, s));
+        SDC_TRY(rows.alloc((size_t)ng * 8, s));
+        iota_i64_kernel<<<grid_for(ng, 256, 4), 256, 0, s>>>(ids.as<int64_t>(), ng);
+        SDC_CHECK_LAUNCH();
+        SDC_TRY(sdcb200_str_group_rows(handle, cap, ids.as<int64_t>(), ng, rows.as<int64_t>(), s));
+        SDC_TRY(soff.alloc((size_t)(ng + 1) * 4, s));
+        int64_t total = 0;
+        SDC_TRY(sdcb200_str_gather_sizes(offsets, rows.as<int64_t>(), ng, soff.as<uint32_t>(), &total, s));
+        SDC_TRY(schars.alloc((size_t)(total > 0 ? total : 1), s));
+        SDC_TRY(sdcb200_str_gather_chars(chars, offsets, nullptr, rows.as<int64_t>(), ng, soff.as<uint32_t>(), schars.as<uint8_t>(),
+                                         nullptr, s));
+        SDC_TRY(order.alloc((size_t)ng * 8, s));
+        SDC_TRY(str_argsort_lsd(schars.as<uint8_t>(), soff.as<uint32_t>(), ng, true, order.as<uint64_t>(), s));
+        SDC_TRY(rank.alloc((size_t)ng * 4, s));
+        rank_of_order_kernel<<<grid_for(ng, 256, 4), 256, 0, s>>>(order.as<uint64_t>(), ng, rank.as<uint32_t>());
+        SDC_CHECK_LAUNCH();
+        // rows ordered by the rank of their string: equal strings keep their input order in both directions
+        SDC_TRY(keys.alloc((size_t)n * 4, s));
+        rank_keys_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(gid.as<int64_t>(), rank.as<uint32_t>(), n, keys.as<uint32_t>());
+        SDC_CHECK_LAUNCH();
+        SDC_TRY(kA.alloc((size_t)n * 4, s));
+        SDC_TRY(kB.alloc((size_t)n * 4, s));
+        SDC_TRY(pA.alloc((size_t)n * 4, s));
+        SDC_TRY(pB.alloc((size_t)n * 4, s));
+        const void *rk = nullptr, *rp = nullptr;
+        SDC_TRY(radix_sort_core(SDCB200_U32, keys.p, kA.p, kB.p, 4, nullptr, pA.p, pB.p, n, true, !ascending, &rk, &rp, s));
+        widen_rows_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(rp), index_out, n);
+        SDC_CHECK_LAUNCH();
+        SDC_CUDA_TRY(cudaStreamSynchronize(s));      // scratch buffers go out of scope
+        *used = 1;
+        return SDCB200_OK;
+    };
+    rc = body();
+    const int32_t rc2 = sdcb200_str_table_free(handle, s);
+    return rc != SDCB200_OK ? rc : rc2;
+}
+
+extern "C" {
+
 int32_t sdcb200_str_argsort(const uint8_t* chars, const uint32_t* offsets, int64_t n, int32_t ascending, uint64_t* index_out,
                             void* stream) {
     SDC_ARG_CHECK(n >= 0, "n");
     SDC_ARG_CHECK(n == 0 || (offsets && index_out), "null pointer");
-    return str_argsort_device(chars, offsets, n, ascending != 0, index_out, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t used = 0;
+    SDC_TRY(str_argsort_by_rank(chars, offsets, n, ascending != 0, index_out, s, &used));
+    if (used) return SDCB200_OK;
+    return str_argsort_lsd(chars, offsets, n, ascending != 0, index_out, s);
 }
 
 int32_t sdcb200_str_factorize(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n,

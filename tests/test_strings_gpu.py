@@ -217,3 +217,45 @@ def test_c4_full_size_properties():
     np.testing.assert_array_equal(res["count"][0].cpu().numpy(), cnt.cpu().numpy()[key_order])
     assert float(res["min"][0].min().item()) == float(val.min().item())
     assert float(res["max"][0].max().item()) == float(val.max().item())
+
+
+@pytest.mark.parametrize("pool_kind", ["mixed", "single", "sample_lies"])
+def test_argsort_few_distinct_strings_rank_path(pool_kind):
+    """>= 2^20 rows with few distinct strings take the factorize -> rank -> radix-sort-of-ranks path of
+    sdcb200_str_argsort: same order as the reference's stable sort in both directions (ties in input order), for
+    strings shorter and longer than the 8-byte key word, the empty string, raw 0xFF bytes; a single distinct string;
+    and a column whose first rows hold few strings but whose tail holds many (back to the LSD sort)."""
+    from sdc_b200.str_arr import StringArray
+    rng = np.random.default_rng(77)
+    n = (1 << 20) + 4321
+    if pool_kind == "mixed":
+        pool = ["", "a", "ab", "ab\x00", "b", "abcdefgh", "abcdefghi", "abcdefghij" * 4, "zz", "été", "Zebra", "zebra"] \
+            + _rand_strings(rng, 300, 12)
+        idx = rng.integers(0, len(pool), n)
+    elif pool_kind == "single":
+        pool = ["only"]
+        idx = np.zeros(n, dtype=np.int64)
+    else:
+        pool = _rand_strings(rng, 200_000, 10)
+        idx = np.concatenate([rng.integers(0, 50, 1 << 18), rng.integers(0, len(pool), n - (1 << 18))])
+    enc = [p.encode("utf-8") for p in pool]
+    lens = np.array([len(e) for e in enc], dtype=np.int64)[idx]
+    offsets = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(lens, out=offsets[1:], dtype=np.uint64)
+    chars = np.frombuffer(b"".join(enc[i] for i in idx), dtype=np.uint8).copy()
+    sa = StringArray(offsets, chars, np.full((n + 7) // 8, 0xFF, dtype=np.uint8), n)
+    # oracle order through the pool: stable sort of the rows by their string's rank
+    order_pool = sorted(range(len(pool)), key=lambda i: enc[i])
+    rank = np.empty(len(pool), dtype=np.int64)
+    r = -1
+    prev = None
+    for i in order_pool:                       # equal byte strings (none here, but the pool is random) share a rank
+        if enc[i] != prev:
+            r += 1
+            prev = enc[i]
+        rank[i] = r
+    row_rank = rank[idx]
+    for asc in (True, False):
+        got = sa.argsort(asc).cpu().numpy()
+        want = np.argsort(row_rank if asc else -row_rank, kind="stable")
+        np.testing.assert_array_equal(got, want, err_msg="%s asc=%s" % (pool_kind, asc))
