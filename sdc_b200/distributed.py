@@ -360,7 +360,29 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
                     r += 1
         allb = torch.empty((P, nrows, cap + 1), dtype=torch.int64, device=lk.device)
         _dist().all_gather_into_tensor(allb, buf, group=group)
-        ngs = allb[:, 0, cap].tolist()                                   # the one host read of this path
+        # the one host read of this path: every rank's group count, and whether all ranks hold the same key row
+        same_keys = (allb[:, 0, :cap] == allb[0:1, 0, :cap]).all().to(torch.int64).reshape(1)
+        host = torch.cat([allb[:, 0, cap], same_keys]).tolist()
+        ngs, same = host[:P], bool(host[P])
+        if same and all(g == ngs[0] for g in ngs) and 0 < ngs[0] <= cap and all(p_ in ("sum", "count") for p_ in need):
+            # every rank found the same groups in the same order (the usual case at low cardinality): the partial
+            # tables add up row by row -- no second aggregate, the result is already in the gathered matrix
+            g0 = ngs[0]
+            out_keys = allb[0, 0, :g0].view(lk.dtype)
+            final, r = {}, 1
+            for p_ in need:
+                final[p_] = {}
+                for i, t in enumerate(lres[p_]):
+                    final[p_][i] = allb[:, r, :g0].view(t.dtype).sum(dim=0)
+                    r += 1
+            res = {}
+            for a in aggs:
+                if a == "mean":
+                    res[a] = [combine_mean_device(final["sum"][i] if final["sum"][i].dtype == torch.float64
+                                                  else final["sum"][i].to(torch.float64), final["count"][i]) for i in range(len(cols))]
+                else:
+                    res[a] = [final[a][i] for i in range(len(cols))]
+            return out_keys, res, "replicated"
         if all(0 <= g <= cap for g in ngs):
             gk = torch.cat([allb[q, 0, :g] for q, g in enumerate(ngs)]).view(lk.dtype)
             part, r = {}, 1

@@ -66,6 +66,7 @@ def main():
 
     check_groupby(keys_lo, ("sum", "mean", "min", "max", "count"), "combine", True, 1000)
     check_groupby(keys_lo, ("sum", "count"), "combine", False, 1000)
+    check_groupby(keys_lo, ("sum", "mean", "count"), "combine", True, 1000)        # every rank holds every key: row-wise add of the partial tables
     check_groupby(keys_hi, ("sum", "mean", "min", "max", "count"), "shuffle", True, 150_000)
     check_groupby(keys_hi, ("var", "std"), "shuffle", True, 150_000)
     check_groupby(keys_hi, ("sum", "mean", "min", "max", "count"), "shuffle", True, 150_000, peer)

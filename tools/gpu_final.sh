@@ -8,6 +8,7 @@ python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_o
 python bench.py > gpurun_out/f_bench.json 2> gpurun_out/f_bench.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/f_bench_ref.json 2> gpurun_out/f_bench_ref.err; echo "bench ref rc=$?"
 python tools/bench_ops.py rolling groupby join sort strings --reps 10 > gpurun_out/f_bench_ops.jsonl 2> gpurun_out/f_bench_ops.err; echo "ops rc=$?"
+python tools/bench_dist.py --cases groupby_lo,join_bcast --reps 5 > gpurun_out/f_dist_n1.jsonl 2> gpurun_out/f_dist_n1.err; echo "dist n=1 rc=$?"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 ncu --metrics $M --clock-control none -c 60 --csv --log-file gpurun_out/f_l_join.csv python tools/prof_case.py join 2 > gpurun_out/f_ncu_join.log 2>&1; echo "ncu join rc=$?"
 ncu --metrics $M --clock-control none -c 60 --csv --log-file gpurun_out/f_l_gb100m.csv python tools/prof_case.py groupby_100m 2 > gpurun_out/f_ncu_gb.log 2>&1; echo "ncu gb rc=$?"
