@@ -40,7 +40,9 @@ namespace {
 
 constexpr unsigned long long kEmptyKey = 0x7ff8dead0000beefull;   // never a canonical float key; an int64 key
                                                                   // equal to it lives in the spare slot [cap]
-constexpr int64_t kOneCtaScanMax = 256 * 1024;     // tile counts up to this many are scanned by one CTA (one launch)
+// tile counts up to this many are scanned by one CTA (one launch, ~4 us per 4096 counts: latency-bound); beyond it the
+// three-kernel device scan spreads the work over the SMs (48 829 counts of C3: 51 us with one CTA)
+constexpr int64_t kOneCtaScanMax = 8192;
 constexpr int kJoinThreads = kScanThreads;         // 256
 constexpr int kItems = kScanItems;                 // 8 rows per thread in the probe tiles
 constexpr int kTile = kScanTile;                   // 2048 rows per CTA
