@@ -197,12 +197,12 @@ __device__ __forceinline__ void load4(const void* col, int64_t base, int64_t n, 
 // all CTAs agree.  s_red: 2 * THREADS / 32 words of shared scratch; the result is valid for thread 0 only.
 template <int THREADS, int PER>
 __device__ __forceinline__ void sample_window(const long long* __restrict__ kp, int64_t n, unsigned long long width,
-                                              unsigned long long* s_red, unsigned long long& lo, unsigned long long& range) {
+                                              unsigned long long* s_red, unsigned long long& lo, unsigned long long& range,
+                                              long long (&kv)[PER], bool tight = false) {
     constexpr int WARPS = THREADS / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t total = (int64_t)THREADS * PER;
     const int64_t stride = n > total ? n / total : 1;
-    long long kv[PER];
 #pragma unroll
     for (int e = 0; e < PER; ++e) {        // independent loads, all in flight together
         const int64_t r = ((int64_t)e * THREADS + tid) * stride;
@@ -230,6 +230,13 @@ __device__ __forceinline__ void sample_window(const long long* __restrict__ kp, 
         for (int w = 1; w < WARPS; ++w) {
             mn = s_red[w] < mn ? s_red[w] : mn;
             mx = s_red[WARPS + w] > mx ? s_red[WARPS + w] : mx;
+        }
+        // tight: the smallest power of two that leaves the sampled span as much room again (the caller replicates the
+        // window across the rest of the table)
+        if (tight && mx - mn < width) {
+            unsigned long long w = 64;
+            while (w < width && w < 2 * (mx - mn + 1)) w <<= 1;
+            width = w < width ? w : width;
         }
         if (mx - mn < width) {
             unsigned long long shift = (width - (mx - mn) - 1) / 2;
@@ -263,7 +270,8 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
         if (tid == 0) { s_dlo = 0ull; s_drange = dh.range; }
     } else if (!KEY_F64 && dh.allow) {
         unsigned long long lo, range;
-        sample_window<kGbThreads, 4>(reinterpret_cast<const long long*>(keys), n, t.cap, s_red, lo, range);
+        long long kv_unused[4];
+        sample_window<kGbThreads, 4>(reinterpret_cast<const long long*>(keys), n, t.cap, s_red, lo, range, kv_unused);
         if (tid == 0) { s_dlo = lo; s_drange = range; }
     } else if (tid == 0) {
         s_dlo = 0ull;
@@ -406,6 +414,8 @@ struct SmallFin {
     long long ddof;
     int by_first, key_f64;
     int write_out;                  // 0: only fold the replicas (var / std continue on the host path)
+    int rf_max;                     // lean loop: most lane-indexed copies of the direct window inside the shared table (1 = off)
+    int hot;                        // lean loop: keep the most frequent sampled keys' aggregates in registers
     DirectHint dh;                  // dh.out = meta + 2
     unsigned long long* meta;       // [0] groups written, [1] CTAs done, [2] direct lo, [3] direct range
 };
@@ -424,7 +434,7 @@ __device__ __forceinline__ uint32_t opaque_u32(uint32_t x) {      // keeps an ad
     return x;
 }
 __device__ __forceinline__ void reds_add_f64(uint32_t a, double v) { asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void reds_inc_u32(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void reds_add_u32(uint32_t a, unsigned v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_min_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void reds_max_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void sts_zero_u32(uint32_t a) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory"); }
@@ -463,16 +473,73 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         if (cv.ncols() > 0) load4<kSmThreads>(cols.data[0], (int64_t)blockIdx.x * kSmTile, n, tid, cols.vec_ok, v0n);
     }
 
-    // ---- 1. key sample -> direct window
+    // ---- 1. key sample -> direct window.  The lean loop takes a TIGHT window (a power of two that leaves the sampled
+    //      span as much room again) so that the rest of the table can hold further copies of it -- see 2 (LEAN)
+    const unsigned long long wmax = (unsigned long long)scap < t.cap ? (unsigned long long)scap : t.cap;
+    const bool tight = LEAN && fin.rf_max > 1;
+    long long kvs[kSamplePerThread];
+    bool sampled = false;
     if (!KEY_F64 && fin.dh.mode == KEYS_GID) {
-        if (tid == 0) { s_dlo = 0ull; s_drange = fin.dh.range <= (unsigned long long)scap ? (unsigned long long)scap : 0ull; }
+        if (tid == 0) {
+            unsigned long long w = wmax;
+            if (tight) { w = 64; while (w < wmax && w < fin.dh.range) w <<= 1; }
+            s_dlo = 0ull;
+            s_drange = fin.dh.range <= w ? w : 0ull;
+        }
     } else if (!KEY_F64 && fin.dh.allow) {
         unsigned long long lo, range;
-        sample_window<kSmThreads, kSamplePerThread>(reinterpret_cast<const long long*>(keys), n, (unsigned long long)scap, s_red, lo, range);
+        sample_window<kSmThreads, kSamplePerThread>(reinterpret_cast<const long long*>(keys), n, wmax, s_red, lo, range, kvs, tight);
         if (tid == 0) { s_dlo = lo; s_drange = range; }
+        sampled = true;
     } else if (tid == 0) {
         s_dlo = 0ull;
         s_drange = 0ull;
+    }
+    // ---- 1b (LEAN). hot keys: a histogram of the samples in the (not yet initialised) table memory, then the kHot
+    //      most frequent slots that hold at least 2 % of the samples each.  Their rows never touch shared memory: a
+    //      thread keeps their aggregates in registers (see row_hot below), so a skewed key distribution does not
+    //      become a CAS retry storm on a few slots.
+    constexpr int kHot = (SPEC >= 0 && (SPEC & (NEED_MIN | NEED_MAX))) ? 2 : 4;
+    uint32_t hot[kHot];
+#pragma unroll
+    for (int h = 0; h < kHot; ++h) hot[h] = 0xffffffffu;
+    int nhot = 0;
+    if (LEAN && fin.hot && sampled) {
+        __syncthreads();                                   // s_dlo / s_drange visible; s_red free again
+        const unsigned long long hlo = s_dlo, hrange = s_drange;
+        if (hrange) {
+            unsigned* hist = reinterpret_cast<unsigned*>(sm);
+            unsigned* s_red32 = reinterpret_cast<unsigned*>(s_red);
+            for (unsigned i = tid; i < (unsigned)hrange; i += kSmThreads) hist[i] = 0u;
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < kSamplePerThread; ++e) {
+                const unsigned long long d = (unsigned long long)kvs[e] - hlo;
+                if (d < hrange) atomicAdd(hist + (unsigned)d, 1u);
+            }
+            __syncthreads();
+            constexpr unsigned kHotMin = (unsigned)(kSmThreads * kSamplePerThread) / 50u;
+#pragma unroll
+            for (int h = 0; h < kHot; ++h) {
+                unsigned best = 0u;
+                for (unsigned i = tid; i < (unsigned)hrange; i += kSmThreads) {
+                    const unsigned pk = (hist[i] << 16) | i;
+                    best = pk > best ? pk : best;
+                }
+                best = __reduce_max_sync(0xffffffffu, best);
+                if (lane == 0) s_red32[warp] = best;
+                __syncthreads();
+                best = 0u;
+#pragma unroll
+                for (int w = 0; w < kSmWarps; ++w) best = s_red32[w] > best ? s_red32[w] : best;
+                if ((best >> 16) >= kHotMin) {
+                    hot[h] = best & 0xffffu;
+                    nhot = h + 1;
+                    if ((int)((best & 0xffffu) % kSmThreads) == tid) hist[best & 0xffffu] = 0u;
+                }
+                __syncthreads();
+            }
+        }
     }
     if (blockIdx.x == 0 && tid == 0) { fin.dh.out[0] = s_dlo; fin.dh.out[1] = s_drange; }
     const bool skip_neg = !KEY_F64 && fin.dh.mode == KEYS_GID;
@@ -489,49 +556,108 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     __syncthreads();
     const unsigned long long dlo = s_dlo, drange = s_drange;
 
-    // ---- 2 (LEAN). aggregate, direct-addressed slots only
+    // ---- 2 (LEAN). aggregate, direct-addressed slots only.  The window of `drange` slots is copied rf times across the
+    //      table and a row uses copy (lane % rf): rows of one warp instruction that share a key no longer share an
+    //      address (with few groups rf reaches 32 and a warp never collides with itself); the flush adds the copies up.
+    const unsigned rf = !LEAN || !drange ? 1u : [&] {
+        unsigned r = (unsigned)((unsigned long long)scap / drange);
+        r = r > 32u ? 32u : r;
+        return r > (unsigned)fin.rf_max ? (unsigned)(fin.rf_max < 1 ? 1 : fin.rf_max) : r;
+    }();
     if (LEAN && drange) {
+        const uint32_t copy = ((uint32_t)lane & (rf - 1u)) * (uint32_t)drange;
         const uint32_t keys_a = opaque_u32(smem_u32(skeys));
-        const uint32_t sum_a = opaque_u32(smem_u32(sm + lay.off_sum[0]));
-        const uint32_t cnt_a = opaque_u32(smem_u32(sm + lay.off_cnt[0]));
-        const uint32_t mn_a = opaque_u32(smem_u32(sm + lay.off_mn[0]));
-        const uint32_t mx_a = opaque_u32(smem_u32(sm + lay.off_mx[0]));
+        const uint32_t sum_a = opaque_u32(smem_u32(sm + lay.off_sum[0]) + copy * 8u);
+        const uint32_t cnt_a = opaque_u32(smem_u32(sm + lay.off_cnt[0]) + copy * 4u);
+        const uint32_t mn_a = opaque_u32(smem_u32(sm + lay.off_mn[0]) + copy * 8u);
+        const uint32_t mx_a = opaque_u32(smem_u32(sm + lay.off_mx[0]) + copy * 8u);
+        auto accumulate = [&](uint32_t d, double s, unsigned c, unsigned long long mn, unsigned long long mx) {
+            const uint32_t o8 = d * 8u;
+            sts_zero_u32(keys_a + o8 + 4u);                 // presence (copy 0 only): the high word of the slot's key leaves the empty pattern
+            if (c) {
+                if (need & NEED_SUM) reds_add_f64(sum_a + o8, s);
+                if (need & NEED_CNT) reds_add_u32(cnt_a + d * 4u, c);
+                if (need & NEED_MIN) reds_min_u64(mn_a + o8, mn);
+                if (need & NEED_MAX) reds_max_u64(mx_a + o8, mx);
+            }
+        };
         auto row = [&](unsigned long long k, unsigned long long vbits) {
             const unsigned long long d = k - dlo;
             if (d < drange && k != kEmptyKey()) {
-                const uint32_t o8 = (uint32_t)d * 8u;
-                sts_zero_u32(keys_a + o8 + 4u);             // presence: the high word of the slot's key leaves the empty pattern
                 const double v = __longlong_as_double((long long)vbits);
-                if (v == v) {
-                    if (need & NEED_SUM) reds_add_f64(sum_a + o8, v);
-                    if (need & NEED_CNT) reds_inc_u32(cnt_a + (uint32_t)d * 4u);
-                    if (need & (NEED_MIN | NEED_MAX)) {
-                        const unsigned long long o = f64_to_ordered(v);
-                        if (need & NEED_MIN) reds_min_u64(mn_a + o8, o);
-                        if (need & NEED_MAX) reds_max_u64(mx_a + o8, o);
-                    }
-                }
+                const unsigned long long o = (need & (NEED_MIN | NEED_MAX)) ? f64_to_ordered(v) : 0ull;
+                accumulate((uint32_t)d, v, v == v ? 1u : 0u, o, o);
             } else if (!(skip_neg && (long long)k < 0)) {
                 *(volatile int*)t.overflow = 2;             // outside the sampled window: rerun with hashing
             }
         };
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t base = tile * kSmTile;
-            unsigned long long kb[kRows], v0[kRows];
+        auto tiles = [&](auto&& full_row) {
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int64_t base = tile * kSmTile;
+                unsigned long long kb[kRows], v0[kRows];
 #pragma unroll
-            for (int e = 0; e < kRows; ++e) { kb[e] = kbn[e]; v0[e] = v0n[e]; }
-            if (tile + gridDim.x < ntiles) {
-                const int64_t nbase = (tile + gridDim.x) * kSmTile;
-                load4<kSmThreads>(keys, nbase, n, tid, cols.vec_ok, kbn);
-                load4<kSmThreads>(cols.data[0], nbase, n, tid, cols.vec_ok, v0n);
+                for (int e = 0; e < kRows; ++e) { kb[e] = kbn[e]; v0[e] = v0n[e]; }
+                if (tile + gridDim.x < ntiles) {
+                    const int64_t nbase = (tile + gridDim.x) * kSmTile;
+                    load4<kSmThreads>(keys, nbase, n, tid, cols.vec_ok, kbn);
+                    load4<kSmThreads>(cols.data[0], nbase, n, tid, cols.vec_ok, v0n);
+                }
+                if (base + kSmTile <= n) {
+#pragma unroll
+                    for (int e = 0; e < kRows; ++e) full_row(kb[e], v0[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < kRows; ++e)
+                        if (tile_row<kSmThreads>(base, tid, e) < n) row(kb[e], v0[e]);
+                }
             }
-            if (base + kSmTile <= n) {
+        };
+        if (!nhot) {
+            tiles(row);
+        } else {
+            // hot keys: aggregates in registers, folded across the warp after the last tile
+            double hs[kHot];
+            unsigned hc[kHot], hseen = 0u;
+            unsigned long long hmn[kHot], hmx[kHot];
 #pragma unroll
-                for (int e = 0; e < kRows; ++e) row(kb[e], v0[e]);
-            } else {
+            for (int h = 0; h < kHot; ++h) { hs[h] = 0.0; hc[h] = 0u; hmn[h] = ~0ull; hmx[h] = 0ull; }
+            auto row_hot = [&](unsigned long long k, unsigned long long vbits) {
+                const unsigned long long d = k - dlo;
+                if (d < drange && k != kEmptyKey()) {
+                    const double v = __longlong_as_double((long long)vbits);
+                    const bool vv = v == v;
+                    const unsigned long long o = (need & (NEED_MIN | NEED_MAX)) ? f64_to_ordered(v) : 0ull;
+                    bool any = false;
 #pragma unroll
-                for (int e = 0; e < kRows; ++e)
-                    if (tile_row<kSmThreads>(base, tid, e) < n) row(kb[e], v0[e]);
+                    for (int h = 0; h < kHot; ++h) {
+                        const bool m = (uint32_t)d == hot[h];
+                        const bool mv = m && vv;
+                        any |= m;
+                        hseen |= m ? (1u << h) : 0u;
+                        if (need & NEED_SUM) hs[h] += mv ? v : 0.0;
+                        hc[h] += mv ? 1u : 0u;
+                        if (need & NEED_MIN) hmn[h] = (mv && o < hmn[h]) ? o : hmn[h];
+                        if (need & NEED_MAX) hmx[h] = (mv && o > hmx[h]) ? o : hmx[h];
+                    }
+                    if (!any) accumulate((uint32_t)d, v, vv ? 1u : 0u, o, o);
+                } else if (!(skip_neg && (long long)k < 0)) {
+                    *(volatile int*)t.overflow = 2;
+                }
+            };
+            tiles(row_hot);
+#pragma unroll
+            for (int h = 0; h < kHot; ++h) {
+                const unsigned seen = __any_sync(0xffffffffu, (hseen >> h) & 1u);
+                double sv = hs[h];
+                unsigned long long mn = hmn[h], mx = hmx[h];
+#pragma unroll
+                for (int x = 16; x > 0; x >>= 1) {
+                    if (need & NEED_SUM) sv += __shfl_xor_sync(0xffffffffu, sv, x);
+                    if (need & NEED_MIN) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mn, x); mn = o < mn ? o : mn; }
+                    if (need & NEED_MAX) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, x); mx = o > mx ? o : mx; }
+                }
+                const unsigned cn = __reduce_add_sync(0xffffffffu, hc[h]);
+                if (lane == 0 && seen) accumulate(hot[h], sv, cn, mn, mx);
             }
         }
     } else
@@ -638,6 +764,36 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     __syncthreads();
 
     // ---- 3. flush the occupied shared slots into this CTA's replica of the global value arrays
+    if (LEAN && drange) {
+        // presence lives in copy 0 of the key words; the value arrays hold rf copies of the window, added up here
+        const unsigned S = (unsigned)drange;
+        for (unsigned d = tid; d < S; d += kSmThreads) {
+            if (skeys[d] == kEmptyKey()) continue;
+            const unsigned long long k = dlo + (unsigned long long)d;
+            if (*reinterpret_cast<volatile unsigned long long*>(&t.keys[d]) != k) t.keys[d] = k;   // same value from every CTA
+            const unsigned long long g = (unsigned long long)rep * per + d;
+            if (need & NEED_CNT) {
+                unsigned cn = 0u;
+                for (unsigned r = 0; r < rf; ++r) cn += reinterpret_cast<unsigned*>(sm + lay.off_cnt[0])[r * S + d];
+                if (cn) atomicAdd(&t.cnt[0][g], (unsigned long long)cn);
+            }
+            if (need & NEED_SUM) {
+                double v = 0.0;
+                for (unsigned r = 0; r < rf; ++r) v += reinterpret_cast<double*>(sm + lay.off_sum[0])[r * S + d];
+                if (v != 0.0) atomicAdd(reinterpret_cast<double*>(t.sum[0]) + g, v);
+            }
+            if (need & NEED_MIN) {
+                unsigned long long m = ~0ull;
+                for (unsigned r = 0; r < rf; ++r) { const unsigned long long o = reinterpret_cast<unsigned long long*>(sm + lay.off_mn[0])[r * S + d]; m = o < m ? o : m; }
+                atomicMin(&t.mn[0][g], m);
+            }
+            if (need & NEED_MAX) {
+                unsigned long long m = 0ull;
+                for (unsigned r = 0; r < rf; ++r) { const unsigned long long o = reinterpret_cast<unsigned long long*>(sm + lay.off_mx[0])[r * S + d]; m = o > m ? o : m; }
+                atomicMax(&t.mx[0][g], m);
+            }
+        }
+    } else
     for (int i = tid; i < scap; i += kSmThreads) {
         unsigned long long k = skeys[i];
         if (k == kEmptyKey()) continue;
@@ -1138,6 +1294,12 @@ bool gb_lean_enabled() {
     return on != 0;
 }
 
+// tuning knobs of the lean loop, read on every call so that one process can compare settings
+int gb_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+
 int need_for(unsigned agg_mask, bool sort) {
     int need = 0;
     if (agg_mask & (AGG_SUM | AGG_MEAN | AGG_VAR | AGG_STD)) need |= NEED_SUM;
@@ -1448,7 +1610,6 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         unsigned long long dlo = 0, drange = 0;
         if (at.smem) {
             // ---- low cardinality: one kernel aggregates, folds and (unless var / std) writes the result
-            SmemLayout lay = make_layout(cols.ncols, need, (int)(2 * (expected_groups > 0 ? expected_groups : 2048)), 100 * 1024, t.cap);
             // one float64 column with a common aggregate set: compile-time specialised loop
             int spec = -1;
             if (cols.ncols == 1 && cols.is_f64[0] && (need == 1 || need == 2 || need == 3 || need == 15)) spec = need;
@@ -1459,14 +1620,21 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             else if (spec == 15) kern = gb_smem_kernel<KEY_F64, 15>;
             // int64 keys / group ids: the instantiation with the lean loop for a direct window (it carries the generic
             // loop as well, for sampled keys that do not fit one)
+            bool lean = false;
             if constexpr (!KEY_F64) {
                 if (spec >= 0 && allow_direct && gb_lean_enabled()) {
+                    lean = true;
                     if (spec == 1) kern = gb_smem_kernel<false, 1, true>;
                     else if (spec == 2) kern = gb_smem_kernel<false, 2, true>;
                     else if (spec == 3) kern = gb_smem_kernel<false, 3, true>;
                     else if (spec == 15) kern = gb_smem_kernel<false, 15, true>;
                 }
             }
+            const int rf_max = gb_env_int("SDCB200_GB_RF", 32);
+            // the lean loop fills whatever the table holds beyond the key window with lane-indexed copies of it
+            int want_slots = (int)(2 * (expected_groups > 0 ? expected_groups : 2048));
+            if (lean && rf_max > 1) want_slots = 4096;
+            SmemLayout lay = make_layout(cols.ncols, need, want_slots, 100 * 1024, t.cap);
             SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
             const int64_t ntiles = ceil_div(n, (int64_t)kSmThreads * kRows);
             int64_t grid = (int64_t)sms * 2;
@@ -1488,6 +1656,8 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             fin.by_first = sort ? 0 : 1;
             fin.key_f64 = KEY_F64 ? 1 : 0;
             fin.write_out = need_ssd ? 0 : 1;
+            fin.rf_max = rf_max;
+            fin.hot = gb_env_int("SDCB200_GB_HOT", 1);
             fin.dh.mode = key_mode;
             fin.dh.allow = allow_direct;
             fin.dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;

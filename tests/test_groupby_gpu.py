@@ -263,11 +263,14 @@ def test_c1_full_size_sum_and_multi():
             np.testing.assert_array_equal(res[agg][0].cpu().numpy(), want[agg].to_numpy())
 
 
-@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide"])
+@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide", "few", "zipf", "hotnan"])
 def test_single_f64_column_specialised_kernels(keys_kind):
     """One float64 column with sum / mean / the five-aggregate set takes gb_smem_kernel's compile-time specialised
     loops (SPEC 1 / 3 / 15): dense keys inside the sampled direct window, a hot key, hashed keys, float keys, keys
-    outside the sampled span (rerun with hashing), more groups than shared slots (global-table fallback)."""
+    outside the sampled span (rerun with hashing), more groups than shared slots (global-table fallback); a handful
+    of groups (the direct window is copied 32 times across the shared table, one copy per lane), Zipf-distributed keys
+    (the most frequent sampled keys are aggregated in registers) and a hot key whose values are all NaN (the group
+    must still appear: sum 0, count 0, min / max / mean NaN)."""
     rng = np.random.default_rng(23)
     n = 300_000
     if keys_kind == "dense":
@@ -283,11 +286,19 @@ def test_single_f64_column_specialised_kernels(keys_kind):
         a = rng.integers(100, 600, n)
         a[rng.integers(0, n, 5)] = 1300          # inside the table window, outside the sampled span
         a[rng.integers(0, n, 5)] = 2
+    elif keys_kind == "few":
+        a = rng.integers(-3, 4, n)
+    elif keys_kind == "zipf":
+        a = np.minimum(rng.zipf(1.3, n), 1000) - 1
+    elif keys_kind == "hotnan":
+        a = np.where(rng.random(n) < 0.3, 41, rng.integers(0, 1000, n))
     else:
         a = rng.integers(0, 3000, n)
     b = rng.standard_normal(n) * 50
     b[rng.integers(0, n, n // 50)] = np.nan
     b[rng.integers(0, n, 20)] = np.inf
+    if keys_kind == "hotnan":
+        b[a == 41] = np.nan
     cols = {"b": b}
     from sdc_b200.groupby import groupby_host
     for aggs in (("sum",), ("mean",), ("sum", "mean", "min", "max", "count"), ("min",)):
