@@ -27,6 +27,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <set>
+#include <utility>
 #include <unordered_map>
 #include <vector>
 
@@ -473,10 +475,10 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         if (cv.ncols() > 0) load4<kSmThreads>(cols.data[0], (int64_t)blockIdx.x * kSmTile, n, tid, cols.vec_ok, v0n);
     }
 
-    // ---- 1. key sample -> direct window.  The lean loop takes a TIGHT window (a power of two that leaves the sampled
-    //      span as much room again) so that the rest of the table can hold further copies of it -- see 2 (LEAN)
+    // ---- 1. key sample -> direct window: a TIGHT one (a power of two that leaves the sampled span as much room
+    //      again) so that the rest of the table can hold further copies of it -- see 2 (LEAN)
     const unsigned long long wmax = (unsigned long long)scap < t.cap ? (unsigned long long)scap : t.cap;
-    const bool tight = LEAN && fin.rf_max > 1;
+    const bool tight = fin.rf_max > 1;
     long long kvs[kSamplePerThread];
     bool sampled = false;
     if (!KEY_F64 && fin.dh.mode == KEYS_GID) {
@@ -559,7 +561,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     // ---- 2 (LEAN). aggregate, direct-addressed slots only.  The window of `drange` slots is copied rf times across the
     //      table and a row uses copy (lane % rf): rows of one warp instruction that share a key no longer share an
     //      address (with few groups rf reaches 32 and a warp never collides with itself); the flush adds the copies up.
-    const unsigned rf = !LEAN || !drange ? 1u : [&] {
+    const unsigned rf = !drange ? 1u : [&] {
         unsigned r = (unsigned)((unsigned long long)scap / drange);
         r = r > 32u ? 32u : r;
         return r > (unsigned)fin.rf_max ? (unsigned)(fin.rf_max < 1 ? 1 : fin.rf_max) : r;
@@ -662,8 +664,9 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         }
     } else
     // ---- 2. aggregate (generic: hashed or direct slots, any columns; a LEAN instantiation lands here when the
-    //      sampled keys do not fit a direct window)
+    //      sampled keys do not fit a direct window).  Direct slots use the lane-indexed copies as well.
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int gcopy = (int)(((unsigned)lane & (rf - 1u)) * (unsigned)drange);
         __syncwarp();
         const int64_t base = tile * kSmTile;
         unsigned long long kb[kRows], v0[kRows];
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                 const unsigned long long d = k - dlo;
                 if (valid) {
                     if (d < drange && k != kEmptyKey()) {
-                        sl = (int)d;
+                        sl = (int)d + gcopy;                // this lane's copy of the window
                         // presence marker: one native 32-bit shared atomic on the slot's key word (the key itself is
                         // dlo + slot); it cannot wrap back to the empty pattern within a CTA's rows
                         atomicAdd(reinterpret_cast<unsigned*>(skeys + sl), 1u);
@@ -799,8 +802,8 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         if (k == kEmptyKey()) continue;
         unsigned long long gs;
         if (drange) {
-            k = dlo + (unsigned long long)i;
-            gs = (unsigned long long)i;
+            gs = (unsigned long long)i & (drange - 1ull);   // any of the window's copies (drange is a power of two)
+            k = dlo + gs;
             if (*reinterpret_cast<volatile unsigned long long*>(&t.keys[gs]) != k) t.keys[gs] = k;   // same value from every CTA
         } else {
             gs = global_upsert(t, k);
@@ -1635,7 +1638,15 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             int want_slots = (int)(2 * (expected_groups > 0 ? expected_groups : 2048));
             if (lean && rf_max > 1) want_slots = 4096;
             SmemLayout lay = make_layout(cols.ncols, need, want_slots, 100 * 1024, t.cap);
-            SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            {   // function attributes are per device and stick: set once per (instantiation, device)
+                static std::mutex mu;
+                static std::set<std::pair<const void*, int>> done;
+                int dev = 0;
+                SDC_CUDA_TRY(cudaGetDevice(&dev));
+                std::lock_guard<std::mutex> lock(mu);
+                if (done.insert({reinterpret_cast<const void*>(kern), dev}).second)
+                    SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            }
             const int64_t ntiles = ceil_div(n, (int64_t)kSmThreads * kRows);
             int64_t grid = (int64_t)sms * 2;
             if (grid > ntiles) grid = ntiles;

@@ -91,7 +91,7 @@ def test_sort_flag_1000_rows_20_groups():
 
 
 @pytest.mark.parametrize("n,groups", [(1, 1), (31, 7), (4095, 1000), (4096, 3), (200_000, 1000), (300_000, 5000),
-                                      (500_000, 200_000)])
+                                      (500_000, 200_000), (250_000, 5), (250_000, 70)])
 def test_random_sizes_all_aggs(n, groups):
     rng = np.random.default_rng(n)
     a = rng.integers(-groups // 2, groups - groups // 2, n)

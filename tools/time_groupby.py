@@ -54,3 +54,16 @@ for _ in range(50):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 print("C call event us median:", float(np.median(ts)), "min", min(ts))
+
+# the wrapper's own share: handle -> tensors (two torch.as_tensor over __cuda_array_interface__ views)
+import sdc_b200.groupby as G  # noqa: E402
+kp, vp, stride = ct.c_void_p(), ct.c_void_p(), ct.c_int64(0)
+native.check(lib.sdcb200_groupby(native.DTYPE_CODES["int64"], a.data_ptr(), n, 1, ptrs, dts, 1, 1, 1, 1000, stream,
+                                 ct.byref(h), ct.byref(ng)))
+native.check(lib.sdcb200_groupby_result(h.value, ct.byref(kp), ct.byref(vp), ct.byref(stride)))
+owner = object()
+t0 = time.perf_counter()
+for _ in range(200):
+    x = torch.as_tensor(G._DeviceView(kp.value, (ng.value,), "<i8", owner), device=a.device)
+print("torch.as_tensor(cuda array interface) us:", (time.perf_counter() - t0) / 200 * 1e6)
+lib.sdcb200_groupby_free(h.value)
