@@ -439,6 +439,11 @@ __device__ __forceinline__ void reds_add_f64(uint32_t a, double v) { asm volatil
 __device__ __forceinline__ void reds_add_u32(uint32_t a, unsigned v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void reds_min_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.min.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ void reds_max_u64(uint32_t a, unsigned long long v) { asm volatile("red.shared.max.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_zero_u32(uint32_t a) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(0u) : "memory"); }
 
 template <bool KEY_F64, int SPEC, bool LEAN = false>
@@ -545,11 +550,17 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     }
     if (blockIdx.x == 0 && tid == 0) { fin.dh.out[0] = s_dlo; fin.dh.out[1] = s_drange; }
     const bool skip_neg = !KEY_F64 && fin.dh.mode == KEYS_GID;
+    // The lean loop does not store a presence mark per row: a slot is occupied when its count is non-zero or, with no
+    // count array (sum only), when its sum no longer holds the initial -0.0 (x + -0.0 == x, and a sum can only come back
+    // to -0.0 from terms that are all -0.0); rows that leave both untouched (NaN values, zeros) store the mark.
+    constexpr bool kCntPresence = LEAN && (SPEC & NEED_CNT) != 0;
+    constexpr bool kSumOnlyLean = LEAN && !kCntPresence;
+    constexpr unsigned long long kNegZero = 0x8000000000000000ull;
     for (int i = tid; i < scap; i += kSmThreads) {
         skeys[i] = kEmptyKey();
         if (need & NEED_FIRST) sfirst[i] = ~0ull;
         for (int c = 0; c < cv.ncols(); ++c) {
-            if (need & NEED_SUM) reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i] = 0ull;
+            if (need & NEED_SUM) reinterpret_cast<unsigned long long*>(sm + lay.off_sum[c])[i] = kSumOnlyLean ? kNegZero : 0ull;
             if (need & NEED_CNT) reinterpret_cast<unsigned*>(sm + lay.off_cnt[c])[i] = 0u;
             if (need & NEED_MIN) reinterpret_cast<unsigned long long*>(sm + lay.off_mn[c])[i] = ~0ull;
             if (need & NEED_MAX) reinterpret_cast<unsigned long long*>(sm + lay.off_mx[c])[i] = 0ull;
@@ -573,14 +584,18 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         const uint32_t cnt_a = opaque_u32(smem_u32(sm + lay.off_cnt[0]) + copy * 4u);
         const uint32_t mn_a = opaque_u32(smem_u32(sm + lay.off_mn[0]) + copy * 8u);
         const uint32_t mx_a = opaque_u32(smem_u32(sm + lay.off_mx[0]) + copy * 8u);
-        auto accumulate = [&](uint32_t d, double s, unsigned c, unsigned long long mn, unsigned long long mx) {
+        auto accumulate = [&](uint32_t d, double s, unsigned c, unsigned long long mn, unsigned long long mx, bool mark = false) {
             const uint32_t o8 = d * 8u;
-            sts_zero_u32(keys_a + o8 + 4u);                 // presence (copy 0 only): the high word of the slot's key leaves the empty pattern
+            // explicit presence (copy 0 only; the high word of the slot's key leaves the empty pattern) for the rows the
+            // count / sum cannot vouch for
+            if (mark || c == 0u || (kSumOnlyLean && s == 0.0)) sts_zero_u32(keys_a + o8 + 4u);
             if (c) {
                 if (need & NEED_SUM) reds_add_f64(sum_a + o8, s);
                 if (need & NEED_CNT) reds_add_u32(cnt_a + d * 4u, c);
-                if (need & NEED_MIN) reds_min_u64(mn_a + o8, mn);
-                if (need & NEED_MAX) reds_max_u64(mx_a + o8, mx);
+                // 64-bit shared min / max are CAS loops too, and a group's extremes settle after a few rows: a plain
+                // load first (a stale value only costs an atomic that changes nothing)
+                if (need & NEED_MIN) { if (mn < lds_u64(mn_a + o8)) reds_min_u64(mn_a + o8, mn); }
+                if (need & NEED_MAX) { if (mx > lds_u64(mx_a + o8)) reds_max_u64(mx_a + o8, mx); }
             }
         };
         auto row = [&](unsigned long long k, unsigned long long vbits) {
@@ -659,7 +674,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                     if (need & NEED_MAX) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, x); mx = o > mx ? o : mx; }
                 }
                 const unsigned cn = __reduce_add_sync(0xffffffffu, hc[h]);
-                if (lane == 0 && seen) accumulate(hot[h], sv, cn, mn, mx);
+                if (lane == 0 && seen) accumulate(hot[h], sv, cn, mn, mx, true);
             }
         }
     } else
@@ -749,14 +764,16 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                         if (v == v) {
                             if (need & NEED_SUM) atomicAdd(ssum + sl, v);
                             if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                            if (need & NEED_MIN) atomicMin(smn + sl, f64_to_ordered(v));
-                            if (need & NEED_MAX) atomicMax(smx + sl, f64_to_ordered(v));
+                            const unsigned long long o = f64_to_ordered(v);      // extremes settle early: load, then atomic
+                            if ((need & NEED_MIN) && o < *(volatile unsigned long long*)(smn + sl)) atomicMin(smn + sl, o);
+                            if ((need & NEED_MAX) && o > *(volatile unsigned long long*)(smx + sl)) atomicMax(smx + sl, o);
                         }
                     } else {
                         if (need & NEED_SUM) atomicAdd(reinterpret_cast<unsigned long long*>(ssum) + sl, v0[e]);
                         if (need & NEED_CNT) atomicAdd(scnt + sl, 1u);
-                        if (need & NEED_MIN) atomicMin(smn + sl, i64_to_ordered((long long)v0[e]));
-                        if (need & NEED_MAX) atomicMax(smx + sl, i64_to_ordered((long long)v0[e]));
+                        const unsigned long long o = i64_to_ordered((long long)v0[e]);
+                        if ((need & NEED_MIN) && o < *(volatile unsigned long long*)(smn + sl)) atomicMin(smn + sl, o);
+                        if ((need & NEED_MAX) && o > *(volatile unsigned long long*)(smx + sl)) atomicMax(smx + sl, o);
                     }
                 }
                 __syncwarp();
@@ -771,7 +788,11 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         // presence lives in copy 0 of the key words; the value arrays hold rf copies of the window, added up here
         const unsigned S = (unsigned)drange;
         for (unsigned d = tid; d < S; d += kSmThreads) {
-            if (skeys[d] == kEmptyKey()) continue;
+            bool present = skeys[d] != kEmptyKey();
+            for (unsigned r = 0; r < rf && !present; ++r)
+                present = kCntPresence ? reinterpret_cast<unsigned*>(sm + lay.off_cnt[0])[r * S + d] != 0u
+                                       : reinterpret_cast<unsigned long long*>(sm + lay.off_sum[0])[r * S + d] != kNegZero;
+            if (!present) continue;
             const unsigned long long k = dlo + (unsigned long long)d;
             if (*reinterpret_cast<volatile unsigned long long*>(&t.keys[d]) != k) t.keys[d] = k;   // same value from every CTA
             const unsigned long long g = (unsigned long long)rep * per + d;
@@ -1275,6 +1296,7 @@ struct GroupbyResult {
     unsigned agg_mask = 0;
     unsigned long long* keys = nullptr;    // [ngcap]
     unsigned long long* vals = nullptr;    // [popc(agg_mask) * ncols * ngcap]
+    bool one_block = false;                // vals lives in the allocation keys points at (low-cardinality path)
 };
 
 std::mutex g_mu;
@@ -1284,7 +1306,7 @@ int64_t g_next_handle = 1;
 void free_result(GroupbyResult* r) {
     if (!r) return;
     if (r->keys) dev_free(r->keys, nullptr);
-    if (r->vals) dev_free(r->vals, nullptr);
+    if (r->vals && !r->one_block) dev_free(r->vals, nullptr);
     delete r;
 }
 
@@ -1654,8 +1676,10 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             memset(&fin, 0, sizeof(fin));
             const int64_t ngcap = (int64_t)per;
             if (!need_ssd) {
-                SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ngcap * 8, s));
-                SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ngcap * 8 * (nagg * cols.ncols + 1), s));
+                // one allocation: the key row, then the value rows
+                SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ngcap * 8 * (nagg * cols.ncols + 2), s));
+                res->vals = res->keys + ngcap;
+                res->one_block = true;
                 res->ngcap = ngcap;
             }
             fin.out_keys = res->keys;
@@ -1681,8 +1705,9 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             const int ovf = (int)(hmeta[8] & 0xffffffffull);
             if (ovf) {
                 if (res->keys) dev_free(res->keys, s);
-                if (res->vals) dev_free(res->vals, s);
+                if (res->vals && !res->one_block) dev_free(res->vals, s);
                 res->keys = res->vals = nullptr;
+                res->one_block = false;
                 if (ovf == 2 && allow_direct) { allow_direct = 0; --attempt; continue; }   // same table, hashing this time
                 if (attempt + 1 < nattempts || big) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);

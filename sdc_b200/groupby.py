@@ -9,6 +9,7 @@ Host-side mirror of the reference's groupby interface:
 The aggregation runs in libsdc_b200.so (csrc/groupby.cu: one hash-aggregate pass); nothing here
 touches a row.  torch only holds device buffers.
 """
+import contextlib
 import ctypes as ct
 
 import numpy as np
@@ -60,7 +61,8 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, gid_r
         ptrs[i] = c.data_ptr()
         dts[i] = native.DTYPE_CODES[cn]
     handle, ng = ct.c_int64(0), ct.c_int64(0)
-    with torch.cuda.device(keys.device):
+    # switching the current device costs ~10 us in torch: only when the keys live on another one
+    with (torch.cuda.device(keys.device) if torch.cuda.current_device() != keys.device.index else contextlib.nullcontext()):
         stream = native.current_stream_ptr()
         if gid_range > 0:
             if kname != "int64":
@@ -80,12 +82,18 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, gid_r
         # the result stays where the library wrote it: tensors view the handle's buffers and keep it alive
         kp, vp, stride = ct.c_void_p(), ct.c_void_p(), ct.c_int64(0)
         native.check(lib.sdcb200_groupby_result(handle.value, ct.byref(kp), ct.byref(vp), ct.byref(stride)))
-        out_keys = torch.as_tensor(_DeviceView(kp.value, (g,), "<i8", owner), device=keys.device).view(keys.dtype)
         ranks = sorted(set(aggs), key=lambda a: native.AGG_BITS[a])
+        nrows = len(ranks) * len(cols)
+        if cols and vp.value == kp.value + 8 * stride.value:
+            # the low-cardinality path writes the key row and the value rows into one allocation: one view
+            block = torch.as_tensor(_DeviceView(kp.value, (nrows + 1, stride.value), "<i8", owner), device=keys.device)
+            out_keys, vals = block[0, :g].view(keys.dtype), block[1:]
+        else:
+            out_keys = torch.as_tensor(_DeviceView(kp.value, (g,), "<i8", owner), device=keys.device).view(keys.dtype)
+            vals = torch.as_tensor(_DeviceView(vp.value, (nrows, stride.value), "<i8", owner),
+                                   device=keys.device) if cols else None
         res = {}
         if cols:
-            vals = torch.as_tensor(_DeviceView(vp.value, (len(ranks) * len(cols), stride.value), "<i8", owner),
-                                   device=keys.device)
             for a in aggs:
                 r = ranks.index(a)
                 res[a] = [vals[r * len(cols) + i, :g].view(_out_dtype(torch, a, c)) for i, c in enumerate(cols)]

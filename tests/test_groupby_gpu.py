@@ -263,7 +263,7 @@ def test_c1_full_size_sum_and_multi():
             np.testing.assert_array_equal(res[agg][0].cpu().numpy(), want[agg].to_numpy())
 
 
-@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide", "few", "zipf", "hotnan"])
+@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide", "few", "zipf", "hotnan", "nanzero"])
 def test_single_f64_column_specialised_kernels(keys_kind):
     """One float64 column with sum / mean / the five-aggregate set takes gb_smem_kernel's compile-time specialised
     loops (SPEC 1 / 3 / 15): dense keys inside the sampled direct window, a hot key, hashed keys, float keys, keys
@@ -292,6 +292,8 @@ def test_single_f64_column_specialised_kernels(keys_kind):
         a = np.minimum(rng.zipf(1.3, n), 1000) - 1
     elif keys_kind == "hotnan":
         a = np.where(rng.random(n) < 0.3, 41, rng.integers(0, 1000, n))
+    elif keys_kind == "nanzero":
+        a = rng.integers(0, 1000, n)
     else:
         a = rng.integers(0, 3000, n)
     b = rng.standard_normal(n) * 50
@@ -299,6 +301,12 @@ def test_single_f64_column_specialised_kernels(keys_kind):
     b[rng.integers(0, n, 20)] = np.inf
     if keys_kind == "hotnan":
         b[a == 41] = np.nan
+    if keys_kind == "nanzero":        # groups the lean loop's implicit presence (count / sum changed) cannot see
+        b[a == 5] = np.nan
+        b[a == 6] = 0.0
+        b[a == 7] = -0.0
+        b[(a == 8) & (np.arange(n) % 2 == 0)] = 1.5
+        b[(a == 8) & (np.arange(n) % 2 == 1)] = -1.5
     cols = {"b": b}
     from sdc_b200.groupby import groupby_host
     for aggs in (("sum",), ("mean",), ("sum", "mean", "min", "max", "count"), ("min",)):
