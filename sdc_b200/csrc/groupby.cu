@@ -503,10 +503,10 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         s_drange = 0ull;
     }
     // ---- 1b (LEAN). hot keys: a histogram of the samples in the (not yet initialised) table memory, then the kHot
-    //      most frequent slots that hold at least 2 % of the samples each.  Their rows never touch shared memory: a
-    //      thread keeps their aggregates in registers (see row_hot below), so a skewed key distribution does not
+    //      most frequent slots that hold at least 2 % of the samples each.  Their rows skip the float64 CAS loop: a
+    //      thread keeps their sums and counts in registers (see row_hot below), so a skewed key distribution does not
     //      become a CAS retry storm on a few slots.
-    constexpr int kHot = (SPEC >= 0 && (SPEC & (NEED_MIN | NEED_MAX))) ? 2 : 4;
+    constexpr int kHot = 4;
     uint32_t hot[kHot];
 #pragma unroll
     for (int h = 0; h < kHot; ++h) hot[h] = 0xffffffffu;
@@ -632,12 +632,12 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         if (!nhot) {
             tiles(row);
         } else {
-            // hot keys: aggregates in registers, folded across the warp after the last tile
+            // hot keys: sum and count in registers, folded across the warp after the last tile; min / max go through
+            // the shared slot, whose extremes settle after a few rows (a broadcast load, rarely an atomic)
             double hs[kHot];
             unsigned hc[kHot], hseen = 0u;
-            unsigned long long hmn[kHot], hmx[kHot];
 #pragma unroll
-            for (int h = 0; h < kHot; ++h) { hs[h] = 0.0; hc[h] = 0u; hmn[h] = ~0ull; hmx[h] = 0ull; }
+            for (int h = 0; h < kHot; ++h) { hs[h] = 0.0; hc[h] = 0u; }
             auto row_hot = [&](unsigned long long k, unsigned long long vbits) {
                 const unsigned long long d = k - dlo;
                 if (d < drange && k != kEmptyKey()) {
@@ -653,10 +653,13 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                         hseen |= m ? (1u << h) : 0u;
                         if (need & NEED_SUM) hs[h] += mv ? v : 0.0;
                         hc[h] += mv ? 1u : 0u;
-                        if (need & NEED_MIN) hmn[h] = (mv && o < hmn[h]) ? o : hmn[h];
-                        if (need & NEED_MAX) hmx[h] = (mv && o > hmx[h]) ? o : hmx[h];
                     }
                     if (!any) accumulate((uint32_t)d, v, vv ? 1u : 0u, o, o);
+                    else if ((need & (NEED_MIN | NEED_MAX)) && vv) {
+                        const uint32_t o8 = (uint32_t)d * 8u;
+                        if (need & NEED_MIN) { if (o < lds_u64(mn_a + o8)) reds_min_u64(mn_a + o8, o); }
+                        if (need & NEED_MAX) { if (o > lds_u64(mx_a + o8)) reds_max_u64(mx_a + o8, o); }
+                    }
                 } else if (!(skip_neg && (long long)k < 0)) {
                     *(volatile int*)t.overflow = 2;
                 }
@@ -666,15 +669,12 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
             for (int h = 0; h < kHot; ++h) {
                 const unsigned seen = __any_sync(0xffffffffu, (hseen >> h) & 1u);
                 double sv = hs[h];
-                unsigned long long mn = hmn[h], mx = hmx[h];
 #pragma unroll
-                for (int x = 16; x > 0; x >>= 1) {
+                for (int x = 16; x > 0; x >>= 1)
                     if (need & NEED_SUM) sv += __shfl_xor_sync(0xffffffffu, sv, x);
-                    if (need & NEED_MIN) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mn, x); mn = o < mn ? o : mn; }
-                    if (need & NEED_MAX) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, mx, x); mx = o > mx ? o : mx; }
-                }
                 const unsigned cn = __reduce_add_sync(0xffffffffu, hc[h]);
-                if (lane == 0 && seen) accumulate(hot[h], sv, cn, mn, mx, true);
+                // min / max are already in the slot: the identities leave them alone
+                if (lane == 0 && seen) accumulate(hot[h], sv, cn, ~0ull, 0ull, true);
             }
         }
     } else
