@@ -1297,6 +1297,7 @@ struct GroupbyResult {
     unsigned long long* keys = nullptr;    // [ngcap]
     unsigned long long* vals = nullptr;    // [popc(agg_mask) * ncols * ngcap]
     bool one_block = false;                // vals lives in the allocation keys points at (low-cardinality path)
+    bool lean_direct = false;              // produced by gb_smem_kernel's lean loop over a direct window
 };
 
 std::mutex g_mu;
@@ -1715,6 +1716,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             }
             if (!need_ssd) {
                 res->ngroups = (int64_t)hmeta[16];
+                res->lean_direct = lean && hmeta[19] != 0ull;
                 return SDCB200_OK;
             }
             dlo = hmeta[18];
@@ -1786,6 +1788,74 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     return SDCB200_ERR_CAPACITY;
 }
 
+void release_buffers(GroupbyResult* r, cudaStream_t s) {
+    if (r->keys) dev_free(r->keys, s);
+    if (r->vals && !r->one_block) dev_free(r->vals, s);
+    r->keys = r->vals = nullptr;
+    r->one_block = false;
+}
+
+// Several float64 columns over low-cardinality int64 keys: the one-column lean loop (lane-indexed window copies, hot
+// keys in registers, ~20 instructions per row) once per column beats the generic loop over all columns at once even
+// though it re-reads the keys -- 2 columns x 100 M rows: 0.82 against 0.89 ms on uniform keys, 1.1 against 4.3 ms on
+// Zipf keys.  The first column tells whether the keys took that path; if not, the generic call runs as before.
+int32_t run_groupby_int_keys(const void* keys, int64_t n, const Cols& cols, unsigned agg_mask, bool sort, long long ddof,
+                             int key_dtype, int key_mode, int64_t expected_groups, cudaStream_t s, GroupbyResult* res) {
+    const int need = need_for(agg_mask, sort);
+    bool split = cols.ncols >= 2 && n >= (int64_t(1) << 22) && expected_groups <= 4096 &&
+                 (need == 1 || need == 2 || need == 3 || need == 15) &&
+                 !(agg_mask & (AGG_VAR | AGG_STD | AGG_PROD | AGG_MEDIAN)) && gb_lean_enabled() &&
+                 gb_env_int("SDCB200_GB_SPLIT_COLS", 1) != 0;
+    for (int c = 0; c < cols.ncols && split; ++c) split = cols.is_f64[c] != 0;
+    if (split) {
+        const int nagg = __builtin_popcount(agg_mask);
+        int64_t ngcap = 0, ng = 0;
+        for (int c = 0; c < cols.ncols; ++c) {
+            Cols one;
+            memset(&one, 0, sizeof(one));
+            one.ncols = 1;
+            one.data[0] = cols.data[c];
+            one.is_f64[0] = 1;
+            GroupbyResult sub;
+            const int32_t rc = run_groupby<false>(keys, n, one, agg_mask, sort, ddof, key_dtype, key_mode, expected_groups, s, &sub);
+            if (rc != SDCB200_OK) { release_buffers(&sub, s); release_buffers(res, s); return rc; }
+            if (!sub.lean_direct || (c > 0 && (sub.ngroups != ng || sub.ngcap != ngcap))) {
+                release_buffers(&sub, s);
+                release_buffers(res, s);
+                split = false;                                   // the generic call below
+                break;
+            }
+            if (c == 0) {
+                ng = sub.ngroups;
+                ngcap = sub.ngcap;
+                const int32_t arc = dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ngcap * 8 * (nagg * cols.ncols + 2), s);
+                if (arc != SDCB200_OK) { release_buffers(&sub, s); return arc; }
+                res->vals = res->keys + ngcap;
+                res->one_block = true;
+            }
+            // the sub-result holds one row per aggregate; here row (rank * ncols + c)
+            cudaError_t ce = cudaSuccess;
+            if (ng && c == 0) ce = cudaMemcpyAsync(res->keys, sub.keys, (size_t)ng * 8, cudaMemcpyDeviceToDevice, s);
+            if (ng && ce == cudaSuccess)
+                ce = cudaMemcpy2DAsync(res->vals + (size_t)c * ngcap, (size_t)cols.ncols * ngcap * 8, sub.vals,
+                                       (size_t)ngcap * 8, (size_t)ng * 8, (size_t)nagg, cudaMemcpyDeviceToDevice, s);
+            release_buffers(&sub, s);
+            if (ce != cudaSuccess) {
+                release_buffers(res, s);
+                set_error("groupby: %s", cudaGetErrorString(ce));
+                return SDCB200_ERR_CUDA;
+            }
+        }
+        if (split) {
+            res->ngroups = ng;
+            res->ngcap = ngcap;
+            res->lean_direct = true;
+            return SDCB200_OK;
+        }
+    }
+    return run_groupby<false>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, expected_groups, s, res);
+}
+
 }  // namespace
 }  // namespace sdcb200
 
@@ -1825,7 +1895,7 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
     if (n > 0) {
         rc = key_dtype == SDCB200_F64
                  ? run_groupby<true>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, KEYS_PLAIN, expected_groups, s, res)
-                 : run_groupby<false>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, key_mode, expected_groups, s, res);
+                 : run_groupby_int_keys(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, key_mode, expected_groups, s, res);
     }
     if (rc != SDCB200_OK) {
         free_result(res);

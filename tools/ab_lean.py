@@ -56,14 +56,17 @@ for cname, keys in cases.items():
                   print(json.dumps({"case": cname, "n": nn, "aggs": "+".join(aggs), "hint": hint, "rf": gs, "hot": m, "ms_median": round(med, 4),
                                     "ms_best": round(best, 4), "Grows_per_s": round(nn / med / 1e6, 1), "same_as_first": ok}), flush=True)
 
-# the generic loop (two value columns, or sort=False): lane-indexed copies only
-b2 = torch.from_numpy(rng.integers(-1000, 1000, n)).cuda()
+# several float64 columns: the generic all-columns kernel (SDCB200_GB_SPLIT_COLS=0) against the lean loop per column
+os.environ["SDCB200_GB_RF"] = "32"
+os.environ["SDCB200_GB_HOT"] = "1"
+b2 = torch.from_numpy(rng.standard_normal(n)).cuda()
+b3 = b2 * 3.0
 for cname in ("dense10", "dense64", "dense1k", "zipf1.3"):
     keys = cases[cname]
-    for label, cols, aggs, sort in (("2cols_sum", [b, b2], ("sum",), True), ("1col_sum_unsorted", [b], ("sum",), False),
-                                    ("2cols_5aggs", [b, b2], ("sum", "mean", "min", "max", "count"), True)):
-        for rf in (1, 32):
-            os.environ["SDCB200_GB_RF"] = str(rf)
-            med, best = timeit(lambda: groupby_device(keys, cols, aggs, sort, 1, 1000), reps)
-            print(json.dumps({"case": cname, "n": n, "aggs": label, "hint": 1000, "rf": rf, "hot": -1, "ms_median": round(med, 4),
-                              "ms_best": round(best, 4), "Grows_per_s": round(n / med / 1e6, 1), "same_as_first": True}), flush=True)
+    for label, cols, aggs in (("2cols_sum", [b, b2], ("sum",)), ("3cols_mean", [b, b2, b3], ("mean",)),
+                              ("2cols_5aggs", [b, b2], ("sum", "mean", "min", "max", "count"))):
+        for split in (0, 1):
+            os.environ["SDCB200_GB_SPLIT_COLS"] = str(split)
+            med, best = timeit(lambda: groupby_device(keys, cols, aggs, True, 1, 1000), reps)
+            print(json.dumps({"case": cname, "n": n, "aggs": label, "hint": 1000, "split_cols": split, "ms_median": round(med, 4),
+                              "ms_best": round(best, 4), "Grows_per_s": round(n / med / 1e6, 1)}), flush=True)
