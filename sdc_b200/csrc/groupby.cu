@@ -420,6 +420,7 @@ struct SmallFin {
     int hot;                        // lean loop: keep the most frequent sampled keys' aggregates in registers
     DirectHint dh;                  // dh.out = meta + 2
     unsigned long long* meta;       // [0] groups written, [1] CTAs done, [2] direct lo, [3] direct range
+    unsigned long long* host_meta;  // mapped pinned host copy of the 256-byte control block, written by the last CTA (or null)
 };
 
 // SPEC >= 0: compile-time `need` mask for ONE float64 value column (the common df.groupby(k).agg() shapes get a
@@ -862,7 +863,14 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (*(volatile int*)t.overflow) return;
+    // the host reads the control block from mapped pinned memory once the stream is idle: no copy-engine round trip
+    auto publish = [&]() {
+        if (!fin.host_meta) return;
+        __syncthreads();
+        if (tid < 32) fin.host_meta[tid] = reinterpret_cast<volatile unsigned long long*>(t.occupied)[tid];
+        __threadfence_system();
+    };
+    if (*(volatile int*)t.overflow) { publish(); return; }
     const unsigned nslots = (unsigned)per;
     // fold replicas 1.. into replica 0: plain L2 loads (every other CTA is done), unconditional (an empty slot folds
     // its initial values), two slots per step so that 2 x nrep loads are in flight per thread
@@ -908,6 +916,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         atomicAdd(&s_counter, cntp);
         __syncthreads();
         if (tid == 0) fin.meta[0] = s_counter;
+        publish();
         return;
     }
     if (drange && !fin.by_first) {
@@ -938,6 +947,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
             ++j;
         }
         if (tid == 0) fin.meta[0] = tot;
+        publish();
         return;
     }
     // hashed slots (or sort=False): compact, bitonic sort of (key | first row, slot) in shared memory, write
@@ -982,6 +992,7 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
     for (unsigned j = tid; j < ng; j += kSmThreads)
         write_group(t, cv.ncols(), fin.is_f64_mask, fin.agg_mask, fin.ddof, sslot[j], j, fin.ngcap, fin.out_keys, fin.out_vals);
     if (tid == 0) fin.meta[0] = ng;
+    publish();
 }
 
 // second pass for var / std: ssd[slot] += (x - mean)^2  (nanvar's two passes, numpy_like.py:850-872)
@@ -1393,8 +1404,16 @@ struct Attempt {
 // pinned landing zone for the control-block read-back (a pageable destination makes the copy a staged one)
 unsigned long long* pinned_meta() {
     static thread_local unsigned long long* p = nullptr;
-    if (!p && cudaMallocHost(reinterpret_cast<void**>(&p), 256) != cudaSuccess) p = nullptr;
+    if (!p && cudaHostAlloc(reinterpret_cast<void**>(&p), 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) p = nullptr;
     return p;
+}
+
+// the address a kernel stores to so that pinned_meta() sees it (null when there is no mapped buffer)
+unsigned long long* pinned_meta_device() {
+    unsigned long long* h = pinned_meta();
+    void* d = nullptr;
+    if (!h || cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<unsigned long long*>(d);
 }
 
 unsigned long long pow2_at_least(unsigned long long v, unsigned long long lo) {
@@ -1699,9 +1718,10 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             fin.dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
             fin.dh.out = dmeta + 2;
             fin.meta = dmeta;
+            fin.host_meta = (hmeta != hstack && gb_env_int("SDCB200_GB_MAPPED", 1)) ? pinned_meta_device() : nullptr;
             kern<<<(unsigned)grid, kSmThreads, lay.alloc_bytes, s>>>(keys, n, cols, t, need, lay, fin);
             SDC_CHECK_LAUNCH();
-            SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
+            if (!fin.host_meta) SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
             const int ovf = (int)(hmeta[8] & 0xffffffffull);
             if (ovf) {

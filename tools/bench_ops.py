@@ -59,6 +59,22 @@ def bench_groupby(reps):
             emit("groupby_sum_sparsekeys n=%d groups=%d" % (n, groups), n, 16 * n, med, best)
             del a2
         del a, b
+    # low cardinality beyond uniform keys: a handful of groups, Zipf-distributed keys, several value columns
+    n = 100_000_000
+    rng = np.random.default_rng(0)
+    b = torch.from_numpy(rng.random(n)).cuda()
+    b2 = torch.from_numpy(rng.standard_normal(n)).cuda()
+    for kname, keys in (("10 groups", rng.integers(0, 10, n, dtype=np.int64)),
+                        ("zipf1.3 over 1000", (np.minimum(rng.zipf(1.3, n), 1000) - 1).astype(np.int64)),
+                        ("uniform 1000", rng.integers(0, 1000, n, dtype=np.int64))):
+        a = torch.from_numpy(keys).cuda()
+        for label, cols, aggs in (("sum", [b], ("sum",)), ("5aggs", [b], ("sum", "mean", "min", "max", "count")),
+                                  ("sum 2 cols", [b, b2], ("sum",))):
+            if kname == "uniform 1000" and len(cols) == 1:
+                continue
+            med, best = timeit(lambda: groupby_device(a, cols, aggs, True, 1, 1000), reps)
+            emit("groupby_%s n=%d keys=%s" % (label, n, kname), n, (8 + 8 * len(cols)) * n, med, best)
+        del a
 
 
 def bench_sort(reps):
