@@ -871,7 +871,9 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
         __threadfence_system();
     };
     if (*(volatile int*)t.overflow) { publish(); return; }
-    const unsigned nslots = (unsigned)per;
+    // a direct window only ever touches slots [0, drange): fold / compact those (without a hint the table has 8193 slots
+    // per replica, the window of 1 K groups 2048)
+    const unsigned nslots = drange ? (unsigned)(drange < per ? drange : per) : (unsigned)per;
     // fold replicas 1.. into replica 0: plain L2 loads (every other CTA is done), unconditional (an empty slot folds
     // its initial values), two slots per step so that 2 x nrep loads are in flight per thread
     if (t.nrep > 1) {
