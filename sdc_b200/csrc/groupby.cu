@@ -494,6 +494,17 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
             s_dlo = 0ull;
             s_drange = fin.dh.range <= w ? w : 0ull;
         }
+        if (LEAN && fin.hot) {             // group ids need no window, but the hot-key search wants the same key samples
+            const long long* kp = reinterpret_cast<const long long*>(keys);
+            const int64_t total = (int64_t)kSmThreads * kSamplePerThread;
+            const int64_t stride = n > total ? n / total : 1;
+#pragma unroll
+            for (int e = 0; e < kSamplePerThread; ++e) {
+                const int64_t r = ((int64_t)e * kSmThreads + tid) * stride;
+                kvs[e] = r < n ? __ldg(kp + r) : -1;        // a negative id is a skipped row
+            }
+            sampled = true;
+        }
     } else if (!KEY_F64 && fin.dh.allow) {
         unsigned long long lo, range;
         sample_window<kSmThreads, kSamplePerThread>(reinterpret_cast<const long long*>(keys), n, wmax, s_red, lo, range, kvs, tight);

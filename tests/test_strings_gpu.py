@@ -145,6 +145,28 @@ def test_groupby_string_keys_inline_and_hashed_slots():
     np.testing.assert_array_equal(res["count"][0].cpu().numpy(), cnt)
 
 
+def test_groupby_string_keys_skewed_one_float_column():
+    """Half of the rows share one string: the dense ids go through the lean loop, whose hot-key search samples the ids
+    (group-id keys have no window search of their own) and keeps the hot group's sum / count in registers."""
+    from sdc_b200.groupby import groupby_host
+    rng = np.random.default_rng(41)
+    n = 120_000
+    pool = _rand_strings(rng, 60, 5, "abcdefghijklmnopqrstuvwxyz")
+    pick = np.where(rng.random(n) < 0.5, 7, rng.integers(0, len(pool), n))
+    keys = [pool[i] for i in pick]
+    v = rng.standard_normal(n) * 3
+    v[rng.integers(0, n, n // 40)] = np.nan
+    for aggs in (("sum",), ("mean",), ("sum", "mean", "min", "max", "count")):
+        rk, res = groupby_host(keys, {"v": v}, aggs, True)
+        for agg in aggs:
+            wk, want = ogroupby.groupby_agg(keys, {"v": v}, agg, True)
+            assert list(rk) == list(wk)
+            if agg in ("min", "max", "count"):
+                np.testing.assert_array_equal(res[agg]["v"], want["v"])
+            else:
+                np.testing.assert_allclose(res[agg]["v"], want["v"], rtol=1e-9)
+
+
 def test_c4_shape_scaled_properties():
     """BASELINE config C4 (string keys, sort + multi-agg) at 20 M rows: fixed-width 8-char keys built natively;
     checked through invariants -- sorted order is non-decreasing, counts sum to n, sums match a float64 total."""
