@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Rolling kernel variants chosen by environment switches read once per process (SDCB200_ROLL_TH, SDCB200_ROLL_R):
-  SDCB200_ROLL_TH=128 python tools/ab_roll.py [--reps N]"""
+"""Rolling kernel variants chosen by environment switches read once per process (SDCB200_ROLL_R = run length), one
+process per setting:  SDCB200_ROLL_R=17 python tools/ab_roll.py [--reps N]
+(The half-size-CTA experiment of DESIGN 4.7 used this script with a build that carried a 128-thread instantiation.)"""
 import json
 import os
 import sys
