@@ -353,3 +353,41 @@ def test_several_f64_columns_take_the_lean_loop_per_column(keys_kind):
                         np.testing.assert_array_equal(g, w["c%d" % i].to_numpy(), err_msg="%s %s c%d" % (keys_kind, agg, i))
                     else:
                         assert_close(g, w["c%d" % i].to_numpy(), rtol=1e-9, atol=1e-12, msg="%s %s c%d hint=%d" % (keys_kind, agg, i, hint))
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("SDCB200_TEST_SWITCHES"),
+                    reason="A/B switch equivalence: written after the round's GPU budget was spent -- tools/ab_lean.py "
+                           "made the same comparison (profiles/r1_ab_groupby_lean_rf_hot.jsonl); set SDCB200_TEST_SWITCHES=1")
+def test_measurement_switches_give_the_same_result(monkeypatch):
+    """The A/B switches of DESIGN 6 (read on every call) select other code paths of the same kernel family -- window
+    copies off, hot keys off, control block through a copy-engine read-back, the generic loop for several columns:
+    every one of them must give what the default path gives."""
+    import torch
+    from sdc_b200.groupby import groupby_device
+    rng = np.random.default_rng(5)
+    n = 4_500_000
+    a = torch.from_numpy(np.minimum(rng.zipf(1.4, n), 300) - 1).cuda()
+    cols = [torch.from_numpy(rng.standard_normal(n)).cuda() for _ in range(2)]
+    cols[0][::77] = float("nan")
+    aggs = ("sum", "mean", "min", "max", "count")
+
+    def run(ncols):
+        k, r = groupby_device(a, cols[:ncols], aggs, True, 1, 0)
+        return k.clone(), {g: [t.clone() for t in r[g]] for g in aggs}
+
+    for ncols in (1, 2):
+        base_k, base = run(ncols)
+        for name, value in (("SDCB200_GB_RF", "1"), ("SDCB200_GB_HOT", "0"), ("SDCB200_GB_MAPPED", "0"),
+                            ("SDCB200_GB_SPLIT_COLS", "0")):
+            monkeypatch.setenv(name, value)
+            k, r = run(ncols)
+            monkeypatch.delenv(name)
+            assert torch.equal(k, base_k), name
+            for g in aggs:
+                for x, y in zip(r[g], base[g]):
+                    if g in ("sum", "mean"):
+                        assert torch.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True), (name, g)
+                    elif g == "count":
+                        assert torch.equal(x, y), (name, g)
+                    else:
+                        assert torch.equal(torch.nan_to_num(x, nan=12345.0), torch.nan_to_num(y, nan=12345.0)), (name, g)
