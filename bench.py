@@ -5,7 +5,10 @@
 
 Headline workload (BASELINE.json configs[1], "C2"): Series.rolling(window=100).mean() on a
 100 M-row float64 column per GPU.  A "step" is one pass of the rolling kernel over the column.
-Prints ONE JSON line (see the contract in DESIGN.md, "Measurement").
+Prints ONE JSON line (see the contract in DESIGN.md, "Measurement").  Under torchrun (N > 1) the same line also
+carries C5 -- the census-shaped groupby and join hash-shuffled across the GPUs, 125 M rows per GPU -- under
+`other_ops`, each case with its own in-run single-GPU time and an oracle parity check of the multi-GPU paths
+(`parity`), so the scaling run certifies the shuffle as well as the rolling halo.
 """
 import argparse
 import json
@@ -25,6 +28,15 @@ N_ROWS = 100_000_000
 WINDOW = 100
 BYTES_PER_ROW = 16          # algorithmic: 8 read + 8 written
 WORKLOAD = "C2: Series.rolling(100).mean(), 100M float64 rows per GPU, min_periods=None"
+C5_ROWS = 125_000_000       # C5: 1 B rows over 8 GPUs, weak scaling
+NVLINK_GBS = 900.0          # per direction per GPU (NVLink 5)
+
+
+def config_dict():
+    """The workload description -- identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rows_per_gpu": N_ROWS, "window": WINDOW, "min_periods": WINDOW,
+            "l2": "inputs (800 MB in + 800 MB out per step) larger than L2",
+            "multi_gpu": "row-sharded series, win-1 halo rows from the previous rank"}
 
 
 def measured_peak():
@@ -57,6 +69,7 @@ class ClockSampler:
         except Exception:
             self.proc = None
             return
+
         def pump():
             for line in self.proc.stdout:
                 self.rows.append(line.strip())
@@ -126,7 +139,7 @@ def run_reference(args):
         "impl": "reference", "metric": "rolling_mean_rows_per_s", "value": value, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows": N_ROWS, "window": WINDOW},
+        "config": config_dict(),
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample,
                          "threading_layer": numba.threading_layer()},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -136,13 +149,14 @@ def run_reference(args):
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the rolling kernel, from the committed
     `ncu --set full` summary (profiles/); None when no capture of the current kernel is on file."""
-    p = os.path.join(ROOT, "profiles", "r1_rolling_mean_ncu_summary.json")
-    try:
-        with open(p) as f:
-            d = json.load(f)
-        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
-    except Exception:
-        return None
+    for name in ("r2_rolling_mean_ncu_summary.json", "r1_rolling_mean_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), "from profile (profiles/%s), not measured in this run" % name
+        except Exception:
+            continue
+    return None, None
 
 
 def _event_times(fn, reps, warm=3):
@@ -198,9 +212,11 @@ def bench_other_ops(dev, peak, cpu_legs=True):
         t0 = time.perf_counter()
         df.groupby("A").sum()
         dtp = time.perf_counter() - t0
-        gb["cpu_baseline"] = {"value": ns / dt, "unit": "rows/s", "cores": numba.config.NUMBA_NUM_THREADS, "kind": "port",
-                              "sample": "first 2M rows of the workload, one call after a compile call",
-                              "pandas_rows_per_s": n / dtp}
+        gb["cpu_baseline"] = {"value": ns / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                              "sample": "first 2M rows of the workload, one call after a compile call; the port builds the "
+                                        "per-chunk dicts in a SERIAL loop (the reference uses prange), so it understates the "
+                                        "reference on a many-core host -- pandas on the full 10M rows is reported beside it",
+                              "numba_threads_available": numba.config.NUMBA_NUM_THREADS, "pandas_rows_per_s": n / dtp}
     # end to end through the C ABI with HOST buffers (pinned): H2D of both columns, aggregate, D2H of keys + sums
     import ctypes as ct
     from sdc_b200 import native
@@ -245,6 +261,16 @@ def bench_other_ops(dev, peak, cpu_legs=True):
           "rows_per_s": npr / (med * 1e-3), "ms_median": med, "ms_best": best, "n_out": n_out, "algorithmic_bytes": alg,
           "achieved_GBps": alg / (med * 1e-3) / 1e9, "frac_of_measured_peak": alg / (med * 1e-3) / 1e9 / peak}
     res.clear()
+    # the same join with keys that are NOT a dense range (every key scaled by 1000003): the hashed / partitioned path
+    r_s, l_s = r * 1000003, l * 1000003
+
+    def run_sparse():
+        res["o"] = join_device(l_s, r_s, "inner")
+    meds, _ = _event_times(run_sparse, 3, warm=1)
+    jn["sparse_keys"] = {"workload": "same join, keys * 1000003 (no dense range: hash table instead of direct addressing)",
+                         "ms_median": meds, "rows_per_s": npr / (meds * 1e-3), "frac_of_measured_peak": alg / (meds * 1e-3) / 1e9 / peak}
+    res.clear()
+    del r_s, l_s
     if cpu_legs:
         import pandas as pd
         ns = 10_000_000
@@ -276,6 +302,169 @@ def bench_other_ops(dev, peak, cpu_legs=True):
                  "d2h_bytes_per_step": 16 * no, "api": "sdcb200_host_join + sdcb200_join_indexers (pinned host buffers)",
                  "ms_median": float(np.median(ts)) * 1e3}
     out["join_inner_c3"] = jn
+    del l, r, l_p, r_p, li_p, ri_p
+
+    # sort_values feeding the path: stable int64 argsort, 100 M full-range keys (1.6 GB algorithmic: keys in, int64 rows out)
+    from sdc_b200.sort import argsort_device
+    ks = torch.from_numpy(np.random.default_rng(6).integers(-2**62, 2**62, 100_000_000, dtype=np.int64)).to(dev)
+    meda, _ = _event_times(lambda: argsort_device(ks), 3, warm=1)
+    out["argsort_i64_100M"] = {"workload": "stable argsort, 100M full-range int64 keys", "ms_median": meda, "rows_per_s": 1e8 / (meda * 1e-3),
+                               "frac_of_measured_peak": 1.6e9 / (meda * 1e-3) / 1e9 / peak,
+                               "frac_per_pass": 2.4e9 / (meda * 1e-3 / 8) / 1e9 / peak}
+    del ks
+    return out
+
+
+# ------------------------------------------------------------------------------ C5 (multi-GPU groupby + join)
+def c5_parity(dev, rank, world, link):
+    """The multi-GPU paths against the oracle on a 400 K-row global table every rank regenerates from one seed
+    (tests/dist_check.py is the long form).  -> {case: bool}; ANDed over ranks by the caller."""
+    import torch
+    from oracle import groupby as ogroupby
+    from oracle import join as ojoin
+    from oracle import rolling as orolling
+    from sdc_b200 import distributed as D
+    res = {}
+    rng = np.random.default_rng(5)
+    n = 400_003
+    keys_lo, keys_hi = rng.integers(0, 1000, n), rng.integers(0, 150_000, n)
+    vals = rng.standard_normal(n)
+    vals[rng.integers(0, n, n // 100)] = np.nan
+    s, e = D.block_range(n, rank, world)
+    v = torch.from_numpy(vals[s:e].copy()).to(dev)
+
+    def gb(keys, mode, hint):
+        k = torch.from_numpy(keys[s:e].copy()).to(dev)
+        gk, r, layout = D.groupby_distributed(k, [v], ("sum", "count"), True, 1, hint, None, mode)
+        sm, ct_ = r["sum"][0], r["count"][0]
+        if layout == "sharded":
+            gk, sm, ct_ = D.allgather_ragged(gk)[0], D.allgather_ragged(sm)[0], D.allgather_ragged(ct_)[0]
+            o = torch.argsort(gk)
+            gk, sm, ct_ = gk[o], sm[o], ct_[o]
+        wk, want = ogroupby.groupby_agg(keys, {"v": vals}, "sum", True)
+        _, wcnt = ogroupby.groupby_agg(keys, {"v": vals}, "count", True)
+        return (np.array_equal(gk.cpu().numpy(), wk) and np.allclose(sm.cpu().numpy(), want["v"], rtol=1e-9, atol=1e-12)
+                and np.array_equal(ct_.cpu().numpy(), wcnt["v"]))
+    res["groupby_combine_1k"] = gb(keys_lo, "combine", 1000)
+    res["groupby_shuffle_150k"] = gb(keys_hi, "shuffle", 150_000)
+    nb = 20_011
+    build = rng.permutation(60_000)[:nb].astype(np.int64)
+    probe = rng.integers(0, 60_000, n)
+    bs, be = D.block_range(nb, rank, world)
+    for mode in ("shuffle", "broadcast"):
+        for how in ("inner", "left"):
+            li, ri = D.join_distributed(torch.from_numpy(probe[s:e].copy()).to(dev), torch.from_numpy(build[bs:be].copy()).to(dev), how, None, mode)
+            got = ojoin.canonical(D.allgather_ragged(li)[0].cpu().numpy(), D.allgather_ragged(ri)[0].cpu().numpy())
+            want = ojoin.join_indexers(probe, build, how)
+            res["join_%s_%s" % (mode, how)] = bool(np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]))
+    x = rng.random(n)
+    x[::977] = np.nan
+    for op in ("mean", "std", "max"):
+        o = D.rolling_distributed(torch.from_numpy(x[s:e].copy()).to(dev), op, WINDOW, WINDOW, 1, None, None, None, link)
+        g = D.allgather_ragged(o)[0].cpu().numpy()
+        want = orolling.rolling(x, op, WINDOW, WINDOW, 1)
+        ok = ~np.isnan(want)
+        res["rolling_link_%s" % op] = bool(np.array_equal(np.isnan(g), np.isnan(want)) and np.allclose(g[ok], want[ok], rtol=1e-9, atol=1e-11))
+    return res
+
+
+def bench_c5(dev, rank, world, peak, reps=3):
+    """C5 at `world` GPUs, 125 M rows per GPU (weak scaling): groupby-sum with K = 1 K (local aggregate + combine of
+    the partial tables) and K = 100 M (hash shuffle + local aggregate), inner join 125 M probe x 12.5 M build rows per
+    GPU (build side all-gathered / both sides shuffled).  Device time, MAX over ranks, median of `reps`.  Every case
+    also times the single-GPU operator on this rank's own shard in the same run (`n1_ms`: what one GPU needs for its
+    125 M rows when nothing has to move), so `efficiency` = n1_ms / ms is a same-run weak-scaling figure."""
+    import torch
+    import torch.distributed as dist
+    from sdc_b200 import distributed as D
+    from sdc_b200.groupby import groupby_device
+    from sdc_b200.join import join_device
+    n = C5_ROWS
+    g = torch.Generator(device=dev).manual_seed(5 + rank)
+
+    def timed(fn, warm=1):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return float(np.median(ts))
+
+    out = {}
+    vals = torch.rand(n, device=dev, dtype=torch.float64, generator=g)
+
+    def case(name, workload, dist_fn, local_fn, shuffle_bytes=None, alg_bytes=None):
+        d = {"workload": workload, "rows_per_gpu": n}
+        n1 = timed(local_fn)
+        d["n1_ms"] = n1
+        if world > 1:
+            ms = timed(dist_fn)
+            d.update({"ms": ms, "rows_per_s": n * world / (ms * 1e-3), "efficiency": n1 / ms})
+            if shuffle_bytes:
+                d["shuffle_bytes_out_per_gpu"] = shuffle_bytes
+                d["nvlink_frac"] = shuffle_bytes / (ms * 1e-3) / 1e9 / NVLINK_GBS
+        else:
+            d.update({"ms": n1, "rows_per_s": n / (n1 * 1e-3), "efficiency": 1.0})
+        if alg_bytes:
+            d["hbm_frac_n1"] = alg_bytes / (n1 * 1e-3) / 1e9 / peak
+        out[name] = d
+
+    keys = torch.randint(0, 1000, (n,), device=dev, generator=g)
+    case("groupby_sum_k1k", "C5 groupby-sum, K = 1K groups: local aggregate, all-gather of the partial tables, combine",
+         lambda: D.groupby_distributed(keys, [vals], ("sum",), True, 1, 1000, None, "combine"),
+         lambda: groupby_device(keys, [vals], ("sum",), True, 1, 1000), None, 16 * n)
+    del keys
+    K = 100_000_000
+    keys = torch.randint(0, K, (n,), device=dev, generator=g)
+    case("groupby_sum_k100m", "C5 groupby-sum, K = 100M possible keys: shuffle of key + value to the key's owner (peer-memory "
+         "stores over NVLink, dense-preserving routing), local aggregate",
+         lambda: D.groupby_distributed(keys, [vals], ("sum",), True, 1, K, None, "shuffle"),
+         lambda: groupby_device(keys, [vals], ("sum",), True, 1, K), n * 16 * (world - 1) / world, 16 * n)
+    if world > 1:
+        ms = timed(lambda: D.hash_shuffle(keys, [vals], None, "auto", "auto"))
+        b = n * 16 * (world - 1) / world
+        out["shuffle_key_value"] = {"workload": "the shuffle alone: 125M rows of key + value per GPU (count pass, counts all-gather, "
+                                                "partition-and-send kernel, barrier)", "ms": ms, "shuffle_bytes_out_per_gpu": b,
+                                    "nvlink_frac": b / (ms * 1e-3) / 1e9 / NVLINK_GBS}
+    del keys, vals
+    nb = n // 10
+    build = torch.randperm(nb * world, device=dev, generator=torch.Generator(device=dev).manual_seed(99))[rank * nb:(rank + 1) * nb].contiguous()
+    probe = torch.randint(0, nb * world, (n,), device=dev, generator=g)
+    lb = torch.randperm(nb, device=dev, generator=torch.Generator(device=dev).manual_seed(98))
+    lp = torch.randint(0, nb, (n,), device=dev, generator=g)
+    res = {}
+
+    def dj(mode):
+        def f():
+            res.clear()
+            res["o"] = D.join_distributed(probe, build, "inner", None, mode)
+        return f
+
+    def lj():
+        res.clear()
+        res["o"] = join_device(lp, lb, "inner")
+    alg = 8 * (n + nb) + 16 * n
+    case("join_inner_shuffle", "C5 inner join, 125M probe x 12.5M build rows per GPU, both sides shuffled to the key's owner with "
+         "their global row ids (generated in the send kernel), local join, ids gathered",
+         dj("shuffle"), lj, (n + nb) * 16 * (world - 1) / world, alg)
+    if world > 1:
+        out["join_inner_shuffle"]["n_out_rank0"] = int(res["o"][0].shape[0])
+        ms = timed(dj("broadcast"))
+        out["join_inner_broadcast"] = {"workload": "same join, build side all-gathered instead (every rank's table holds all %d build rows)" % (nb * world),
+                                       "ms": ms, "rows_per_s": n * world / (ms * 1e-3), "n1_ms": out["join_inner_shuffle"]["n1_ms"],
+                                       "efficiency": out["join_inner_shuffle"]["n1_ms"] / ms}
+    res.clear()
     return out
 
 
@@ -292,29 +481,25 @@ def run_gpu(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    link = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        from sdc_b200 import distributed as D
+        link = D.HaloLink()
     lib = native.load()
 
     x_host = make_column(rank)
     col = torch.from_numpy(x_host).to(dev)
     out = torch.empty(N_ROWS, dtype=torch.float64, device=dev)
-    halo_n = WINDOW - 1
-    halo = torch.empty(halo_n, dtype=torch.float64, device=dev) if world > 1 else None
 
     def step():
-        # row-sharded series: rank r's window needs rank r-1's last win-1 rows
-        h = None
-        if world > 1:
-            ops = []
-            if rank + 1 < world:
-                ops.append(dist.P2POp(dist.isend, col[N_ROWS - halo_n:], rank + 1))
-            if rank > 0:
-                ops.append(dist.P2POp(dist.irecv, halo, rank - 1))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            h = halo if rank > 0 else None
-        rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=h, row_offset=rank * N_ROWS)
+        # row-sharded series: rank r's first windows need rank r-1's last win-1 rows.  The exchange is part
+        # of the kernel: CTA 0 stores this rank's tail into the next rank's mailbox over NVLink, the tile that needs the
+        # previous rank's rows runs last and finds them there (sdcb200_rolling_linked) -- one launch per step, no collective
+        if link is not None:
+            link.rolling(col, "mean", WINDOW, WINDOW, 1, rank * N_ROWS, out)
+        else:
+            rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=None, row_offset=0)
 
     def barrier():
         if world > 1:
@@ -345,53 +530,79 @@ def run_gpu(args):
     total_ms = float(t.item())
     value = world * N_ROWS * args.steps / (total_ms * 1e-3)
 
-    # kernel-only duration for the roofline: events directly around the launch (N=1: == step)
-    kern_ms = []
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+    # the result of the timed steps against the oracle: this rank's first rows (they see the previous rank's tail
+    # through the link) and a stretch from the middle of the shard
+    from oracle import rolling as orolling
+    head = 4096
+    prev_tail = make_column(rank - 1)[N_ROWS - (WINDOW - 1):] if rank > 0 else np.empty(0)
+    want_head = orolling.rolling(np.concatenate([prev_tail, x_host[:head]]), "mean", WINDOW, WINDOW, 1)[len(prev_tail):]
+    got_head = out[:head].cpu().numpy()
+    mid = N_ROWS // 2
+    want_mid = orolling.rolling(x_host[mid - WINDOW + 1:mid + head], "mean", WINDOW, WINDOW, 1)[WINDOW - 1:]
+    got_mid = out[mid:mid + head].cpu().numpy()
+    ok_roll = bool(np.allclose(got_head, want_head, rtol=1e-9, atol=0, equal_nan=True) and np.allclose(got_mid, want_mid, rtol=1e-9, atol=0))
+
+    # kernel-only duration for the roofline: back-to-back launches of the local kernel between two events (the launch
+    # path overlaps the previous kernel, so this is the kernel's duration, not the call's)
+    reps = 10
+    rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=None, row_offset=0)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
         rolling_device(col, "mean", WINDOW, WINDOW, 1, out=out, halo=None, row_offset=0)
-        b.record()
-        torch.cuda.synchronize()
-        kern_ms.append(a.elapsed_time(b))
-    kern = float(np.mean(kern_ms))
+    b.record()
+    torch.cuda.synchronize()
+    kern = a.elapsed_time(b) / reps
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_ROW * N_ROWS / (kern * 1e-3) / 1e9
 
     # ---- e2e: host buffers through the C-ABI host entry point (pinned), copies inside the timed region
-    e2e = None
-    if True:
-        import ctypes as ct
-        nbytes = N_ROWS * 8
-        pin_in, pin_out = ct.c_void_p(), ct.c_void_p()
-        native.check(lib.sdcb200_host_alloc(ct.byref(pin_in), nbytes))
-        native.check(lib.sdcb200_host_alloc(ct.byref(pin_out), nbytes))
-        ct.memmove(pin_in.value, x_host.ctypes.data, nbytes)
-        def e2e_step():
-            native.check(lib.sdcb200_host_rolling(1, 9, pin_in.value, pin_out.value, N_ROWS, WINDOW, WINDOW, 1))
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 5))
-        for _ in range(e2e_steps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        res = np.ctypeslib.as_array(ct.cast(pin_out.value, ct.POINTER(ct.c_double)), shape=(N_ROWS,))
-        check = float(np.nanmean(res[::1000]))
-        e2e = {"value": world * N_ROWS * e2e_steps / float(tt.item()), "unit": "rows/s",
-               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
-               "api": "sdcb200_host_rolling (pinned host buffers, 3-stream chunk pipeline)",
-               "result_check_mean": check}
-        lib.sdcb200_host_free(pin_in)
-        lib.sdcb200_host_free(pin_out)
+    import ctypes as ct
+    nbytes = N_ROWS * 8
+    pin_in, pin_out = ct.c_void_p(), ct.c_void_p()
+    native.check(lib.sdcb200_host_alloc(ct.byref(pin_in), nbytes))
+    native.check(lib.sdcb200_host_alloc(ct.byref(pin_out), nbytes))
+    ct.memmove(pin_in.value, x_host.ctypes.data, nbytes)
 
-    ops = None
-    if rank == 0 and world == 1 and not args.no_ops:
-        ops = bench_other_ops(dev, peak, cpu_legs=not args.no_cpu)
+    def e2e_step():
+        native.check(lib.sdcb200_host_rolling(1, 9, pin_in.value, pin_out.value, N_ROWS, WINDOW, WINDOW, 1))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    res = np.ctypeslib.as_array(ct.cast(pin_out.value, ct.POINTER(ct.c_double)), shape=(N_ROWS,))
+    check = float(np.nanmean(res[::1000]))
+    e2e = {"value": world * N_ROWS * e2e_steps / float(tt.item()), "unit": "rows/s",
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps,
+           "api": "sdcb200_host_rolling (pinned host buffers, 3-stream chunk pipeline)",
+           "result_check_mean": check}
+    lib.sdcb200_host_free(pin_in)
+    lib.sdcb200_host_free(pin_out)
+    del col, out
+
+    ops, parity = None, {"rolling_timed_steps": ok_roll}
+    if not args.no_ops:
+        if world > 1:
+            parity.update(c5_parity(dev, rank, world, link))
+        ops = {}
+        if rank == 0 and world == 1:
+            ops.update(bench_other_ops(dev, peak, cpu_legs=not args.no_cpu))
+        if not args.no_c5:
+            ops.update(bench_c5(dev, rank, world, peak))
+    # a parity flag counts only when it holds on every rank
+    names = sorted(parity)
+    flags = torch.tensor([1 if parity[k] else 0 for k in names], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    parity = {k: bool(f) for k, f in zip(names, flags.tolist())}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -400,24 +611,27 @@ def run_gpu(args):
                "sample": "full workload (100M rows), best of 5", "threading_layer": layer}
 
     if rank == 0:
+        traffic, traffic_src = ncu_traffic_bytes()
         line = {
             "metric": "rolling_mean_rows_per_s", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rows_per_gpu": N_ROWS, "window": WINDOW,
-                       "l2": "inputs (800 MB in + 800 MB out per step) larger than L2",
-                       "multi_gpu": "row-sharded series, win-1 halo rows from the previous rank (NCCL send/recv)"},
+            "config": config_dict(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "rolling_run_kernel<MEAN,f64,R=17>", "kernel_ms": kern,
+                         "kernel_ms_how": "10 back-to-back launches between two CUDA events / 10",
                          "algorithmic_bytes_per_launch": BYTES_PER_ROW * N_ROWS},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_each": per_step,
+            "halo": None if world == 1 else "peer-memory mailbox inside the rolling kernel (sdcb200_rolling_linked), no collective per step",
+            "parity_ok": all(parity.values()), "parity": parity,
             "other_ops": ops,
         }
         print(json.dumps(line))
     if world > 1:
+        link.close()
         dist.destroy_process_group()
 
 
@@ -428,7 +642,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-ops", action="store_true", help="skip the groupby (C1) / join (C3) side measurements")
+    ap.add_argument("--no-ops", action="store_true", help="skip the groupby / join side measurements and the C5 parity run")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5-shaped (125M rows per GPU) groupby / join cases")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -97,6 +97,19 @@ int32_t sdcb200_rolling(int32_t op, int32_t dtype, const void* in, double* out, 
  * the kernel and D2H on three streams.                                          */
 int32_t sdcb200_host_rolling(int32_t op, int32_t dtype, const void* in, double* out, int64_t n,
                              int64_t win, int64_t minp, int64_t ddof);
+/* Row-sharded series, one process per GPU of an NVLink node: the win-1 rows in front of this rank's shard come from
+ * the previous rank THROUGH PEER MEMORY INSIDE THE ROLLING KERNEL instead of a send / recv in front of it (the
+ * analogue of the per-chunk prelude, hpat_pandas_series_rolling_functions.py:609-617, across GPUs).  Every rank owns
+ * a mailbox of sdcb200_halo_mailbox_bytes() bytes (sdcb200_ipc_alloc, zeroed once, mapped by both neighbours with
+ * sdcb200_ipc_open).  The kernel's first CTA stores this rank's last win-1 rows and a flag (epoch << 32 | rows) into
+ * next_mailbox; the tile that needs the previous rank's rows runs last and waits for the flag in own_mailbox, then
+ * acknowledges into prev_mailbox (a slot is reused only after the ack of epoch - 2).  next_mailbox / prev_mailbox are
+ * NULL on the last / first rank.  epoch >= 1 and increases by one per call, identically on every rank.  Shards
+ * shorter than win-1 rows forward rows they received themselves (exact for any shard lengths).                  */
+int64_t sdcb200_halo_mailbox_bytes(void);
+int32_t sdcb200_rolling_linked(int32_t op, int32_t dtype, const void* in, double* out, int64_t n, int64_t win,
+                               int64_t minp, int64_t ddof, int64_t row_offset, void* own_mailbox, void* next_mailbox,
+                               void* prev_mailbox, uint32_t epoch, void* stream);
 
 /* Series.rolling(win, minp).skew() / .kurt() / .cov(other, ddof) / .corr(other) on float64 DEVICE columns
  * (sdc/datatypes/hpat_pandas_series_rolling_functions.py: skew :408-431, :548-556; kurt :303-331, :520-536;
@@ -249,8 +262,16 @@ void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int
  * all-to-all issued by sdc_b200/distributed.py.  perm_out = row numbers grouped by destination rank
  * (rows of one destination keep their input order), counts_out[nparts] = rows per destination (int64).
  * Columns are packed for sending with sdcb200_gather(perm).                                           */
-int32_t sdcb200_hash_partition(int32_t key_dtype, const void* keys, int64_t n, int32_t nparts, int64_t* perm_out,
-                               int64_t* counts_out, void* stream);
+/* route: how a row finds its owner rank.
+ *   SDCB200_ROUTE_HASH  destination = top bits of mix64(canonical key) scaled to nparts; the key travels unchanged.
+ *   SDCB200_ROUTE_MOD   int64 keys only: destination = key mod nparts (Euclidean) and the key that travels is
+ *                       floor(key / nparts): a dense key range stays dense on every rank, so the local join /
+ *                       groupby keep their direct-addressed tables after the shuffle.  key = shipped * nparts + rank.
+ * shipped_keys_out (nullable, n rows, input order): the key column as it travels.                              */
+#define SDCB200_ROUTE_HASH 0
+#define SDCB200_ROUTE_MOD 1
+int32_t sdcb200_hash_partition(int32_t key_dtype, int32_t route, const void* keys, int64_t n, int32_t nparts,
+                               int64_t* perm_out, int64_t* counts_out, void* shipped_keys_out, void* stream);
 /* out[i] = cnt[i] ? sum[i] / cnt[i] : NaN: final step of a distributed mean (partials are exchanged).  */
 int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, int64_t n, double* out, void* stream);
 
@@ -274,11 +295,20 @@ int32_t sdcb200_ipc_close(void* p);
  * counts_out[nparts] (device); after the totals of every rank are known, shuffle_send re-hashes, ranks the rows of
  * each destination inside the tile in row order, stages them in shared memory and stores each destination's run
  * into that rank's arena.  cols[0] must be the key column.  Row order in the arenas = the NCCL path's.            */
-int32_t sdcb200_shuffle_plan(int32_t key_dtype, const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off,
-                             int64_t* counts_out, void* stream);
-int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t ncols, const void* const* cols, int64_t n, int32_t nparts,
-                             const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
-                             int64_t arena_rows, void* stream);
+int32_t sdcb200_shuffle_plan(int32_t key_dtype, int32_t route, const void* keys, int64_t n, int32_t nparts,
+                             uint32_t* tile_off, int64_t* counts_out, void* stream);
+/* iota_col: -1, or the index (>= 1) of a payload column that is generated instead of read -- its value for input
+ * row r is iota_base + r (the global row id a join ships with every key; cols[iota_col] is ignored).        */
+int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_t ncols, const void* const* cols, int32_t iota_col,
+                             int64_t iota_base, int64_t n, int32_t nparts, const uint32_t* tile_off,
+                             const int64_t* dst_off, void* const* peer_bases, int64_t arena_rows, void* stream);
+/* row-wise helpers of the distributed pass (device pointers):
+ *   affine_i64   x[i] = x[i] * mul + add, in place; keep_negative != 0 leaves rows < 0 alone (the -1 "no partner"
+ *                marker).  Shipped keys back to keys (mul = nparts, add = rank), local rows to global rows (add = offset).
+ *   gather_ids   dst[i] = idx[i] < 0 ? -1 : src[idx[i]]: the local row numbers a join returns -> the global row ids
+ *                that travelled with the rows.                                                                   */
+int32_t sdcb200_affine_i64(int64_t* x, int64_t n, int64_t mul, int64_t add, int32_t keep_negative, void* stream);
+int32_t sdcb200_gather_ids(const int64_t* src, const int64_t* idx, int64_t n, int64_t* dst, void* stream);
 
 /* The reference's own entry points (sdc/native/module.cpp:31-92), same names and signatures,
  * HOST buffers, void return -- bind them exactly as sdc/functions/sort.py:39-72 does.  The

@@ -256,7 +256,8 @@ enum { KEYS_PLAIN = 0, KEYS_GID = 1 };      // GID: dense group ids in [0, range
 
 struct DirectHint {
     int mode;                       // KEYS_PLAIN: sample the keys (allow != 0); KEYS_GID: window [0, range)
-    int allow;                      // 0: hashing only (a previous attempt saw a key outside its window)
+    int allow;                      // 0: hashing only (a previous attempt saw a key outside its window); 2: a direct
+                                    // window or nothing (overflow code 3 when the sampled keys do not fit one)
     unsigned long long range;       // KEYS_GID: the id range
     unsigned long long* out;        // [2] device: the window the kernel used (lo, range), read back by the host
 };
@@ -282,6 +283,10 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
     __syncthreads();
     const unsigned long long dlo = s_dlo, drange = s_drange;
     if (blockIdx.x == 0 && tid == 0) { dh.out[0] = dlo; dh.out[1] = drange; }
+    if (dh.allow == 2 && drange == 0) {              // block-uniform: the caller takes the sort path instead of hashing
+        if (blockIdx.x == 0 && tid == 0) *(volatile int*)t.overflow = 3;
+        return;
+    }
     const bool skip_neg = !KEY_F64 && dh.mode == KEYS_GID;
     const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1069,6 +1074,10 @@ int64_t sort_path_groups() {        // expected groups above this go straight to
     const char* e = getenv("SDCB200_GB_SORT_GROUPS");
     return e ? atoll(e) : (4ll << 20);
 }
+int64_t dense_try_groups() {        // ... unless int64 keys turn out dense: direct table up to this many expected groups
+    const char* e = getenv("SDCB200_GB_DENSE_GROUPS");
+    return e ? atoll(e) : (48ll << 20);
+}
 constexpr int kSegItems = 8;
 constexpr int kSegTile = kGbThreads * kSegItems;
 
@@ -1412,6 +1421,7 @@ struct Attempt {
     bool smem;
     unsigned long long cap;
     int nrep;
+    bool direct_only = false;      // dense int64 keys or nothing: a table this large is only worth having without hashing
 };
 
 // pinned landing zone for the control-block read-back (a pageable destination makes the copy a staged one)
@@ -1592,11 +1602,18 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     const bool big = n >= sort_path_rows();
     if (agg_mask & (AGG_PROD | AGG_MEDIAN))      // only the sort-and-segment path computes these
         return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
-    if (big && expected_groups > sort_path_groups())
-        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     Attempt plan[3];
     int nattempts = 0;
-    if (expected_groups <= 0) {
+    if (big && expected_groups > sort_path_groups()) {
+        // Tens of millions of groups: a HASHED table costs two random HBM bursts per row and loses to sorting, but a
+        // DIRECT-addressed one (dense int64 keys: what a ROUTE_MOD shuffle delivers, sdc_b200/distributed.py) costs one
+        // reduction per row.  One attempt that gives up at once when the sampled keys do not fit a window.
+        const bool try_dense = !KEY_F64 && key_mode == KEYS_PLAIN && expected_groups <= dense_try_groups();
+        if (!try_dense)
+            return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
+        plan[nattempts] = {false, pow2_at_least(2ull * (unsigned long long)expected_groups, 1024), 1};
+        plan[nattempts++].direct_only = true;
+    } else if (expected_groups <= 0) {
         if (n >= 4096) plan[nattempts++] = {true, 8192, kSmallReplicas};
         if ((1ull << 22) < worst) plan[nattempts++] = {false, 1ull << 22, 1};
     } else if (expected_groups <= 4096 && n >= 4096) {
@@ -1607,7 +1624,8 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         const unsigned long long c = pow2_at_least(2ull * (unsigned long long)expected_groups, 1024);
         if (c < worst) plan[nattempts++] = {false, c, 1};
     }
-    if (!big && key_mode != KEYS_GID) plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
+    if (!big && key_mode != KEYS_GID && !(nattempts && plan[0].direct_only))
+        plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
 
     int allow_direct = 1;
     for (int attempt = 0; attempt < nattempts; ++attempt) {
@@ -1761,7 +1779,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             if (grid > ntiles) grid = ntiles;
             DirectHint dh;
             dh.mode = key_mode;
-            dh.allow = allow_direct;
+            dh.allow = at.direct_only ? 2 : allow_direct;
             dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
             dh.out = dmeta + 2;
             gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need, dh);
@@ -1769,6 +1787,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
             const int ovf = (int)(hmeta[8] & 0xffffffffull);
+            if (ovf && at.direct_only) break;                 // not dense (or a key outside the window): the sort path
             if (ovf) {
                 if (ovf == 2 && allow_direct && key_mode != KEYS_GID) { allow_direct = 0; --attempt; continue; }
                 if (ovf == 2 && key_mode == KEYS_GID) { set_error("groupby: a group id lies outside [0, %lld)", (long long)expected_groups); return SDCB200_ERR_ARG; }

@@ -19,6 +19,7 @@ ROLL_MOMENT_OPS = {"skew": 7, "kurt": 8, "cov": 9, "corr": 10}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
                "int64": 6, "uint64": 7, "float32": 8, "float64": 9}
 DTYPE_GID = 100     # SDCB200_GID: dense int64 group ids as a groupby key column
+ROUTE_HASH, ROUTE_MOD = 0, 1
 
 _i32, _i64, _vp, _u8 = ct.c_int32, ct.c_int64, ct.c_void_p, ct.c_uint8
 
@@ -37,6 +38,8 @@ SIGNATURES = {
     "sdcb200_stream_sync": (_i32, [_vp]),
     "sdcb200_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "sdcb200_host_rolling": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64]),
+    "sdcb200_halo_mailbox_bytes": (_i64, []),
+    "sdcb200_rolling_linked": (_i32, [_i32, _i32, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, ct.c_uint32, _vp]),
     "sdcb200_rolling_moments": (_i32, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "sdcb200_sort": (_i32, [_i32, _vp, _i64, _vp]),
     "sdcb200_argsort": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp]),
@@ -68,15 +71,18 @@ SIGNATURES = {
     "sdcb200_str_gather_sizes": (_i32, [_vp, _vp, _i64, _vp, ct.POINTER(_i64), _vp]),
     "sdcb200_str_gather_chars": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "stable_argsort": (None, [_vp, _vp, ct.c_uint64, ct.c_int8, _vp]),
-    "sdcb200_hash_partition": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "sdcb200_hash_partition": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "sdcb200_combine_mean": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "sdcb200_ipc_alloc": (_i32, [ct.POINTER(_vp), _i64]),
     "sdcb200_ipc_free": (_i32, [_vp]),
     "sdcb200_ipc_get_handle": (_i32, [_vp, _vp]),
     "sdcb200_ipc_open": (_i32, [_vp, ct.POINTER(_vp)]),
     "sdcb200_ipc_close": (_i32, [_vp]),
-    "sdcb200_shuffle_plan": (_i32, [_i32, _vp, _i64, _i32, _vp, _vp, _vp]),
-    "sdcb200_shuffle_send": (_i32, [_i32, _i32, ct.POINTER(_vp), _i64, _i32, _vp, ct.POINTER(_i64), ct.POINTER(_vp), _i64, _vp]),
+    "sdcb200_shuffle_plan": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "sdcb200_shuffle_send": (_i32, [_i32, _i32, _i32, ct.POINTER(_vp), _i32, _i64, _i64, _i32, _vp, ct.POINTER(_i64),
+                                    ct.POINTER(_vp), _i64, _vp]),
+    "sdcb200_affine_i64": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp]),
+    "sdcb200_gather_ids": (_i32, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 # the reference's sdc.concurrent_sort entry points (sdc/native/module.cpp:31-92)

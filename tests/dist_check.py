@@ -42,9 +42,9 @@ def main():
 
     peer = D.PeerShuffle(2 * n // P + 4096, max_cols=3, narenas=2)      # NVLink peer-memory shuffle (CUDA IPC)
 
-    def check_groupby(keys, aggs, mode, sort, hint, peer=None):          # peer=None: NCCL all-to-all
+    def check_groupby(keys, aggs, mode, sort, hint, peer=None, route="auto"):          # peer=None: NCCL all-to-all
         k = torch.from_numpy(keys[s:e].copy()).to(dev)
-        gk, res, layout = D.groupby_distributed(k, cols, aggs, sort, 1, hint, None, mode, peer)
+        gk, res, layout = D.groupby_distributed(k, cols, aggs, sort, 1, hint, None, mode, peer, route)
         if layout == "sharded":
             gk_all, _ = D.allgather_ragged(gk)
             res = {a: [D.allgather_ragged(t)[0] for t in ts] for a, ts in res.items()}
@@ -80,34 +80,86 @@ def main():
         for x_a, x_b in zip(c_a, c_b):
             assert torch.equal(x_a.view(torch.int64), x_b.view(torch.int64)), "peer shuffle column differs (rep %d)" % rep
 
+    # ROUTE_MOD (dense key ranges stay dense): same rows in the same order over both transports, keys travel as
+    # floor(key / P) and every row lands on rank key mod P
+    k_a, c_a = D.hash_shuffle(kh, cols, None, None, D.ROUTE_MOD)
+    k_b, c_b = D.hash_shuffle(kh, cols, None, peer, D.ROUTE_MOD)
+    assert torch.equal(k_a, k_b), "ROUTE_MOD: peer / NCCL keys differ"
+    for x_a, x_b in zip(c_a, c_b):
+        assert torch.equal(x_a.view(torch.int64), x_b.view(torch.int64)), "ROUTE_MOD: peer / NCCL column differs"
+    back = (k_b * P + rank).cpu().numpy()
+    assert np.all(np.mod(back, P) == rank), "ROUTE_MOD: a row landed on the wrong rank"
+    all_back, _ = D.allgather_ragged(torch.from_numpy(back).to(dev))
+    np.testing.assert_array_equal(np.sort(all_back.cpu().numpy()), np.sort(keys_hi), err_msg="ROUTE_MOD: key multiset changed")
+    # negative keys: Euclidean mod / floor division
+    kneg = torch.from_numpy((keys_hi[s:e] - 75_000).copy()).to(dev)
+    k_n, _ = D.hash_shuffle(kneg, [], None, peer, D.ROUTE_MOD)
+    backn = (k_n * P + rank).cpu().numpy()
+    alln, _ = D.allgather_ragged(torch.from_numpy(backn).to(dev))
+    np.testing.assert_array_equal(np.sort(alln.cpu().numpy()), np.sort(keys_hi - 75_000), err_msg="ROUTE_MOD: negative keys")
+    # groupby through both routes gives the same groups
+    check_groupby(keys_hi, ("sum", "count", "min"), "shuffle", True, 150_000, peer, D.ROUTE_HASH)
+    check_groupby(keys_hi, ("sum", "count", "min"), "shuffle", True, 150_000, peer, D.ROUTE_MOD)
+    check_groupby(keys_hi * 2, ("sum", "count"), "shuffle", True, 150_000, "auto", "auto")   # key mod 2 == 0 everywhere: auto falls back to hashing
+
     # join: probe rows sharded, build rows sharded; global row numbers come back
     nb = 20_011
     build = rng.permutation(60_000)[:nb].astype(np.int64)
     probe = rng.integers(0, 60_000, n)
     bs, be = D.block_range(nb, rank, P)
-    for mode in ("broadcast", "shuffle", "shuffle_peer"):
-        for how in ("inner", "left"):
-            li, ri = D.join_distributed(torch.from_numpy(probe[s:e].copy()).to(dev), torch.from_numpy(build[bs:be].copy()).to(dev),
-                                        how, None, "shuffle" if mode == "shuffle_peer" else mode,
-                                        peer if mode == "shuffle_peer" else None)
-            li_all, _ = D.allgather_ragged(li)
-            ri_all, _ = D.allgather_ragged(ri)
-            got = ojoin.canonical(li_all.cpu().numpy(), ri_all.cpu().numpy())
-            want = ojoin.join_indexers(probe, build, how)
-            np.testing.assert_array_equal(got[0], want[0], err_msg="%s %s" % (mode, how))
-            np.testing.assert_array_equal(got[1], want[1], err_msg="%s %s" % (mode, how))
+    def check_join(probe, build, mode, how, route="auto", pr=None):
+        ps, pe = D.block_range(len(probe), rank, P)
+        bs, be = D.block_range(len(build), rank, P)
+        li, ri = D.join_distributed(torch.from_numpy(probe[ps:pe].copy()).to(dev), torch.from_numpy(build[bs:be].copy()).to(dev),
+                                    how, None, "shuffle" if mode.startswith("shuffle") else mode, pr, route)
+        li_all, _ = D.allgather_ragged(li)
+        ri_all, _ = D.allgather_ragged(ri)
+        got = ojoin.canonical(li_all.cpu().numpy(), ri_all.cpu().numpy())
+        want = ojoin.join_indexers(probe, build, how)
+        np.testing.assert_array_equal(got[0], want[0], err_msg="%s %s %s" % (mode, how, route))
+        np.testing.assert_array_equal(got[1], want[1], err_msg="%s %s %s" % (mode, how, route))
 
-    # rolling: row-sharded with the halo from the previous rank
+    for mode, pr in (("broadcast", None), ("shuffle", None), ("shuffle_peer", peer), ("shuffle_auto", "auto")):
+        for how in ("inner", "left"):
+            check_join(probe, build, mode, how, "auto", pr)
+    for route in (D.ROUTE_HASH, D.ROUTE_MOD):
+        check_join(probe, build, "shuffle_peer", "inner", route, peer)
+    check_join(probe, build, "shuffle_peer", "outer", "auto", peer)
+    # duplicate build keys, negative keys, and a build side about twice the probe side (the cached context was sized
+    # for smaller inputs: it has to grow BEFORE anything is sent, with nothing dangling)
+    dupb = rng.integers(-5_000, 5_000, 30_000)
+    check_join(rng.integers(-6_000, 6_000, 15_000), dupb, "shuffle_auto", "inner", "auto", "auto")
+    big_build = rng.integers(0, 3_000_000, 2 * n)
+    check_join(rng.integers(0, 3_000_000, n), big_build, "shuffle_auto", "left", "auto", "auto")
+
+    # rolling: row-sharded with the halo from the previous rank -- through the all-gather of the shard tails and
+    # through the peer-memory link inside the kernel (HaloLink); several calls in a row exercise the slot rotation
     x = rng.random(n)
     x[::977] = np.nan
-    for op in ("mean", "std", "count", "max"):
-        out = D.rolling_distributed(torch.from_numpy(x[s:e].copy()).to(dev), op, 100, 100, 1)
+    link = D.HaloLink()
+
+    def check_rolling(xx, op, win, minp, lk, bounds=None):
+        ss, ee = bounds if bounds is not None else D.block_range(len(xx), rank, P)
+        out = D.rolling_distributed(torch.from_numpy(xx[ss:ee].copy()).to(dev), op, win, minp, 1, None, None, None, lk)
         full, _ = D.allgather_ragged(out)
-        want = orolling.rolling(x, op, 100, 100, 1)
+        want = orolling.rolling(xx, op, win, minp, 1)
         g = full.cpu().numpy()
-        assert np.array_equal(np.isnan(g), np.isnan(want)), op
+        assert np.array_equal(np.isnan(g), np.isnan(want)), (op, win, lk is not None)
         ok = ~np.isnan(want)
-        np.testing.assert_allclose(g[ok], want[ok], rtol=1e-9, atol=1e-11, err_msg=op)
+        np.testing.assert_allclose(g[ok], want[ok], rtol=1e-9, atol=1e-11, err_msg="%s %d" % (op, win))
+
+    for lk in (None, link):
+        for op in ("mean", "std", "count", "max", "sum", "min"):
+            check_rolling(x, op, 100, 100, lk)
+        check_rolling(x, "max", 5, 2, lk)               # short window: the segmented min / max kernel (generic link form)
+        check_rolling(x, "mean", 3000, 10, lk)
+        check_rolling(x, "sum", 1, 1, lk)
+        # shards shorter than the window: rank r holds 7 + r rows, a window of 40 reaches several shards back
+        tiny = rng.random(sum(7 + r for r in range(P)))
+        lo = sum(7 + r for r in range(rank))
+        check_rolling(tiny, "mean", 40, 1, lk, (lo, lo + 7 + rank))
+        check_rolling(tiny, "min", 40, 3, lk, (lo, lo + 7 + rank))
+    link.close()
 
     peer.close()
     dist.barrier()

@@ -109,6 +109,42 @@ def test_halo_exchange_and_block_partition():
     assert [D.block_range(9, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 9)]
 
 
+def _halo_short_case(rank, P):
+    """Shards shorter than the halo: the rows come from as many previous ranks as needed, oldest first."""
+    from sdc_b200 import distributed as D
+    lens = [5, 1, 0, 4]
+    x = np.arange(float(lens[rank])) + 100 * rank
+    h = D.halo_exchange(torch.from_numpy(x), 3)
+    return None if h is None else h.numpy()
+
+
+def test_halo_exchange_reaches_several_shards_back():
+    got = _run("_halo_short_case", world_size=4)
+    assert got[0] is None
+    np.testing.assert_array_equal(got[1], [2.0, 3.0, 4.0])
+    np.testing.assert_array_equal(got[2], [3.0, 4.0, 100.0])          # rank 1 holds one row only
+    np.testing.assert_array_equal(got[3], [3.0, 4.0, 100.0])          # rank 2 is empty: same rows
+
+
+def _rolling_short_shards_case(rank, P):
+    from oracle import rolling as orolling
+    from sdc_b200 import distributed as D
+    x = np.random.default_rng(11).random(23)
+    bounds = [(0, 9), (9, 11), (11, 11), (11, 23)][rank]
+    loc = x[bounds[0]:bounds[1]]
+    h = D.halo_exchange(torch.from_numpy(loc.copy()), 9)
+    full = loc if h is None else np.concatenate([h.numpy(), loc])
+    out = orolling.rolling(full, "sum", 10, 1, 1)
+    return out[len(full) - len(loc):]
+
+
+def test_row_sharded_rolling_with_short_and_empty_shards():
+    from oracle import rolling as orolling
+    got = np.concatenate(_run("_rolling_short_shards_case", world_size=4))
+    want = orolling.rolling(np.random.default_rng(11).random(23), "sum", 10, 1, 1)
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+
+
 def _rolling_halo_oracle_case(rank, P):
     """Row-sharded rolling with the halo exchange, the window arithmetic done by the oracle on each shard:
     shard + halo must reproduce the tail of the whole-series result."""

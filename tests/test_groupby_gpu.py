@@ -355,9 +355,6 @@ def test_several_f64_columns_take_the_lean_loop_per_column(keys_kind):
                         assert_close(g, w["c%d" % i].to_numpy(), rtol=1e-9, atol=1e-12, msg="%s %s c%d hint=%d" % (keys_kind, agg, i, hint))
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("SDCB200_TEST_SWITCHES"),
-                    reason="A/B switch equivalence: written after the round's GPU budget was spent -- tools/ab_lean.py "
-                           "made the same comparison (profiles/r1_ab_groupby_lean_rf_hot.jsonl); set SDCB200_TEST_SWITCHES=1")
 def test_measurement_switches_give_the_same_result(monkeypatch):
     """The A/B switches of DESIGN 6 (read on every call) select other code paths of the same kernel family -- window
     copies off, hot keys off, control block through a copy-engine read-back, the generic loop for several columns:
@@ -391,3 +388,41 @@ def test_measurement_switches_give_the_same_result(monkeypatch):
                         assert torch.equal(x, y), (name, g)
                     else:
                         assert torch.equal(torch.nan_to_num(x, nan=12345.0), torch.nan_to_num(y, nan=12345.0)), (name, g)
+
+
+
+def test_dense_high_cardinality_takes_direct_table_and_matches_sort_path(monkeypatch):
+    """Tens of millions of expected groups: dense int64 keys (what a ROUTE_MOD shuffle delivers) aggregate in a
+    direct-addressed table, anything else goes to sort-and-segment -- same result either way.  Thresholds lowered so
+    the test stays small."""
+    import torch
+    from sdc_b200.groupby import groupby_device
+    rng = np.random.default_rng(9)
+    n = 600_000
+    dense = rng.integers(-40_000, 160_000, n)
+    sparse = dense * 1_000_003
+    v = rng.standard_normal(n)
+    v[::91] = np.nan
+    dv = torch.from_numpy(v).cuda()
+    monkeypatch.setenv("SDCB200_GB_SORT_ROWS", "1000")
+    monkeypatch.setenv("SDCB200_GB_SORT_GROUPS", "1000")
+    aggs = ("sum", "count", "min", "max", "mean")
+    for keys in (dense, sparse):
+        dk = torch.from_numpy(keys).cuda()
+        got = {}
+        for dense_groups in ("0", str(48 << 20)):       # 0: never try the direct table
+            monkeypatch.setenv("SDCB200_GB_DENSE_GROUPS", dense_groups)
+            for sort in (True, False):
+                gk, res = groupby_device(dk, [dv], aggs, sort, 1, 200_000)
+                got[(dense_groups, sort)] = (gk.clone(), {a: res[a][0].clone() for a in aggs})
+        df = pd.DataFrame({"k": keys, "v": v})
+        for sort in (True, False):
+            want = df.groupby("k", sort=sort)["v"]
+            for dg in ("0", str(48 << 20)):
+                gk, res = got[(dg, sort)]
+                np.testing.assert_array_equal(gk.cpu().numpy(), want.sum().index.to_numpy(), err_msg="keys dg=%s sort=%s" % (dg, sort))
+                np.testing.assert_array_equal(res["count"].cpu().numpy(), want.count().to_numpy())
+                np.testing.assert_array_equal(res["min"].cpu().numpy(), want.min().to_numpy())
+                np.testing.assert_array_equal(res["max"].cpu().numpy(), want.max().to_numpy())
+                assert_close(res["sum"].cpu().numpy(), want.sum().to_numpy(), rtol=1e-9, atol=1e-12, msg="sum")
+                assert_close(res["mean"].cpu().numpy(), want.mean().to_numpy(), rtol=1e-9, atol=1e-12, msg="mean")
