@@ -66,6 +66,15 @@ struct Scratch {
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// murmur3 finaliser.  hash_mix64 picks hash-table slots and partition buckets (top bits); the shuffle's destination
+// rank comes from the top bits of the same mixer over the UNSALTED key (shuffle.cu), so the salt here keeps the two
+// independent: the keys a rank owns after a hash shuffle still spread over all buckets / slots.
+__host__ __device__ inline unsigned long long mix64_fin(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__host__ __device__ inline unsigned long long hash_mix64(unsigned long long x) { return mix64_fin(x ^ 0xa0761d6478bd642full); }
+
 // -------------------------------------------------------------- device side
 #ifdef __CUDACC__
 

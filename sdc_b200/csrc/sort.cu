@@ -17,6 +17,11 @@
 // The digit is taken from a canonical key computed on the fly from the raw bits, so the rows
 // that move are the original values (a stable keys-only sort keeps -0.0 / +0.0 / NaN payloads
 // in input order exactly as a comparison sort with these comparators would).
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "radix_sort.cuh"
 
 namespace sdcb200 {
@@ -109,14 +114,37 @@ __global__ void __launch_bounds__(256) scan_kernel(const unsigned long long* __r
     if (d == 0) trivial[p] = is_all;
 }
 
+#ifndef SDCB200_SORT_LB
+#define SDCB200_SORT_LB 4
+#endif
 constexpr int kSortThreads = 256;
-constexpr int kSortWarps = kSortThreads / 32;
 
 // rows per thread: tiles of 4096 rows keep the number of tiles in flight (and so the length of the
 // look-back chains) down without costing a resident CTA
 template <typename U> struct Items { static constexpr int v = 16; };
 
 struct NoPay {};
+
+// ---- digit functors: which of the 256 buckets a row goes to in one pass
+// LSD sort pass: 8 bits of the canonical key (order-preserving unsigned image of the raw bits) at `shift`
+template <typename U, int KIND, bool DESC>
+struct SortDigit {
+    int shift;
+    __device__ __forceinline__ unsigned operator()(U raw) const { return (unsigned)(canon_key<U>(raw, KIND, DESC) >> shift) & 255u; }
+};
+// partition pass: the top byte of mix64(canonical key) -- rows of one bucket later touch one contiguous 1/256 slice of
+// a hash table whose slot index is taken from the TOP bits of the same hash (join / groupby on keys with no dense range)
+struct HashTopDigit {
+    int f64;
+    __device__ __forceinline__ unsigned operator()(unsigned long long b) const {
+        if (f64) {
+            const unsigned long long mag = b & 0x7fffffffffffffffull;
+            if (mag > 0x7ff0000000000000ull) b = 0x7ff8000000000000ull;
+            else if (mag == 0) b = 0;
+        }
+        return (unsigned)(hash_mix64(b) >> 56);
+    }
+};
 
 // look-back status word: bits 0-1 flag (1 = tile count, 2 = inclusive prefix), bits 2-9 epoch (the pass
 // number + 1: entries of earlier passes are simply stale, so the buffer is zeroed once per sort, not once
@@ -125,132 +153,232 @@ __device__ __forceinline__ unsigned long long lb_pack(unsigned long long v, unsi
     return (v << 10) | ((unsigned long long)epoch << 2) | flag;
 }
 
-// 16-byte rows stage 80 KB per tile: two CTAs per SM fit, so the register budget is that of two
-template <typename U, typename P, bool HAS_PAY, int KIND, bool DESC, int ITEMS>
-__global__ void __launch_bounds__(kSortThreads, (HAS_PAY && sizeof(U) + sizeof(P) > 12) ? 2 : 3)
-onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __restrict__ pin, P* __restrict__ pout,
-                int64_t n, int shift, int iota,
-                const unsigned long long* __restrict__ gbase, unsigned long long* lookback, unsigned epoch) {
-    constexpr int TILE = kSortThreads * ITEMS;
-    extern __shared__ __align__(16) unsigned char smem[];
-    unsigned* wh = reinterpret_cast<unsigned*>(smem);                        // [kSortWarps][256]
-    unsigned* tile_off = wh + kSortWarps * 256;                              // [256]
+// One pass of the onesweep: tile -> 256 buckets, stable.
+//   * tiles are handed out by a TICKET (one atomic per CTA), so a tile's predecessors in the look-back chain have all
+//     started -- no assumption about the order in which the hardware dispatches CTAs;
+//   * a full tile of keys (and payload) is staged by ONE bulk TMA copy each (cp.async.bulk + mbarrier): the loads cost
+//     no registers and no issue slots and are in flight while the histogram is cleared; partial / unaligned tiles
+//     take plain loads;
+//   * ranks inside a warp: peers of a digit from eight ballots (`match.any` measured slower: 7.5 against 6.7 ms per
+//     100 M-row argsort); the lowest peer lane bumps the warp's bucket counter with ONE shared atomic whose return
+//     value is the count of earlier rows -- program order inside the warp makes that stable, and successive rows'
+//     atomics do not wait for each other;
+//   * decoupled look-back per digit (thread d), four predecessors per L2 round trip (2 / 8 / 16 measured the same or
+//     slower: 6.73 / 6.91 / 7.44 ms);
+//   * the tile is staged in shared memory in bucket order and leaves as contiguous runs.
+// LAST_IDX: the final pass of an argsort -- keys are not written at all and the 32-bit payload leaves as int64.
+// CTA geometry: THREADS x ITEMS rows per tile, CTAS resident per SM (launch bound)
+template <typename U, typename P, bool HAS_PAY, typename DIG, int THREADS, int ITEMS, int CTAS, bool LAST_IDX>
+__global__ void __launch_bounds__(THREADS, CTAS)
+onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __restrict__ pin, void* __restrict__ pout_raw,
+                int64_t n, int iota, const unsigned long long* __restrict__ gbase, unsigned long long* lookback, unsigned epoch,
+                unsigned* __restrict__ ticket, int use_tma, DIG dig) {
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int LB = SDCB200_SORT_LB;
+    extern __shared__ __align__(128) unsigned char smem[];
+    U* skeys = reinterpret_cast<U*>(smem);                                   // [TILE]   (first: TMA destination, 128-B aligned)
+    P* spay = reinterpret_cast<P*>(skeys + TILE);                            // [TILE]
+    unsigned* wh = reinterpret_cast<unsigned*>(spay + (HAS_PAY ? TILE : 0));  // [WARPS][256]
+    unsigned* tile_off = wh + WARPS * 256;                              // [256]
     long long* digit_dst = reinterpret_cast<long long*>(tile_off + 256);    // [256]
-    unsigned* warp_tot = reinterpret_cast<unsigned*>(digit_dst + 256);      // [8]
-    U* skeys = reinterpret_cast<U*>(warp_tot + 16);
-    P* spay = reinterpret_cast<P*>(skeys + TILE);
-    unsigned char* sdig = reinterpret_cast<unsigned char*>(spay + (HAS_PAY ? TILE : 0));   // [TILE] digit of the staged row
+    unsigned* warp_tot = reinterpret_cast<unsigned*>(digit_dst + 256);      // [8 digit warps] + s_tile at [8]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(warp_tot + 16);            // [2]
+    unsigned char* sdig = reinterpret_cast<unsigned char*>(bars + 2);       // [TILE] digit of the staged row
+    P* pout = reinterpret_cast<P*>(pout_raw);
+    long long* pout64 = reinterpret_cast<long long*>(pout_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    // tile = blockIdx.x: CTAs are dispatched in blockIdx order, so a tile's predecessors are resident or done
-    const unsigned tile = blockIdx.x;
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    if (tid == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        warp_tot[8] = t;
+        if (use_tma) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_mbar_init();
+            if ((int64_t)t + 1 < ntiles || n == ntiles * (int64_t)TILE) {      // a full tile
+                const int64_t base = (int64_t)t * TILE;
+                mbar_expect_tx(&bars[0], (uint32_t)(TILE * sizeof(U)));
+                tma_load_1d(skeys, kin + base, (uint32_t)(TILE * sizeof(U)), &bars[0]);
+                if (HAS_PAY && !iota) {
+                    mbar_expect_tx(&bars[1], (uint32_t)(TILE * sizeof(P)));
+                    tma_load_1d(spay, pin + base, (uint32_t)(TILE * sizeof(P)), &bars[1]);
+                }
+            }
+        }
+    }
+    for (int i = tid; i < WARPS * 256; i += THREADS) wh[i] = 0;
+    __syncthreads();
+    const unsigned tile = warp_tot[8];
     const int64_t tile_base = (int64_t)tile * TILE;
     const int tile_n = (int)((n - tile_base) < (int64_t)TILE ? (n - tile_base) : (int64_t)TILE);
+    const bool bulk = use_tma && tile_n == TILE;                             // block-uniform
 
-    // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
+    // ---- keys (warp-striped: item i of lane l sits at warp_base + i*32 + l) ----
     U key[ITEMS];
-    unsigned short rank[ITEMS];
     const int wbase = w * 32 * ITEMS;
+    if (bulk) {
+        mbar_wait(&bars[0], 0);
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-        const int pos = wbase + i * 32 + lane;
-        key[i] = pos < tile_n ? kin[tile_base + pos] : U(0);
-    }
-    // the payload rides along in registers: its loads are in flight while the tile is ranked
-    P pay[HAS_PAY ? ITEMS : 1];
-    if (HAS_PAY) {
+        for (int i = 0; i < ITEMS; ++i) key[i] = skeys[wbase + i * 32 + lane];
+    } else {
 #pragma unroll
         for (int i = 0; i < ITEMS; ++i) {
             const int pos = wbase + i * 32 + lane;
-            pay[i] = iota ? P(tile_base + pos) : (pos < tile_n ? pin[tile_base + pos] : P(0));
+            key[i] = pos < tile_n ? kin[tile_base + pos] : U(0);
         }
     }
-    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) wh[i] = 0;
-    __syncthreads();
-    // ---- rank inside the warp: ballot multisplit, stable in lane order ----
+    // ---- rank inside the warp, stable in (item, lane) order ----
     unsigned* mywh = wh + w * 256;
     const unsigned lt = (1u << lane) - 1u;
+    unsigned short rank[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = wbase + i * 32 + lane;
         const bool valid = pos < tile_n;
-        const unsigned d = (unsigned)(canon_key<U>(key[i], KIND, DESC) >> shift) & 255u;
-        unsigned peers = __ballot_sync(0xffffffffu, valid);
+        const unsigned d = dig(key[i]);
+        unsigned peers;
+        {
+            peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            peers &= bit ? m : ~m;
+            for (int b = 0; b < 8; ++b) {
+                unsigned m;
+                // one predicate-setting LOP3, one VOTE and the select-and-mask per bit
+                asm volatile(
+                    "{\n"
+                    ".reg .pred p;\n"
+                    ".reg .b32 t;\n"
+                    "and.b32 t, %2, %3;\n"
+                    "setp.ne.u32 p, t, 0;\n"
+                    "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
+                    "@p and.b32 %1, %1, %0;\n"
+                    "@!p lop3.b32 %1, %1, %0, 0, 0x30;\n"           // a & ~b
+                    "}\n"
+                    : "=&r"(m), "+r"(peers)
+                    : "r"(d), "r"(1u << b));
+            }
         }
-        const unsigned prior = mywh[d];
-        __syncwarp();
-        if (valid && (peers & lt) == 0) mywh[d] = prior + __popc(peers);   // lowest peer lane updates
-        __syncwarp();
+        const int leader = __ffs(peers) - 1;
+        unsigned prior = 0;
+        {
+            const unsigned add = (unsigned)__popc(peers);
+            const unsigned addr = smem_u32(&mywh[d]);
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                "setp.eq.s32 p, %1, %2;\n"
+                "@p atom.shared.add.u32 %0, [%3], %4;\n"
+                "}\n"
+                : "+r"(prior)
+                : "r"(lane), "r"(valid ? leader : -1), "r"(addr), "r"(add)
+                : "memory");
+        }
+        prior = __shfl_sync(0xffffffffu, prior, leader);
         rank[i] = (unsigned short)(prior + __popc(peers & lt));
     }
     __syncthreads();
     // ---- per digit (thread d): prefix over warps, tile count published at once, scan over digits ----
     volatile unsigned long long* lb = lookback;
-    unsigned long long cnt;
+    unsigned long long cnt = 0;
     {
-        const int d = tid;
+        const int d = tid & 255;
         unsigned run = 0;
+        if (tid < 256) {
 #pragma unroll
-        for (int ww = 0; ww < kSortWarps; ++ww) {
+        for (int ww = 0; ww < WARPS; ++ww) {
             const unsigned t = wh[ww * 256 + d];
             wh[ww * 256 + d] = run;
             run += t;
         }
         cnt = run;
         lb[(size_t)tile * 256 + d] = lb_pack(cnt, tile == 0 ? 2u : 1u, epoch);
+        }
         unsigned x = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             unsigned t = __shfl_up_sync(0xffffffffu, x, o);
             if (lane >= o) x += t;
         }
-        if (lane == 31) warp_tot[w] = x;
+        if (lane == 31 && tid < 256) warp_tot[w] = x;
         __syncthreads();
         unsigned add = 0;
-        for (int i = 0; i < w; ++i) add += warp_tot[i];
-        tile_off[d] = add + x - run;
+        for (int i = 0; i < w && i < 8; ++i) add += warp_tot[i];
+        if (tid < 256) tile_off[d] = add + x - run;
     }
     __syncthreads();
-    // ---- stage the tile in digit order (needs only tile-local offsets; predecessors publish meanwhile) ----
+    // ---- stage the tile in bucket order (every thread holds its keys in registers: the buffer can be overwritten) ----
+    unsigned short slot[ITEMS];
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = wbase + i * 32 + lane;
+        slot[i] = 0;
         if (pos < tile_n) {
-            const unsigned d = (unsigned)(canon_key<U>(key[i], KIND, DESC) >> shift) & 255u;
+            const unsigned d = dig(key[i]);
             const unsigned p = tile_off[d] + mywh[d] + rank[i];
-            skeys[p] = key[i];
+            slot[i] = (unsigned short)p;
+            if (!LAST_IDX) skeys[p] = key[i];
             sdig[p] = (unsigned char)d;
-            if (HAS_PAY) spay[p] = pay[i];
         }
     }
-    // ---- decoupled look-back per digit ----
-    {
+    if (HAS_PAY) {
+        P pay[ITEMS];
+        if (bulk && !iota) {
+            mbar_wait(&bars[1], 0);
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) pay[i] = spay[wbase + i * 32 + lane];
+            __syncthreads();                       // every thread has its payload before anyone overwrites the buffer
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int pos = wbase + i * 32 + lane;
+                pay[i] = iota ? P(tile_base + pos) : (pos < tile_n ? pin[tile_base + pos] : P(0));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i)
+            if (wbase + i * 32 + lane < tile_n) spay[slot[i]] = pay[i];
+    }
+    // ---- decoupled look-back per digit, four predecessors per round trip ----
+    if (tid < 256) {
         const int d = tid;
         unsigned long long excl = 0;
         if (tile != 0) {
+            // A window of LB predecessors per L2 round trip.  Tiles retire every ~30 ns while a round trip takes several
+            // hundred: a narrow window cannot catch up with the tiles that have published their count but not yet their
+            // prefix, and every look-back ends up walking back over all tiles in flight.
             long long t = (long long)tile - 1;
-            while (true) {
-                unsigned long long v;
-                do { v = lb[(size_t)t * 256 + d]; } while ((v & 3ull) == 0 || (unsigned)((v >> 2) & 255ull) != epoch);
-                excl += v >> 10;
-                if ((v & 3ull) == 2ull) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                unsigned long long v[LB];
+#pragma unroll
+                for (int j = 0; j < LB; ++j) v[j] = (t - j >= 0) ? lb[(size_t)(t - j) * 256 + d] : lb_pack(0ull, 2u, epoch);
+                int used = 0;
+#pragma unroll
+                for (int j = 0; j < LB; ++j) {
+                    if (done || used != j) continue;
+                    const unsigned long long x = v[j];
+                    if ((x & 3ull) == 0 || (unsigned)((x >> 2) & 255ull) != epoch) continue;   // not published yet
+                    excl += x >> 10;
+                    used = j + 1;
+                    if ((x & 3ull) == 2ull) done = true;
+                }
+                t -= used;
+                if (used == 0) __nanosleep(64);    // the nearest predecessor has not published yet: do not burn issue slots
             }
             lb[(size_t)tile * 256 + d] = lb_pack(excl + cnt, 2u, epoch);
         }
         digit_dst[d] = (long long)(gbase[d] + excl) - (long long)tile_off[d];
     }
     __syncthreads();
-    // ---- scatter: consecutive staged slots of one digit go to consecutive global slots ----
-    for (int p = tid; p < tile_n; p += kSortThreads) {
+    // ---- scatter: consecutive staged slots of one bucket go to consecutive global slots ----
+    for (int p = tid; p < tile_n; p += THREADS) {
         const long long dst = digit_dst[sdig[p]] + p;
-        kout[dst] = skeys[p];
-        if (HAS_PAY) pout[dst] = spay[p];
+        if (!LAST_IDX) kout[dst] = skeys[p];
+        if (HAS_PAY) {
+            if (LAST_IDX) pout64[dst] = (long long)spay[p];
+            else pout[dst] = spay[p];
+        }
     }
 }
 
@@ -271,21 +399,86 @@ __global__ void gather_kernel(const T* __restrict__ src, const int64_t* __restri
         dst[i] = src[idx[i]];
 }
 
+// measurement switch (read once): SDCB200_SORT_TMA = 0 plain loads instead of bulk copies
+int sort_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+int sort_use_tma() { static const int v = sort_env("SDCB200_SORT_TMA", 1); return v; }
+
+template <typename U, typename P, bool HAS_PAY, int THREADS, int ITEMS>
+constexpr size_t onesweep_smem() {
+    return (size_t)THREADS * ITEMS * (sizeof(U) + (HAS_PAY ? sizeof(P) : 0) + 1) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 4 +
+           256 * 8 + 16 * 4 + 2 * 8;
+}
+
+// tile geometry: rows per tile are the same for every configuration (look-back buffers are sized by it)
+constexpr int kTileRows = 4096;
+
+// one launch of the pass kernel for digit functor `dig`
+template <typename U, typename P, bool HAS_PAY, typename DIG, int THREADS, int ITEMS, int CTAS, bool LAST_IDX>
+int32_t launch_cfg(const U* kin, U* kout, const P* pin, void* pout, int64_t n, bool iota, const unsigned long long* gbase,
+                   unsigned long long* lookback, unsigned epoch, unsigned* ticket, DIG dig, cudaStream_t s) {
+    constexpr int TILE = THREADS * ITEMS;
+    const int64_t ntiles = ceil_div(n, TILE);
+    const size_t smem = onesweep_smem<U, P, HAS_PAY, THREADS, ITEMS>();
+    auto k0 = onesweep_kernel<U, P, HAS_PAY, DIG, THREADS, ITEMS, CTAS, LAST_IDX>;
+    auto kern = k0;
+    {   // function attributes are per device and stick: set once per (instantiation, device)
+        static std::mutex mu;
+        static std::set<std::pair<const void*, int>> done;
+        int dev = 0;
+        SDC_CUDA_TRY(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lock(mu);
+        if (done.insert({reinterpret_cast<const void*>(kern), dev}).second)
+            SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    // bulk copies need 16-byte aligned rows on both sides (tile bases are multiples of the tile size)
+    int use_tma = sort_use_tma() && (reinterpret_cast<uintptr_t>(kin) & 15) == 0 && (TILE * sizeof(U)) % 16 == 0;
+    if (HAS_PAY && !iota && ((reinterpret_cast<uintptr_t>(pin) & 15) != 0 || (TILE * sizeof(P)) % 16 != 0)) use_tma = 0;
+    kern<<<(unsigned)ntiles, THREADS, smem, s>>>(kin, kout, pin, pout, n, iota ? 1 : 0, gbase, lookback, epoch, ticket, use_tma, dig);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+template <typename U, typename P, bool HAS_PAY, typename DIG, int ITEMS_UNUSED, bool LAST_IDX>
+int32_t launch_pass(const U* kin, U* kout, const P* pin, void* pout, int64_t n, bool iota, const unsigned long long* gbase,
+                    unsigned long long* lookback, unsigned epoch, unsigned* ticket, DIG dig, cudaStream_t s) {
+    constexpr bool wide = HAS_PAY && sizeof(U) + sizeof(P) > 12;      // 16-byte rows: 64 KB of staging per 4096 rows
+#define SDC_CFG(T_, I_, C_) launch_cfg<U, P, HAS_PAY, DIG, T_, I_, C_, LAST_IDX>(kin, kout, pin, pout, n, iota, gbase, lookback, epoch, ticket, dig, s)
+    return SDC_CFG(256, 16, wide ? 2 : 3);
+#undef SDC_CFG
+}
+
+template <typename U, typename P, bool HAS_PAY, int KIND, bool DESC, int ITEMS>
+int32_t launch_sort_pass(const U* kin, U* kout, const P* pin, void* pout, int64_t n, bool iota, int shift, bool last_idx,
+                         const unsigned long long* gbase, unsigned long long* lookback, unsigned epoch, unsigned* ticket,
+                         cudaStream_t s) {
+    SortDigit<U, KIND, DESC> dig{shift};
+    if (last_idx) {
+        if constexpr (HAS_PAY && sizeof(P) == 4)
+            return launch_pass<U, P, HAS_PAY, SortDigit<U, KIND, DESC>, ITEMS, true>(kin, kout, pin, pout, n, iota, gbase, lookback, epoch, ticket, dig, s);
+    }
+    return launch_pass<U, P, HAS_PAY, SortDigit<U, KIND, DESC>, ITEMS, false>(kin, kout, pin, pout, n, iota, gbase, lookback, epoch, ticket, dig, s);
+}
+
+// idx64_out != nullptr (argsort, 32-bit payload): the LAST pass writes no keys and stores the row numbers as int64
+// straight into idx64_out; *rpay then points at idx64_out.
 template <typename U, typename P, bool HAS_PAY, int ITEMS>
 int32_t sort_impl_items(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, int64_t n, int kind, bool iota,
-                  bool desc, const void** rkeys, const void** rpay, cudaStream_t s) {
+                  bool desc, const void** rkeys, const void** rpay, int64_t* idx64_out, cudaStream_t s) {
     constexpr int NP = sizeof(U);
-    constexpr int TILE = kSortThreads * ITEMS;
+    constexpr int TILE = kTileRows;
     const int64_t ntiles = ceil_div(n, TILE);
     Scratch meta, lb;
-    // meta: ghist[NP*256] u64 | gbase[NP*256] u64 | counters[NP] u32 | trivial[NP] i32
+    // meta: ghist[NP*256] u64 | gbase[NP*256] u64 | tickets[NP] u32 | trivial[NP] i32
     const size_t meta_bytes = (size_t)NP * 256 * 8 * 2 + NP * 4 + NP * 4;
     SDC_TRY(meta.alloc(meta_bytes, s));
     SDC_TRY(lb.alloc((size_t)ntiles * 256 * 8, s));
     unsigned long long* ghist = meta.as<unsigned long long>();
     unsigned long long* gbase = ghist + NP * 256;
-    unsigned* counters = reinterpret_cast<unsigned*>(gbase + NP * 256);
-    int* trivial = reinterpret_cast<int*>(counters + NP);
+    unsigned* tickets = reinterpret_cast<unsigned*>(gbase + NP * 256);
+    int* trivial = reinterpret_cast<int*>(tickets + NP);
     SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, meta_bytes, s));
     SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
     int hgrid = (int)(ceil_div(n, kHistThreads * 8) < (int64_t)sm_count() * 4 ? ceil_div(n, kHistThreads * 8) : (int64_t)sm_count() * 4);
@@ -297,15 +490,9 @@ int32_t sort_impl_items(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P*
     int htriv[8];
     SDC_CUDA_TRY(cudaMemcpyAsync(htriv, trivial, NP * sizeof(int), cudaMemcpyDeviceToHost, s));
     SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    int last = -1;
+    for (int p = 0; p < NP; ++p) if (!htriv[p]) last = p;
 
-    using KernT = void (*)(const U*, U*, const P*, P*, int64_t, int, int, const unsigned long long*, unsigned long long*, unsigned);
-    KernT kern = nullptr;
-    if (kind == KIND_FLOAT) kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_FLOAT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_FLOAT, false, ITEMS>;
-    else if (kind == KIND_SINT) kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_SINT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_SINT, false, ITEMS>;
-    else kern = desc ? (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_UINT, true, ITEMS> : (KernT)onesweep_kernel<U, P, HAS_PAY, KIND_UINT, false, ITEMS>;
-    const size_t smem = (size_t)kSortWarps * 256 * 4 + 256 * 4 + 256 * 8 + 16 * 4 + (size_t)TILE * sizeof(U) +
-                        (HAS_PAY ? (size_t)TILE * sizeof(P) : 0) + (size_t)TILE;
-    SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const U* kcur = src;
     const P* pcur = psrc;
     bool first = true;
@@ -314,19 +501,36 @@ int32_t sort_impl_items(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P*
         if (htriv[p]) continue;
         U* kdst = flip ? bufB : bufA;
         P* pdst = flip ? pB : pA;
-        kern<<<(unsigned)ntiles, kSortThreads, smem, s>>>(kcur, kdst, pcur, pdst, n, 8 * p,
-                                                          (first && iota) ? 1 : 0, gbase + p * 256,
-                                                          lb.as<unsigned long long>(), (unsigned)(p + 1));
-        SDC_CHECK_LAUNCH();
-        kcur = kdst;
-        pcur = pdst;
+        const bool last_idx = HAS_PAY && idx64_out != nullptr && p == last;
+        void* pout = last_idx ? (void*)idx64_out : (void*)pdst;
+        const bool io = first && iota;
+        int32_t rc;
+#define SDC_PASS(KIND_, DESC_) launch_sort_pass<U, P, HAS_PAY, KIND_, DESC_, ITEMS>(kcur, kdst, pcur, pout, n, io, 8 * p, last_idx, \
+                                                                                  gbase + p * 256, lb.as<unsigned long long>(), (unsigned)(p + 1), tickets + p, s)
+        if (kind == KIND_FLOAT) rc = desc ? SDC_PASS(KIND_FLOAT, true) : SDC_PASS(KIND_FLOAT, false);
+        else if (kind == KIND_SINT) rc = desc ? SDC_PASS(KIND_SINT, true) : SDC_PASS(KIND_SINT, false);
+        else rc = desc ? SDC_PASS(KIND_UINT, true) : SDC_PASS(KIND_UINT, false);
+#undef SDC_PASS
+        SDC_TRY(rc);
+        kcur = last_idx ? nullptr : kdst;
+        pcur = last_idx ? reinterpret_cast<const P*>(idx64_out) : pdst;
         first = false;
         flip ^= 1;
     }
     if (first && HAS_PAY && iota) {   // every digit constant: the identity permutation
-        iota_kernel<P><<<sm_count() * 4, 256, 0, s>>>(pA, n);
+        if (idx64_out) {
+            iota_kernel<long long><<<sm_count() * 4, 256, 0, s>>>(reinterpret_cast<long long*>(idx64_out), n);
+            pcur = reinterpret_cast<const P*>(idx64_out);
+        } else {
+            iota_kernel<P><<<sm_count() * 4, 256, 0, s>>>(pA, n);
+            pcur = pA;
+        }
         SDC_CHECK_LAUNCH();
-        pcur = pA;
+    } else if (first && HAS_PAY && idx64_out) {
+        // no pass ran and the payload was given: widen it
+        widen_u32_kernel<<<sm_count() * 8, 256, 0, s>>>(reinterpret_cast<const uint32_t*>(psrc), idx64_out, n);
+        SDC_CHECK_LAUNCH();
+        pcur = reinterpret_cast<const P*>(idx64_out);
     }
     *rkeys = kcur;
     *rpay = pcur;
@@ -335,25 +539,56 @@ int32_t sort_impl_items(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P*
 
 template <typename U, typename P, bool HAS_PAY>
 int32_t sort_impl(const U* src, U* bufA, U* bufB, const P* psrc, P* pA, P* pB, int64_t n, int kind, bool iota,
-                  bool desc, const void** rkeys, const void** rpay, cudaStream_t s) {
-    return sort_impl_items<U, P, HAS_PAY, 16>(src, bufA, bufB, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
+                  bool desc, const void** rkeys, const void** rpay, int64_t* idx64_out, cudaStream_t s) {
+    return sort_impl_items<U, P, HAS_PAY, 16>(src, bufA, bufB, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
 }
 
 template <typename U>
 int32_t sort_dispatch_pay(const void* src, void* bufA, void* bufB, int pay_bytes, const void* psrc, void* pA, void* pB,
-                          int64_t n, int kind, bool iota, bool desc, const void** rkeys, const void** rpay,
+                          int64_t n, int kind, bool iota, bool desc, const void** rkeys, const void** rpay, int64_t* idx64_out,
                           cudaStream_t s) {
     if (pay_bytes == 0)
         return sort_impl<U, uint32_t, false>((const U*)src, (U*)bufA, (U*)bufB, nullptr, nullptr, nullptr, n, kind,
-                                             false, desc, rkeys, rpay, s);
+                                             false, desc, rkeys, rpay, nullptr, s);
     if (pay_bytes == 4)
         return sort_impl<U, uint32_t, true>((const U*)src, (U*)bufA, (U*)bufB, (const uint32_t*)psrc, (uint32_t*)pA,
-                                            (uint32_t*)pB, n, kind, iota, desc, rkeys, rpay, s);
+                                            (uint32_t*)pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
     if (pay_bytes == 8)
         return sort_impl<U, uint64_t, true>((const U*)src, (U*)bufA, (U*)bufB, (const uint64_t*)psrc, (uint64_t*)pA,
-                                            (uint64_t*)pB, n, kind, iota, desc, rkeys, rpay, s);
+                                            (uint64_t*)pB, n, kind, iota, desc, rkeys, rpay, nullptr, s);
     set_error("radix sort: payload size %d", pay_bytes);
     return SDCB200_ERR_ARG;
+}
+
+// ---- one stable partition pass by hash bucket (HashTopDigit): 256 buckets, bucket b = rows whose
+// hash_mix64(canonical key) has top byte b, in input order.  part_begin (device, u64[257]) receives the bucket starts.
+__global__ void __launch_bounds__(kHistThreads) hash_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n, HashTopDigit dig,
+                                                                 unsigned long long* __restrict__ ghist) {
+    __shared__ unsigned sh[256];
+    for (int i = threadIdx.x; i < 256; i += kHistThreads) sh[i] = 0;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * kHistThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kHistThreads + threadIdx.x; i < n; i += stride) atomicAdd(&sh[dig(keys[i])], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += kHistThreads)
+        if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
+}
+__global__ void __launch_bounds__(256) hash_scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase) {
+    __shared__ unsigned long long warp_tot[8];
+    const int d = threadIdx.x, lane = d & 31, w = d >> 5;
+    const unsigned long long v = ghist[d];
+    unsigned long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+    }
+    if (lane == 31) warp_tot[w] = x;
+    __syncthreads();
+    unsigned long long add = 0;
+    for (int i = 0; i < w; ++i) add += warp_tot[i];
+    gbase[d] = add + x - v;
+    if (d == 255) gbase[256] = add + x;
 }
 
 }  // namespace
@@ -362,13 +597,13 @@ int32_t sort_dispatch_pay(const void* src, void* bufA, void* bufB, int pay_bytes
 // whichever buffer holds the sorted rows afterwards (src itself when no pass had to run).
 int32_t radix_sort_core(int dtype, const void* src, void* bufA, void* bufB, int pay_bytes, const void* psrc, void* pA,
                         void* pB, int64_t n, bool iota, bool desc, const void** rkeys, const void** rpay,
-                        cudaStream_t s) {
+                        cudaStream_t s, int64_t* idx64_out) {
     const int kind = dtype_kind(dtype);
     switch (dtype_size(dtype)) {
-        case 1: return sort_dispatch_pay<uint8_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
-        case 2: return sort_dispatch_pay<uint16_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
-        case 4: return sort_dispatch_pay<uint32_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
-        case 8: return sort_dispatch_pay<uint64_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, s);
+        case 1: return sort_dispatch_pay<uint8_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
+        case 2: return sort_dispatch_pay<uint16_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
+        case 4: return sort_dispatch_pay<uint32_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
+        case 8: return sort_dispatch_pay<uint64_t>(src, bufA, bufB, pay_bytes, psrc, pA, pB, n, kind, iota, desc, rkeys, rpay, idx64_out, s);
     }
     set_error("radix sort: bad dtype %d", dtype);
     return SDCB200_ERR_ARG;
@@ -384,11 +619,10 @@ int32_t argsort_device(int dtype, const void* keys, int64_t n, bool ascending, i
     SDC_TRY(kb.alloc((size_t)n * ks, s));
     const void *rk, *rp;
     if (n <= 0xffffffffll) {
+        // 32-bit row numbers ride through the passes; the last pass stores them as int64 into index_out
         SDC_TRY(pa.alloc((size_t)n * 4, s));
         SDC_TRY(pb.alloc((size_t)n * 4, s));
-        SDC_TRY(radix_sort_core(dtype, keys, ka.p, kb.p, 4, nullptr, pa.p, pb.p, n, true, !ascending, &rk, &rp, s));
-        widen_u32_kernel<<<sm_count() * 8, 256, 0, s>>>((const uint32_t*)rp, index_out, n);
-        SDC_CHECK_LAUNCH();
+        SDC_TRY(radix_sort_core(dtype, keys, ka.p, kb.p, 4, nullptr, pa.p, pb.p, n, true, !ascending, &rk, &rp, s, index_out));
     } else {
         SDC_TRY(pa.alloc((size_t)n * 8, s));
         SDC_TRY(radix_sort_core(dtype, keys, ka.p, kb.p, 8, nullptr, pa.p, index_out, n, true, !ascending, &rk, &rp, s));
@@ -396,6 +630,45 @@ int32_t argsort_device(int dtype, const void* keys, int64_t n, bool ascending, i
             SDC_CUDA_TRY(cudaMemcpyAsync(index_out, rp, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
     }
     return SDCB200_OK;
+}
+
+// One stable partition pass of 8-byte keys (+ payload) into the 256 buckets of HashTopDigit.
+int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int pay_bytes, const void* pay, void* pay_out,
+                            int64_t n, bool iota, unsigned long long* part_begin /* device u64[257] */, cudaStream_t s) {
+    if (n == 0) {
+        SDC_CUDA_TRY(cudaMemsetAsync(part_begin, 0, 257 * 8, s));
+        return SDCB200_OK;
+    }
+    constexpr int ITEMS = 16;
+    constexpr int TILE = kTileRows;
+    const int64_t ntiles = ceil_div(n, TILE);
+    Scratch meta, lb;
+    SDC_TRY(meta.alloc(256 * 8 + 16, s));
+    SDC_TRY(lb.alloc((size_t)ntiles * 256 * 8, s));
+    unsigned long long* ghist = meta.as<unsigned long long>();
+    unsigned* ticket = reinterpret_cast<unsigned*>(ghist + 256);
+    SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, 256 * 8 + 16, s));
+    SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
+    HashTopDigit dig{key_f64 ? 1 : 0};
+    int hgrid = (int)(ceil_div(n, kHistThreads * 8) < (int64_t)sm_count() * 4 ? ceil_div(n, kHistThreads * 8) : (int64_t)sm_count() * 4);
+    if (hgrid < 1) hgrid = 1;
+    const unsigned long long* k = reinterpret_cast<const unsigned long long*>(keys);
+    hash_hist_kernel<<<hgrid, kHistThreads, 0, s>>>(k, n, dig, ghist);
+    SDC_CHECK_LAUNCH();
+    hash_scan_kernel<<<1, 256, 0, s>>>(ghist, part_begin);
+    SDC_CHECK_LAUNCH();
+    unsigned long long* ko = reinterpret_cast<unsigned long long*>(keys_out);
+    if (pay_bytes == 0)
+        return launch_pass<unsigned long long, uint32_t, false, HashTopDigit, ITEMS, false>(k, ko, nullptr, nullptr, n, false, part_begin,
+                                                                                          lb.as<unsigned long long>(), 1u, ticket, dig, s);
+    if (pay_bytes == 4)
+        return launch_pass<unsigned long long, uint32_t, true, HashTopDigit, ITEMS, false>(k, ko, reinterpret_cast<const uint32_t*>(pay), pay_out, n, iota,
+                                                                                         part_begin, lb.as<unsigned long long>(), 1u, ticket, dig, s);
+    if (pay_bytes == 8)
+        return launch_pass<unsigned long long, unsigned long long, true, HashTopDigit, ITEMS, false>(
+            k, ko, reinterpret_cast<const unsigned long long*>(pay), pay_out, n, iota, part_begin, lb.as<unsigned long long>(), 1u, ticket, dig, s);
+    set_error("hash partition: payload size %d", pay_bytes);
+    return SDCB200_ERR_ARG;
 }
 
 }  // namespace sdcb200

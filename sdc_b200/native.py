@@ -9,7 +9,7 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsdc_b200.so")
+LIB_PATH = os.environ.get("SDCB200_LIB_PATH") or os.path.join(_HERE, "lib", "libsdc_b200.so")   # override: A/B builds (tools/)
 
 OK = 0
 JOIN_HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}

@@ -36,7 +36,7 @@ for r in rows:
         stalls = {k[6:]: int(v) for k, v in d.items() if k.startswith("stall_") and "(Not Issued)" not in k and v.isdigit() and int(v)}
         lines.append((samples, cur_file, int(r[0]), r[1].strip()[:90], int(d.get("Instructions Executed", "0") or 0), stalls))
 tot = sum(x[0] for x in lines) or 1
-lines.sort(reverse=True)
+lines.sort(key=lambda x: x[0], reverse=True)
 print("total samples", tot)
 for s, f, ln, src, inst, stalls in lines[:top]:
     st = ",".join("%s=%d" % kv for kv in sorted(stalls.items(), key=lambda kv: -kv[1])[:3])
