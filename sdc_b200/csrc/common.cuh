@@ -66,14 +66,15 @@ struct Scratch {
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// murmur3 finaliser.  hash_mix64 picks hash-table slots and partition buckets (top bits); the shuffle's destination
-// rank comes from the top bits of the same mixer over the UNSALTED key (shuffle.cu), so the salt here keeps the two
-// independent: the keys a rank owns after a hash shuffle still spread over all buckets / slots.
-__host__ __device__ inline unsigned long long mix64_fin(unsigned long long x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-    return x;
+// hash_mix64 picks hash-table slots and partition buckets from its TOP bits (partitioned join / groupby): one xor-shift and
+// one multiply by an odd constant (Fibonacci hashing over the folded key) -- 7 instructions instead of the 19 of a full
+// murmur finaliser, which the partition pass pays per row.  The shuffle's destination rank comes from a murmur finaliser
+// over the same key (shuffle.cu): a different function, so the keys a rank owns after a hash shuffle still spread over
+// all buckets / slots.
+__host__ __device__ inline unsigned long long hash_mix64(unsigned long long x) {
+    x ^= x >> 32;
+    return x * 0x9e3779b97f4a7c15ull;
 }
-__host__ __device__ inline unsigned long long hash_mix64(unsigned long long x) { return mix64_fin(x ^ 0xa0761d6478bd642full); }
 
 // -------------------------------------------------------------- device side
 #ifdef __CUDACC__

@@ -33,6 +33,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace sdcb200 {
@@ -68,11 +69,24 @@ struct JTable {
     unsigned long long* dense;  // dense mode: val of key k at dense[k - dlo]
     uint32_t* dense32;          // dense mode with unique build keys: right row + 1 (0 = absent), 4 bytes per key
     unsigned long long dlo, drange;   // drange == 0: hash mode
+    int shift;                  // hash mode: 0 -> slot = low bits of jmix64(key); else slot = hash_mix64(key) >> shift (the TOP
+                                // bits: rows partitioned by the top byte of the same hash, radix_sort.cuh, walk the table
+                                // one contiguous 1/256 slice after the other -- the partitioned join)
 };
+
+// Home slots are EVEN: a lookup reads the 32-byte pair {slot, slot + 1} with one 256-bit load (one sector either way),
+// so a probe chain is half as many dependent round trips long -- the probe kernels are bound by the LONGEST chain among
+// a warp's 32 lanes, not by the average.
+__device__ __forceinline__ unsigned long long jt_home(const JTable& t, unsigned long long key) {
+    return (t.shift ? (hash_mix64(key) >> t.shift) : (jmix64(key) & (t.cap - 1))) & ~1ull;
+}
+__device__ __forceinline__ void ld_slot_pair(const ulonglong2* p, ulonglong2& a, ulonglong2& b) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
+}
 
 __device__ __forceinline__ unsigned long long jt_upsert(const JTable& t, unsigned long long key) {
     if (key == kEmptyKey) return t.cap;
-    unsigned long long s = jmix64(key) & (t.cap - 1);
+    unsigned long long s = jt_home(t, key);
     while (true) {
         const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].x);
         if (cur == key) return s;
@@ -91,12 +105,15 @@ __device__ __forceinline__ unsigned long long jt_lookup(const JTable& t, unsigne
         return d < t.drange ? __ldg(t.dense + d) : 0ull;
     }
     if (key == kEmptyKey) return t.slots[t.cap].y;
-    unsigned long long s = jmix64(key) & (t.cap - 1);
+    unsigned long long s = jt_home(t, key);
     while (true) {
-        const ulonglong2 sl = __ldg(reinterpret_cast<const ulonglong2*>(&t.slots[s]));
-        if (sl.x == key) return sl.y;
-        if (sl.x == kEmptyKey) return 0ull;
-        s = (s + 1) & (t.cap - 1);
+        ulonglong2 a, b;
+        ld_slot_pair(&t.slots[s], a, b);
+        if (a.x == key) return a.y;
+        if (a.x == kEmptyKey) return 0ull;
+        if (b.x == key) return b.y;
+        if (b.x == kEmptyKey) return 0ull;
+        s = (s + 2) & (t.cap - 1);
     }
 }
 
@@ -111,7 +128,8 @@ template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                  JTable t, uint32_t* __restrict__ rslot,
                                                                  uint32_t* __restrict__ rrank,
-                                                                 unsigned long long* __restrict__ dup_flag) {
+                                                                 unsigned long long* __restrict__ dup_flag,
+                                                                 const uint32_t* __restrict__ rowmap /* partitioned: row of keys[j] */) {
     const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
     const int lane = threadIdx.x & 31;
     // warp-uniform loop; the probe loop of jt_upsert ends at different times per lane, so reconverge before the
@@ -125,7 +143,8 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
             // one add carries the count (low word) AND the row (high word): with unique build keys the slot then
             // already reads row << 32 | 1 -- no scan, no scatter, and the probe needs no row-id indirection.  With
             // duplicates the high words are garbage; the scan below rebuilds them from the counts.
-            rank = atomicAdd(&t.slots[s].y, ((unsigned long long)j << 32) | 1ull) & 0xffffffffull;
+            const unsigned long long row = rowmap ? (unsigned long long)rowmap[j] : (unsigned long long)j;
+            rank = atomicAdd(&t.slots[s].y, (row << 32) | 1ull) & 0xffffffffull;
             if (rank) *dup_flag = 1ull;
         }
         __syncwarp();
@@ -203,11 +222,11 @@ struct SlotStartStore {          // val = start << 32 | count
 };
 __global__ void __launch_bounds__(kJoinThreads) jt_scatter_kernel(const uint32_t* __restrict__ rslot,
                                                                   const uint32_t* __restrict__ rrank, int64_t n, JTable t,
-                                                                  uint32_t* __restrict__ rid) {
+                                                                  uint32_t* __restrict__ rid, const uint32_t* __restrict__ rowmap) {
     const int64_t stride = (int64_t)gridDim.x * kJoinThreads;
     for (int64_t j = (int64_t)blockIdx.x * kJoinThreads + threadIdx.x; j < n; j += stride) {
         const unsigned long long val = t.slots[rslot[j]].y;
-        rid[(val >> 32) + rrank[j]] = (uint32_t)j;
+        rid[(val >> 32) + rrank[j]] = rowmap ? rowmap[j] : (uint32_t)j;
     }
 }
 
@@ -284,7 +303,8 @@ template <bool LEFT>
 __global__ void __launch_bounds__(kJoinThreads) probe_emit_kernel(const unsigned long long* __restrict__ pval, int64_t n,
                                                                   const unsigned long long* __restrict__ tile_offs,
                                                                   const uint32_t* __restrict__ rid,
-                                                                  int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+                                                                  int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
+                                                                  const uint32_t* __restrict__ lmap /* partitioned: left row of probe position */) {
     constexpr int kWarps = kJoinThreads / 32;
     constexpr int kWRows = 32 * kItems;                       // 256 rows per warp
     __shared__ unsigned long long wsum[kWarps];
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(kJoinThreads) probe_emit_kernel(const unsigned
         const unsigned long long val = wval[warp][lo];
         const unsigned cnt = (unsigned)(val & 0xffffffffull);
         const unsigned m = o - off[lo];
-        lidx[wbase + o] = wrow0 + lo;
+        lidx[wbase + o] = lmap ? (int64_t)lmap[wrow0 + lo] : wrow0 + lo;
         ridx[wbase + o] = cnt ? (int64_t)rid[(val >> 32) + m] : -1;
     }
 }
@@ -532,7 +552,8 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_row1_kernel(const u
 
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(const uint32_t* __restrict__ row1_in, int64_t n,
                                                                             const unsigned long long* __restrict__ tile_offs,
-                                                                            int64_t* __restrict__ lidx, int64_t* __restrict__ ridx) {
+                                                                            int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
+                                                                            const uint32_t* __restrict__ lmap) {
     constexpr int kWarps = kJoinThreads / 32;
     __shared__ unsigned wcnt[kWarps];
     const uint64_t stream_pol = l2_policy_evict_first();
@@ -575,14 +596,24 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(cons
     for (int j = 0; j < kItems / 2; ++j) {
         const int64_t r = probe_row(tile0, warp, lane, 2 * j);
         const unsigned long long p0 = base + rank[2 * j];
+        int64_t l0 = r, l1 = r + 1;
+        if (lmap) {                                   // partitioned probe side: the left rows travel beside the keys
+            if (r + 1 < n) {
+                const uint2 m = __ldcs(reinterpret_cast<const uint2*>(lmap + r));
+                l0 = m.x;
+                l1 = m.y;
+            } else if (r < n) {
+                l0 = lmap[r];
+            }
+        }
         if (((fullmask >> j) & 1u) && even) {
-            st_hint_v2s64(lidx + p0, r, r + 1, stream_pol);
+            st_hint_v2s64(lidx + p0, l0, l1, stream_pol);
             st_hint_v2s64(ridx + p0, (int64_t)row1[2 * j] - 1, (int64_t)row1[2 * j + 1] - 1, stream_pol);
         } else {
-            if (row1[2 * j]) { lidx[p0] = r; ridx[p0] = (int64_t)row1[2 * j] - 1; }
+            if (row1[2 * j]) { lidx[p0] = l0; ridx[p0] = (int64_t)row1[2 * j] - 1; }
             if (row1[2 * j + 1]) {
                 const unsigned long long p1 = base + rank[2 * j + 1];
-                lidx[p1] = r + 1;
+                lidx[p1] = l1;
                 ridx[p1] = (int64_t)row1[2 * j + 1] - 1;
             }
         }
@@ -652,7 +683,12 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     // ---- build ----
     JTable t;
     memset(&t, 0, sizeof(t));
-    Scratch slots, slots32, rslot, rrank, rid, tsum_b, meta;
+    Scratch slots, slots32, rslot, rrank, rid, tsum_b, meta, rk2, rrow2, lk2, lrow2, pbeg;
+    const unsigned long long* rk = r;          // the build / probe key columns the kernels read: the caller's, or the
+    const unsigned long long* lk = l;          // copies partitioned by hash bucket
+    const uint32_t* rmap = nullptr;            // partitioned: original row of every partitioned position
+    const uint32_t* lmap = nullptr;
+    bool part = false;
     SDC_TRY(meta.alloc(64, s));                  // [0] ticket, [1] n_out, [2] duplicate build key seen, [4] min, [5] max
     unsigned long long* dmeta = meta.as<unsigned long long>();
     {
@@ -705,8 +741,31 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         }
     } else {
         t.cap = 1024;
-        while (t.cap * 3 < (unsigned long long)nr * 4) t.cap <<= 1;        // load factor <= 0.75
+        while (t.cap < 2ull * (unsigned long long)nr) t.cap <<= 1;         // load factor <= 0.5: short chains (see jt_home)
         const int64_t nslots = (int64_t)t.cap + 1;
+        // Partitioned join (inner joins over keys with no dense range): once the table is far larger than L2 every
+        // probe is a random HBM burst (154 B of DRAM traffic per probe measured).  Both sides are first split into the 256
+        // buckets of the top hash byte (one unordered partition pass each, row numbers riding along as 32-bit payload)
+        // and the slot index comes from the top bits of the same hash, so the build and the probe walk the table one
+        // contiguous 1/256 slice after the other: the slice in use stays in L2.  The pairs come out in bucket order --
+        // an inner join's contract is the row SET; how='left' keeps left-row order and stays on the direct path.
+        const int part_on = [] { const char* e = getenv("SDCB200_JOIN_PART"); return e ? atoi(e) : 1; }();   // 0 off, 2 always (tests)
+        static const bool chained = [] { const char* e = getenv("SDCB200_JOIN_INNER"); return e && !strcmp(e, "chained"); }();
+        part = part_on && !chained && !LEFT && extra == 0 && nl < 0xffffffffll &&
+               (part_on == 2 || ((int64_t)t.cap * 16 >= (int64_t(48) << 20) && nl >= (int64_t(1) << 22)));
+        if (part) {
+            int lg = 0;
+            while ((1ull << lg) < t.cap) ++lg;
+            t.shift = 64 - lg;
+            SDC_TRY(pbeg.alloc(2 * 257 * 8, s));
+            if (nr > 0) {
+                SDC_TRY(rk2.alloc((size_t)nr * 8, s));
+                SDC_TRY(rrow2.alloc((size_t)nr * 4 + 16, s));
+                SDC_TRY(hash_partition_pass(r, KEY_F64, rk2.p, 4, nullptr, rrow2.p, nr, true, pbeg.as<unsigned long long>(), s));
+                rk = rk2.as<unsigned long long>();
+                rmap = rrow2.as<uint32_t>();
+            }
+        }
         SDC_TRY(rslot.alloc((size_t)nr * 4 + 16, s));
         SDC_TRY(rrank.alloc((size_t)nr * 4 + 16, s));
         SDC_TRY(slots.alloc((size_t)nslots * 16, s));
@@ -715,7 +774,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
         SDC_CHECK_LAUNCH();
         if (nr > 0) {
-            jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(r, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2);
+            jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(rk, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2, rmap);
             SDC_CHECK_LAUNCH();
             SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
@@ -723,7 +782,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                 // duplicate build keys: counts -> starts, right rows grouped by key
                 SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
                                               tsum_b.as<unsigned long long>(), s));
-                jt_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>());
+                jt_scatter_kernel<<<bgrid, kJoinThreads, 0, s>>>(rslot.as<uint32_t>(), rrank.as<uint32_t>(), nr, t, rid.as<uint32_t>(), rmap);
                 SDC_CHECK_LAUNCH();
             }
             unique = hdup == 0;
@@ -733,13 +792,20 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     if (nl == 0) return SDCB200_OK;
     const int64_t nt = ceil_div(nl, kTile);
     void* p = nullptr;
+    if (part) {
+        SDC_TRY(lk2.alloc((size_t)nl * 8, s));
+        SDC_TRY(lrow2.alloc((size_t)nl * 4 + 16, s));
+        SDC_TRY(hash_partition_pass(l, KEY_F64, lk2.p, 4, nullptr, lrow2.p, nl, true, pbeg.as<unsigned long long>() + 257, s));
+        lk = lk2.as<unsigned long long>();
+        lmap = lrow2.as<uint32_t>();
+    }
     if (unique) {
         // every left row has at most one partner: one kernel, n_out <= nl
         SDC_TRY(dev_alloc(&p, (size_t)(nl + extra) * 8, s));
         res->lidx = reinterpret_cast<int64_t*>(p);
         SDC_TRY(dev_alloc(&p, (size_t)(nl + extra) * 8, s));
         res->ridx = reinterpret_cast<int64_t*>(p);
-        const int vec = (reinterpret_cast<uintptr_t>(l) & 15) == 0;
+        const int vec = (reinterpret_cast<uintptr_t>(lk) & 15) == 0;
         if (LEFT) {
             probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx, vec);
             SDC_CHECK_LAUNCH();
@@ -753,7 +819,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                 SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
                 unsigned long long* tile_counts = tcnt.as<unsigned long long>();
                 unsigned long long* tsum_p = tile_counts + nt + 1;
-                probe_unique_row1_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), row1.as<uint32_t>(),
+                probe_unique_row1_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(lk, nl, t, rid.as<uint32_t>(), row1.as<uint32_t>(),
                                                                                         tile_counts, vec);
                 SDC_CHECK_LAUNCH();
                 if (nt <= kOneCtaScanMax) {
@@ -763,7 +829,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                     SDC_TRY(device_exclusive_scan(ArrayLoad{tile_counts}, ArrayStore{tile_counts}, nt, tsum_p, s));
                     SDC_CUDA_TRY(cudaMemcpyAsync(tile_counts + nt, tsum_p + ceil_div(nt, kTile), 8, cudaMemcpyDeviceToDevice, s));
                 }
-                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx);
+                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx, lmap);
                 SDC_CHECK_LAUNCH();
                 unsigned long long total = 0;
                 SDC_CUDA_TRY(cudaMemcpyAsync(&total, tile_counts + nt, 8, cudaMemcpyDeviceToHost, s));
@@ -805,8 +871,8 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
     unsigned long long* tile_counts = tcnt.as<unsigned long long>();
     unsigned long long* tsum_p = tile_counts + nt + 1;
-    probe_count_kernel<KEY_F64, LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, pval.as<unsigned long long>(), tile_counts,
-                                                                            (reinterpret_cast<uintptr_t>(l) & 15) == 0);
+    probe_count_kernel<KEY_F64, LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(lk, nl, t, pval.as<unsigned long long>(), tile_counts,
+                                                                            (reinterpret_cast<uintptr_t>(lk) & 15) == 0);
     SDC_CHECK_LAUNCH();
     // exclusive scan of the tile counts in place; total lands in tile_counts[nt]
     if (nt <= kOneCtaScanMax) {
@@ -827,7 +893,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     SDC_TRY(dev_alloc(&p, (size_t)(total + extra) * 8, s));
     res->ridx = reinterpret_cast<int64_t*>(p);
     probe_emit_kernel<LEFT><<<(unsigned)nt, kJoinThreads, 0, s>>>(pval.as<unsigned long long>(), nl, tile_counts,
-                                                                  rid.as<uint32_t>(), res->lidx, res->ridx);
+                                                                  rid.as<uint32_t>(), res->lidx, res->ridx, lmap);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

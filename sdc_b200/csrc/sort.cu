@@ -129,13 +129,15 @@ struct NoPay {};
 // LSD sort pass: 8 bits of the canonical key (order-preserving unsigned image of the raw bits) at `shift`
 template <typename U, int KIND, bool DESC>
 struct SortDigit {
+    static constexpr bool kStable = true;
     int shift;
     __device__ __forceinline__ unsigned operator()(U raw) const { return (unsigned)(canon_key<U>(raw, KIND, DESC) >> shift) & 255u; }
 };
 // partition pass: the top byte of mix64(canonical key) -- rows of one bucket later touch one contiguous 1/256 slice of
 // a hash table whose slot index is taken from the TOP bits of the same hash (join / groupby on keys with no dense range)
 struct HashTopDigit {
-    int f64;
+    static constexpr bool kStable = false;      // consumers only need the rows grouped: a row's place inside its bucket is
+    int f64;                                    // whatever one shared atomic per row hands out (no ballots, no per-warp counts)
     __device__ __forceinline__ unsigned operator()(unsigned long long b) const {
         if (f64) {
             const unsigned long long mag = b & 0x7fffffffffffffffull;
@@ -229,15 +231,23 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             key[i] = pos < tile_n ? kin[tile_base + pos] : U(0);
         }
     }
-    // ---- rank inside the warp, stable in (item, lane) order ----
-    unsigned* mywh = wh + w * 256;
+    // ---- rank inside the warp, stable in (item, lane) order -- or, for an unordered partition, inside the tile by one
+    // shared atomic per row ----
+    constexpr bool STABLE = DIG::kStable;
+    unsigned* mywh = STABLE ? wh + w * 256 : wh;
     const unsigned lt = (1u << lane) - 1u;
     unsigned short rank[ITEMS];
+    unsigned char dcache[ITEMS];                 // a row's bucket, computed once (a hashed digit costs a 64-bit multiply)
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         const int pos = wbase + i * 32 + lane;
         const bool valid = pos < tile_n;
         const unsigned d = dig(key[i]);
+        dcache[i] = (unsigned char)d;
+        if (!STABLE) {
+            rank[i] = valid ? (unsigned short)atomicAdd(&wh[d], 1u) : (unsigned short)0;
+            continue;
+        }
         unsigned peers;
         {
             peers = __ballot_sync(0xffffffffu, valid);
@@ -285,11 +295,15 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         const int d = tid & 255;
         unsigned run = 0;
         if (tid < 256) {
+        if (STABLE) {
 #pragma unroll
-        for (int ww = 0; ww < WARPS; ++ww) {
-            const unsigned t = wh[ww * 256 + d];
-            wh[ww * 256 + d] = run;
-            run += t;
+            for (int ww = 0; ww < WARPS; ++ww) {
+                const unsigned t = wh[ww * 256 + d];
+                wh[ww * 256 + d] = run;
+                run += t;
+            }
+        } else {
+            run = wh[d];
         }
         cnt = run;
         lb[(size_t)tile * 256 + d] = lb_pack(cnt, tile == 0 ? 2u : 1u, epoch);
@@ -314,8 +328,8 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         const int pos = wbase + i * 32 + lane;
         slot[i] = 0;
         if (pos < tile_n) {
-            const unsigned d = dig(key[i]);
-            const unsigned p = tile_off[d] + mywh[d] + rank[i];
+            const unsigned d = dcache[i];
+            const unsigned p = tile_off[d] + (STABLE ? mywh[d] : 0u) + rank[i];
             slot[i] = (unsigned short)p;
             if (!LAST_IDX) skeys[p] = key[i];
             sdig[p] = (unsigned char)d;
@@ -344,9 +358,7 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
         const int d = tid;
         unsigned long long excl = 0;
         if (tile != 0) {
-            // A window of LB predecessors per L2 round trip.  Tiles retire every ~30 ns while a round trip takes several
-            // hundred: a narrow window cannot catch up with the tiles that have published their count but not yet their
-            // prefix, and every look-back ends up walking back over all tiles in flight.
+            // a window of LB predecessors per L2 round trip, consumed in order up to the first inclusive prefix
             long long t = (long long)tile - 1;
             bool done = false;
             while (!done) {
@@ -639,8 +651,10 @@ int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int 
         SDC_CUDA_TRY(cudaMemsetAsync(part_begin, 0, 257 * 8, s));
         return SDCB200_OK;
     }
-    constexpr int ITEMS = 16;
-    constexpr int TILE = kTileRows;
+    // tile geometry of the partition pass (SDCB200_PART_CFG, experiments): 0 = 256 x 16 rows, 3 CTAs per SM;
+    // 1 = 256 x 8 rows, 6 CTAs per SM; 2 = 512 x 8, 3 CTAs
+    const int cfg = sort_env("SDCB200_PART_CFG", 0);
+    const int TILE = cfg == 1 ? 2048 : 4096;
     const int64_t ntiles = ceil_div(n, TILE);
     Scratch meta, lb;
     SDC_TRY(meta.alloc(256 * 8 + 16, s));
@@ -658,15 +672,15 @@ int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int 
     hash_scan_kernel<<<1, 256, 0, s>>>(ghist, part_begin);
     SDC_CHECK_LAUNCH();
     unsigned long long* ko = reinterpret_cast<unsigned long long*>(keys_out);
-    if (pay_bytes == 0)
-        return launch_pass<unsigned long long, uint32_t, false, HashTopDigit, ITEMS, false>(k, ko, nullptr, nullptr, n, false, part_begin,
-                                                                                          lb.as<unsigned long long>(), 1u, ticket, dig, s);
-    if (pay_bytes == 4)
-        return launch_pass<unsigned long long, uint32_t, true, HashTopDigit, ITEMS, false>(k, ko, reinterpret_cast<const uint32_t*>(pay), pay_out, n, iota,
-                                                                                         part_begin, lb.as<unsigned long long>(), 1u, ticket, dig, s);
-    if (pay_bytes == 8)
-        return launch_pass<unsigned long long, unsigned long long, true, HashTopDigit, ITEMS, false>(
-            k, ko, reinterpret_cast<const unsigned long long*>(pay), pay_out, n, iota, part_begin, lb.as<unsigned long long>(), 1u, ticket, dig, s);
+    typedef unsigned long long K;
+#define SDC_PART(P_, HAS_, pin_) \
+    (cfg == 1 ? launch_cfg<K, P_, HAS_, HashTopDigit, 256, 8, 6, false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s) \
+     : cfg == 2 ? launch_cfg<K, P_, HAS_, HashTopDigit, 512, 8, 3, false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s) \
+                : launch_cfg<K, P_, HAS_, HashTopDigit, 256, 16, (sizeof(P_) > 4 ? 2 : 3), false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s))
+    if (pay_bytes == 0) return SDC_PART(uint32_t, false, (const uint32_t*)nullptr);
+    if (pay_bytes == 4) return SDC_PART(uint32_t, true, reinterpret_cast<const uint32_t*>(pay));
+    if (pay_bytes == 8) return SDC_PART(K, true, reinterpret_cast<const K*>(pay));
+#undef SDC_PART
     set_error("hash partition: payload size %d", pay_bytes);
     return SDCB200_ERR_ARG;
 }
