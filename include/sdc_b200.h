@@ -252,6 +252,16 @@ int32_t sdcb200_str_gather_sizes(const uint32_t* offsets, const int64_t* rows, i
                                  int64_t* total_chars, void* stream);
 int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, const int64_t* rows,
                                  int64_t m, const uint32_t* out_offsets, uint8_t* out_chars, uint8_t* out_bitmap, void* stream);
+/* String columns in the multi-GPU shuffle: the reference's wire format -- a LENGTH array plus the characters, offsets
+ * rebuilt on the receiving side by a scan (sdc/shuffle_utils.py:277-297, convert_len_arr_to_offset
+ * sdc/native/str_ext/sdc_str_arr.hpp:242-252).  The validity bit travels in bit 31 of the length.
+ *   str_hash         out[i] = 64-bit hash of row i's bytes (NA rows: one fixed value): the routing key of a string column
+ *   str_pack_lens    lens_out[i] = byte length | (NA ? 1 << 31 : 0)
+ *   str_unpack_lens  lens -> offsets_out[n + 1], bitmap_out[(n + 7) / 8] (nullable), *total_chars (host)           */
+int32_t sdcb200_str_hash(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint64_t* out, void* stream);
+int32_t sdcb200_str_pack_lens(const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint32_t* lens_out, void* stream);
+int32_t sdcb200_str_unpack_lens(const uint32_t* lens, int64_t n, uint32_t* offsets_out, uint8_t* bitmap_out, int64_t* total_chars,
+                                void* stream);
 /* the reference's own symbol (HOST buffers, void return), exactly as sdc/str_arr_ext.py:94-99 declares it */
 void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result);
 

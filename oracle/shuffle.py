@@ -47,3 +47,23 @@ def shuffle(columns_per_rank, dests_per_rank):
                 outs[c][rdisp[src]:rdisp[src] + len(sel)] = columns_per_rank[src][c][sel]
         received.append(outs)
     return received, send_counts
+
+
+def shuffle_strings(strings_per_rank, dests_per_rank):
+    """String column through the shuffle in the reference's wire format (shuffle_utils.py:277-297): every rank sends a
+    LENGTH array and the concatenated characters per destination; the receiver rebuilds the offsets with a prefix sum
+    (convert_len_arr_to_offset, sdc/native/str_ext/sdc_str_arr.hpp:242-252).
+    strings_per_rank[r] = list of bytes objects -> received[r] = (offsets uint32[m + 1], chars uint8[total])."""
+    P = len(strings_per_rank)
+    out = []
+    for r in range(P):
+        lens, chunks = [], []
+        for src in range(P):
+            for s, d in zip(strings_per_rank[src], dests_per_rank[src]):
+                if d == r:
+                    lens.append(len(s))
+                    chunks.append(s)
+        offsets = np.zeros(len(lens) + 1, dtype=np.uint32)
+        offsets[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64)) if lens else []
+        out.append((offsets, np.frombuffer(b"".join(chunks), dtype=np.uint8)))
+    return out

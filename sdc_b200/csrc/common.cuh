@@ -71,6 +71,10 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // murmur finaliser, which the partition pass pays per row.  The shuffle's destination rank comes from a murmur finaliser
 // over the same key (shuffle.cu): a different function, so the keys a rank owns after a hash shuffle still spread over
 // all buckets / slots.
+__host__ __device__ inline unsigned long long mix64_fin(unsigned long long x) {      // murmur3 finaliser
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
 __host__ __device__ inline unsigned long long hash_mix64(unsigned long long x) {
     x ^= x >> 32;
     return x * 0x9e3779b97f4a7c15ull;

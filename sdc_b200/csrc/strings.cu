@@ -530,6 +530,103 @@ int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, 
     return SDCB200_OK;
 }
 
+// ------------------------------------------------------------------ string columns in the multi-GPU shuffle
+// The reference ships a string column as a LENGTH array plus the characters and rebuilds the offsets on the receiving
+// side with a scan (sdc/shuffle_utils.py:277-297, convert_len_arr_to_offset sdc_str_arr.hpp:242-252).  Same wire format
+// here; the validity bit rides in bit 31 of the length (a string is shorter than 2 GiB), so no bitmap travels.
+//   str_hash          out[i] = 64-bit hash of the string's bytes (NA rows: one fixed value) -- the routing key
+//   str_pack_lens     lens[i] = byte length | (NA ? 1 << 31 : 0)
+//   str_unpack_lens   lens -> offsets[n + 1] (exclusive scan), validity bitmap, total characters
+}  // extern "C"
+
+namespace sdcb200 { namespace {
+__global__ void __launch_bounds__(256) str_hash_kernel(const uint8_t* __restrict__ chars, const uint32_t* __restrict__ offsets,
+                                                       const uint8_t* __restrict__ bitmap, int64_t n, unsigned long long* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long h = 0xcbf29ce484222325ull;
+        if (!bitmap || ((bitmap[i >> 3] >> (i & 7)) & 1)) {
+            const uint32_t b = offsets[i], e = offsets[i + 1];
+            for (uint32_t j = b; j < e; ++j) h = (h ^ chars[j]) * 0x100000001b3ull;        // FNV-1a over the bytes
+            h ^= (unsigned long long)(e - b) << 32;
+        } else {
+            h = 0x6e756c6c6e756c6cull;
+        }
+        out[i] = mix64_fin(h);
+    }
+}
+__global__ void __launch_bounds__(256) str_pack_lens_kernel(const uint32_t* __restrict__ offsets, const uint8_t* __restrict__ bitmap,
+                                                            int64_t n, uint32_t* __restrict__ lens) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = !bitmap || ((bitmap[i >> 3] >> (i & 7)) & 1);
+        lens[i] = (offsets[i + 1] - offsets[i]) | (valid ? 0u : 0x80000000u);
+    }
+}
+struct PackedLenLoad {
+    const uint32_t* lens;
+    __device__ unsigned long long operator()(int64_t i) const { return lens[i] & 0x7fffffffu; }
+};
+// one thread per bitmap byte: 8 rows
+__global__ void __launch_bounds__(256) str_lens_bitmap_kernel(const uint32_t* __restrict__ lens, int64_t n, uint8_t* __restrict__ bitmap) {
+    const int64_t nb = (n + 7) / 8;
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        unsigned v = 0;
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = b * 8 + k;
+            if (i < n && !(lens[i] >> 31)) v |= 1u << k;
+        }
+        bitmap[b] = (uint8_t)v;
+    }
+}
+}}
+
+extern "C" {
+
+int32_t sdcb200_str_hash(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint64_t* out, void* stream) {
+    SDC_ARG_CHECK(n >= 0, "n");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(offsets != nullptr && out != nullptr, "null pointer");
+    str_hash_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(chars, offsets, bitmap, n, reinterpret_cast<unsigned long long*>(out));
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_pack_lens(const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint32_t* lens_out, void* stream) {
+    SDC_ARG_CHECK(n >= 0, "n");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(offsets != nullptr && lens_out != nullptr, "null pointer");
+    str_pack_lens_kernel<<<grid_for(n, 256, 4), 256, 0, (cudaStream_t)stream>>>(offsets, bitmap, n, lens_out);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_unpack_lens(const uint32_t* lens, int64_t n, uint32_t* offsets_out, uint8_t* bitmap_out, int64_t* total_chars,
+                                void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(n >= 0 && offsets_out != nullptr && total_chars != nullptr, "args");
+    *total_chars = 0;
+    if (n == 0) {
+        SDC_CUDA_TRY(cudaMemsetAsync(offsets_out, 0, 4, s));
+        return SDCB200_OK;
+    }
+    SDC_ARG_CHECK(lens != nullptr, "null lens");
+    Scratch tsum;
+    SDC_TRY(tsum.alloc((size_t)(ceil_div(n, kScanTile) + 1) * 8, s));
+    SDC_TRY(device_exclusive_scan(PackedLenLoad{lens}, OffsetStore{offsets_out}, n, tsum.as<unsigned long long>(), s));
+    if (bitmap_out) {
+        str_lens_bitmap_kernel<<<grid_for((n + 7) / 8, 256, 1), 256, 0, s>>>(lens, n, bitmap_out);
+        SDC_CHECK_LAUNCH();
+    }
+    unsigned long long total = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&total, tsum.as<unsigned long long>() + ceil_div(n, kScanTile), 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    SDC_ARG_CHECK(total < 0xffffffffull, "received chars exceed the uint32 offset range (sdc_str_arr.hpp:206)");
+    const uint32_t t32 = (uint32_t)total;
+    SDC_CUDA_TRY(cudaMemcpyAsync(offsets_out + n, &t32, 4, cudaMemcpyHostToDevice, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    *total_chars = (int64_t)total;
+    return SDCB200_OK;
+}
+
 // The reference's own symbol (sdc/native/str_ext/sdc_str_arr.hpp:565-593, bound in sdc/str_arr_ext.py:94-99):
 // HOST buffers, void return.
 void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result) {

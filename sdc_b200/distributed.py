@@ -663,6 +663,80 @@ def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"
     return gather_ids_device(lid2, li), gather_ids_device(rid2, ri)
 
 
+# ------------------------------------------------------------------ string columns (str_arr) in the shuffle
+def str_hash_device(sa):
+    """64-bit hash of every string of a device StringArray (NA rows share one value) -> int64 CUDA tensor: the routing
+    key of a string column (the reference hashes the decoded unicode object, shuffle_utils.py:119-140)."""
+    torch = _torch()
+    lib = native.load()
+    d = sa.cuda()
+    out = torch.empty(d.n, dtype=torch.int64, device=d.offsets.device)
+    with torch.cuda.device(d.offsets.device):
+        native.check(lib.sdcb200_str_hash(d.chars.data_ptr(), d.offsets.data_ptr(), d.bitmap.data_ptr(), d.n, out.data_ptr(),
+                                          native.current_stream_ptr()))
+    return out
+
+
+def str_shuffle(keys, cols, group=None):
+    """Route every row of a string-keyed table to rank hash(string) % P.  The string column travels in the reference's
+    wire format -- a length array plus the characters, offsets rebuilt by a scan on the receiving side
+    (sdc/shuffle_utils.py:277-297, sdc_str_arr.hpp:242-252; the validity bit rides in bit 31 of the length) -- the
+    numeric columns as in the numeric shuffle.  keys: device StringArray; cols: 8-byte CUDA columns.
+    -> (StringArray of the rows this rank now owns, [cols'...]); rows of one source keep their order."""
+    from .sort import gather_device
+    from .str_arr import StringArray
+    torch = _torch()
+    lib = native.load()
+    rank, P = world(group)
+    d = keys.cuda()
+    if P == 1:
+        return d, list(cols)
+    dev = d.offsets.device
+    h = str_hash_device(d)
+    perm, counts = hash_partition_device(h, P, ROUTE_HASH)
+    packed = d.take(perm)                                     # strings grouped by destination (two-phase gather)
+    lens = torch.empty(max(packed.n, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        native.check(lib.sdcb200_str_pack_lens(packed.offsets.data_ptr(), packed.bitmap.data_ptr(), packed.n, lens.data_ptr(),
+                                               native.current_stream_ptr()))
+    lens = lens[:packed.n]
+    # characters per destination: differences of the packed offsets at the destination boundaries (P + 1 values)
+    bounds = torch.zeros(P + 1, dtype=torch.int64, device=dev)
+    bounds[1:] = torch.cumsum(counts, 0)
+    char_bounds = packed.offsets[bounds].to(torch.int64) & 0xffffffff        # P + 1 values (offsets are uint32 bits)
+    send_chars = char_bounds[1:] - char_bounds[:-1]
+    both = exchange_counts(torch.cat([counts, send_chars]).view(2, P).t().contiguous().view(-1), group).view(P, 2)
+    recv_rows, recv_chars = both[:, 0].contiguous(), both[:, 1].contiguous()
+    lens_r = exchange_rows(lens, counts, recv_rows, group)
+    chars_r = exchange_rows(packed.chars[:int(char_bounds[-1])], send_chars, recv_chars, group)
+    n_r = lens_r.shape[0]
+    offsets = torch.empty(n_r + 1, dtype=torch.int32, device=dev)
+    bitmap = torch.empty(max(1, (n_r + 7) // 8), dtype=torch.uint8, device=dev)
+    total = ct.c_int64(0)
+    with torch.cuda.device(dev):
+        native.check(lib.sdcb200_str_unpack_lens(lens_r.data_ptr() if n_r else None, n_r, offsets.data_ptr(), bitmap.data_ptr(),
+                                                 ct.byref(total), native.current_stream_ptr()))
+    if chars_r.shape[0] == 0:
+        chars_r = torch.zeros(1, dtype=torch.uint8, device=dev)[:0]
+    out_keys = StringArray(offsets, chars_r if chars_r.shape[0] else torch.zeros(1, dtype=torch.uint8, device=dev), bitmap[:(n_r + 7) // 8] if n_r else bitmap[:0], n_r)
+    out_cols = [exchange_rows(gather_device(c, perm), counts, recv_rows, group) for c in cols]
+    return out_keys, out_cols
+
+
+def groupby_str_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, group=None):
+    """df.groupby(<string column>).<aggs>() over row-sharded columns: rows go to rank hash(string) % P (str_shuffle), every
+    rank aggregates the strings it owns (factorize + aggregate + key strings, str_arr.groupby_str_device).
+    -> (StringArray of this rank's group keys, {agg: [tensor per column]}, 'sharded' | 'replicated')"""
+    from .str_arr import groupby_str_device
+    _, P = world(group)
+    if P == 1:
+        k, r = groupby_str_device(keys, cols, aggs, sort, ddof, expected_groups)
+        return k, r, "replicated"
+    k2, c2 = str_shuffle(keys, cols, group)
+    k, r = groupby_str_device(k2, c2, aggs, sort, ddof, max(1, expected_groups // P) if expected_groups > 0 else 0)
+    return k, r, "sharded"
+
+
 class HaloLink:
     """Neighbour links for a row-sharded series: every rank owns a small mailbox in peer-mapped memory (CUDA IPC);
     the rolling kernel itself stores this rank's last win-1 rows into the next rank's mailbox over NVLink and waits

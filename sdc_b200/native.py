@@ -70,6 +70,9 @@ SIGNATURES = {
     "sdcb200_str_table_free": (_i32, [_i64, _vp]),
     "sdcb200_str_gather_sizes": (_i32, [_vp, _vp, _i64, _vp, ct.POINTER(_i64), _vp]),
     "sdcb200_str_gather_chars": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "sdcb200_str_hash": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_pack_lens": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_unpack_lens": (_i32, [_vp, _i64, _vp, _vp, ct.POINTER(_i64), _vp]),
     "stable_argsort": (None, [_vp, _vp, ct.c_uint64, ct.c_int8, _vp]),
     "sdcb200_hash_partition": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "sdcb200_combine_mean": (_i32, [_vp, _vp, _i64, _vp, _vp]),

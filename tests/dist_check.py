@@ -161,6 +161,42 @@ def main():
         check_rolling(tiny, "min", 40, 3, lk, (lo, lo + 7 + rank))
     link.close()
 
+    # string keys (str_arr offsets + chars): length array + characters travel, offsets rebuilt by a scan on arrival
+    from sdc_b200.str_arr import StringArray
+    words = np.array(["k%05d" % i if i % 7 else "key-%d-long-%s" % (i, "x" * (i % 13)) for i in range(3000)], dtype=object)
+    skeys = words[rng.integers(0, 3000, n)]
+    skeys[rng.integers(0, n, n // 200)] = None                       # NA keys are skipped by the aggregate
+    sa = StringArray.from_pylist(list(skeys[s:e])).cuda()
+    gk, res, layout = D.groupby_str_distributed(sa, cols, ("sum", "count", "max"), True, 1, 3000)
+    assert layout == "sharded"
+    mine = gk.to_pylist()
+    assert mine == sorted(mine), "string groups of a rank come out in string order"
+    import pandas as pd
+    want = pd.DataFrame({"k": skeys, "v": vals, "w": ivals}).groupby("k")
+    got_keys = [None] * P
+    dist.all_gather_object(got_keys, mine)
+    flat = [k for part in got_keys for k in part]
+    assert sorted(flat) == sorted(want.sum().index.tolist()) and len(set(flat)) == len(flat), "string group keys"
+    wsum, wcnt, wmax = want.sum(), want.count(), want.max()
+    np.testing.assert_allclose(res["sum"][0].cpu().numpy(), wsum.loc[mine, "v"].to_numpy(), rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(res["sum"][1].cpu().numpy(), wsum.loc[mine, "w"].to_numpy())
+    np.testing.assert_array_equal(res["count"][0].cpu().numpy(), wcnt.loc[mine, "v"].to_numpy())
+    np.testing.assert_array_equal(res["max"][1].cpu().numpy(), wmax.loc[mine, "w"].to_numpy())
+    # the shuffle alone: every string lands on exactly one rank, with its payload row
+    k2, (v2,) = D.str_shuffle(sa, [cols[1]])
+    back = pd.DataFrame({"k": k2.to_pylist(), "w": v2.cpu().numpy()})
+    allb = [None] * P
+    dist.all_gather_object(allb, back)
+    allb = pd.concat(allb)
+    ref = pd.DataFrame({"k": skeys, "w": ivals})
+    key = lambda d: d.fillna("<NA>").sort_values(["k", "w"]).reset_index(drop=True)
+    pd.testing.assert_frame_equal(key(allb), key(ref))
+    per_rank = [None] * P
+    dist.all_gather_object(per_rank, set(x for x in k2.to_pylist() if x is not None))
+    for a in range(P):
+        for b in range(a + 1, P):
+            assert not (per_rank[a] & per_rank[b]), "a string key landed on two ranks"
+
     peer.close()
     dist.barrier()
     if rank == 0:

@@ -166,3 +166,39 @@ def test_row_sharded_rolling_via_halo():
     # rank 1's first rows see the halo, so only rank 0's own warm-up rows are NaN
     np.testing.assert_allclose(got[200:], want[200:], rtol=1e-12)
     np.testing.assert_allclose(got[:200], want[:200], rtol=1e-12, equal_nan=True)
+
+
+def _string_wire_case(rank, P):
+    """The string column's wire format over gloo: lengths and characters grouped by destination, one alltoallv each,
+    offsets by a prefix sum on arrival (what distributed.str_shuffle does around its kernels)."""
+    from sdc_b200 import distributed as D
+    rng = np.random.default_rng(40 + rank)
+    strs = [("s%d" % v).encode() * (1 + v % 3) for v in rng.integers(0, 30, 200 + 11 * rank)]
+    dest = np.array([sum(b) % P for b in strs])
+    perm = np.argsort(dest, kind="stable")
+    packed = [strs[i] for i in perm]
+    lens = torch.tensor([len(b) for b in packed], dtype=torch.int32)
+    chars = torch.from_numpy(np.frombuffer(b"".join(packed), dtype=np.uint8).copy())
+    counts = torch.from_numpy(np.bincount(dest, minlength=P).astype(np.int64))
+    send_chars = torch.tensor([sum(len(strs[i]) for i in perm if dest[i] == d) for d in range(P)], dtype=torch.int64)
+    both = D.exchange_counts(torch.stack([counts, send_chars], 1).reshape(-1)).view(P, 2)
+    lens_r = D.exchange_rows(lens, counts, both[:, 0].contiguous())
+    chars_r = D.exchange_rows(chars, send_chars, both[:, 1].contiguous())
+    offsets = np.zeros(len(lens_r) + 1, dtype=np.uint32)
+    offsets[1:] = np.cumsum(lens_r.numpy().astype(np.uint64))
+    return offsets, chars_r.numpy()
+
+
+def test_string_column_wire_format_matches_reference_restatement():
+    from oracle import shuffle as oshuffle
+    got = _run("_string_wire_case")
+    strs, dests = [], []
+    for rank in range(2):
+        rng = np.random.default_rng(40 + rank)
+        ss = [("s%d" % v).encode() * (1 + v % 3) for v in rng.integers(0, 30, 200 + 11 * rank)]
+        strs.append(ss)
+        dests.append([sum(b) % 2 for b in ss])
+    want = oshuffle.shuffle_strings(strs, dests)
+    for r in range(2):
+        np.testing.assert_array_equal(got[r][0], want[r][0])
+        np.testing.assert_array_equal(got[r][1], want[r][1])
