@@ -165,6 +165,15 @@ int32_t sdcb200_host_argsort(int32_t dtype, const void* keys, int64_t n, int32_t
 int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
                         const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
                         int64_t expected_groups, void* stream, int64_t* handle_out, int64_t* ngroups_out);
+/* Asynchronous form for pipelines of small aggregates: _begin enqueues the work on `stream` and returns, _end waits
+ * for the stream and yields the group count; the accessors below work on the handle after _end.  Requests on the
+ * one-kernel low-cardinality path (at most one value column, sum / mean / min / max / count, group hint <= 4096 or 0,
+ * n >= 4096) do not block in _begin; anything else completes inside it.  The input columns must stay valid until _end
+ * (an optimistic attempt that overflowed is rerun there).  Same argument meaning as sdcb200_groupby.               */
+int32_t sdcb200_groupby_begin(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
+                              const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof,
+                              int64_t expected_groups, void* stream, int64_t* handle_out);
+int32_t sdcb200_groupby_end(int64_t handle, int64_t* ngroups_out);
 int32_t sdcb200_groupby_keys(int64_t handle, void* dst, int32_t dst_is_host, void* stream);
 int32_t sdcb200_groupby_values(int64_t handle, int32_t col, uint32_t agg, void* dst, int32_t dst_is_host, void* stream);
 /* zero-copy access: device pointers of the handle's result, valid until sdcb200_groupby_free.

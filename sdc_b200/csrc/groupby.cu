@@ -1321,6 +1321,7 @@ __global__ void combine_ids_kernel(const long long* __restrict__ a, const long l
     }
 }
 
+struct PendingSmall;
 struct GroupbyResult {
     int key_dtype = 0;
     int ncols = 0;
@@ -1331,14 +1332,17 @@ struct GroupbyResult {
     unsigned long long* vals = nullptr;    // [popc(agg_mask) * ncols * ngcap]
     bool one_block = false;                // vals lives in the allocation keys points at (low-cardinality path)
     bool lean_direct = false;              // produced by gb_smem_kernel's lean loop over a direct window
+    struct PendingSmall* pending = nullptr;   // sdcb200_groupby_begin: the kernel is in flight, sdcb200_groupby_end finishes
 };
 
 std::mutex g_mu;
 std::unordered_map<int64_t, GroupbyResult*> g_results;
 int64_t g_next_handle = 1;
 
+void free_pending(GroupbyResult* r);
 void free_result(GroupbyResult* r) {
     if (!r) return;
+    free_pending(r);
     if (r->keys) dev_free(r->keys, nullptr);
     if (r->vals && !r->one_block) dev_free(r->vals, nullptr);
     delete r;
@@ -1408,6 +1412,11 @@ struct TableMem {
         end = cur + bytes;
         return SDCB200_OK;
     }
+    void* detach() {                       // the caller takes over the allocation (dev_free on the same stream later)
+        void* p = block.p;
+        block.p = nullptr;
+        return p;
+    }
     int32_t get(void** p, size_t bytes, cudaStream_t) {
         const size_t b = (bytes + 255) & ~size_t(255);
         if (cur + b > end) { set_error("groupby: table arena exhausted"); return SDCB200_ERR_NOMEM; }
@@ -1437,6 +1446,61 @@ unsigned long long* pinned_meta_device() {
     void* d = nullptr;
     if (!h || cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return reinterpret_cast<unsigned long long*>(d);
+}
+
+// ---- asynchronous low-cardinality groupby (sdcb200_groupby_begin / _end) ----
+// A call in flight owns a 256-byte slot of mapped pinned memory (the control block the kernel's last CTA publishes) and
+// the table it aggregates into; sdcb200_groupby_end waits for the stream, reads the slot and finishes the result.
+struct PinnedSlots {
+    std::mutex mu;
+    std::vector<unsigned long long*> free_host;          // host addresses of free 256-byte slots
+    unsigned long long* take() {
+        std::lock_guard<std::mutex> lock(mu);
+        if (free_host.empty()) {
+            unsigned long long* chunk = nullptr;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&chunk), 64 * 256, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            for (int i = 0; i < 64; ++i) free_host.push_back(chunk + i * 32);
+        }
+        unsigned long long* p = free_host.back();
+        free_host.pop_back();
+        return p;
+    }
+    void give(unsigned long long* p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(mu);
+        free_host.push_back(p);
+    }
+};
+PinnedSlots g_slots;
+
+struct PendingSmall {
+    unsigned long long* slot = nullptr;     // pinned control-block copy (host address)
+    void* table = nullptr;                  // the table allocation (stream-ordered), released by _end
+    cudaStream_t stream = nullptr;
+    bool lean = false;
+    // what a rerun needs when the optimistic attempt overflowed (a key outside the sampled window, too many groups):
+    // the caller keeps the input columns alive until sdcb200_groupby_end
+    const void* keys = nullptr;
+    int64_t n = 0;
+    Cols cols;
+    unsigned agg_mask = 0;
+    bool sort = true;
+    long long ddof = 1;
+    int key_dtype = 0, key_mode = 0;
+    int64_t expected_groups = 0;
+};
+
+void free_pending(GroupbyResult* r) {        // a handle dropped without sdcb200_groupby_end: wait, then release
+    PendingSmall* ps = r->pending;
+    if (!ps) return;
+    r->pending = nullptr;
+    cudaStreamSynchronize(ps->stream);
+    g_slots.give(ps->slot);
+    dev_free(ps->table, ps->stream);
+    delete ps;
 }
 
 unsigned long long pow2_at_least(unsigned long long v, unsigned long long lo) {
@@ -1583,9 +1647,12 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     return SDCB200_OK;
 }
 
+// pend != nullptr: the caller can finish later -- when the FIRST attempt is the one-kernel low-cardinality path and needs no
+// second pass, the function returns right after the launch with *pend filled (sdcb200_groupby_end does the rest)
 template <bool KEY_F64>
 int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, bool sort, long long ddof,
-                    int key_dtype, int key_mode, int64_t expected_groups, cudaStream_t s, GroupbyResult* res) {
+                    int key_dtype, int key_mode, int64_t expected_groups, cudaStream_t s, GroupbyResult* res,
+                    PendingSmall** pend = nullptr) {
     const int need = need_for(agg_mask, sort);
     const bool need_ssd = (agg_mask & (AGG_VAR | AGG_STD)) != 0;
     const int sms = sm_count();
@@ -1683,6 +1750,9 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         unsigned long long hstack[32];
         unsigned long long* hmeta = pinned_meta();
         if (!hmeta) hmeta = hstack;
+        // asynchronous call: its own pinned slot, so that several calls can be in flight
+        unsigned long long* aslot = nullptr;
+        if (pend && attempt == 0 && at.smem && !need_ssd && gb_env_int("SDCB200_GB_MAPPED", 1)) aslot = g_slots.take();
         unsigned long long dlo = 0, drange = 0;
         if (at.smem) {
             // ---- low cardinality: one kernel aggregates, folds and (unless var / std) writes the result
@@ -1750,8 +1820,25 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             fin.dh.out = dmeta + 2;
             fin.meta = dmeta;
             fin.host_meta = (hmeta != hstack && gb_env_int("SDCB200_GB_MAPPED", 1)) ? pinned_meta_device() : nullptr;
+            if (aslot) {
+                void* d = nullptr;
+                if (cudaHostGetDevicePointer(&d, aslot, 0) == cudaSuccess) fin.host_meta = reinterpret_cast<unsigned long long*>(d);
+                else { cudaGetLastError(); g_slots.give(aslot); aslot = nullptr; }
+            }
+            if (aslot) aslot[8] = ~0ull;            // "not published": the kernel overwrites the whole block
             kern<<<(unsigned)grid, kSmThreads, lay.alloc_bytes, s>>>(keys, n, cols, t, need, lay, fin);
             SDC_CHECK_LAUNCH();
+            if (aslot) {
+                PendingSmall* ps = new PendingSmall();
+                ps->slot = aslot;
+                ps->table = mem.detach();
+                ps->stream = s;
+                ps->lean = lean;
+                ps->keys = keys; ps->n = n; ps->cols = cols; ps->agg_mask = agg_mask; ps->sort = sort; ps->ddof = ddof;
+                ps->key_dtype = key_dtype; ps->key_mode = key_mode; ps->expected_groups = expected_groups;
+                *pend = ps;
+                return SDCB200_OK;
+            }
             if (!fin.host_meta) SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
             const int ovf = (int)(hmeta[8] & 0xffffffffull);
@@ -1958,6 +2045,94 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
     g_results[h] = res;
     *handle_out = h;
     *ngroups_out = res->ngroups;
+    return SDCB200_OK;
+}
+
+// Asynchronous form of sdcb200_groupby for pipelines of small aggregates (C1: 10 M rows take ~50 us of kernel time, a
+// blocking call adds a stream synchronisation and the host's launch path to every one of them).  _begin enqueues the work
+// and returns; _end waits for the stream and yields the group count.  When the request takes the one-kernel
+// low-cardinality path (int64 / float64 keys, no var / std / prod / median, at most one value column, a group hint
+// <= 4096 or none) nothing blocks in _begin: the kernel's last CTA publishes the control block to mapped pinned memory.
+// Anything else runs to completion inside _begin.  THE INPUT COLUMNS MUST STAY VALID UNTIL _end: an optimistic attempt
+// that overflowed (a key outside the sampled window, more groups than hinted) is rerun there.
+int32_t sdcb200_groupby_begin(int32_t key_dtype, const void* keys, int64_t n, int32_t ncols, const void* const* cols,
+                              const int32_t* col_dtypes, uint32_t agg_mask, int32_t sort, int64_t ddof, int64_t expected_groups,
+                              void* stream, int64_t* handle_out) {
+    const bool simple = ncols <= 1 && !(agg_mask & (AGG_VAR | AGG_STD | AGG_PROD | AGG_MEDIAN)) && n >= 4096 &&
+                        expected_groups <= 4096 && (key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64);
+    if (!simple) {
+        int64_t ng = 0;
+        return sdcb200_groupby(key_dtype, keys, n, ncols, cols, col_dtypes, agg_mask, sort, ddof, expected_groups, stream, handle_out, &ng);
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(agg_mask != 0 && (agg_mask & ~0x1ffu) == 0, "agg mask");
+    SDC_ARG_CHECK(handle_out != nullptr && keys != nullptr, "null pointer");
+    Cols c;
+    memset(&c, 0, sizeof(c));
+    c.ncols = ncols;
+    for (int i = 0; i < ncols; ++i) {
+        SDC_ARG_CHECK(col_dtypes[i] == SDCB200_I64 || col_dtypes[i] == SDCB200_F64, "column dtype must be I64 or F64");
+        SDC_ARG_CHECK(cols[i] != nullptr, "null column");
+        c.data[i] = cols[i];
+        c.is_f64[i] = col_dtypes[i] == SDCB200_F64;
+    }
+    GroupbyResult* res = new GroupbyResult();
+    res->key_dtype = key_dtype;
+    res->ncols = ncols;
+    res->agg_mask = agg_mask;
+    PendingSmall* pend = nullptr;
+    const int32_t rc = key_dtype == SDCB200_F64
+                           ? run_groupby<true>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, KEYS_PLAIN, expected_groups, s, res, &pend)
+                           : run_groupby<false>(keys, n, c, agg_mask, sort != 0, ddof, key_dtype, KEYS_PLAIN, expected_groups, s, res, &pend);
+    if (rc != SDCB200_OK) {
+        free_result(res);
+        return rc;
+    }
+    res->pending = pend;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t h = g_next_handle++;
+    g_results[h] = res;
+    *handle_out = h;
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_groupby_end(int64_t handle, int64_t* ngroups_out) {
+    GroupbyResult* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_results.find(handle);
+        if (it != g_results.end()) r = it->second;
+    }
+    if (!r) { set_error("groupby: unknown handle %lld", (long long)handle); return SDCB200_ERR_HANDLE; }
+    SDC_ARG_CHECK(ngroups_out != nullptr, "null out pointer");
+    if (PendingSmall* ps = r->pending) {
+        r->pending = nullptr;
+        const cudaError_t e = cudaStreamSynchronize(ps->stream);
+        const int ovf = (int)(ps->slot[8] & 0xffffffffull);
+        const int64_t ng = (int64_t)ps->slot[16];
+        const bool direct = ps->slot[19] != 0ull;
+        g_slots.give(ps->slot);
+        dev_free(ps->table, ps->stream);
+        int32_t rc = SDCB200_OK;
+        if (e != cudaSuccess) {
+            set_error("groupby: %s", cudaGetErrorString(e));
+            rc = SDCB200_ERR_CUDA;
+        } else if (ovf) {
+            // the optimistic attempt did not fit: the blocking path, from the start (it falls through to hashing / larger tables)
+            release_buffers(r, ps->stream);
+            rc = ps->key_dtype == SDCB200_F64
+                     ? run_groupby<true>(ps->keys, ps->n, ps->cols, ps->agg_mask, ps->sort, ps->ddof, ps->key_dtype, ps->key_mode,
+                                         ps->expected_groups, ps->stream, r)
+                     : run_groupby<false>(ps->keys, ps->n, ps->cols, ps->agg_mask, ps->sort, ps->ddof, ps->key_dtype, ps->key_mode,
+                                          ps->expected_groups, ps->stream, r);
+        } else {
+            r->ngroups = ng;
+            r->lean_direct = ps->lean && direct;
+        }
+        delete ps;
+        if (rc != SDCB200_OK) return rc;
+    }
+    *ngroups_out = r->ngroups;
     return SDCB200_OK;
 }
 

@@ -97,6 +97,86 @@ def groupby_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, gid_r
     return out_keys, res
 
 
+class PendingGroupby:
+    """A groupby whose kernel is in flight (`sdcb200_groupby_begin`); result() waits and returns what groupby_device returns.
+    The key and value columns are kept alive until then (the library reruns an overflowed optimistic attempt from them)."""
+
+    def __init__(self, handle, keys, cols, aggs):
+        self._handle, self._keys, self._cols, self._aggs = handle, keys, cols, aggs
+        self._done = None
+
+    def result(self):
+        if self._done is None:
+            torch = _torch()
+            lib = native.load()
+            ng = ct.c_int64(0)
+            keys, cols, aggs = self._keys, self._cols, self._aggs
+            with (torch.cuda.device(keys.device) if torch.cuda.current_device() != keys.device.index else contextlib.nullcontext()):
+                native.check(lib.sdcb200_groupby_end(self._handle, ct.byref(ng)))
+                self._done = _wrap_result(lib, torch, self._handle, ng.value, keys, cols, aggs, _tname(keys))
+            self._keys = self._cols = None
+        return self._done
+
+
+def groupby_device_async(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
+    """groupby_device without the wait: enqueues the aggregate on torch's current stream and returns a PendingGroupby.
+    Back-to-back small aggregates (C1: 10 M rows) then pipeline -- the host prepares the next call while the kernel of
+    the previous one runs -- instead of paying a stream synchronisation each."""
+    torch = _torch()
+    lib = native.load()
+    aggs = tuple(aggs)
+    mask, ptrs, dts, kname = _marshal(keys, cols, aggs)
+    handle = ct.c_int64(0)
+    with (torch.cuda.device(keys.device) if torch.cuda.current_device() != keys.device.index else contextlib.nullcontext()):
+        native.check(lib.sdcb200_groupby_begin(native.DTYPE_CODES[kname], keys.data_ptr(), keys.shape[0], len(cols), ptrs, dts, mask,
+                                               1 if sort else 0, int(ddof), int(expected_groups), native.current_stream_ptr(),
+                                               ct.byref(handle)))
+    return PendingGroupby(handle.value, keys, list(cols), aggs)
+
+
+def _marshal(keys, cols, aggs):
+    assert keys.is_cuda and keys.dim() == 1 and keys.is_contiguous()
+    kname = _tname(keys)
+    if kname not in ("int64", "float64"):
+        raise TypeError("groupby: key dtype %s is not supported (int64 / float64 / str_arr)" % kname)
+    n = keys.shape[0]
+    mask = 0
+    for a in aggs:
+        if a not in native.AGG_BITS:
+            raise ValueError("groupby: unknown aggregate %r" % (a,))
+        mask |= native.AGG_BITS[a]
+    ptrs = (ct.c_void_p * max(1, len(cols)))()
+    dts = (ct.c_int32 * max(1, len(cols)))()
+    for i, c in enumerate(cols):
+        assert c.is_cuda and c.dim() == 1 and c.is_contiguous() and c.shape[0] == n
+        cn = _tname(c)
+        if cn not in ("int64", "float64"):
+            raise TypeError("groupby: value column dtype %s is not supported" % cn)
+        ptrs[i] = c.data_ptr()
+        dts[i] = native.DTYPE_CODES[cn]
+    return mask, ptrs, dts, kname
+
+
+def _wrap_result(lib, torch, handle, g, keys, cols, aggs, kname):
+    owner = _ResultHandle(handle)
+    if g == 0:
+        out_keys = torch.empty(0, dtype=keys.dtype, device=keys.device)
+        return out_keys, {a: [torch.empty(0, dtype=_out_dtype(torch, a, c), device=keys.device) for c in cols] for a in aggs}
+    kp, vp, stride = ct.c_void_p(), ct.c_void_p(), ct.c_int64(0)
+    native.check(lib.sdcb200_groupby_result(handle, ct.byref(kp), ct.byref(vp), ct.byref(stride)))
+    dev = keys.device
+    out_keys = torch.as_tensor(_DeviceView(kp.value, (g,), "<f8" if kname == "float64" else "<i8", owner), device=dev)
+    ranks = sorted(set(aggs), key=lambda a: native.AGG_BITS[a])
+    row_bytes = 8 * stride.value
+    res = {}
+    for a in aggs:
+        base = vp.value + ranks.index(a) * len(cols) * row_bytes if cols else 0
+        res[a] = [torch.as_tensor(_DeviceView(base + i * row_bytes, (g,),
+                                              "<i8" if _out_dtype(torch, a, c) == torch.int64 else "<f8", owner), device=dev)
+                  for i, c in enumerate(cols)]
+    return out_keys, res
+
+
 def _out_dtype(torch, agg, col):
     is_int = agg == "count" or (col.dtype == torch.int64 and agg in ("sum", "min", "max", "prod"))
     return torch.int64 if is_int else torch.float64

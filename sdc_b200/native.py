@@ -49,6 +49,9 @@ SIGNATURES = {
     "set_number_of_threads": (None, [ct.c_uint64]),
     "sdcb200_groupby": (_i32, [_i32, _vp, _i64, _i32, ct.POINTER(_vp), ct.POINTER(_i32), ct.c_uint32, _i32, _i64,
                                _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
+    "sdcb200_groupby_begin": (_i32, [_i32, _vp, _i64, _i32, ct.POINTER(_vp), ct.POINTER(_i32), ct.c_uint32, _i32, _i64,
+                                     _i64, _vp, ct.POINTER(_i64)]),
+    "sdcb200_groupby_end": (_i32, [_i64, ct.POINTER(_i64)]),
     "sdcb200_groupby_keys": (_i32, [_i64, _vp, _i32, _vp]),
     "sdcb200_groupby_values": (_i32, [_i64, _i32, ct.c_uint32, _vp, _i32, _vp]),
     "sdcb200_groupby_result": (_i32, [_i64, ct.POINTER(_vp), ct.POINTER(_vp), ct.POINTER(_i64)]),

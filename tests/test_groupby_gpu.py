@@ -426,3 +426,36 @@ def test_dense_high_cardinality_takes_direct_table_and_matches_sort_path(monkeyp
                 np.testing.assert_array_equal(res["max"].cpu().numpy(), want.max().to_numpy())
                 assert_close(res["sum"].cpu().numpy(), want.sum().to_numpy(), rtol=1e-9, atol=1e-12, msg="sum")
                 assert_close(res["mean"].cpu().numpy(), want.mean().to_numpy(), rtol=1e-9, atol=1e-12, msg="mean")
+
+
+def test_async_begin_end_matches_the_blocking_call():
+    """sdcb200_groupby_begin / _end: several aggregates in flight at once, every result equal to the blocking call's --
+    including a request whose optimistic attempt overflows (more groups than hinted) and is rerun in _end, and requests
+    that complete inside _begin (var, many groups)."""
+    import torch
+    from sdc_b200.groupby import groupby_device, groupby_device_async
+    rng = np.random.default_rng(21)
+    n = 1_000_000
+    cases = []
+    for groups, hint, aggs in ((1000, 1000, ("sum",)), (50, 0, ("sum", "mean", "min", "max", "count")), (3000, 100, ("sum", "count")),
+                               (200_000, 0, ("sum",)), (500, 500, ("var",))):
+        k = torch.from_numpy(rng.integers(-5, groups - 5, n)).cuda()
+        v = torch.from_numpy(rng.standard_normal(n)).cuda()
+        v[::97] = float("nan")
+        cases.append((k, v, aggs, hint))
+    kf = torch.from_numpy(rng.integers(0, 40, n).astype(np.float64)).cuda()
+    cases.append((kf, cases[0][1], ("sum", "max"), 64))
+    pend = [groupby_device_async(k, [v], aggs, True, 1, hint) for k, v, aggs, hint in cases]      # all in flight
+    for (k, v, aggs, hint), p in zip(cases, pend):
+        gk, res = p.result()
+        wk, want = groupby_device(k, [v], aggs, True, 1, hint)
+        assert torch.equal(gk, wk)
+        for a in aggs:
+            x, y = res[a][0], want[a][0]
+            if a in ("sum", "mean", "var"):
+                assert torch.allclose(x, y, rtol=1e-9, atol=1e-12, equal_nan=True), a
+            else:
+                assert torch.equal(torch.nan_to_num(x.double(), nan=1e300), torch.nan_to_num(y.double(), nan=1e300)), a
+    # a handle dropped without result() releases its table after the kernel
+    groupby_device_async(cases[0][0], [cases[0][1]], ("sum",), True, 1, 1000)
+    torch.cuda.synchronize()
