@@ -256,8 +256,7 @@ enum { KEYS_PLAIN = 0, KEYS_GID = 1 };      // GID: dense group ids in [0, range
 
 struct DirectHint {
     int mode;                       // KEYS_PLAIN: sample the keys (allow != 0); KEYS_GID: window [0, range)
-    int allow;                      // 0: hashing only (a previous attempt saw a key outside its window); 2: a direct
-                                    // window or nothing (overflow code 3 when the sampled keys do not fit one)
+    int allow;                      // 0: hashing only (a previous attempt saw a key outside its window)
     unsigned long long range;       // KEYS_GID: the id range
     unsigned long long* out;        // [2] device: the window the kernel used (lo, range), read back by the host
 };
@@ -283,10 +282,6 @@ __global__ void __launch_bounds__(kGbThreads) gb_global_kernel(const void* __res
     __syncthreads();
     const unsigned long long dlo = s_dlo, drange = s_drange;
     if (blockIdx.x == 0 && tid == 0) { dh.out[0] = dlo; dh.out[1] = drange; }
-    if (dh.allow == 2 && drange == 0) {              // block-uniform: the caller takes the sort path instead of hashing
-        if (blockIdx.x == 0 && tid == 0) *(volatile int*)t.overflow = 3;
-        return;
-    }
     const bool skip_neg = !KEY_F64 && dh.mode == KEYS_GID;
     const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1076,7 +1071,7 @@ int64_t sort_path_groups() {        // expected groups above this go straight to
 }
 int64_t dense_try_groups() {        // ... unless int64 keys turn out dense: direct table up to this many expected groups
     const char* e = getenv("SDCB200_GB_DENSE_GROUPS");
-    return e ? atoll(e) : (48ll << 20);
+    return e ? atoll(e) : (256ll << 20);
 }
 constexpr int kSegItems = 8;
 constexpr int kSegTile = kGbThreads * kSegItems;
@@ -1235,6 +1230,27 @@ __global__ void __launch_bounds__(kGbThreads) gb_seg_kernel(const unsigned long 
             }
         }
         flush();
+    }
+}
+
+// exact min / max of an int64 key column (order-preserving unsigned image)
+__global__ void __launch_bounds__(256) gb_key_minmax_kernel(const long long* __restrict__ keys, int64_t n,
+                                                            unsigned long long* __restrict__ mm /* [0] min (init ~0), [1] max (init 0) */) {
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long u = (unsigned long long)keys[i] ^ 0x8000000000000000ull;
+        mn = u < mn ? u : mn;
+        mx = u > mx ? u : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, d), b = __shfl_xor_sync(0xffffffffu, mx, d);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm, mn);
+        atomicMax(mm + 1, mx);
     }
 }
 
@@ -1430,7 +1446,6 @@ struct Attempt {
     bool smem;
     unsigned long long cap;
     int nrep;
-    bool direct_only = false;      // dense int64 keys or nothing: a table this large is only worth having without hashing
 };
 
 // pinned landing zone for the control-block read-back (a pageable destination makes the copy a staged one)
@@ -1647,6 +1662,245 @@ int32_t run_groupby_sorted(const void* keys, int64_t n, Cols cols, unsigned agg_
     return SDCB200_OK;
 }
 
+// ------------------------------------------------------------------ dense window path
+// int64 keys that fill a DENSE range [lo, lo + range) with tens of millions of groups, one float64 column, aggregates out
+// of {sum, mean, min, max, count}, sort=True.  The table is direct-addressed (slot = key - lo) and holds only what the
+// aggregates need -- no key words: a slot's key is lo + slot, and a slot is occupied when its count is non-zero (without a
+// count array: when its sum left the initial -0.0), or when a row that changes neither (a NaN value; -0.0 for sum alone)
+// stored its mark byte.  So a row costs ONE fire-and-forget L2 reduction per aggregate and nothing else.
+//   gb_key_minmax_kernel   exact key range (one read of the keys)
+//   range_partition_pass   (tables beyond L2 only) ONE unordered onesweep pass of (key, value) into <= 256 key-range
+//                          buckets: the rows then walk the table slice by slice and the slice in use stays in L2
+//   gb_window_kernel       the reductions; CTAs take tiles in row order
+//   gb_window_count_kernel / scan_tiles_kernel / gb_window_write_kernel
+//                          occupied slots counted per tile of 2048 slots, scanned, written in slot = key order
+struct WinTable {
+    double* sum;                    // [range] init -0.0 (sum alone) / 0.0
+    unsigned* cnt;                  // [range] non-NaN rows
+    unsigned long long* mn;         // [range] ordered u64, init ~0
+    unsigned long long* mx;         // [range] ordered u64, init 0
+    unsigned char* mark;            // [range] 1 = a row of this key left the other arrays untouched
+    unsigned long long lo, range;
+};
+constexpr unsigned long long kWinNegZero = 0x8000000000000000ull;
+
+__global__ void __launch_bounds__(kGbThreads) gb_window_kernel(const unsigned long long* __restrict__ keys,
+                                                              const unsigned long long* __restrict__ vals, int64_t n, int vec_ok,
+                                                              WinTable w, int need, unsigned long long* __restrict__ ticket) {
+    // Tiles are handed out by a ticket counter, not by a fixed stride: CTAs drift apart over a hundred tiles each, and
+    // with a stride the rows in flight then span dozens of key-range buckets -- tens of megabytes of table -- instead of
+    // the one or two that the resident CTAs cover when they always take the next tile in row order.
+    __shared__ unsigned long long s_tile[2];
+    const int tid = threadIdx.x;
+    const int64_t ntiles = (n + kGbTile - 1) / kGbTile;
+    if (tid == 0) s_tile[0] = atomicAdd(ticket, 1ull);
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const int64_t tile = (int64_t)s_tile[it & 1];
+        if (tile >= ntiles) break;
+        const int64_t base = tile * kGbTile;
+        unsigned long long kb[kRows], vb[kRows];
+        load4(keys, base, n, tid, vec_ok, kb);
+        load4(vals, base, n, tid, vec_ok, vb);
+        if (tid == 0) s_tile[(it + 1) & 1] = atomicAdd(ticket, 1ull);      // the next tile, read after the barrier below
+#pragma unroll
+        for (int e = 0; e < kRows; ++e) {
+            if (tile_row(base, tid, e) >= n) continue;
+            const unsigned long long d = kb[e] - w.lo;
+            if (d >= w.range) continue;                              // cannot happen: the range is exact
+            const double v = __longlong_as_double((long long)vb[e]);
+            if (v != v) { w.mark[d] = 1; continue; }                 // skipna: the group exists, nothing is added
+            if (need & NEED_SUM) atomicAdd(w.sum + d, v);
+            if (need & NEED_CNT) atomicAdd(w.cnt + d, 1u);
+            else if (vb[e] == kWinNegZero) w.mark[d] = 1;            // sum alone: -0.0 + -0.0 stays -0.0
+            if (need & NEED_MIN) atomicMin(w.mn + d, f64_to_ordered(v));
+            if (need & NEED_MAX) atomicMax(w.mx + d, f64_to_ordered(v));
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool win_present(const WinTable& w, int need, unsigned long long d) {
+    if (w.mark[d]) return true;
+    if (need & NEED_CNT) return w.cnt[d] != 0u;
+    return reinterpret_cast<const unsigned long long*>(w.sum)[d] != kWinNegZero;
+}
+
+constexpr int kWinTile = 2048;          // slots per CTA of the count / write kernels: 256 threads x 8 consecutive slots
+__global__ void __launch_bounds__(256) gb_window_count_kernel(WinTable w, int need, unsigned long long* __restrict__ tcnt) {
+    __shared__ unsigned s_w[8];
+    const unsigned long long d0 = (unsigned long long)blockIdx.x * kWinTile + (unsigned long long)threadIdx.x * 8;
+    unsigned c = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (d0 + e < w.range && win_present(w, need, d0 + e)) ++c;
+#pragma unroll
+    for (int x = 16; x > 0; x >>= 1) c += __shfl_xor_sync(0xffffffffu, c, x);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot += s_w[i];
+        tcnt[blockIdx.x] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) gb_window_write_kernel(WinTable w, int need, unsigned agg_mask,
+                                                             const unsigned long long* __restrict__ tcnt, int64_t ng,
+                                                             unsigned long long* __restrict__ out_keys,
+                                                             unsigned long long* __restrict__ out_vals) {
+    __shared__ unsigned s_w[8];
+    const unsigned long long d0 = (unsigned long long)blockIdx.x * kWinTile + (unsigned long long)threadIdx.x * 8;
+    unsigned pres = 0, c = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (d0 + e < w.range && win_present(w, need, d0 + e)) { pres |= 1u << e; ++c; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = c;
+#pragma unroll
+    for (int x = 1; x < 32; x <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, incl, x);
+        if (lane >= x) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned wbase = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (i < warp) wbase += s_w[i];
+    int64_t j = (int64_t)tcnt[blockIdx.x] + wbase + incl - c;
+    const unsigned long long nanb = 0x7ff8000000000000ull;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (!((pres >> e) & 1u)) continue;
+        const unsigned long long d = d0 + e;
+        out_keys[j] = w.lo + d;
+        const unsigned cn = (need & NEED_CNT) ? w.cnt[d] : 0u;
+        const double sm = (need & NEED_SUM) ? w.sum[d] + 0.0 : 0.0;       // -0.0 (nothing added) reads as the reference's 0.0
+        int rank = 0;
+        if (agg_mask & AGG_SUM) out_vals[(int64_t)rank++ * ng + j] = (unsigned long long)__double_as_longlong(sm);
+        if (agg_mask & AGG_MEAN) out_vals[(int64_t)rank++ * ng + j] = cn ? (unsigned long long)__double_as_longlong(sm / (double)cn) : nanb;
+        if (agg_mask & AGG_MIN) out_vals[(int64_t)rank++ * ng + j] = cn ? (unsigned long long)__double_as_longlong(ordered_to_f64(w.mn[d])) : nanb;
+        if (agg_mask & AGG_MAX) out_vals[(int64_t)rank++ * ng + j] = cn ? (unsigned long long)__double_as_longlong(ordered_to_f64(w.mx[d])) : nanb;
+        if (agg_mask & AGG_COUNT) out_vals[(int64_t)rank++ * ng + j] = (unsigned long long)cn;
+        ++j;
+    }
+}
+
+// *done = false (and SDCB200_OK): the keys are not dense, or the table does not fit -- the caller sorts instead
+int32_t run_groupby_window(const void* keys, int64_t n, const Cols& cols, unsigned agg_mask, int64_t expected_groups,
+                           cudaStream_t s, GroupbyResult* res, bool* done) {
+    *done = false;
+    const int need = need_for(agg_mask, true);
+    const int sms = sm_count();
+    const int nagg = __builtin_popcount(agg_mask);
+    Scratch mm;
+    SDC_TRY(mm.alloc(32, s));
+    const unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};           // min, max, the tile ticket of gb_window_kernel
+    SDC_CUDA_TRY(cudaMemcpyAsync(mm.p, init, 32, cudaMemcpyHostToDevice, s));
+    gb_key_minmax_kernel<<<sms * 8, 256, 0, s>>>(reinterpret_cast<const long long*>(keys), n, mm.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    unsigned long long h[2];
+    SDC_CUDA_TRY(cudaMemcpyAsync(h, mm.p, 16, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    const unsigned long long span = h[1] - h[0];                     // ordered images: no overflow
+    if (span >= 4ull * (unsigned long long)expected_groups || span >= (1ull << 30)) return SDCB200_OK;
+    WinTable w;
+    memset(&w, 0, sizeof(w));
+    w.lo = h[0] ^ 0x8000000000000000ull;
+    w.range = span + 1;
+    const size_t r8 = ((size_t)w.range * 8 + 255) & ~size_t(255), r4 = ((size_t)w.range * 4 + 255) & ~size_t(255),
+                 r1 = ((size_t)w.range + 255) & ~size_t(255);
+    const size_t table_bytes = ((need & NEED_SUM) ? r8 : 0) + ((need & NEED_CNT) ? r4 : 0) + ((need & NEED_MIN) ? r8 : 0) +
+                               ((need & NEED_MAX) ? r8 : 0) + r1;
+    TableMem mem;
+    if (mem.reserve(table_bytes + 256, s) != SDCB200_OK) { cudaGetLastError(); return SDCB200_OK; }
+    InitPlan ip;
+    ip.count = 0;
+    void* p;
+    if (need & NEED_SUM) {
+        SDC_TRY(mem.get(&p, r8, s));
+        w.sum = reinterpret_cast<double*>(p);
+        ip.ptr[ip.count] = reinterpret_cast<unsigned long long*>(p);
+        ip.len[ip.count] = w.range;
+        ip.val[ip.count++] = (need & NEED_CNT) ? 0ull : kWinNegZero;
+    }
+    if (need & NEED_MIN) {
+        SDC_TRY(mem.get(&p, r8, s));
+        w.mn = reinterpret_cast<unsigned long long*>(p);
+        ip.ptr[ip.count] = w.mn;
+        ip.len[ip.count] = w.range;
+        ip.val[ip.count++] = ~0ull;
+    }
+    if (need & NEED_MAX) {
+        SDC_TRY(mem.get(&p, r8, s));
+        w.mx = reinterpret_cast<unsigned long long*>(p);
+        SDC_CUDA_TRY(cudaMemsetAsync(p, 0, r8, s));
+    }
+    if (need & NEED_CNT) {
+        SDC_TRY(mem.get(&p, r4, s));
+        w.cnt = reinterpret_cast<unsigned*>(p);
+        SDC_CUDA_TRY(cudaMemsetAsync(p, 0, r4, s));
+    }
+    SDC_TRY(mem.get(&p, r1, s));
+    w.mark = reinterpret_cast<unsigned char*>(p);
+    SDC_CUDA_TRY(cudaMemsetAsync(p, 0, r1, s));
+    if (ip.count) {
+        unsigned gx = (unsigned)(ceil_div((int64_t)w.range, 1024) < (int64_t)sms * 4 ? ceil_div((int64_t)w.range, 1024) : (int64_t)sms * 4);
+        gb_init_kernel<<<dim3(gx ? gx : 1, ip.count), 256, 0, s>>>(ip);
+        SDC_CHECK_LAUNCH();
+    }
+    // a table around the size of L2 takes the rows as they come; a larger one gets them bucketed by key range first
+    // (SDCB200_GB_WIN_PART: 0 / 1 force it off / on)
+    const int part_env = gb_env_int("SDCB200_GB_WIN_PART", -1);
+    const bool part = part_env >= 0 ? part_env != 0 : table_bytes > (size_t(48) << 20);
+    Scratch part_keys, part_vals, part_begin;
+    const void* k = keys;
+    const void* v = cols.data[0];
+    int vec_ok = cols.vec_ok;
+    if (part) {
+        int shift = 0;
+        while ((w.range >> shift) > 256ull) ++shift;
+        SDC_TRY(part_keys.alloc((size_t)n * 8, s));
+        SDC_TRY(part_vals.alloc((size_t)n * 8, s));
+        SDC_TRY(part_begin.alloc(257 * 8, s));
+        SDC_TRY(range_partition_pass(keys, w.lo, shift, part_keys.p, 8, cols.data[0], part_vals.p, n, false,
+                                     part_begin.as<unsigned long long>(), s));
+        k = part_keys.p;
+        v = part_vals.p;
+        vec_ok = 1;
+    }
+    {
+        const int64_t ntiles = ceil_div(n, kGbTile);
+        int64_t grid = (int64_t)sms * 8;
+        if (grid > ntiles) grid = ntiles;
+        gb_window_kernel<<<(unsigned)grid, kGbThreads, 0, s>>>(reinterpret_cast<const unsigned long long*>(k),
+                                                             reinterpret_cast<const unsigned long long*>(v), n, vec_ok, w, need,
+                                                             mm.as<unsigned long long>() + 2);
+        SDC_CHECK_LAUNCH();
+    }
+    const int64_t nt = ceil_div((int64_t)w.range, kWinTile);
+    Scratch tcnt;
+    SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8, s));
+    gb_window_count_kernel<<<(unsigned)nt, 256, 0, s>>>(w, need, tcnt.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tcnt.as<unsigned long long>(), nt);
+    SDC_CHECK_LAUNCH();
+    unsigned long long total = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&total, tcnt.as<unsigned long long>() + nt, 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    const int64_t ng = (int64_t)total;
+    res->ngroups = ng;
+    res->ngcap = ng;
+    *done = true;
+    if (ng == 0) return SDCB200_OK;
+    SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->keys), (size_t)ng * 8, s));
+    SDC_TRY(dev_alloc(reinterpret_cast<void**>(&res->vals), (size_t)ng * 8 * (nagg + 1), s));
+    gb_window_write_kernel<<<(unsigned)nt, 256, 0, s>>>(w, need, agg_mask, tcnt.as<unsigned long long>(), ng, res->keys, res->vals);
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
 // pend != nullptr: the caller can finish later -- when the FIRST attempt is the one-kernel low-cardinality path and needs no
 // second pass, the function returns right after the launch with *pend filled (sdcb200_groupby_end does the rest)
 template <bool KEY_F64>
@@ -1672,14 +1926,16 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     Attempt plan[3];
     int nattempts = 0;
     if (big && expected_groups > sort_path_groups()) {
-        // Tens of millions of groups: a HASHED table costs two random HBM bursts per row and loses to sorting, but a
-        // DIRECT-addressed one (dense int64 keys: what a ROUTE_MOD shuffle delivers, sdc_b200/distributed.py) costs one
-        // reduction per row.  One attempt that gives up at once when the sampled keys do not fit a window.
-        const bool try_dense = !KEY_F64 && key_mode == KEYS_PLAIN && expected_groups <= dense_try_groups();
-        if (!try_dense)
-            return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
-        plan[nattempts] = {false, pow2_at_least(2ull * (unsigned long long)expected_groups, 1024), 1};
-        plan[nattempts++].direct_only = true;
+        // Tens of millions of groups: a HASHED table costs two random HBM bursts per row and loses to sorting; int64 keys
+        // that turn out to fill a dense range (what a ROUTE_MOD shuffle delivers, sdc_b200/distributed.py) take the
+        // direct-addressed window path instead (run_groupby_window below), everything else the sort-and-segment path.
+        if (!KEY_F64 && key_mode == KEYS_PLAIN && expected_groups <= dense_try_groups() && cols.ncols == 1 && cols.is_f64[0] &&
+            !(need & NEED_FIRST) && !need_ssd && n < 0xffffffffll) {
+            bool done = false;
+            SDC_TRY(run_groupby_window(keys, n, cols, agg_mask, expected_groups, s, res, &done));
+            if (done) return SDCB200_OK;
+        }
+        return run_groupby_sorted<KEY_F64>(keys, n, cols, agg_mask, sort, ddof, key_dtype, key_mode, s, res);
     } else if (expected_groups <= 0) {
         if (n >= 4096) plan[nattempts++] = {true, 8192, kSmallReplicas};
         if ((1ull << 22) < worst) plan[nattempts++] = {false, 1ull << 22, 1};
@@ -1691,7 +1947,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
         const unsigned long long c = pow2_at_least(2ull * (unsigned long long)expected_groups, 1024);
         if (c < worst) plan[nattempts++] = {false, c, 1};
     }
-    if (!big && key_mode != KEYS_GID && !(nattempts && plan[0].direct_only))
+    if (!big && key_mode != KEYS_GID)
         plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
 
     int allow_direct = 1;
@@ -1866,7 +2122,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             if (grid > ntiles) grid = ntiles;
             DirectHint dh;
             dh.mode = key_mode;
-            dh.allow = at.direct_only ? 2 : allow_direct;
+            dh.allow = allow_direct;
             dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
             dh.out = dmeta + 2;
             gb_global_kernel<KEY_F64><<<(unsigned)grid, kGbThreads, 0, s>>>(keys, n, cols, t, need, dh);
@@ -1874,7 +2130,6 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             SDC_CUDA_TRY(cudaMemcpyAsync(hmeta, t.occupied, 256, cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
             const int ovf = (int)(hmeta[8] & 0xffffffffull);
-            if (ovf && at.direct_only) break;                 // not dense (or a key outside the window): the sort path
             if (ovf) {
                 if (ovf == 2 && allow_direct && key_mode != KEYS_GID) { allow_direct = 0; --attempt; continue; }
                 if (ovf == 2 && key_mode == KEYS_GID) { set_error("groupby: a group id lies outside [0, %lld)", (long long)expected_groups); return SDCB200_ERR_ARG; }

@@ -27,6 +27,11 @@ int32_t radix_sort_core(int dtype, const void* src, void* bufA, void* bufB, int 
 int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int pay_bytes, const void* pay, void* pay_out,
                             int64_t n, bool iota, unsigned long long* part_begin, cudaStream_t s);
 
+// The same pass over a DENSE key range: bucket = (key - lo) >> shift (the caller picks shift so that at most 256 buckets
+// cover the range).  Rows of one bucket touch one contiguous slice of a direct-addressed table indexed by key - lo.
+int32_t range_partition_pass(const void* keys, unsigned long long lo, int shift, void* keys_out, int pay_bytes, const void* pay,
+                             void* pay_out, int64_t n, bool iota, unsigned long long* part_begin, cudaStream_t s);
+
 // stable argsort of a device column -> int64 row numbers
 int32_t argsort_device(int dtype, const void* keys, int64_t n, bool ascending, int64_t* index_out, cudaStream_t s);
 

@@ -148,6 +148,15 @@ struct HashTopDigit {
     }
 };
 
+// partition pass over a dense key range: bucket = (key - lo) >> shift.  Rows of one bucket touch one contiguous slice of a
+// direct-addressed table indexed by key - lo (groupby over tens of millions of dense int64 keys)
+struct RangeDigit {
+    static constexpr bool kStable = false;
+    unsigned long long lo;
+    int shift;
+    __device__ __forceinline__ unsigned operator()(unsigned long long k) const { return (unsigned)((k - lo) >> shift) & 255u; }
+};
+
 // look-back status word: bits 0-1 flag (1 = tile count, 2 = inclusive prefix), bits 2-9 epoch (the pass
 // number + 1: entries of earlier passes are simply stale, so the buffer is zeroed once per sort, not once
 // per pass), bits 10.. value
@@ -574,7 +583,8 @@ int32_t sort_dispatch_pay(const void* src, void* bufA, void* bufB, int pay_bytes
 
 // ---- one stable partition pass by hash bucket (HashTopDigit): 256 buckets, bucket b = rows whose
 // hash_mix64(canonical key) has top byte b, in input order.  part_begin (device, u64[257]) receives the bucket starts.
-__global__ void __launch_bounds__(kHistThreads) hash_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n, HashTopDigit dig,
+template <typename DIG>
+__global__ void __launch_bounds__(kHistThreads) hash_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n, DIG dig,
                                                                  unsigned long long* __restrict__ ghist) {
     __shared__ unsigned sh[256];
     for (int i = threadIdx.x; i < 256; i += kHistThreads) sh[i] = 0;
@@ -645,16 +655,17 @@ int32_t argsort_device(int dtype, const void* keys, int64_t n, bool ascending, i
 }
 
 // One stable partition pass of 8-byte keys (+ payload) into the 256 buckets of HashTopDigit.
-int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int pay_bytes, const void* pay, void* pay_out,
-                            int64_t n, bool iota, unsigned long long* part_begin /* device u64[257] */, cudaStream_t s) {
+namespace {
+template <typename DIG>
+int32_t partition_pass_impl(DIG dig, const void* keys, void* keys_out, int pay_bytes, const void* pay, void* pay_out, int64_t n,
+                            bool iota, unsigned long long* part_begin /* device u64[257] */, cudaStream_t s) {
     if (n == 0) {
         SDC_CUDA_TRY(cudaMemsetAsync(part_begin, 0, 257 * 8, s));
         return SDCB200_OK;
     }
-    // tile geometry of the partition pass (SDCB200_PART_CFG, experiments): 0 = 256 x 16 rows, 3 CTAs per SM;
-    // 1 = 256 x 8 rows, 6 CTAs per SM; 2 = 512 x 8, 3 CTAs
-    const int cfg = sort_env("SDCB200_PART_CFG", 0);
-    const int TILE = cfg == 1 ? 2048 : 4096;
+    // tiles of 256 x 16 rows, 3 CTAs per SM (2 with 16-byte rows): 256 x 8 rows with 6 CTAs and 512 x 8 with 3 measured
+    // slower (2.83 / 2.64 against 2.55 ms for the partitioned C3 join)
+    const int TILE = 4096;
     const int64_t ntiles = ceil_div(n, TILE);
     Scratch meta, lb;
     SDC_TRY(meta.alloc(256 * 8 + 16, s));
@@ -663,26 +674,35 @@ int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int 
     unsigned* ticket = reinterpret_cast<unsigned*>(ghist + 256);
     SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, 256 * 8 + 16, s));
     SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
-    HashTopDigit dig{key_f64 ? 1 : 0};
     int hgrid = (int)(ceil_div(n, kHistThreads * 8) < (int64_t)sm_count() * 4 ? ceil_div(n, kHistThreads * 8) : (int64_t)sm_count() * 4);
     if (hgrid < 1) hgrid = 1;
     const unsigned long long* k = reinterpret_cast<const unsigned long long*>(keys);
-    hash_hist_kernel<<<hgrid, kHistThreads, 0, s>>>(k, n, dig, ghist);
+    hash_hist_kernel<DIG><<<hgrid, kHistThreads, 0, s>>>(k, n, dig, ghist);
     SDC_CHECK_LAUNCH();
     hash_scan_kernel<<<1, 256, 0, s>>>(ghist, part_begin);
     SDC_CHECK_LAUNCH();
     unsigned long long* ko = reinterpret_cast<unsigned long long*>(keys_out);
     typedef unsigned long long K;
 #define SDC_PART(P_, HAS_, pin_) \
-    (cfg == 1 ? launch_cfg<K, P_, HAS_, HashTopDigit, 256, 8, 6, false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s) \
-     : cfg == 2 ? launch_cfg<K, P_, HAS_, HashTopDigit, 512, 8, 3, false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s) \
-                : launch_cfg<K, P_, HAS_, HashTopDigit, 256, 16, (sizeof(P_) > 4 ? 2 : 3), false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s))
+    launch_cfg<K, P_, HAS_, DIG, 256, 16, (sizeof(P_) > 4 ? 2 : 3), false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s)
     if (pay_bytes == 0) return SDC_PART(uint32_t, false, (const uint32_t*)nullptr);
     if (pay_bytes == 4) return SDC_PART(uint32_t, true, reinterpret_cast<const uint32_t*>(pay));
     if (pay_bytes == 8) return SDC_PART(K, true, reinterpret_cast<const K*>(pay));
 #undef SDC_PART
-    set_error("hash partition: payload size %d", pay_bytes);
+    set_error("partition pass: payload size %d", pay_bytes);
     return SDCB200_ERR_ARG;
+}
+
+}  // namespace
+
+int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int pay_bytes, const void* pay, void* pay_out,
+                            int64_t n, bool iota, unsigned long long* part_begin, cudaStream_t s) {
+    return partition_pass_impl(HashTopDigit{key_f64 ? 1 : 0}, keys, keys_out, pay_bytes, pay, pay_out, n, iota, part_begin, s);
+}
+
+int32_t range_partition_pass(const void* keys, unsigned long long lo, int shift, void* keys_out, int pay_bytes, const void* pay,
+                             void* pay_out, int64_t n, bool iota, unsigned long long* part_begin, cudaStream_t s) {
+    return partition_pass_impl(RangeDigit{lo, shift}, keys, keys_out, pay_bytes, pay, pay_out, n, iota, part_begin, s);
 }
 
 }  // namespace sdcb200

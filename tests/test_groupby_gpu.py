@@ -393,8 +393,8 @@ def test_measurement_switches_give_the_same_result(monkeypatch):
 
 def test_dense_high_cardinality_takes_direct_table_and_matches_sort_path(monkeypatch):
     """Tens of millions of expected groups: dense int64 keys (what a ROUTE_MOD shuffle delivers) aggregate in a
-    direct-addressed table, anything else goes to sort-and-segment -- same result either way.  Thresholds lowered so
-    the test stays small."""
+    direct-addressed window table (csrc/groupby.cu run_groupby_window, with and without the key-range partition pass in
+    front), anything else goes to sort-and-segment -- same result either way.  Thresholds lowered so the test stays small."""
     import torch
     from sdc_b200.groupby import groupby_device
     rng = np.random.default_rng(9)
@@ -403,29 +403,35 @@ def test_dense_high_cardinality_takes_direct_table_and_matches_sort_path(monkeyp
     sparse = dense * 1_000_003
     v = rng.standard_normal(n)
     v[::91] = np.nan
+    v[dense == 77] = np.nan               # a group without a single value: sum 0, count 0, mean / min / max NaN
+    v[dense == 78] = -0.0                 # a group whose sum never leaves -0.0
+    v[dense == 79] = 0.0
     dv = torch.from_numpy(v).cuda()
     monkeypatch.setenv("SDCB200_GB_SORT_ROWS", "1000")
     monkeypatch.setenv("SDCB200_GB_SORT_GROUPS", "1000")
-    aggs = ("sum", "count", "min", "max", "mean")
+    all_aggs = ("sum", "count", "min", "max", "mean")
+    modes = (("0", "0"), (str(256 << 20), "0"), (str(256 << 20), "1"))      # (dense threshold, partition pass)
     for keys in (dense, sparse):
         dk = torch.from_numpy(keys).cuda()
-        got = {}
-        for dense_groups in ("0", str(48 << 20)):       # 0: never try the direct table
-            monkeypatch.setenv("SDCB200_GB_DENSE_GROUPS", dense_groups)
-            for sort in (True, False):
-                gk, res = groupby_device(dk, [dv], aggs, sort, 1, 200_000)
-                got[(dense_groups, sort)] = (gk.clone(), {a: res[a][0].clone() for a in aggs})
         df = pd.DataFrame({"k": keys, "v": v})
-        for sort in (True, False):
-            want = df.groupby("k", sort=sort)["v"]
-            for dg in ("0", str(48 << 20)):
-                gk, res = got[(dg, sort)]
-                np.testing.assert_array_equal(gk.cpu().numpy(), want.sum().index.to_numpy(), err_msg="keys dg=%s sort=%s" % (dg, sort))
-                np.testing.assert_array_equal(res["count"].cpu().numpy(), want.count().to_numpy())
-                np.testing.assert_array_equal(res["min"].cpu().numpy(), want.min().to_numpy())
-                np.testing.assert_array_equal(res["max"].cpu().numpy(), want.max().to_numpy())
-                assert_close(res["sum"].cpu().numpy(), want.sum().to_numpy(), rtol=1e-9, atol=1e-12, msg="sum")
-                assert_close(res["mean"].cpu().numpy(), want.mean().to_numpy(), rtol=1e-9, atol=1e-12, msg="mean")
+        for aggs in (all_aggs, ("sum",), ("count",), ("min", "max"), ("mean",)):
+            for sort in (True, False):
+                want = df.groupby("k", sort=sort)["v"]
+                for dg, part in modes:
+                    monkeypatch.setenv("SDCB200_GB_DENSE_GROUPS", dg)   # 0: never try the window table
+                    monkeypatch.setenv("SDCB200_GB_WIN_PART", part)
+                    gk, res = groupby_device(dk, [dv], aggs, sort, 1, 200_000)
+                    msg = "aggs=%s sort=%s dense=%s part=%s" % (aggs, sort, dg, part)
+                    np.testing.assert_array_equal(gk.cpu().numpy(), want.sum().index.to_numpy(), err_msg="keys " + msg)
+                    for a in aggs:
+                        x = res[a][0].cpu().numpy()
+                        w = getattr(want, a)().to_numpy()
+                        if a in ("sum", "mean"):
+                            assert_close(x, w, rtol=1e-9, atol=1e-12, msg=a + " " + msg)
+                        else:
+                            np.testing.assert_array_equal(x, w, err_msg=a + " " + msg)
+                        if a == "sum":
+                            assert not np.signbit(x[w == 0]).any(), "sum of nothing / of -0.0 is +0.0 like the reference's nansum: " + msg
 
 
 def test_async_begin_end_matches_the_blocking_call():
