@@ -281,13 +281,14 @@ def bench_other_ops(dev, peak, cpu_legs=True):
           "rows_per_s": npr / (med * 1e-3), "ms_median": med, "ms_best": best, "n_out": n_out, "algorithmic_bytes": alg,
           "achieved_GBps": alg / (med * 1e-3) / 1e9, "frac_of_measured_peak": alg / (med * 1e-3) / 1e9 / peak}
     res.clear()
+
     # the same join with keys that are NOT a dense range (every key scaled by 1000003): the hashed / partitioned path
     r_s, l_s = r * 1000003, l * 1000003
 
     def run_sparse():
         res["o"] = join_device(l_s, r_s, "inner")
     meds, _ = _event_times(run_sparse, 3, warm=1)
-    jn["sparse_keys"] = {"workload": "same join, keys * 1000003 (no dense range: hash table instead of direct addressing)",
+    jn["sparse_keys"] = {"workload": "same join, keys * 1000003 (no dense range: partitioned hash join, pairs as a row set)",
                          "ms_median": meds, "rows_per_s": npr / (meds * 1e-3), "frac_of_measured_peak": alg / (meds * 1e-3) / 1e9 / peak}
     res.clear()
     del r_s, l_s

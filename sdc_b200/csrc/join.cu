@@ -677,7 +677,8 @@ int64_t g_next_join = 1;
 
 template <bool KEY_F64, bool LEFT>
 int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long long* r, int64_t nr, cudaStream_t s,
-                 JoinResult* res, int64_t extra = 0 /* rows of spare capacity behind the pairs (how='outer') */) {
+                 JoinResult* res, int64_t extra = 0 /* rows of spare capacity behind the pairs (how='outer') */,
+                 bool any_order = false /* how='inner': the caller wants the row set, not left-row order */) {
     const int sms = sm_count();
     const int wide = sms * 8;
     // ---- build ----
@@ -751,7 +752,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         // an inner join's contract is the row SET; how='left' keeps left-row order and stays on the direct path.
         const int part_on = [] { const char* e = getenv("SDCB200_JOIN_PART"); return e ? atoi(e) : 1; }();   // 0 off, 2 always (tests)
         static const bool chained = [] { const char* e = getenv("SDCB200_JOIN_INNER"); return e && !strcmp(e, "chained"); }();
-        part = part_on && !chained && !LEFT && extra == 0 && nl < 0xffffffffll &&
+        part = part_on && !chained && !LEFT && any_order && extra == 0 && nl < 0xffffffffll &&
                (part_on == 2 || ((int64_t)t.cap * 16 >= (int64_t(48) << 20) && nl >= (int64_t(1) << 22)));
         if (part) {
             int lg = 0;
@@ -982,7 +983,10 @@ extern "C" {
 int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                      void* stream, int64_t* handle_out, int64_t* n_out) {
     cudaStream_t s = (cudaStream_t)stream;
+    const bool any_order = (how & SDCB200_JOIN_ANY_ORDER) != 0;
+    how &= ~SDCB200_JOIN_ANY_ORDER;
     SDC_ARG_CHECK(how >= SDCB200_JOIN_INNER && how <= SDCB200_JOIN_OUTER, "how must be INNER, LEFT, RIGHT or OUTER");
+    SDC_ARG_CHECK(!any_order || how == SDCB200_JOIN_INNER, "SDCB200_JOIN_ANY_ORDER goes with how = INNER only");
     SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
     SDC_ARG_CHECK(nl >= 0 && nr >= 0, "row counts");
     SDC_ARG_CHECK((how == SDCB200_JOIN_RIGHT ? nl : nr) < 0xffffffffll, "build side must have fewer than 2^32 - 1 rows");
@@ -1002,8 +1006,8 @@ int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int6
         if (rc == SDCB200_OK) rc = append_unmatched_right(res, nr, s);
     } else {
         const bool left = how == SDCB200_JOIN_LEFT;
-        if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res) : run_join<true, false>(l, nl, r, nr, s, res);
-        else rc = left ? run_join<false, true>(l, nl, r, nr, s, res) : run_join<false, false>(l, nl, r, nr, s, res);
+        if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res) : run_join<true, false>(l, nl, r, nr, s, res, 0, any_order);
+        else rc = left ? run_join<false, true>(l, nl, r, nr, s, res) : run_join<false, false>(l, nl, r, nr, s, res, 0, any_order);
     }
     if (rc != SDCB200_OK) {
         free_join(res, s);

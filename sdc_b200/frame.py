@@ -458,7 +458,7 @@ class DeviceFrame:
             if lk.dtype != rk.dtype or lk.dtype not in (torch.int64, torch.float64):
                 both_int = not lk.dtype.is_floating_point and not rk.dtype.is_floating_point
                 lk, rk = lk.to(torch.int64 if both_int else torch.float64), rk.to(torch.int64 if both_int else torch.float64)
-            li, ri = join_device(lk.contiguous(), rk.contiguous(), how)
+            li, ri = join_device(lk.contiguous(), rk.contiguous(), how, ordered=True)      # pandas keeps left-row order
         else:
             # several key columns: both sides get ids over the RIGHT side's distinct keys, column
             # by column; a left key tuple the right side does not hold (or a NaN on either side) gets an id that
@@ -466,7 +466,7 @@ class DeviceFrame:
             rcols = [right._cols[k] for k in rkeys]
             rgid, _ = _composite_ids(rcols, invalid=-2)
             lgid, _ = _composite_ids([self._cols[k] for k in lkeys], domains=rcols, invalid=-1)
-            li, ri = join_device(lgid, rgid, how)
+            li, ri = join_device(lgid, rgid, how, ordered=True)
         left_null, right_null = how in ("right", "outer"), how in ("left", "outer")
         shared = {l for l, r in zip(lkeys, rkeys) if l == r}           # key columns that appear once in the result
         out = {}

@@ -22,9 +22,11 @@ def _torch():
     return torch
 
 
-def join_device(left_keys, right_keys, how="inner"):
-    """-> (left_idx, right_idx): int64 CUDA tensors of the joined row positions (left-row order,
-    right_idx == -1 where a left row has no partner under how='left')."""
+def join_device(left_keys, right_keys, how="inner", ordered=False):
+    """-> (left_idx, right_idx): int64 CUDA tensors of the joined row positions (right_idx == -1 where a left row has
+    no partner under how='left').  how='inner' returns the pairs as a row SET by default (SDCB200_JOIN_ANY_ORDER: keys
+    with no dense range may take the partitioned join, whose pairs come out bucket by bucket); ordered=True asks for
+    left-row order as pandas.merge gives it.  The other joins always come out in the order include/sdc_b200.h states."""
     torch = _torch()
     lib = native.load()
     if how not in native.JOIN_HOW:
@@ -39,7 +41,8 @@ def join_device(left_keys, right_keys, how="inner"):
     handle, n_out = ct.c_int64(0), ct.c_int64(0)
     with torch.cuda.device(left_keys.device):
         stream = native.current_stream_ptr()
-        native.check(lib.sdcb200_join(native.JOIN_HOW[how], native.DTYPE_CODES[name], left_keys.data_ptr(),
+        how_code = native.JOIN_HOW[how] | (native.JOIN_ANY_ORDER if how == "inner" and not ordered else 0)
+        native.check(lib.sdcb200_join(how_code, native.DTYPE_CODES[name], left_keys.data_ptr(),
                                       left_keys.shape[0], right_keys.data_ptr(), right_keys.shape[0], stream,
                                       ct.byref(handle), ct.byref(n_out)))
         owner = _JoinHandle(handle.value, left_keys.device)
@@ -156,7 +159,7 @@ def merge(left, right, how="inner", on=None, left_on=None, right_on=None):
     lk, rk = _key_column(left[left_on].to_numpy()), _key_column(right[right_on].to_numpy())
     if lk.dtype != rk.dtype:
         lk, rk = lk.astype(np.float64), rk.astype(np.float64)
-    li, ri = join_device(torch.from_numpy(lk).cuda(), torch.from_numpy(rk).cuda(), how)
+    li, ri = join_device(torch.from_numpy(lk).cuda(), torch.from_numpy(rk).cuda(), how, ordered=True)
     right_missing = how in ("left", "outer") and bool((ri < 0).any().item())
     left_missing = how in ("right", "outer") and bool((li < 0).any().item())
     shared_key = left_on == right_on

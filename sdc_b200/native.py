@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("SDCB200_LIB_PATH") or os.path.join(_HERE, "lib", "lib
 
 OK = 0
 JOIN_HOW = {"inner": 0, "left": 1, "right": 2, "outer": 3}
+JOIN_ANY_ORDER = 0x100          # SDCB200_JOIN_ANY_ORDER: how="inner" returns the pairs as a row set, any order
 AGG_BITS = {"sum": 1, "mean": 2, "min": 4, "max": 8, "count": 16, "var": 32, "std": 64, "prod": 128, "median": 256}
 ROLL_OPS = {"sum": 0, "mean": 1, "var": 2, "std": 3, "count": 4, "min": 5, "max": 6}
 ROLL_MOMENT_OPS = {"skew": 7, "kurt": 8, "cov": 9, "corr": 10}

@@ -8,14 +8,18 @@ from oracle import join as ojoin
 pytestmark = pytest.mark.gpu
 
 
-def _device_pairs(l, r, how):
+def _device_pairs(l, r, how, ordered=True):
     import torch
     from sdc_b200.join import join_device
-    li, ri = join_device(torch.from_numpy(np.ascontiguousarray(l)).cuda(), torch.from_numpy(np.ascontiguousarray(r)).cuda(), how)
+    li, ri = join_device(torch.from_numpy(np.ascontiguousarray(l)).cuda(), torch.from_numpy(np.ascontiguousarray(r)).cuda(), how,
+                         ordered=ordered)
     li, ri = li.cpu().numpy(), ri.cpu().numpy()
-    # inner / left: pairs come out in left-row order (how='left' keeps the left order like pandas); right: in
-    # right-row order; outer: the left join's pairs in left-row order, then the unmatched right rows in row order
-    if how in ("inner", "left"):
+    # inner (ordered=True) / left: pairs come out in left-row order (how='left' keeps the left order like pandas); right:
+    # in right-row order; outer: the left join's pairs in left-row order, then the unmatched right rows in row order;
+    # inner with ordered=False (SDCB200_JOIN_ANY_ORDER) is a row set
+    if how == "inner" and not ordered:
+        pass
+    elif how in ("inner", "left"):
         assert np.all(np.diff(li) >= 0)
     elif how == "right":
         assert np.all(np.diff(ri) >= 0)
@@ -28,10 +32,11 @@ def _device_pairs(l, r, how):
 
 
 def _check(l, r, how):
-    got = _device_pairs(l, r, how)
     want = ojoin.join_indexers(l, r, how)
-    np.testing.assert_array_equal(got[0], want[0])
-    np.testing.assert_array_equal(got[1], want[1])
+    for ordered in ((True, False) if how == "inner" else (True,)):
+        got = _device_pairs(l, r, how, ordered)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
 
 
 @pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
@@ -114,10 +119,19 @@ def test_c3_shape_row_count_and_properties():
     perm = np.random.default_rng(2).permutation(nb).astype(np.int64)
     probe = np.random.default_rng(3).integers(0, nb, npr, dtype=np.int64)
     r, l = torch.from_numpy(perm).cuda(), torch.from_numpy(probe).cuda()
-    li, ri = join_device(l, r, "inner")
+    li, ri = join_device(l, r, "inner", ordered=True)
     assert li.shape[0] == npr
     assert bool((li == torch.arange(npr, device="cuda")).all())
     assert bool((r[ri] == l).all())
+    del li, ri
+    # the row-set form (one kernel, a tile takes its output range with an atomic): the same pairs in some order
+    li, ri = join_device(l, r, "inner")
+    assert li.shape[0] == npr
+    assert bool((r[ri] == l[li]).all())
+    seen = torch.zeros(npr, dtype=torch.bool, device="cuda")
+    seen[li] = True
+    assert bool(seen.all())                                   # npr pairs covering every left row: each exactly once
+    del li, ri, seen
     # 50 % hit rate, left join: every probe row appears once, misses carry -1
     probe2 = np.random.default_rng(3).integers(0, 2 * nb, npr, dtype=np.int64)
     l2 = torch.from_numpy(probe2).cuda()

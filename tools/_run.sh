@@ -1,3 +1,3 @@
-python tools/time_groupby_hi.py > gpurun_out/r2b_time_groupby_hi2.log 2>&1; cat gpurun_out/r2b_time_groupby_hi2.log
-SDCB200_GB_WIN_PART=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2b_l_gbwin_100m_b.csv python tools/prof_groupby_hi.py 100000000 > gpurun_out/r2b_ncu_gbwin.log 2>&1
-SDCB200_GB_WIN_PART=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 60 --csv --log-file gpurun_out/r2b_l_gbwin_p1_b.csv python tools/prof_groupby_hi.py 12500000 > gpurun_out/r2b_ncu_gbwin.log 2>&1
+python -m pytest tests/test_join_gpu.py -x -q -m gpu > gpurun_out/r2b_pytest_join.log 2>&1; tail -3 gpurun_out/r2b_pytest_join.log
+python tools/time_join_c3.py > gpurun_out/r2b_time_join_c3.log 2>&1; cat gpurun_out/r2b_time_join_c3.log
+python tools/time_groupby_async.py > gpurun_out/r2b_time_groupby_async.log 2>&1; cat gpurun_out/r2b_time_groupby_async.log
