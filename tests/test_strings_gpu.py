@@ -53,6 +53,23 @@ def test_reference_symbol_stable_argsort_host_buffers():
         np.testing.assert_array_equal(out, ostr.stable_argsort(offsets, chars, bool(asc)))
 
 
+def test_stable_argsort_against_the_compiled_reference():
+    """Same symbol, same buffers, into the reference's OWN stable_argsort (oracle/_ref, compiled from
+    sdc/native/str_ext/sdc_str_arr.hpp:565-593) and into this library's: 300 K strings, both directions, bit for bit."""
+    from oracle import ref as oref
+    if not oref.available():
+        pytest.skip("oracle/_ref not built")
+    from sdc_b200 import native
+    lib = native.load()
+    rng = np.random.default_rng(31)
+    for vals in (_rand_strings(rng, 300_000, 8), _rand_strings(rng, 100_000, 30, "ab"), _rand_strings(rng, 50_000, 12, "aé日Z0")):
+        offsets, chars, _ = ostr.to_str_arr(vals)
+        for asc in (1, 0):
+            out = np.empty(len(vals), dtype=np.uint64)
+            lib.stable_argsort(chars.ctypes.data, offsets.ctypes.data, len(vals), asc, out.ctypes.data)
+            np.testing.assert_array_equal(out, oref.stable_argsort(offsets, chars, bool(asc)))
+
+
 def test_take_and_round_trip():
     import torch
     from sdc_b200.str_arr import StringArray
