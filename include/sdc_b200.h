@@ -66,6 +66,9 @@ int32_t sdcb200_stream_sync(void* stream);
  *            (row-sharded multi-GPU: the previous rank's last win-1 rows, the
  *            analogue of the per-chunk prelude at :609-617); NULL / 0 otherwise
  *   row_offset  global row index of in[0] (count's "rows seen < minp" rule, :249-250)
+ * Any window up to the length of the series, as in the reference: win <= 4097 runs the tiled kernel (one read and
+ * one write per row); longer windows are cut at 2048-row chunk borders -- suffix of the first chunk, whole chunks
+ * from a segment tree of chunk totals, prefix of the row's own chunk (four reads and one write per row).
  */
 #define SDCB200_ROLL_SUM   0
 #define SDCB200_ROLL_MEAN  1
@@ -105,7 +108,8 @@ int32_t sdcb200_host_rolling(int32_t op, int32_t dtype, const void* in, double* 
  * next_mailbox; the tile that needs the previous rank's rows runs last and waits for the flag in own_mailbox, then
  * acknowledges into prev_mailbox (a slot is reused only after the ack of epoch - 2).  next_mailbox / prev_mailbox are
  * NULL on the last / first rank.  epoch >= 1 and increases by one per call, identically on every rank.  Shards
- * shorter than win-1 rows forward rows they received themselves (exact for any shard lengths).                  */
+ * shorter than win-1 rows forward rows they received themselves (exact for any shard lengths).  win - 1 must fit a
+ * mailbox slot (4096 rows); for longer windows exchange the halo rows and call sdcb200_rolling.                 */
 int64_t sdcb200_halo_mailbox_bytes(void);
 int32_t sdcb200_rolling_linked(int32_t op, int32_t dtype, const void* in, double* out, int64_t n, int64_t win,
                                int64_t minp, int64_t ddof, int64_t row_offset, void* own_mailbox, void* next_mailbox,

@@ -792,6 +792,11 @@ class HaloLink:
         if window <= 1:                               # no row of another shard is ever needed: no exchange, no epoch
             from .rolling import rolling_device
             return rolling_device(col, op, window, minp, ddof, out=out, row_offset=row_offset)
+        if (window - 1) * 8 * 2 > int(self.lib.sdcb200_halo_mailbox_bytes()) - 128:
+            # the halo no longer fits a mailbox slot (windows beyond the tiled limit): collective exchange instead
+            from .rolling import rolling_device
+            halo = halo_exchange(col, window - 1, self.group)
+            return rolling_device(col, op, window, minp, ddof, out=out, halo=halo, row_offset=row_offset)
         self.epoch += 1
         with torch.cuda.device(col.device):
             native.check(self.lib.sdcb200_rolling_linked(

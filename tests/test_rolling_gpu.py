@@ -143,6 +143,46 @@ def test_row_sharded_halo(split):
             check(op, got, whole[split:], x, win, msg="%s split=%d" % (op, split))
 
 
+@pytest.mark.parametrize("n", [300, 4098, 5000, 20_000, 250_003])
+def test_windows_beyond_the_tile_limit(n):
+    """win > 4097 (the reference accepts any window up to the series' length): chunk-decomposed windows over a segment
+    tree of chunk totals (csrc/rolling.cu rl_*_kernel), every op, windows longer than the series included; the oracle's
+    sliding accumulators drift over the whole chunk, so sums are held to the same conditioning floor as elsewhere."""
+    from sdc_b200.rolling import rolling_device
+    x = _mixed(n, n + 1)
+    d = _dev(x)
+    for win in (4098, 4099, 6144, 10_000, 65_537, 300_000):
+        if win > 4 * n + 5000:
+            continue
+        for mp in sorted({0, 1, win // 2, win}):
+            for op in OPS:
+                got = rolling_device(d, op, win, mp, 1).cpu().numpy()
+                want = orolling.rolling(x, op, win, mp, 1, nchunks=1)
+                check(op, got, want, x, win, msg="%s n=%d w=%d mp=%d" % (op, n, win, mp))
+
+
+def test_large_window_halo_int64_and_host():
+    from sdc_b200.rolling import rolling_device, rolling_host
+    x = _mixed(60_000, 21)
+    d = _dev(x)
+    win = 7000
+    for op in OPS:
+        whole = rolling_device(d, op, win, 3000, 1).cpu().numpy()
+        for split in (1, 2047, 6999, 7000, 30_001):
+            h0 = max(0, split - (win - 1))
+            got = rolling_device(d[split:].clone(), op, win, 3000, 1, halo=d[h0:split].clone(), row_offset=split).cpu().numpy()
+            check(op, got, whole[split:], x, win, msg="%s split=%d" % (op, split))
+    xi = np.random.default_rng(3).integers(-1000, 1000, 30_000)
+    di = _dev(xi)
+    for op in OPS:
+        got = rolling_device(di, op, 5000, 100, 1).cpu().numpy()
+        check(op, got, orolling.rolling(xi, op, 5000, 100, 1, nchunks=1), xi, 5000, msg="int64 " + op)
+    xh = np.random.default_rng(4).random(3_000_000)
+    xh[::1009] = np.nan
+    for op in ("mean", "max", "count", "std"):
+        check(op, rolling_host(xh, op, 50_000, 100, 1), orolling.rolling(xh, op, 50_000, 100, 1), xh, 50_000, msg="host " + op)
+
+
 def test_host_abi_chunked_large():
     """Host entry point with several pipeline chunks (n > 8 Mi rows)."""
     from sdc_b200.rolling import rolling_host
