@@ -1349,6 +1349,10 @@ struct GroupbyResult {
     bool one_block = false;                // vals lives in the allocation keys points at (low-cardinality path)
     bool lean_direct = false;              // produced by gb_smem_kernel's lean loop over a direct window
     struct PendingSmall* pending = nullptr;   // sdcb200_groupby_begin: the kernel is in flight, sdcb200_groupby_end finishes
+    cudaStream_t stream = nullptr;            // the caller's stream the result was produced on: the buffers are handed out
+                                              // as zero-copy views and consumed there, so they are freed in ITS order
+                                              // (the host-buffer forms run on streams of their own, synchronise them and
+                                              // reset this to the default stream before they destroy them)
 };
 
 std::mutex g_mu;
@@ -1359,8 +1363,8 @@ void free_pending(GroupbyResult* r);
 void free_result(GroupbyResult* r) {
     if (!r) return;
     free_pending(r);
-    if (r->keys) dev_free(r->keys, nullptr);
-    if (r->vals && !r->one_block) dev_free(r->vals, nullptr);
+    if (r->keys) dev_free(r->keys, r->stream);
+    if (r->vals && !r->one_block) dev_free(r->vals, r->stream);
     delete r;
 }
 
@@ -2282,6 +2286,7 @@ int32_t sdcb200_groupby(int32_t key_dtype, const void* keys, int64_t n, int32_t 
         c.is_f64[i] = col_dtypes[i] == SDCB200_F64;
     }
     GroupbyResult* res = new GroupbyResult();
+    res->stream = s;
     res->key_dtype = key_dtype;
     res->ncols = ncols;
     res->agg_mask = agg_mask;
@@ -2332,6 +2337,7 @@ int32_t sdcb200_groupby_begin(int32_t key_dtype, const void* keys, int64_t n, in
         c.is_f64[i] = col_dtypes[i] == SDCB200_F64;
     }
     GroupbyResult* res = new GroupbyResult();
+    res->stream = s;
     res->key_dtype = key_dtype;
     res->ncols = ncols;
     res->agg_mask = agg_mask;
@@ -2492,6 +2498,12 @@ extern "C" int32_t sdcb200_host_groupby(int32_t key_dtype, const void* keys, int
         return SDCB200_OK;
     };
     const int32_t rc = body();
+    if (rc == SDCB200_OK) {
+        // the result was produced on st[0], which is synchronised and destroyed below: later frees go to the default stream
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_results.find(*handle_out);
+        if (it != g_results.end()) it->second->stream = nullptr;
+    }
     if (dkeys) dev_free(dkeys, st[0]);
     for (int i = 0; i < ncols; ++i)
         if (dcols[i]) dev_free(dcols[i], st[0]);

@@ -669,6 +669,9 @@ struct JoinResult {
     int64_t n_out = 0;
     int64_t* lidx = nullptr;
     int64_t* ridx = nullptr;
+    cudaStream_t stream = nullptr;     // the caller's stream the indexers were produced on (zero-copy views are consumed
+                                       // there): sdcb200_join_free(handle, NULL) frees in its order
+    bool own_stream = false;           // produced by sdcb200_host_join on a stream that no longer exists
 };
 
 std::mutex g_jmu;
@@ -993,6 +996,7 @@ int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int6
     SDC_ARG_CHECK((nl == 0 || left_keys) && (nr == 0 || right_keys), "null key column");
     SDC_ARG_CHECK(handle_out && n_out, "null out pointer");
     JoinResult* res = new JoinResult();
+    res->stream = s;
     const unsigned long long* l = reinterpret_cast<const unsigned long long*>(left_keys);
     const unsigned long long* r = reinterpret_cast<const unsigned long long*>(right_keys);
     int32_t rc;
@@ -1056,7 +1060,8 @@ int32_t sdcb200_join_free(int64_t handle, void* stream) {
         r = it->second;
         g_joins.erase(it);
     }
-    free_join(r, (cudaStream_t)stream);
+    // stream NULL: the stream the join ran on (the default stream for results of sdcb200_host_join)
+    free_join(r, stream ? (cudaStream_t)stream : (r->own_stream ? nullptr : r->stream));
     return SDCB200_OK;
 }
 
@@ -1097,6 +1102,11 @@ int32_t sdcb200_host_join(int32_t how, int32_t key_dtype, const void* left_keys,
         return SDCB200_OK;
     };
     const int32_t rc = body();
+    if (rc == SDCB200_OK) {
+        std::lock_guard<std::mutex> lk(g_jmu);
+        auto it = g_joins.find(*handle_out);
+        if (it != g_joins.end()) it->second->own_stream = true;      // st[0] is synchronised and destroyed below
+    }
     if (dl) dev_free(dl, st[0]);
     if (dr) dev_free(dr, st[0]);
     for (int i = 0; i < 2; ++i)
