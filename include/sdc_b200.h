@@ -225,6 +225,12 @@ int32_t sdcb200_combine_ids(const int64_t* a, const int64_t* b, int64_t nb, int6
                                   _sdc_internal_join (sdc/datatypes/common_functions.py:225-455) */
 int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
                      void* stream, int64_t* handle_out, int64_t* n_out);
+/* The same join with the caller's ids in place of local row numbers: the result holds left_ids[l] / right_ids[r]
+ * (device int64 columns, either may be NULL; -1 stays -1).  After a shuffle the rows carry the GLOBAL row numbers
+ * they had before it (sdc_b200/distributed.py join_distributed); the mapping is folded into the probe's last kernel
+ * (unique build keys) instead of two gather passes over the result.                                             */
+int32_t sdcb200_join_ids(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                         const int64_t* left_ids, const int64_t* right_ids, void* stream, int64_t* handle_out, int64_t* n_out);
 int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_idx, int32_t dst_is_host, void* stream);
 /* zero-copy access: device pointers of the handle's indexer arrays (n_out int64 each), valid until
  * sdcb200_join_free                                                                                  */
@@ -304,6 +310,23 @@ int32_t sdcb200_hash_partition(int32_t key_dtype, int32_t route, const void* key
                                int64_t* perm_out, int64_t* counts_out, void* shipped_keys_out, void* stream);
 /* out[i] = cnt[i] ? sum[i] / cnt[i] : NaN: final step of a distributed mean (partials are exchanged).  */
 int32_t sdcb200_combine_mean(const double* sum, const int64_t* cnt, int64_t n, double* out, void* stream);
+/* Partial tables of a low-cardinality distributed groupby (the reference's per-chunk-dict-then-merge,
+ * hpat_pandas_dataframe_functions.py:3080-3102, with GPUs as the chunks).  pack: `nrows` device rows of ng 8-byte
+ * values (row 0 = the group keys) -> one int64 matrix dst[nrows][cap + 1], zero padded, dst[0][cap] = ng (an all-zero
+ * body when ng > cap) -- what one all-gather moves.  combine: the gathered [nranks][nrows][cap + 1] block reduced over
+ * the ranks into out[nrows][cap + 1], row r by ops[r] (SDCB200_PART_*: keys are copied from rank 0, float minima /
+ * maxima skip NaN partials); flag[0] = 1 when some rank's key row or group count differs from rank 0's -- the caller
+ * then merges by key instead -- flag[1] = rank 0's group count.  Table-sized work, one launch each.              */
+#define SDCB200_PART_KEY 0
+#define SDCB200_PART_SUM_F64 1
+#define SDCB200_PART_SUM_I64 2
+#define SDCB200_PART_MIN_F64 3
+#define SDCB200_PART_MAX_F64 4
+#define SDCB200_PART_MIN_I64 5
+#define SDCB200_PART_MAX_I64 6
+int32_t sdcb200_pack_partials(const void* const* rows, int32_t nrows, int64_t ng, int64_t cap, int64_t* dst, void* stream);
+int32_t sdcb200_combine_partials(const int64_t* gathered, int32_t nranks, int32_t nrows, const int32_t* ops, int64_t cap,
+                                 int64_t* out, int64_t* flag, void* stream);
 
 /* ---- peer-memory shuffle over NVLink (one node, one process per GPU) --------------------------------------
  * Replaces the per-column alltoallv of the reference's shuffle (sdc/shuffle_utils.py:268-270,

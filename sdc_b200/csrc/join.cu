@@ -553,7 +553,9 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_row1_kernel(const u
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(const uint32_t* __restrict__ row1_in, int64_t n,
                                                                             const unsigned long long* __restrict__ tile_offs,
                                                                             int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
-                                                                            const uint32_t* __restrict__ lmap) {
+                                                                            const uint32_t* __restrict__ lmap,
+                                                                            const long long* __restrict__ lids,
+                                                                            const long long* __restrict__ rids) {
     constexpr int kWarps = kJoinThreads / 32;
     __shared__ unsigned wcnt[kWarps];
     const uint64_t stream_pol = l2_policy_evict_first();
@@ -606,15 +608,24 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(cons
                 l0 = lmap[r];
             }
         }
+        int64_t r0 = (int64_t)row1[2 * j] - 1, r1 = (int64_t)row1[2 * j + 1] - 1;
+        if (lids) {                                   // caller's ids in place of the local row numbers (sdcb200_join_ids)
+            if (row1[2 * j]) l0 = lids[l0];
+            if (row1[2 * j + 1]) l1 = lids[l1];
+        }
+        if (rids) {
+            if (row1[2 * j]) r0 = rids[r0];
+            if (row1[2 * j + 1]) r1 = rids[r1];
+        }
         if (((fullmask >> j) & 1u) && even) {
             st_hint_v2s64(lidx + p0, l0, l1, stream_pol);
-            st_hint_v2s64(ridx + p0, (int64_t)row1[2 * j] - 1, (int64_t)row1[2 * j + 1] - 1, stream_pol);
+            st_hint_v2s64(ridx + p0, r0, r1, stream_pol);
         } else {
-            if (row1[2 * j]) { lidx[p0] = l0; ridx[p0] = (int64_t)row1[2 * j] - 1; }
+            if (row1[2 * j]) { lidx[p0] = l0; ridx[p0] = r0; }
             if (row1[2 * j + 1]) {
                 const unsigned long long p1 = base + rank[2 * j + 1];
                 lidx[p1] = l1;
-                ridx[p1] = (int64_t)row1[2 * j + 1] - 1;
+                ridx[p1] = r1;
             }
         }
     }
@@ -625,7 +636,8 @@ template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                          JTable t, const uint32_t* __restrict__ rid,
                                                                          int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
-                                                                         int vec) {
+                                                                         int vec, const long long* __restrict__ lids,
+                                                                         const long long* __restrict__ rids) {
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * kTile;
@@ -637,19 +649,39 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const u
         rr[e] = (probe_row(tile0, warp, lane, e) < n) ? (int64_t)lookup_row1(t, rid, k[e], keep_pol) - 1 : -1;
         __syncwarp();                                  // hash probes end at different times per lane
     }
+    if (rids) {
+#pragma unroll
+        for (int e = 0; e < kItems; ++e)
+            if (rr[e] >= 0) rr[e] = rids[rr[e]];
+    }
     if (tile0 + kTile <= n) {
 #pragma unroll
         for (int e = 0; e < kItems; e += 2) {
             const int64_t r = probe_row(tile0, warp, lane, e);
-            st_hint_v2s64(lidx + r, r, r + 1, stream_pol);
+            int64_t l0 = r, l1 = r + 1;
+            if (lids) {
+                const longlong2 v = *reinterpret_cast<const longlong2*>(lids + r);      // r is even, lids 16-byte aligned
+                l0 = v.x;
+                l1 = v.y;
+            }
+            st_hint_v2s64(lidx + r, l0, l1, stream_pol);
             st_hint_v2s64(ridx + r, rr[e], rr[e + 1], stream_pol);
         }
     } else {
 #pragma unroll
         for (int e = 0; e < kItems; ++e) {
             const int64_t r = probe_row(tile0, warp, lane, e);
-            if (r < n) { lidx[r] = r; ridx[r] = rr[e]; }
+            if (r < n) { lidx[r] = lids ? lids[r] : r; ridx[r] = rr[e]; }
         }
+    }
+}
+
+// idx[i] = ids[idx[i]] (-1 stays -1): the caller's ids in place of local row numbers, for the paths that do not fold
+// the mapping into their last kernel
+__global__ void remap_ids_kernel(int64_t* __restrict__ idx, int64_t n, const long long* __restrict__ ids) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = idx[i];
+        if (v >= 0) idx[i] = ids[v];
     }
 }
 
@@ -681,7 +713,9 @@ int64_t g_next_join = 1;
 template <bool KEY_F64, bool LEFT>
 int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long long* r, int64_t nr, cudaStream_t s,
                  JoinResult* res, int64_t extra = 0 /* rows of spare capacity behind the pairs (how='outer') */,
-                 bool any_order = false /* how='inner': the caller wants the row set, not left-row order */) {
+                 bool any_order = false /* how='inner': the caller wants the row set, not left-row order */,
+                 const long long* lids = nullptr, const long long* rids = nullptr /* sdcb200_join_ids */,
+                 bool* ids_applied = nullptr) {
     const int sms = sm_count();
     const int wide = sms * 8;
     // ---- build ----
@@ -811,8 +845,12 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         res->ridx = reinterpret_cast<int64_t*>(p);
         const int vec = (reinterpret_cast<uintptr_t>(lk) & 15) == 0;
         if (LEFT) {
-            probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx, vec);
+            // the pair loads of lids need 16-byte alignment (allocations are; a sliced view may not be)
+            const bool fold = ids_applied && (reinterpret_cast<uintptr_t>(lids) & 15) == 0;
+            probe_unique_left_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(l, nl, t, rid.as<uint32_t>(), res->lidx, res->ridx, vec,
+                                                                                    fold ? lids : nullptr, fold ? rids : nullptr);
             SDC_CHECK_LAUNCH();
+            if (fold) *ids_applied = true;
         } else {
             // 4096-row tiles halve the number of look-backs per row (1.31 -> 1.26 ms on C3); the hashed table's probe
             // loops run better with the smaller tile (5.8 vs 5.4 ms), so only the dense table takes the big one
@@ -833,8 +871,10 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                     SDC_TRY(device_exclusive_scan(ArrayLoad{tile_counts}, ArrayStore{tile_counts}, nt, tsum_p, s));
                     SDC_CUDA_TRY(cudaMemcpyAsync(tile_counts + nt, tsum_p + ceil_div(nt, kTile), 8, cudaMemcpyDeviceToDevice, s));
                 }
-                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx, lmap);
+                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx, lmap,
+                                                                                  ids_applied ? lids : nullptr, ids_applied ? rids : nullptr);
                 SDC_CHECK_LAUNCH();
+                if (ids_applied) *ids_applied = true;
                 unsigned long long total = 0;
                 SDC_CUDA_TRY(cudaMemcpyAsync(&total, tile_counts + nt, 8, cudaMemcpyDeviceToHost, s));
                 SDC_CUDA_TRY(cudaStreamSynchronize(s));
@@ -983,8 +1023,8 @@ using namespace sdcb200;
 
 extern "C" {
 
-int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
-                     void* stream, int64_t* handle_out, int64_t* n_out) {
+static int32_t join_entry(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                          const long long* lids, const long long* rids, void* stream, int64_t* handle_out, int64_t* n_out) {
     cudaStream_t s = (cudaStream_t)stream;
     const bool any_order = (how & SDCB200_JOIN_ANY_ORDER) != 0;
     how &= ~SDCB200_JOIN_ANY_ORDER;
@@ -1000,6 +1040,7 @@ int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int6
     const unsigned long long* l = reinterpret_cast<const unsigned long long*>(left_keys);
     const unsigned long long* r = reinterpret_cast<const unsigned long long*>(right_keys);
     int32_t rc;
+    bool applied = false;
     const bool f = key_dtype == SDCB200_F64;
     if (how == SDCB200_JOIN_RIGHT) {
         // a left join with the sides swapped: every right row once per partner (or once with -1)
@@ -1010,8 +1051,16 @@ int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int6
         if (rc == SDCB200_OK) rc = append_unmatched_right(res, nr, s);
     } else {
         const bool left = how == SDCB200_JOIN_LEFT;
-        if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res) : run_join<true, false>(l, nl, r, nr, s, res, 0, any_order);
-        else rc = left ? run_join<false, true>(l, nl, r, nr, s, res) : run_join<false, false>(l, nl, r, nr, s, res, 0, any_order);
+        bool* ap = (lids || rids) ? &applied : nullptr;
+        if (f) rc = left ? run_join<true, true>(l, nl, r, nr, s, res, 0, false, lids, rids, ap) : run_join<true, false>(l, nl, r, nr, s, res, 0, any_order, lids, rids, ap);
+        else rc = left ? run_join<false, true>(l, nl, r, nr, s, res, 0, false, lids, rids, ap) : run_join<false, false>(l, nl, r, nr, s, res, 0, any_order, lids, rids, ap);
+    }
+    if (rc == SDCB200_OK && !applied && res->n_out > 0) {
+        // a path that did not fold the id mapping into its last kernel (duplicate build keys, partitioned, right / outer)
+        const int g = (int)(ceil_div(res->n_out, 256) < (int64_t)sm_count() * 8 ? ceil_div(res->n_out, 256) : (int64_t)sm_count() * 8);
+        if (lids) { remap_ids_kernel<<<g, 256, 0, s>>>(res->lidx, res->n_out, lids); count_launch(); }
+        if (rids) { remap_ids_kernel<<<g, 256, 0, s>>>(res->ridx, res->n_out, rids); count_launch(); }
+        if (cudaGetLastError() != cudaSuccess) { set_error("join: id remap launch failed"); rc = SDCB200_ERR_CUDA; }
     }
     if (rc != SDCB200_OK) {
         free_join(res, s);
@@ -1023,6 +1072,17 @@ int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int6
     *handle_out = h;
     *n_out = res->n_out;
     return SDCB200_OK;
+}
+
+int32_t sdcb200_join(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                     void* stream, int64_t* handle_out, int64_t* n_out) {
+    return join_entry(how, key_dtype, left_keys, nl, right_keys, nr, nullptr, nullptr, stream, handle_out, n_out);
+}
+
+int32_t sdcb200_join_ids(int32_t how, int32_t key_dtype, const void* left_keys, int64_t nl, const void* right_keys, int64_t nr,
+                         const int64_t* left_ids, const int64_t* right_ids, void* stream, int64_t* handle_out, int64_t* n_out) {
+    return join_entry(how, key_dtype, left_keys, nl, right_keys, nr, reinterpret_cast<const long long*>(left_ids),
+                      reinterpret_cast<const long long*>(right_ids), stream, handle_out, n_out);
 }
 
 int32_t sdcb200_join_indexers(int64_t handle, int64_t* left_idx, int64_t* right_idx, int32_t dst_is_host, void* stream) {

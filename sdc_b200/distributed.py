@@ -554,32 +554,34 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
         # group count in the extra last column) travels in a single int64 matrix
         nrows = 1 + len(need) * len(cols)
         ng = lk.shape[0]
-        buf = torch.zeros((nrows, cap + 1), dtype=torch.int64, device=lk.device)
-        buf[0, cap] = ng
-        if ng <= cap:
-            buf[0, :ng] = lk.view(torch.int64)
-            r = 1
-            for p_ in need:
-                for t in lres[p_]:
-                    buf[r, :ng] = t.view(torch.int64)
-                    r += 1
+        lib = native.load()
+        rows = [lk] + [t for p_ in need for t in lres[p_]]
+        ops = [0]
+        for p_ in need:
+            for t in lres[p_]:
+                f = t.dtype == torch.float64
+                ops.append({"sum": 1 if f else 2, "count": 2, "min": 3 if f else 5, "max": 4 if f else 6}[p_])
+        buf = torch.empty((nrows, cap + 1), dtype=torch.int64, device=lk.device)
         allb = torch.empty((P, nrows, cap + 1), dtype=torch.int64, device=lk.device)
-        _dist().all_gather_into_tensor(allb, buf, group=group)
-        # the one host read of this path: every rank's group count, and whether all ranks hold the same key row
-        same_keys = (allb[:, 0, :cap] == allb[0:1, 0, :cap]).all().to(torch.int64).reshape(1)
-        host = torch.cat([allb[:, 0, cap], same_keys]).tolist()
-        ngs, same = host[:P], bool(host[P])
-        if same and all(g == ngs[0] for g in ngs) and 0 < ngs[0] <= cap and all(p_ in ("sum", "count") for p_ in need):
-            # every rank found the same groups in the same order (the usual case at low cardinality): the partial
-            # tables add up row by row -- no second aggregate, the result is already in the gathered matrix
-            # (P x groups values: table-sized, not row-sized, work)
-            g0 = ngs[0]
-            out_keys = allb[0, 0, :g0].view(lk.dtype)
+        comb = torch.empty((nrows, cap + 1), dtype=torch.int64, device=lk.device)
+        flag = torch.empty(2, dtype=torch.int64, device=lk.device)
+        with torch.cuda.device(lk.device):
+            ptrs = (ct.c_void_p * nrows)(*[t.data_ptr() if t.numel() else None for t in rows])
+            native.check(lib.sdcb200_pack_partials(ptrs, nrows, ng, cap, buf.data_ptr(), native.current_stream_ptr()))
+            _dist().all_gather_into_tensor(allb, buf, group=group)
+            # ONE launch reduces the gathered tables over the ranks and tells whether that was legal: every rank found
+            # the same groups in the same order (the usual case at low cardinality) -- then the partial tables add up
+            # row by row and there is no second aggregate (P x groups values: table-sized, not row-sized, work)
+            native.check(lib.sdcb200_combine_partials(allb.data_ptr(), P, nrows, (ct.c_int32 * nrows)(*ops), cap, comb.data_ptr(),
+                                                      flag.data_ptr(), native.current_stream_ptr()))
+        differ, g0 = flag.tolist()                 # the one host read of this path
+        if not differ and 0 < g0 <= cap:
+            out_keys = comb[0, :g0].view(lk.dtype)
             final, r = {}, 1
             for p_ in need:
                 final[p_] = {}
                 for i, t in enumerate(lres[p_]):
-                    final[p_][i] = allb[:, r, :g0].view(t.dtype).sum(dim=0)
+                    final[p_][i] = comb[r, :g0].view(t.dtype)
                     r += 1
             res = {}
             for a in aggs:
@@ -589,6 +591,7 @@ def groupby_distributed(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, 
                 else:
                     res[a] = [final[a][i] for i in range(len(cols))]
             return out_keys, res, "replicated"
+        ngs = allb[:, 0, cap].tolist()
         if all(0 <= g <= cap for g in ngs):
             gk = torch.cat([allb[q, 0, :g] for q, g in enumerate(ngs)]).view(lk.dtype)
             part, r = {}, 1
@@ -659,8 +662,8 @@ def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"
         return affine_i64_(li, 1, loff, keep_negative=True), ri
     _, out = shuffle_many([(left_keys, [None], (0, loff)), (right_keys, [None], (0, roff))], group, peer, route)
     (lk2, (lid2,)), (rk2, (rid2,)) = out
-    li, ri = join_device(lk2, rk2, how)
-    return gather_ids_device(lid2, li), gather_ids_device(rid2, ri)
+    # the global row ids that travelled with the rows replace the local row numbers inside the join's last kernel
+    return join_device(lk2, rk2, how, left_ids=lid2, right_ids=rid2)
 
 
 # ------------------------------------------------------------------ string columns (str_arr) in the shuffle

@@ -22,11 +22,13 @@ def _torch():
     return torch
 
 
-def join_device(left_keys, right_keys, how="inner", ordered=False):
+def join_device(left_keys, right_keys, how="inner", ordered=False, left_ids=None, right_ids=None):
     """-> (left_idx, right_idx): int64 CUDA tensors of the joined row positions (right_idx == -1 where a left row has
     no partner under how='left').  how='inner' returns the pairs as a row SET by default (SDCB200_JOIN_ANY_ORDER: keys
     with no dense range may take the partitioned join, whose pairs come out bucket by bucket); ordered=True asks for
-    left-row order as pandas.merge gives it.  The other joins always come out in the order include/sdc_b200.h states."""
+    left-row order as pandas.merge gives it.  The other joins always come out in the order include/sdc_b200.h states.
+    left_ids / right_ids (int64 CUDA tensors, one id per row): the result holds these ids instead of local row numbers
+    (sdcb200_join_ids: rows that arrived through a shuffle carry their global row numbers)."""
     torch = _torch()
     lib = native.load()
     if how not in native.JOIN_HOW:
@@ -42,9 +44,18 @@ def join_device(left_keys, right_keys, how="inner", ordered=False):
     with torch.cuda.device(left_keys.device):
         stream = native.current_stream_ptr()
         how_code = native.JOIN_HOW[how] | (native.JOIN_ANY_ORDER if how == "inner" and not ordered else 0)
-        native.check(lib.sdcb200_join(how_code, native.DTYPE_CODES[name], left_keys.data_ptr(),
-                                      left_keys.shape[0], right_keys.data_ptr(), right_keys.shape[0], stream,
-                                      ct.byref(handle), ct.byref(n_out)))
+        if left_ids is None and right_ids is None:
+            native.check(lib.sdcb200_join(how_code, native.DTYPE_CODES[name], left_keys.data_ptr(),
+                                          left_keys.shape[0], right_keys.data_ptr(), right_keys.shape[0], stream,
+                                          ct.byref(handle), ct.byref(n_out)))
+        else:
+            for ids, keys in ((left_ids, left_keys), (right_ids, right_keys)):
+                assert ids is None or (ids.is_cuda and ids.dtype == torch.int64 and ids.is_contiguous() and ids.shape[0] == keys.shape[0])
+            native.check(lib.sdcb200_join_ids(how_code, native.DTYPE_CODES[name], left_keys.data_ptr(), left_keys.shape[0],
+                                              right_keys.data_ptr(), right_keys.shape[0],
+                                              left_ids.data_ptr() if left_ids is not None and left_ids.numel() else None,
+                                              right_ids.data_ptr() if right_ids is not None and right_ids.numel() else None,
+                                              stream, ct.byref(handle), ct.byref(n_out)))
         owner = _JoinHandle(handle.value, left_keys.device)
         if n_out.value == 0:
             e = torch.empty(0, dtype=torch.int64, device=left_keys.device)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "sdcb200_host_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, ct.POINTER(_i64), ct.POINTER(_i64)]),
     "sdcb200_combine_ids": (_i32, [_vp, _vp, _i64, _i64, _vp, _i64, _vp]),
     "sdcb200_join": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
+    "sdcb200_join_ids": (_i32, [_i32, _i32, _vp, _i64, _vp, _i64, _vp, _vp, _vp, ct.POINTER(_i64), ct.POINTER(_i64)]),
     "sdcb200_join_indexers": (_i32, [_i64, _vp, _vp, _i32, _vp]),
     "sdcb200_join_result": (_i32, [_i64, ct.POINTER(_vp), ct.POINTER(_vp)]),
     "sdcb200_join_free": (_i32, [_i64, _vp]),
@@ -80,6 +81,8 @@ SIGNATURES = {
     "stable_argsort": (None, [_vp, _vp, ct.c_uint64, ct.c_int8, _vp]),
     "sdcb200_hash_partition": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "sdcb200_combine_mean": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_pack_partials": (_i32, [_vp, _i32, _i64, _i64, _vp, _vp]),
+    "sdcb200_combine_partials": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _vp, _vp]),
     "sdcb200_ipc_alloc": (_i32, [ct.POINTER(_vp), _i64]),
     "sdcb200_ipc_free": (_i32, [_vp]),
     "sdcb200_ipc_get_handle": (_i32, [_vp, _vp]),

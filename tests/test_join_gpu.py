@@ -110,6 +110,34 @@ def test_merge_frames_like_reference_tests():
         merge(df1, df2, how="cross", on="key1")
 
 
+@pytest.mark.parametrize("how", ["inner", "left", "right", "outer"])
+def test_join_ids_replace_row_numbers(how):
+    """sdcb200_join_ids: the caller's ids come out in place of local row numbers (-1 stays -1) on every path -- unique
+    build keys (mapping folded into the probe's last kernel), duplicate build keys, keys with no dense range."""
+    import torch
+    from sdc_b200.join import join_device
+    rng = np.random.default_rng(101)
+    cases = [(rng.integers(0, 60_000, 200_001, dtype=np.int64), rng.permutation(80_000)[:50_000].astype(np.int64)),   # unique, dense
+             (rng.integers(0, 5_000, 50_000, dtype=np.int64), rng.integers(0, 5_000, 20_000, dtype=np.int64)),        # duplicates
+             (rng.integers(0, 60_000, 100_000, dtype=np.int64) * 1_000_003, rng.permutation(80_000)[:50_000].astype(np.int64) * 1_000_003)]
+    for l, r in cases:
+        lid = rng.permutation(len(l)).astype(np.int64) + 10**12
+        rid = rng.permutation(len(r)).astype(np.int64) + 2 * 10**12
+        dl, dr = torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda()
+        for ordered in ((True, False) if how == "inner" else (True,)):
+            li, ri = join_device(dl, dr, how, ordered=ordered, left_ids=torch.from_numpy(lid).cuda(), right_ids=torch.from_numpy(rid).cuda())
+            pl, pr = join_device(dl, dr, how, ordered=ordered)
+            pl, pr = pl.cpu().numpy(), pr.cpu().numpy()
+            want_l = np.where(pl < 0, -1, lid[np.maximum(pl, 0)])
+            want_r = np.where(pr < 0, -1, rid[np.maximum(pr, 0)])
+            got = ojoin.canonical(li.cpu().numpy(), ri.cpu().numpy())
+            want = ojoin.canonical(want_l, want_r)
+            np.testing.assert_array_equal(got[0], want[0])
+            np.testing.assert_array_equal(got[1], want[1])
+        li, _ = join_device(dl, dr, how, ordered=True, left_ids=torch.from_numpy(lid).cuda())          # one side only
+        np.testing.assert_array_equal(np.sort(li.cpu().numpy()), np.sort(want_l))
+
+
 def test_c3_shape_row_count_and_properties():
     """BASELINE config C3 at 1/10 scale through the oracle, and at full size through invariants:
     unique build keys, every probe row matches once -> n_out == n_probe, ridx is the inverse permutation."""

@@ -1,1 +1,3 @@
-python -m pytest tests/test_rolling_gpu.py -x -q -m gpu > gpurun_out/r2b_pytest_rolling.log 2>&1; tail -15 gpurun_out/r2b_pytest_rolling.log
+set -u
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dist_check.py > gpurun_out/r2f_dist_check_n2.log 2>&1; echo "dist_check rc=$?"; tail -2 gpurun_out/r2f_dist_check_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2f_bench_n2.json 2> gpurun_out/r2f_bench_n2.err; echo "bench2 rc=$?"
