@@ -405,12 +405,17 @@ constexpr int kSdThreads = 512;
 constexpr int kSdItems = kShTile / kSdThreads;      // 8
 constexpr int kSdWarps = kSdThreads / 32;           // 16
 
+constexpr int kSdStage = kShTile + 2 * kPeerMax;     // a run may start one slot late (see below)
+
 template <bool KEY_F64, bool MOD>
-__global__ void __launch_bounds__(kSdThreads) shuffle_send_kernel(SendArgs a, long long n, const unsigned* __restrict__ tile_off) {
-    __shared__ unsigned long long stage[kShTile];
+__global__ void __launch_bounds__(kSdThreads, 2) shuffle_send_kernel(SendArgs a, long long n, const unsigned* __restrict__ tile_off,
+                                                                  int bulk) {
+    // two staging buffers: column c + 1 is staged while the bulk stores of column c still read the other one
+    extern __shared__ __align__(128) unsigned long long stage_all[];
     __shared__ unsigned wcnt[kSdWarps][kPeerMax];      // running count of (warp, destination); the warp total at the end
     __shared__ unsigned wbase[kSdWarps][kPeerMax];
-    __shared__ unsigned stage_off[kPeerMax + 1];
+    __shared__ unsigned stage_off[kPeerMax + 1];       // first staged slot of destination d
+    __shared__ unsigned stage_cnt[kPeerMax];
     __shared__ long long run_dst[kPeerMax];            // arena row of the first staged row of destination d
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const long long tile_base = (long long)blockIdx.x * kShTile;
@@ -467,8 +472,13 @@ __global__ void __launch_bounds__(kSdThreads) shuffle_send_kernel(SendArgs a, lo
         for (int d = 0; d < kPeerMax; ++d) {
             unsigned t = 0;
             for (int x = 0; x < kSdWarps; ++x) t += wcnt[x][d];
+            const long long dst = d < a.rt.nparts ? a.dst_off[d] + (long long)tile_off[(size_t)blockIdx.x * kPeerMax + d] : 0;
+            // bulk stores want source and destination 16-byte aligned together: a run starts on a staged slot of the
+            // same parity as its first arena row (the arena's row capacity is even, so every column agrees)
+            if (bulk && ((acc ^ (unsigned)dst) & 1u)) ++acc;
             stage_off[d] = acc;
-            run_dst[d] = d < a.rt.nparts ? a.dst_off[d] + (long long)tile_off[(size_t)blockIdx.x * kPeerMax + d] : 0;
+            stage_cnt[d] = t;
+            run_dst[d] = dst;
             acc += t;
         }
         stage_off[kPeerMax] = acc;
@@ -478,6 +488,11 @@ __global__ void __launch_bounds__(kSdThreads) shuffle_send_kernel(SendArgs a, lo
     for (int i = 0; i < kSdItems; ++i)
         if (dd[i] != 0xff) slot[i] = (unsigned short)(stage_off[dd[i]] + wbase[w][dd[i]] + slot[i]);
     for (int c = 0; c < a.ncols; ++c) {
+        unsigned long long* stage = stage_all + (size_t)(c & 1) * kSdStage;
+        if (bulk && c >= 2) {
+            if (lane == 0 && w < kPeerMax) tma_store_wait_read();      // column c - 2 has left this buffer
+            __syncthreads();
+        }
 #pragma unroll
         for (int i = 0; i < kSdItems; ++i)
             if (dd[i] != 0xff) stage[slot[i]] = cur[i];
@@ -498,15 +513,39 @@ __global__ void __launch_bounds__(kSdThreads) shuffle_send_kernel(SendArgs a, lo
                 }
             }
         }
-        __syncthreads();
+        if (bulk) {
+            // ONE bulk (TMA) store per destination run: the copy engine moves each ~4 KB run to the peer's arena over
+            // NVLink in large packets; an odd first / last row goes by a plain store
+            fence_proxy_async();
+            __syncthreads();
+            if (lane == 0 && w < kPeerMax) {
+                const int d = w;
+                const unsigned cnt = stage_cnt[d];
+                if (cnt) {
+                    const unsigned lo = stage_off[d];
+                    unsigned long long* dst = a.peer[d] + ((long long)c * a.cap + run_dst[d]);
+                    const unsigned head = (unsigned)(run_dst[d] & 1);          // == lo & 1
+                    if (head) dst[0] = stage[lo];
+                    const unsigned body = (cnt - head) & ~1u;
+                    if (body) {
+                        tma_store_1d(dst + head, stage + lo + head, body * 8u);
+                        tma_store_commit();
+                    }
+                    if (head + body < cnt) dst[cnt - 1] = stage[lo + cnt - 1];
+                }
+            }
+        } else {
+            __syncthreads();
 #pragma unroll
-        for (int d = 0; d < kPeerMax; ++d) {
-            const int lo = (int)stage_off[d], hi = (int)stage_off[d + 1];
-            unsigned long long* dst = a.peer[d] + ((long long)c * a.cap + run_dst[d] - lo);
-            for (int q = lo + tid; q < hi; q += kSdThreads) dst[q] = stage[q];
+            for (int d = 0; d < kPeerMax; ++d) {
+                const int lo = (int)stage_off[d], hi = lo + (int)stage_cnt[d];
+                unsigned long long* dst = a.peer[d] + ((long long)c * a.cap + run_dst[d] - lo);
+                for (int q = lo + tid; q < hi; q += kSdThreads) dst[q] = stage[q];
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
+    if (bulk && lane == 0 && w < kPeerMax) tma_store_wait_all();
 }
 }}
 
@@ -578,12 +617,16 @@ extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_
     a.iota_base = iota_base;
     const int64_t ntiles = ceil_div(n, kShTile);
     cudaStream_t s = (cudaStream_t)stream;
-    if (route == SDCB200_ROUTE_MOD)
-        shuffle_send_kernel<false, true><<<(unsigned)ntiles, kSdThreads, 0, s>>>(a, n, tile_off);
-    else if (key_dtype == SDCB200_F64)
-        shuffle_send_kernel<true, false><<<(unsigned)ntiles, kSdThreads, 0, s>>>(a, n, tile_off);
-    else
-        shuffle_send_kernel<false, false><<<(unsigned)ntiles, kSdThreads, 0, s>>>(a, n, tile_off);
+    // bulk (TMA) stores need 16-byte aligned arenas with an even row capacity (PeerShuffle allocates them so);
+    // SDCB200_SHUFFLE_BULK=0 keeps the plain stores (A/B measurements)
+    static const int bulk_env = [] { const char* e = getenv("SDCB200_SHUFFLE_BULK"); return e ? atoi(e) : 1; }();
+    int bulk = bulk_env && (arena_rows & 1) == 0;
+    for (int d = 0; d < nparts; ++d) if (reinterpret_cast<uintptr_t>(peer_bases[d]) & 15) bulk = 0;
+    const size_t smem = (size_t)2 * kSdStage * 8;
+    auto kern = route == SDCB200_ROUTE_MOD ? shuffle_send_kernel<false, true>
+                : key_dtype == SDCB200_F64 ? shuffle_send_kernel<true, false> : shuffle_send_kernel<false, false>;
+    SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+    kern<<<(unsigned)ntiles, kSdThreads, smem, s>>>(a, n, tile_off, bulk);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
 }

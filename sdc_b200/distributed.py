@@ -222,7 +222,7 @@ class PeerShuffle:
         self.rank, self.P = world(group)
         if self.P > 8:
             raise ValueError("PeerShuffle: at most 8 ranks (one NVSwitch node)")
-        self.cap, self.max_cols, self.narenas = int(capacity_rows), int(max_cols), int(narenas)
+        self.cap, self.max_cols, self.narenas = (int(capacity_rows) + 1) & ~1, int(max_cols), int(narenas)   # even: bulk stores
         self.lib = native.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.mine, self.peers, self.turn = [], [], 0

@@ -1,3 +1,4 @@
 set -u
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dist_check.py > gpurun_out/r2f_dist_check_n2.log 2>&1; echo "dist_check rc=$?"; tail -2 gpurun_out/r2f_dist_check_n2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2f_bench_n2.json 2> gpurun_out/r2f_bench_n2.err; echo "bench2 rc=$?"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dist_check.py > gpurun_out/r2h_dist_check_n2.log 2>&1; echo "dist_check rc=$?"; tail -2 gpurun_out/r2h_dist_check_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2h_bench_n2.json 2> gpurun_out/r2h_bench_n2.err; echo "bench2 rc=$?"
+SDCB200_SHUFFLE_BULK=0 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29613 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2h_bench_n2_nobulk.json 2> gpurun_out/r2h_bench_n2_nobulk.err; echo "bench2 rc=$?"

@@ -16,7 +16,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 g = torch.Generator(device="cuda").manual_seed(5)
 keys = torch.randint(0, 100_000_000, (n,), device="cuda", generator=g)
 vals = torch.rand(n, device="cuda", dtype=torch.float64, generator=g)
-cap = n // P * 5 // 4 + 4096
+cap = (n // P * 5 // 4 + 4096) & ~1
 arenas = [torch.empty(2 * cap, dtype=torch.int64, device="cuda") for _ in range(P)]
 counts = torch.empty(P, dtype=torch.int64, device="cuda")
 tile_off = torch.empty(-(-n // 4096) * 8, dtype=torch.int32, device="cuda")
