@@ -226,6 +226,7 @@ class PeerShuffle:
         self.lib = native.load()
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.mine, self.peers, self.turn = [], [], 0
+        self._tok = None
         self._views = weakref.WeakSet()
         nbytes = self.cap * self.max_cols * 8
         for _ in range(self.narenas):
@@ -337,8 +338,12 @@ class PeerShuffle:
             native.check(self.lib.sdcb200_shuffle_send(plan.kcode, plan.route, len(allc), cptr, int(iota_col), int(iota_base), n, P,
                                                        plan.tile_off.data_ptr(), offc, basec, self.cap,
                                                        native.current_stream_ptr()))
-        # every rank's stores have landed once every rank's kernel is done: a collective on the same stream
-        dist.barrier(group=self.group, device_ids=[self.dev.index])
+        # every rank's stores have landed once every rank's kernel is done: a collective on the same stream (a one-word
+        # all-reduce, not dist.barrier -- the barrier also blocks the HOST until the stream has drained, and every
+        # launch behind it then pays its latency in the open)
+        if self._tok is None:
+            self._tok = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        dist.all_reduce(self._tok, group=self.group)
         out = []
         for c, col in enumerate(allc):
             dt = torch.int64 if c == iota_col else col.dtype
@@ -451,7 +456,7 @@ def shuffle_many(sides, group=None, peer="auto", route="auto"):
         if route_try == ROUTE_MOD and not int_keys:
             raise TypeError("ROUTE_MOD needs int64 keys")
     if P == 1:
-        return ROUTE_HASH, [(k, [torch.arange(io[1], io[1] + k.shape[0], dtype=torch.int64, device=k.device)
+        return ROUTE_HASH, [(k, [torch.arange(io[1] or 0, (io[1] or 0) + k.shape[0], dtype=torch.int64, device=k.device)
                                  if io is not None and i == io[0] else c for i, c in enumerate(cols)]) for k, cols, io in sides]
     ctx = None
     if all(k.is_cuda for k, _, _ in sides):
@@ -460,6 +465,13 @@ def shuffle_many(sides, group=None, peer="auto", route="auto"):
         elif peer is not None:
             ctx = peer
     if ctx is None:
+        if any(io is not None and io[1] is None for _, _, io in sides):
+            fixed = []
+            for k, cols, io in sides:
+                if io is not None and io[1] is None:
+                    io = (io[0], sum(allgather_sizes(k.shape[0], k.device, group)[:rank]))
+                fixed.append((k, cols, io))
+            sides = fixed
         if route == "auto" and route_try == ROUTE_MOD:
             # the balance test needs the counts of every rank: one partition pass + all-gather, only for the first side
             _, counts = hash_partition_device(sides[0][0], P, ROUTE_MOD)
@@ -482,7 +494,11 @@ def shuffle_many(sides, group=None, peer="auto", route="auto"):
             return route_try, [_nccl_shuffle(k, cols, route_try, group, io) for k, cols, io in sides]
     out = []
     for pl, (k, cols, io) in zip(plans, sides):
-        out.append(ctx.send(pl, cols, -1 if io is None else io[0] + 1, 0 if io is None else io[1]))
+        base = 0
+        if io is not None:
+            # base None: global row ids, rank-major -- the rows of lower ranks are the row sums of the count matrix
+            base = int(pl.matrix[:rank].sum()) if io[1] is None else io[1]
+        out.append(ctx.send(pl, cols, -1 if io is None else io[0] + 1, base))
     return route_try, out
 
 
@@ -646,6 +662,11 @@ def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"
     if P == 1:
         return join_device(left_keys, right_keys, how)
     dev = left_keys.device
+    if mode == "shuffle":
+        # the global row ids' bases come out of the shuffle's own count matrices: no size exchange of its own
+        _, out = shuffle_many([(left_keys, [None], (0, None)), (right_keys, [None], (0, None))], group, peer, route)
+        (lk2, (lid2,)), (rk2, (rid2,)) = out
+        return join_device(lk2, rk2, how, left_ids=lid2, right_ids=rid2)
     sizes = allgather_sizes(left_keys.shape[0] * (1 << 32) + right_keys.shape[0], dev, group)   # both lengths in one word
     nl_all, nr_all = [s >> 32 for s in sizes], [s & 0xffffffff for s in sizes]
     loff, roff = sum(nl_all[:rank]), sum(nr_all[:rank])
