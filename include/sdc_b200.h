@@ -355,6 +355,17 @@ int32_t sdcb200_shuffle_plan(int32_t key_dtype, int32_t route, const void* keys,
 int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_t ncols, const void* const* cols, int32_t iota_col,
                              int64_t iota_base, int64_t n, int32_t nparts, const uint32_t* tile_off,
                              const int64_t* dst_off, void* const* peer_bases, int64_t arena_rows, void* stream);
+/* Range routing (sample sort: Series.sort_values over row-sharded columns): destination = the number of
+ * `splitters` (host array of nparts - 1 ascending ORDERED IMAGES: int64 key ^ 2^63; float64 bits with the sign bit set
+ * for non-negative values and all bits flipped for negative ones, -0.0 as +0.0) that are <= the key's image, reversed
+ * when `descending`; NaN keys all go to rank nan_dest.  Keys travel unchanged; everything else as in plan / send.  */
+int32_t sdcb200_shuffle_plan_range(int32_t key_dtype, const uint64_t* splitters, int32_t descending, int32_t nan_dest,
+                                   const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off, int64_t* counts_out,
+                                   void* stream);
+int32_t sdcb200_shuffle_send_range(int32_t key_dtype, const uint64_t* splitters, int32_t descending, int32_t nan_dest,
+                                   int32_t ncols, const void* const* cols, int32_t iota_col, int64_t iota_base, int64_t n,
+                                   int32_t nparts, const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
+                                   int64_t arena_rows, void* stream);
 /* row-wise helpers of the distributed pass (device pointers):
  *   affine_i64   x[i] = x[i] * mul + add, in place; keep_negative != 0 leaves rows < 0 alone (the -1 "no partner"
  *                marker).  Shipped keys back to keys (mul = nparts, add = rank), local rows to global rows (add = offset).

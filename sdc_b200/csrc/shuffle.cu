@@ -284,12 +284,34 @@ constexpr int kShWarps = kShThreads / 32;
 // dense key range [lo, hi] arrives as the dense range [lo / P, hi / P] on every rank -- the local join / groupby
 // keep their direct-addressed tables after the shuffle (hashing the keys destroys exactly that).  The owner maps
 // a shipped key back with key = q * P + rank.  lg = log2(P) when P is a power of two, else -1.
+// ROUTE_RANGE (sample sort, sort_values across GPUs): destination = the number of splitters <= the key's ordered image
+// (order-preserving unsigned image, -0.0 == +0.0), reversed for a descending sort; NaN keys all go to one rank (the last
+// one, or the first for na_position='first').  The key travels unchanged.
 struct Route {
     int nparts, lg;
+    int desc, nan_dest;                          // ROUTE_RANGE
+    unsigned long long split[7];                 // ROUTE_RANGE: nparts - 1 ascending ordered images
 };
-template <bool KEY_F64, bool MOD>
+enum { MODE_HASH = 0, MODE_MOD = 1, MODE_RANGE = 2 };
+template <bool KEY_F64, int MODE>
 __device__ __forceinline__ unsigned shuffle_dest(unsigned long long b, const Route& rt, unsigned long long& shipped) {
-    if (MOD) {
+    if (MODE == MODE_RANGE) {
+        shipped = b;
+        unsigned long long c;
+        if (KEY_F64) {
+            const unsigned long long mag = b & 0x7fffffffffffffffull;
+            if (mag > 0x7ff0000000000000ull) return (unsigned)rt.nan_dest;
+            if (mag == 0) b = 0;
+            c = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+        } else {
+            c = b ^ 0x8000000000000000ull;
+        }
+        int d = 0;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) d += (i < rt.nparts - 1 && c >= rt.split[i]) ? 1 : 0;
+        return (unsigned)(rt.desc ? rt.nparts - 1 - d : d);
+    }
+    if (MODE == MODE_MOD) {
         const long long k = (long long)b;
         if (rt.lg >= 0) {
             shipped = (unsigned long long)(k >> rt.lg);
@@ -313,7 +335,7 @@ __device__ __forceinline__ unsigned shuffle_dest(unsigned long long b, const Rou
 // thread), the fields are widened to 16 bits for the warp reduction (<= 512 per warp) and meet in shared counters: four
 // instructions per row next to the load -- the earlier ballot-per-destination loop (8 votes per row) ran the count pass
 // at 0.47 ms per 125 M rows, a third of the HBM rate.
-template <bool KEY_F64, bool MOD>
+template <bool KEY_F64, int MODE>
 __global__ void __launch_bounds__(kShThreads) shuffle_count_kernel(const unsigned long long* __restrict__ keys, long long n,
                                                                    Route rt, unsigned* __restrict__ tile_counts,
                                                                    unsigned long long* __restrict__ counts) {
@@ -333,7 +355,7 @@ __global__ void __launch_bounds__(kShThreads) shuffle_count_kernel(const unsigne
     for (int i = 0; i < kShItems; ++i) {
         const long long r = base + i * 32 + lane;
         unsigned long long unused;
-        const unsigned d = shuffle_dest<KEY_F64, MOD>(k[i], rt, unused);
+        const unsigned d = shuffle_dest<KEY_F64, MODE>(k[i], rt, unused);
         if (r < n) packed += 1ull << (8 * d);
     }
     unsigned long long even = packed & 0x00ff00ff00ff00ffull, odd = (packed >> 8) & 0x00ff00ff00ff00ffull;
@@ -407,7 +429,7 @@ constexpr int kSdWarps = kSdThreads / 32;           // 16
 
 constexpr int kSdStage = kShTile + 2 * kPeerMax;     // a run may start one slot late (see below)
 
-template <bool KEY_F64, bool MOD>
+template <bool KEY_F64, int MODE>
 __global__ void __launch_bounds__(kSdThreads, 2) shuffle_send_kernel(SendArgs a, long long n, const unsigned* __restrict__ tile_off,
                                                                   int bulk) {
     // two staging buffers: column c + 1 is staged while the bulk stores of column c still read the other one
@@ -444,7 +466,7 @@ __global__ void __launch_bounds__(kSdThreads, 2) shuffle_send_kernel(SendArgs a,
         const long long r = base + i * 32 + lane;
         const bool valid = r < n;
         unsigned long long shipped = 0ull;
-        const unsigned d = shuffle_dest<KEY_F64, MOD>(cur[i], a.rt, shipped) & (kPeerMax - 1);
+        const unsigned d = shuffle_dest<KEY_F64, MODE>(cur[i], a.rt, shipped) & (kPeerMax - 1);
         cur[i] = shipped;
         dd[i] = valid ? (unsigned char)d : (unsigned char)0xff;
         unsigned peers = __ballot_sync(0xffffffffu, valid);
@@ -560,14 +582,28 @@ int32_t make_route(int32_t key_dtype, int32_t route, int32_t nparts, Route* rt) 
 }
 }}
 
-extern "C" int32_t sdcb200_shuffle_plan(int32_t key_dtype, int32_t route, const void* keys, int64_t n, int32_t nparts,
-                                        uint32_t* tile_off, int64_t* counts_out, void* stream) {
-    cudaStream_t s = (cudaStream_t)stream;
+namespace sdcb200 { namespace {
+int32_t make_range_route(int32_t key_dtype, int32_t nparts, const uint64_t* splitters, int32_t descending, int32_t nan_dest, Route* rt) {
+    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax && (nparts == 1 || splitters != nullptr), "nparts / splitters");
+    SDC_ARG_CHECK(nan_dest >= 0 && nan_dest < nparts, "nan_dest");
+    memset(rt, 0, sizeof(*rt));
+    rt->nparts = nparts;
+    rt->lg = -1;
+    rt->desc = descending ? 1 : 0;
+    rt->nan_dest = nan_dest;
+    for (int i = 0; i + 1 < nparts; ++i) {
+        rt->split[i] = splitters[i];
+        SDC_ARG_CHECK(i == 0 || splitters[i] >= splitters[i - 1], "splitters must ascend");
+    }
+    (void)key_dtype;
+    return SDCB200_OK;
+}
+
+int32_t plan_impl(int32_t key_dtype, int mode, const Route& rt, const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off,
+                  int64_t* counts_out, cudaStream_t s) {
     SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
     SDC_ARG_CHECK(n >= 0 && n < 0xffffffffll && nparts >= 1 && nparts <= kPeerMax, "n (< 2^32) / nparts (<= 8)");
     SDC_ARG_CHECK(counts_out != nullptr && (n == 0 || (keys && tile_off)), "null pointer");
-    Route rt;
-    SDC_TRY(make_route(key_dtype, route, nparts, &rt));
     SDC_CUDA_TRY(cudaMemsetAsync(counts_out, 0, (size_t)nparts * 8, s));
     if (n == 0) return SDCB200_OK;
     const int64_t ntiles = ceil_div(n, kShTile);
@@ -575,23 +611,42 @@ extern "C" int32_t sdcb200_shuffle_plan(int32_t key_dtype, int32_t route, const 
     Scratch cnt8;                                   // the kernels always keep kPeerMax counters
     SDC_TRY(cnt8.alloc(kPeerMax * 8, s));
     SDC_CUDA_TRY(cudaMemsetAsync(cnt8.p, 0, kPeerMax * 8, s));
-    if (route == SDCB200_ROUTE_MOD)
-        shuffle_count_kernel<false, true><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, cnt8.as<unsigned long long>());
-    else if (key_dtype == SDCB200_F64)
-        shuffle_count_kernel<true, false><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, cnt8.as<unsigned long long>());
-    else
-        shuffle_count_kernel<false, false><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, cnt8.as<unsigned long long>());
+    unsigned long long* c8 = cnt8.as<unsigned long long>();
+    const bool f = key_dtype == SDCB200_F64;
+    if (mode == MODE_MOD) shuffle_count_kernel<false, MODE_MOD><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, c8);
+    else if (mode == MODE_RANGE && f) shuffle_count_kernel<true, MODE_RANGE><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, c8);
+    else if (mode == MODE_RANGE) shuffle_count_kernel<false, MODE_RANGE><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, c8);
+    else if (f) shuffle_count_kernel<true, MODE_HASH><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, c8);
+    else shuffle_count_kernel<false, MODE_HASH><<<(unsigned)ntiles, kShThreads, 0, s>>>(k, n, rt, tile_off, c8);
     SDC_CHECK_LAUNCH();
     shuffle_tile_scan<<<kPeerMax, 1024, 0, s>>>(tile_off, ntiles);
     SDC_CHECK_LAUNCH();
     SDC_CUDA_TRY(cudaMemcpyAsync(counts_out, cnt8.p, (size_t)nparts * 8, cudaMemcpyDeviceToDevice, s));
     return SDCB200_OK;
 }
+}}
 
-extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_t ncols, const void* const* cols,
-                                        int32_t iota_col, int64_t iota_base, int64_t n, int32_t nparts,
-                                        const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
-                                        int64_t arena_rows, void* stream) {
+extern "C" int32_t sdcb200_shuffle_plan(int32_t key_dtype, int32_t route, const void* keys, int64_t n, int32_t nparts,
+                                        uint32_t* tile_off, int64_t* counts_out, void* stream) {
+    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax, "nparts (<= 8)");
+    Route rt;
+    memset(&rt, 0, sizeof(rt));
+    SDC_TRY(make_route(key_dtype, route, nparts, &rt));
+    return plan_impl(key_dtype, route == SDCB200_ROUTE_MOD ? MODE_MOD : MODE_HASH, rt, keys, n, nparts, tile_off, counts_out, (cudaStream_t)stream);
+}
+
+extern "C" int32_t sdcb200_shuffle_plan_range(int32_t key_dtype, const uint64_t* splitters, int32_t descending, int32_t nan_dest,
+                                              const void* keys, int64_t n, int32_t nparts, uint32_t* tile_off, int64_t* counts_out,
+                                              void* stream) {
+    Route rt;
+    SDC_TRY(make_range_route(key_dtype, nparts, splitters, descending, nan_dest, &rt));
+    return plan_impl(key_dtype, MODE_RANGE, rt, keys, n, nparts, tile_off, counts_out, (cudaStream_t)stream);
+}
+
+namespace sdcb200 { namespace {
+int32_t send_impl(int32_t key_dtype, int mode, const Route& rt, int32_t ncols, const void* const* cols, int32_t iota_col,
+                  int64_t iota_base, int64_t n, int32_t nparts, const uint32_t* tile_off, const int64_t* dst_off,
+                  void* const* peer_bases, int64_t arena_rows, void* stream) {
     SDC_ARG_CHECK(key_dtype == SDCB200_I64 || key_dtype == SDCB200_F64, "key dtype must be I64 or F64");
     SDC_ARG_CHECK(ncols >= 1 && ncols <= kMaxCols, "ncols");
     SDC_ARG_CHECK(iota_col == -1 || (iota_col >= 1 && iota_col < ncols), "iota_col must be -1 or a payload column");
@@ -601,7 +656,7 @@ extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_
     SDC_ARG_CHECK(tile_off != nullptr, "null tile offsets");
     SendArgs a;
     memset(&a, 0, sizeof(a));
-    SDC_TRY(make_route(key_dtype, route, nparts, &a.rt));
+    a.rt = rt;
     for (int c = 0; c < ncols; ++c) {
         SDC_ARG_CHECK(c == iota_col || cols[c] != nullptr, "null column");
         a.cols[c] = reinterpret_cast<const unsigned long long*>(cols[c]);
@@ -623,12 +678,37 @@ extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_
     int bulk = bulk_env && (arena_rows & 1) == 0;
     for (int d = 0; d < nparts; ++d) if (reinterpret_cast<uintptr_t>(peer_bases[d]) & 15) bulk = 0;
     const size_t smem = (size_t)2 * kSdStage * 8;
-    auto kern = route == SDCB200_ROUTE_MOD ? shuffle_send_kernel<false, true>
-                : key_dtype == SDCB200_F64 ? shuffle_send_kernel<true, false> : shuffle_send_kernel<false, false>;
+    const bool f = key_dtype == SDCB200_F64;
+    auto kern = mode == MODE_MOD ? shuffle_send_kernel<false, MODE_MOD>
+                : mode == MODE_RANGE ? (f ? shuffle_send_kernel<true, MODE_RANGE> : shuffle_send_kernel<false, MODE_RANGE>)
+                : (f ? shuffle_send_kernel<true, MODE_HASH> : shuffle_send_kernel<false, MODE_HASH>);
     SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
     kern<<<(unsigned)ntiles, kSdThreads, smem, s>>>(a, n, tile_off, bulk);
     SDC_CHECK_LAUNCH();
     return SDCB200_OK;
+}
+}}
+
+extern "C" int32_t sdcb200_shuffle_send(int32_t key_dtype, int32_t route, int32_t ncols, const void* const* cols,
+                                        int32_t iota_col, int64_t iota_base, int64_t n, int32_t nparts,
+                                        const uint32_t* tile_off, const int64_t* dst_off, void* const* peer_bases,
+                                        int64_t arena_rows, void* stream) {
+    SDC_ARG_CHECK(nparts >= 1 && nparts <= kPeerMax, "nparts (<= 8 GPUs of one node)");
+    Route rt;
+    memset(&rt, 0, sizeof(rt));
+    SDC_TRY(make_route(key_dtype, route, nparts, &rt));
+    return send_impl(key_dtype, route == SDCB200_ROUTE_MOD ? MODE_MOD : MODE_HASH, rt, ncols, cols, iota_col, iota_base, n, nparts,
+                     tile_off, dst_off, peer_bases, arena_rows, stream);
+}
+
+extern "C" int32_t sdcb200_shuffle_send_range(int32_t key_dtype, const uint64_t* splitters, int32_t descending, int32_t nan_dest,
+                                              int32_t ncols, const void* const* cols, int32_t iota_col, int64_t iota_base, int64_t n,
+                                              int32_t nparts, const uint32_t* tile_off, const int64_t* dst_off,
+                                              void* const* peer_bases, int64_t arena_rows, void* stream) {
+    Route rt;
+    SDC_TRY(make_range_route(key_dtype, nparts, splitters, descending, nan_dest, &rt));
+    return send_impl(key_dtype, MODE_RANGE, rt, ncols, cols, iota_col, iota_base, n, nparts, tile_off, dst_off, peer_bases,
+                     arena_rows, stream);
 }
 
 // ------------------------------------------------------------------ small row-wise helpers of the distributed pass

@@ -21,7 +21,7 @@ import weakref
 
 from . import native
 
-ROUTE_HASH, ROUTE_MOD = native.ROUTE_HASH, native.ROUTE_MOD
+ROUTE_HASH, ROUTE_MOD, ROUTE_RANGE = native.ROUTE_HASH, native.ROUTE_MOD, native.ROUTE_RANGE
 
 
 def _torch():
@@ -201,7 +201,7 @@ class ArenaOverflow(native.NativeError):
 
 class _Plan:
     """Counting pass of one key column: per-tile offsets per destination (device) + per-destination totals."""
-    __slots__ = ("keys", "kcode", "route", "tile_off", "counts", "matrix")
+    __slots__ = ("keys", "kcode", "route", "tile_off", "counts", "matrix", "range")
 
 
 class PeerShuffle:
@@ -273,7 +273,7 @@ class PeerShuffle:
         return True
 
     # -- the three steps
-    def plan(self, keys, route=ROUTE_HASH):
+    def plan(self, keys, route=ROUTE_HASH, rng=None):
         torch = _torch()
         kname = str(keys.dtype).replace("torch.", "")
         if kname not in ("int64", "float64"):
@@ -287,9 +287,16 @@ class PeerShuffle:
         pl.keys, pl.kcode, pl.route, pl.matrix = keys, native.DTYPE_CODES[kname], int(route), None
         pl.counts = torch.empty(self.P, dtype=torch.int64, device=keys.device)
         pl.tile_off = torch.empty(max(1, -(-n // 4096)) * 8, dtype=torch.int32, device=keys.device)
+        pl.range = rng                      # ROUTE_RANGE: (splitters uint64[P - 1] (host), descending, nan_dest)
         with torch.cuda.device(keys.device):
-            native.check(self.lib.sdcb200_shuffle_plan(pl.kcode, pl.route, keys.data_ptr(), n, self.P, pl.tile_off.data_ptr(),
-                                                       pl.counts.data_ptr(), native.current_stream_ptr()))
+            if route == ROUTE_RANGE:
+                sp = (ct.c_uint64 * max(1, self.P - 1))(*[int(x) for x in rng[0]])
+                native.check(self.lib.sdcb200_shuffle_plan_range(pl.kcode, sp, int(rng[1]), int(rng[2]), keys.data_ptr(), n, self.P,
+                                                                 pl.tile_off.data_ptr(), pl.counts.data_ptr(),
+                                                                 native.current_stream_ptr()))
+            else:
+                native.check(self.lib.sdcb200_shuffle_plan(pl.kcode, pl.route, keys.data_ptr(), n, self.P, pl.tile_off.data_ptr(),
+                                                           pl.counts.data_ptr(), native.current_stream_ptr()))
         return pl
 
     def exchange(self, plans):
@@ -335,9 +342,15 @@ class PeerShuffle:
         basec = (ct.c_void_p * P)(*self.peers[a])
         dev = plan.keys.device
         with torch.cuda.device(dev):
-            native.check(self.lib.sdcb200_shuffle_send(plan.kcode, plan.route, len(allc), cptr, int(iota_col), int(iota_base), n, P,
-                                                       plan.tile_off.data_ptr(), offc, basec, self.cap,
-                                                       native.current_stream_ptr()))
+            if plan.route == ROUTE_RANGE:
+                sp = (ct.c_uint64 * max(1, P - 1))(*[int(x) for x in plan.range[0]])
+                native.check(self.lib.sdcb200_shuffle_send_range(plan.kcode, sp, int(plan.range[1]), int(plan.range[2]), len(allc), cptr,
+                                                                 int(iota_col), int(iota_base), n, P, plan.tile_off.data_ptr(), offc,
+                                                                 basec, self.cap, native.current_stream_ptr()))
+            else:
+                native.check(self.lib.sdcb200_shuffle_send(plan.kcode, plan.route, len(allc), cptr, int(iota_col), int(iota_base), n, P,
+                                                           plan.tile_off.data_ptr(), offc, basec, self.cap,
+                                                           native.current_stream_ptr()))
         # every rank's stores have landed once every rank's kernel is done: a collective on the same stream (a one-word
         # all-reduce, not dist.barrier -- the barrier also blocks the HOST until the stream has drained, and every
         # launch behind it then pays its latency in the open)
@@ -685,6 +698,93 @@ def join_distributed(left_keys, right_keys, how="inner", group=None, mode="auto"
     (lk2, (lid2,)), (rk2, (rid2,)) = out
     # the global row ids that travelled with the rows replace the local row numbers inside the join's last kernel
     return join_device(lk2, rk2, how, left_ids=lid2, right_ids=rid2)
+
+
+# ------------------------------------------------------------------ sort_values across GPUs (sample sort)
+def ordered_image(values):
+    """Order-preserving uint64 image of an int64 / float64 NumPy array (the library's canonical sort key: int64 ^ 2^63;
+    float64 with -0.0 as +0.0, the sign bit set for non-negative values and every bit flipped for negative ones).
+    NaN has no image here -- callers drop NaNs first."""
+    import numpy as np
+    v = np.ascontiguousarray(values)
+    if v.dtype == np.int64:
+        return v.view(np.uint64) ^ np.uint64(1 << 63)
+    if v.dtype != np.float64:
+        raise TypeError("ordered_image: int64 / float64 only")
+    b = (v + 0.0).view(np.uint64)                    # -0.0 + 0.0 = +0.0
+    neg = (b >> np.uint64(63)) != 0
+    return np.where(neg, ~b, b | np.uint64(1 << 63))
+
+
+def sort_values_distributed(keys, ascending=True, na_position="last", group=None, payload=(), samples_per_rank=512):
+    """Series.sort_values over a row-sharded column (sample sort).  Every rank ends with one contiguous slice
+    of the global result: concatenating the ranks' outputs in rank order gives exactly the single-GPU stable
+    sort_values (sdc/datatypes/hpat_pandas_series_functions.py:3853-3959; NaN last in both directions unless
+    na_position='first', ties in original row order).
+
+      1. every rank contributes a strided sample of its non-NaN keys to ONE all-gather; the P - 1 splitters are picked
+         from the sorted samples (host work on P x samples_per_rank values);
+      2. rows travel to the rank that owns their key range through the peer-memory shuffle with range routing
+         (sdcb200_shuffle_plan_range / _send_range), carrying their global row number (generated in the send kernel) and
+         the payload columns; rows of one source arrive in source order and sources in rank order, so equal keys sit in
+         global row order on arrival;
+      3. a local STABLE argsort orders the slice (the library's onesweep), NaN block first or last.
+    keys: int64 / float64 CUDA tensor; payload: 8-byte CUDA columns of the same length.
+    -> (sorted keys, global row numbers of the sorted rows, [payload columns in sorted order])"""
+    import numpy as np
+    from .sort import gather_device, sort_values_indexer_device
+    torch, dist = _torch(), _dist()
+    rank, P = world(group)
+    if na_position not in ("last", "first"):
+        raise ValueError("Method sort_values(). Unsupported parameter. Given na_position != 'last', 'first'")
+    kname = str(keys.dtype).replace("torch.", "")
+    if kname not in ("int64", "float64"):
+        raise TypeError("sort_values_distributed: int64 / float64 keys")
+    n = keys.shape[0]
+    if P == 1:
+        idx = sort_values_indexer_device(keys, bool(ascending), na_position)
+        return gather_device(keys, idx), idx, [gather_device(c, idx) for c in payload]
+    # ---- 1. splitters
+    S = int(samples_per_rank)
+    take = min(S, n)
+    if take:
+        pos = torch.div(torch.arange(take, device=keys.device, dtype=torch.int64) * n, take, rounding_mode="floor")
+        smp = gather_device(keys, pos)
+    else:
+        smp = keys[:0]
+    buf = torch.zeros(S + 1, dtype=torch.int64, device=keys.device)
+    buf[:take] = smp.view(torch.int64)
+    buf[S] = take
+    allb = torch.empty(P * (S + 1), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(allb, buf, group=group)
+    hb = allb.cpu().numpy().reshape(P, S + 1)
+    vals = np.concatenate([hb[q, :hb[q, S]] for q in range(P)]).view(np.float64 if kname == "float64" else np.int64)
+    if kname == "float64":
+        vals = vals[~np.isnan(vals)]
+    img = np.sort(ordered_image(vals))
+    if img.size:
+        splitters = [int(img[min(img.size - 1, (i * img.size) // P)]) for i in range(1, P)]
+    else:
+        splitters = [0] * (P - 1)
+    nan_dest = 0 if na_position == "first" else P - 1
+    # ---- 2. range shuffle of (key, global row id, payload...)
+    ncols = 2 + len(payload)
+    ctx = auto_peer(group, n, ncols)
+    if ctx is None:
+        raise RuntimeError("sort_values_distributed needs the peer-memory transport (one NVLink node, NCCL backend)")
+    pl = ctx.plan(keys, ROUTE_RANGE, (splitters, 0 if ascending else 1, nan_dest))
+    ctx.exchange([pl])
+    need = ctx.max_recv(pl)
+    if need > ctx.cap:
+        ctx = auto_peer(group, 0, ncols, need)
+        pl = ctx.plan(keys, ROUTE_RANGE, (splitters, 0 if ascending else 1, nan_dest))
+        ctx.exchange([pl])
+    base = int(pl.matrix[:rank].sum())
+    k2, cols2 = ctx.send(pl, [None] + list(payload), 1, base)
+    ids2, pay2 = cols2[0], cols2[1:]
+    # ---- 3. local stable order
+    idx = sort_values_indexer_device(k2, bool(ascending), na_position)
+    return gather_device(k2, idx), gather_device(ids2, idx), [gather_device(c, idx) for c in pay2]
 
 
 # ------------------------------------------------------------------ string columns (str_arr) in the shuffle

@@ -20,7 +20,7 @@ ROLL_MOMENT_OPS = {"skew": 7, "kurt": 8, "cov": 9, "corr": 10}
 DTYPE_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5,
                "int64": 6, "uint64": 7, "float32": 8, "float64": 9}
 DTYPE_GID = 100     # SDCB200_GID: dense int64 group ids as a groupby key column
-ROUTE_HASH, ROUTE_MOD = 0, 1
+ROUTE_HASH, ROUTE_MOD, ROUTE_RANGE = 0, 1, 2
 
 _i32, _i64, _vp, _u8 = ct.c_int32, ct.c_int64, ct.c_void_p, ct.c_uint8
 
@@ -91,6 +91,9 @@ SIGNATURES = {
     "sdcb200_shuffle_plan": (_i32, [_i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
     "sdcb200_shuffle_send": (_i32, [_i32, _i32, _i32, ct.POINTER(_vp), _i32, _i64, _i64, _i32, _vp, ct.POINTER(_i64),
                                     ct.POINTER(_vp), _i64, _vp]),
+    "sdcb200_shuffle_plan_range": (_i32, [_i32, ct.POINTER(ct.c_uint64), _i32, _i32, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "sdcb200_shuffle_send_range": (_i32, [_i32, ct.POINTER(ct.c_uint64), _i32, _i32, _i32, ct.POINTER(_vp), _i32, _i64, _i64, _i32,
+                                          _vp, ct.POINTER(_i64), ct.POINTER(_vp), _i64, _vp]),
     "sdcb200_affine_i64": (_i32, [_vp, _i64, _i64, _i64, _i32, _vp]),
     "sdcb200_gather_ids": (_i32, [_vp, _vp, _i64, _vp, _vp]),
 }

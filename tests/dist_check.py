@@ -197,6 +197,28 @@ def main():
         for b in range(a + 1, P):
             assert not (per_rank[a] & per_rank[b]), "a string key landed on two ranks"
 
+    # sort_values across GPUs (sample sort with range routing): the ranks' slices, concatenated in rank order, are the
+    # single-GPU stable sort_values -- keys, original row numbers (ties in row order) and a payload column
+    from oracle import sort as osort
+    fk = rng.standard_normal(n).round(2)                       # many ties
+    fk[rng.integers(0, n, n // 50)] = np.nan
+    fk[rng.integers(0, n, 100)] = -0.0
+    fk[rng.integers(0, n, 100)] = np.inf
+    ik = rng.integers(-500, 500, n)
+    pay = rng.integers(0, 1 << 40, n)
+    for gkeys in (fk, ik, np.full(n, 7, dtype=np.int64), rng.standard_normal(n)):
+        for asc in (True, False):
+            for nap in ("last", "first"):
+                dk = torch.from_numpy(gkeys[s:e].copy()).to(dev)
+                sk, sid, (sp,) = D.sort_values_distributed(dk, asc, nap, payload=[torch.from_numpy(pay[s:e].copy()).to(dev)])
+                all_k, _ = D.allgather_ragged(sk)
+                all_i, _ = D.allgather_ragged(sid)
+                all_p, _ = D.allgather_ragged(sp)
+                want = osort.sort_values_indexer(gkeys, asc, nap)
+                np.testing.assert_array_equal(all_i.cpu().numpy(), want, err_msg="sort_values rows asc=%s na=%s" % (asc, nap))
+                np.testing.assert_array_equal(all_k.cpu().numpy(), gkeys[want])
+                np.testing.assert_array_equal(all_p.cpu().numpy(), pay[want])
+
     peer.close()
     dist.barrier()
     if rank == 0:

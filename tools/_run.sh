@@ -1,8 +1,3 @@
 set -u
-python -m pytest tests/test_rolling_gpu.py -x -q -m gpu > gpurun_out/r2i_pytest_rolling.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/r2i_pytest_rolling.log
-python tools/bench_ops.py rolling --reps 7 > gpurun_out/r2i_bench_ops_rolling.jsonl 2> gpurun_out/r2i_bench_ops.err; echo "ops rc=$?"
-python - <<'PY'
-import json
-for l in open('gpurun_out/r2i_bench_ops_rolling.jsonl'):
-    d=json.loads(l); print(d['case'], round(d['ms_median'],3), round(d['frac_of_measured_peak'],3))
-PY
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dist_check.py > gpurun_out/r2j_dist_check_n2.log 2>&1; echo "dist_check rc=$?"; tail -12 gpurun_out/r2j_dist_check_n2.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2j_bench_n2.json 2> gpurun_out/r2j_bench_n2.err; echo "bench2 rc=$?"
