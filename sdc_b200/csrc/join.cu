@@ -44,6 +44,7 @@ constexpr unsigned long long kEmptyKey = 0x7ff8dead0000beefull;   // never a can
 // tile counts up to this many are scanned by one CTA (one launch, ~4 us per 4096 counts: latency-bound); beyond it the
 // three-kernel device scan spreads the work over the SMs (48 829 counts of C3: 51 us with one CTA)
 constexpr int64_t kOneCtaScanMax = 8192;
+constexpr int kTileGroup = 256;               // tiles per group of the two-level hit counts of the two-pass inner probe
 constexpr int kJoinThreads = kScanThreads;         // 256
 constexpr int kItems = kScanItems;                 // 8 rows per thread in the probe tiles
 constexpr int kTile = kScanTile;                   // 2048 rows per CTA
@@ -513,7 +514,9 @@ template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_row1_kernel(const unsigned long long* __restrict__ keys, int64_t n,
                                                                          JTable t, const uint32_t* __restrict__ rid,
                                                                          uint32_t* __restrict__ row1_out,
-                                                                         unsigned long long* __restrict__ tile_counts, int vec) {
+                                                                         unsigned long long* __restrict__ tile_counts,
+                                                                         unsigned long long* __restrict__ group_counts,
+                                                                         unsigned long long* __restrict__ total, int vec) {
     __shared__ unsigned wcnt[kJoinThreads / 32];
     const uint64_t stream_pol = l2_policy_evict_first(), keep_pol = l2_policy_evict_last();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -547,17 +550,25 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_row1_kernel(const u
 #pragma unroll
         for (int w = 0; w < kJoinThreads / 32; ++w) tot += wcnt[w];
         tile_counts[blockIdx.x] = tot;
+        // two-level counts instead of a scan between the passes: a tile of pass 2 adds up the groups before its own
+        // and the tiles before it inside its group (kTileGroup tiles per group)
+        if (tot) {
+            atomicAdd(&group_counts[blockIdx.x / kTileGroup], (unsigned long long)tot);
+            atomicAdd(total, (unsigned long long)tot);
+        }
     }
 }
 
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(const uint32_t* __restrict__ row1_in, int64_t n,
-                                                                            const unsigned long long* __restrict__ tile_offs,
+                                                                            const unsigned long long* __restrict__ tile_counts,
+                                                                            const unsigned long long* __restrict__ group_counts,
                                                                             int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
                                                                             const uint32_t* __restrict__ lmap,
                                                                             const long long* __restrict__ lids,
                                                                             const long long* __restrict__ rids) {
     constexpr int kWarps = kJoinThreads / 32;
     __shared__ unsigned wcnt[kWarps];
+    __shared__ unsigned long long wpart[kWarps];
     const uint64_t stream_pol = l2_policy_evict_first();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -587,12 +598,25 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(cons
         if ((ba & bb) == 0xffffffffu && !(wtot & 1u)) fullmask |= 1u << j;
         wtot += __popc(ba) + __popc(bb);
     }
-    if (lane == 0) wcnt[warp] = wtot;
-    __syncthreads();
-    unsigned long long base = tile_offs[blockIdx.x];
+    // this tile's first output row: the groups before its own + the tiles before it inside its group (one or two
+    // loads per thread, issued before the ranking above would be ideal -- they hit L2 and overlap the ballots)
+    unsigned long long part = 0;
+    {
+        const int64_t g = (int64_t)blockIdx.x / kTileGroup;
+        for (int64_t i = threadIdx.x; i < g; i += kJoinThreads) part += group_counts[i];
+        const int64_t t = g * kTileGroup + threadIdx.x;
+        if (threadIdx.x < kTileGroup && t < (int64_t)blockIdx.x) part += tile_counts[t];
+    }
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w)
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if (lane == 0) { wcnt[warp] = wtot; wpart[warp] = part; }
+    __syncthreads();
+    unsigned long long base = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        base += wpart[w];
         if (w < warp) base += wcnt[w];
+    }
     const bool even = !(base & 1ull);
 #pragma unroll
     for (int j = 0; j < kItems / 2; ++j) {
@@ -856,27 +880,27 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
             // loops run better with the smaller tile (5.8 vs 5.4 ms), so only the dense table takes the big one
             static const int two_pass = [] { const char* e = getenv("SDCB200_JOIN_INNER"); return !(e && !strcmp(e, "chained")); }();
             if (two_pass) {
+                // no scan between the passes: pass 1 leaves per-tile counts, per-group counts (256 tiles) and the total;
+                // a tile of pass 2 adds up what lies before it (the three-kernel scan of 48 829 counts was 51 us of a
+                // 0.92 ms join under ncu)
                 Scratch row1, tcnt;
+                const int64_t ngroups = ceil_div(nt, kTileGroup);
                 SDC_TRY(row1.alloc((size_t)(nt * kTile) * 4, s));
-                SDC_TRY(tcnt.alloc((size_t)(nt + 1) * 8 + (size_t)(ceil_div(nt, kTile) + 1) * 8, s));
+                SDC_TRY(tcnt.alloc((size_t)(nt + ngroups + 2) * 8, s));
                 unsigned long long* tile_counts = tcnt.as<unsigned long long>();
-                unsigned long long* tsum_p = tile_counts + nt + 1;
+                unsigned long long* group_counts = tile_counts + nt;
+                unsigned long long* dtotal = group_counts + ngroups;
+                SDC_CUDA_TRY(cudaMemsetAsync(group_counts, 0, (size_t)(ngroups + 1) * 8, s));
                 probe_unique_row1_kernel<KEY_F64><<<(unsigned)nt, kJoinThreads, 0, s>>>(lk, nl, t, rid.as<uint32_t>(), row1.as<uint32_t>(),
-                                                                                        tile_counts, vec);
+                                                                                        tile_counts, group_counts, dtotal, vec);
                 SDC_CHECK_LAUNCH();
-                if (nt <= kOneCtaScanMax) {
-                    scan_tiles_kernel<<<1, kScanTilesThreads, 0, s>>>(tile_counts, nt);
-                    SDC_CHECK_LAUNCH();
-                } else {
-                    SDC_TRY(device_exclusive_scan(ArrayLoad{tile_counts}, ArrayStore{tile_counts}, nt, tsum_p, s));
-                    SDC_CUDA_TRY(cudaMemcpyAsync(tile_counts + nt, tsum_p + ceil_div(nt, kTile), 8, cudaMemcpyDeviceToDevice, s));
-                }
-                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, res->lidx, res->ridx, lmap,
-                                                                                  ids_applied ? lids : nullptr, ids_applied ? rids : nullptr);
+                probe_unique_compact_kernel<<<(unsigned)nt, kJoinThreads, 0, s>>>(row1.as<uint32_t>(), nl, tile_counts, group_counts, res->lidx,
+                                                                                  res->ridx, lmap, ids_applied ? lids : nullptr,
+                                                                                  ids_applied ? rids : nullptr);
                 SDC_CHECK_LAUNCH();
                 if (ids_applied) *ids_applied = true;
                 unsigned long long total = 0;
-                SDC_CUDA_TRY(cudaMemcpyAsync(&total, tile_counts + nt, 8, cudaMemcpyDeviceToHost, s));
+                SDC_CUDA_TRY(cudaMemcpyAsync(&total, dtotal, 8, cudaMemcpyDeviceToHost, s));
                 SDC_CUDA_TRY(cudaStreamSynchronize(s));
                 res->n_out = (int64_t)total;
                 return SDCB200_OK;

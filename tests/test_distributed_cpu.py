@@ -202,3 +202,18 @@ def test_string_column_wire_format_matches_reference_restatement():
     for r in range(2):
         np.testing.assert_array_equal(got[r][0], want[r][0])
         np.testing.assert_array_equal(got[r][1], want[r][1])
+
+
+def test_ordered_image_preserves_the_sort_order():
+    """Splitters of the distributed sort_values travel as order-preserving uint64 images of the keys (host side of
+    sdcb200_shuffle_plan_range): image order == numeric order, -0.0 == +0.0, int64 extremes included."""
+    import numpy as np
+    from sdc_b200.distributed import ordered_image
+    rng = np.random.default_rng(12)
+    f = np.concatenate([rng.standard_normal(1000) * 1e6, [0.0, -0.0, np.inf, -np.inf, 5e-324, -5e-324, 1.7e308, -1.7e308]])
+    img = ordered_image(f)
+    order = np.argsort(img, kind="stable")
+    assert np.array_equal(f[order], np.sort(f, kind="stable"))
+    assert img[f == 0.0].min() == img[f == 0.0].max()                 # both zeros share one image
+    i = np.concatenate([rng.integers(-10**18, 10**18, 1000), [np.iinfo(np.int64).min, np.iinfo(np.int64).max, 0, -1]])
+    assert np.array_equal(i[np.argsort(ordered_image(i), kind="stable")], np.sort(i, kind="stable"))

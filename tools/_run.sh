@@ -1,3 +1,2 @@
-set -u
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/dist_check.py > gpurun_out/r2j_dist_check_n2.log 2>&1; echo "dist_check rc=$?"; tail -12 gpurun_out/r2j_dist_check_n2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/r2j_bench_n2.json 2> gpurun_out/r2j_bench_n2.err; echo "bench2 rc=$?"
+python -m pytest tests/test_join_gpu.py tests/test_frame_gpu.py -x -q -m gpu > gpurun_out/r2k_pytest_join.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/r2k_pytest_join.log
+python tools/time_join_c3.py > gpurun_out/r2k_time_join_c3.log 2>&1; cat gpurun_out/r2k_time_join_c3.log
