@@ -378,6 +378,16 @@ def c5_parity(dev, rank, world, link):
             got = ojoin.canonical(D.allgather_ragged(li)[0].cpu().numpy(), D.allgather_ragged(ri)[0].cpu().numpy())
             want = ojoin.join_indexers(probe, build, how)
             res["join_%s_%s" % (mode, how)] = bool(np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]))
+    if world > 1:
+        # sort_values across GPUs (sample sort): the ranks' slices in rank order = the stable single-GPU order
+        from oracle import sort as osort
+        sk = rng.standard_normal(n).round(2)
+        sk[rng.integers(0, n, n // 50)] = np.nan
+        ok_all = True
+        for asc, nap in ((True, "last"), (False, "first")):
+            _, sid, _ = D.sort_values_distributed(torch.from_numpy(sk[s:e].copy()).to(dev), asc, nap)
+            ok_all = ok_all and np.array_equal(D.allgather_ragged(sid)[0].cpu().numpy(), osort.sort_values_indexer(sk, asc, nap))
+        res["sort_values_sample_sort"] = bool(ok_all)
     x = rng.random(n)
     x[::977] = np.nan
     for op in ("mean", "std", "max"):
@@ -458,7 +468,23 @@ def bench_c5(dev, rank, world, peak, reps=3):
         out["shuffle_key_value"] = {"workload": "the shuffle alone: 125M rows of key + value per GPU (count pass, counts all-gather, "
                                                 "partition-and-send kernel, barrier)", "ms": ms, "shuffle_bytes_out_per_gpu": b,
                                     "nvlink_frac": b / (ms * 1e-3) / 1e9 / NVLINK_GBS}
-    del keys, vals
+    del keys
+    # sort_values of a row-sharded float64 column (sample sort: splitters from one all-gather, range-routed shuffle of key +
+    # global row id, local stable argsort + gathers) against the single-GPU sort_values of one shard
+    from sdc_b200.sort import gather_device, sort_values_indexer_device
+
+    def local_sort():
+        idx = sort_values_indexer_device(vals, True, "last")
+        res_s["o"] = (gather_device(vals, idx), idx)
+    res_s = {}
+
+    def dist_sort():
+        res_s["o"] = D.sort_values_distributed(vals, True, "last")
+    case("sort_values_f64", "Series.sort_values over 125M float64 rows per GPU (stable, NaN last): sample sort -- range-routed "
+         "shuffle of key + global row id over NVLink, local onesweep argsort", dist_sort, local_sort,
+         n * 16 * (world - 1) / world, 16 * n)
+    res_s.clear()
+    del vals
     nb = n // 10
     build = torch.randperm(nb * world, device=dev, generator=torch.Generator(device=dev).manual_seed(99))[rank * nb:(rank + 1) * nb].contiguous()
     probe = torch.randint(0, nb * world, (n,), device=dev, generator=g)

@@ -1,2 +1,6 @@
-python -m pytest tests/test_join_gpu.py tests/test_frame_gpu.py -x -q -m gpu > gpurun_out/r2k_pytest_join.log 2>&1; echo "rc=$?"; tail -2 gpurun_out/r2k_pytest_join.log
-python tools/time_join_c3.py > gpurun_out/r2k_time_join_c3.log 2>&1; cat gpurun_out/r2k_time_join_c3.log
+set -u
+python -m pytest tests -m gpu -q -x > gpurun_out/r2m_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r2m_pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2m_smoke.log 2>&1; echo "smoke rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2m_bench_ref.json 2> gpurun_out/r2m_bench_ref.err; echo "bench ref rc=$?"
+python bench.py > gpurun_out/r2m_bench.json 2> gpurun_out/r2m_bench.err; echo "bench rc=$?"
+python tools/bench_ops.py rolling groupby join --reps 5 > gpurun_out/r2m_bench_ops.jsonl 2> gpurun_out/r2m_bench_ops.err; echo "ops rc=$?"
