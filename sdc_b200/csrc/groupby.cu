@@ -551,13 +551,14 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                 best = 0u;
 #pragma unroll
                 for (int w = 0; w < kSmWarps; ++w) best = s_red32[w] > best ? s_red32[w] : best;
-                if ((best >> 16) >= kHotMin) {
-                    hot[h] = best & 0xffffu;
-                    nhot = h + 1;
-                    if ((int)((best & 0xffffu) % kSmThreads) == tid) hist[best & 0xffffu] = 0u;
-                }
+                if ((best >> 16) < kHotMin) break;         // block-uniform: no further slot reaches 2 % either (uniform keys
+                                                           // leave after the first round instead of searching four times)
+                hot[h] = best & 0xffffu;
+                nhot = h + 1;
+                if ((int)((best & 0xffffu) % kSmThreads) == tid) hist[best & 0xffffu] = 0u;
                 __syncthreads();
             }
+            __syncthreads();                               // every thread has read s_red32 / hist before they are reused
         }
     }
     if (blockIdx.x == 0 && tid == 0) { fin.dh.out[0] = s_dlo; fin.dh.out[1] = s_drange; }
