@@ -288,6 +288,21 @@ int32_t sdcb200_str_hash(const uint8_t* chars, const uint32_t* offsets, const ui
 int32_t sdcb200_str_pack_lens(const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint32_t* lens_out, void* stream);
 int32_t sdcb200_str_unpack_lens(const uint32_t* lens, int64_t n, uint32_t* offsets_out, uint8_t* bitmap_out, int64_t* total_chars,
                                 void* stream);
+/* Short string keys as 64-bit words: a key column whose strings all fit one machine word goes through the numeric hash
+ * groupby (sdcb200_groupby on int64 keys) without being factorized first.  The reference hashes the unboxed Python
+ * strings into a numba Dict (hpat_pandas_dataframe_functions.py:3076-3097); the result is the same group set.
+ *   str_profile       out3 (host) = {shortest length, longest length, number of NA rows} of the column
+ *   str_pack_words    words_out[i] = bytes (little-endian, zero padded) | length << 56; every length <= 7
+ *                     (a column of exactly-8-byte strings needs no packing: its chars buffer is the word column)
+ *   str_unpack_words  result words -> offsets_out[m + 1] + chars_out (room for 8 m bytes); fixed8 != 0: every word is
+ *                     an 8-byte string, else the length sits in the top byte                                          */
+int32_t sdcb200_str_profile(const uint32_t* offsets, const uint8_t* bitmap, int64_t n, int64_t* out3, void* stream);
+int32_t sdcb200_str_pack_words(const uint8_t* chars, const uint32_t* offsets, int64_t n, uint64_t* words_out, void* stream);
+int32_t sdcb200_str_unpack_words(const uint64_t* words, int64_t m, int32_t fixed8, uint32_t* offsets_out, uint8_t* chars_out,
+                                 int64_t* total_chars, void* stream);
+/*   str_words_order   order_out[j] = the row of `words` that comes j-th in the reference's string order (unsigned bytes,
+ *                     a proper prefix first: std::string `<`, sdc_str_arr.hpp:565-593) -- orders a groupby's result keys  */
+int32_t sdcb200_str_words_order(const uint64_t* words, int64_t m, int32_t fixed8, int64_t* order_out, void* stream);
 /* the reference's own symbol (HOST buffers, void return), exactly as sdc/str_arr_ext.py:94-99 declares it */
 void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result);
 

@@ -126,6 +126,9 @@ __device__ __forceinline__ unsigned long long global_upsert(const Table& t, unsi
             if (old == key) return slot;
         }
         slot = (slot + 1) & (t.cap - 1);
+        // a table that filled up is abandoned by the host anyway: without this test every row still in flight walks
+        // all `cap` slots of it (200 M rows over 1 M sparse keys and no hint: 94 ms in the 8 K-slot first attempt)
+        if ((probes & 63ull) == 63ull && *(volatile int*)t.overflow) return ~0ull;
     }
     *(volatile int*)t.overflow = 1;
     return ~0ull;
@@ -397,6 +400,7 @@ __device__ __forceinline__ void write_group(const Table& t, int ncols, unsigned 
 // HBM traffic = keys + values read once.
 constexpr int kSmThreads = 512;                 // two CTAs per SM: two private tables halve the CAS contention
 constexpr int kSmemProbes = 16;
+constexpr int kLeanProbes = 64;                  // hashed lean loop: a longer walk is cheaper than the rerun it would cause
 constexpr int kSamplePerThread = 4;              // 2048 strided samples per CTA
 constexpr int kSmallReplicas = 8;                // replicas of the small global table's value arrays
 
@@ -418,6 +422,7 @@ struct SmallFin {
     int write_out;                  // 0: only fold the replicas (var / std continue on the host path)
     int rf_max;                     // lean loop: most lane-indexed copies of the direct window inside the shared table (1 = off)
     int hot;                        // lean loop: keep the most frequent sampled keys' aggregates in registers
+    int lean_hash;                  // lean instantiation: keys without a direct window take the hashed lean loop (2b)
     DirectHint dh;                  // dh.out = meta + 2
     unsigned long long* meta;       // [0] groups written, [1] CTAs done, [2] direct lo, [3] direct range
     unsigned long long* host_meta;  // mapped pinned host copy of the 256-byte control block, written by the last CTA (or null)
@@ -450,7 +455,7 @@ __device__ __forceinline__ void sts_zero_u32(uint32_t a) { asm volatile("st.shar
 template <bool KEY_F64, int SPEC, bool LEAN = false>
 __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __restrict__ keys, int64_t n, Cols cols_rt, Table t,
                                                                 int need_rt, SmemLayout lay, SmallFin fin) {
-    static_assert(!LEAN || (SPEC >= 0 && !KEY_F64), "lean loop: one float64 column, int64 keys / group ids");
+    static_assert(!LEAN || SPEC >= 0, "lean loops: one float64 value column");
     const int need = SPEC >= 0 ? SPEC : need_rt;
     struct ColsView {
         const Cols& c;
@@ -690,9 +695,89 @@ __global__ void __launch_bounds__(kSmThreads, 2) gb_smem_kernel(const void* __re
                 if (lane == 0 && seen) accumulate(hot[h], sv, cn, ~0ull, 0ull, true);
             }
         }
+    } else if (LEAN && fin.lean_hash) {
+        // ---- 2b (LEAN, hashed). Keys with no dense window -- sparse int64 ids, float64 keys, the 8-byte words of a
+        //      fixed-width string column: the slot comes from a probe of the CTA's shared key table (each lane walks its
+        //      own chain; at the load factors the layout allows one or two steps), the aggregates then take the lean
+        //      loop's explicit shared addresses.  There is no global-table fallback inside the loop: a key that finds
+        //      no slot within kLeanProbes steps (more groups than the table holds) raises overflow = 3 and the host
+        //      reruns with the generic loop below.  The generic loop costs 2.2 ms per 100 M rows and five aggregates
+        //      over 1 K sparse keys, the direct lean loop 0.61.
+        const uint32_t keys_a = opaque_u32(smem_u32(skeys));
+        const uint32_t sum_a = opaque_u32(smem_u32(sm + lay.off_sum[0]));
+        const uint32_t cnt_a = opaque_u32(smem_u32(sm + lay.off_cnt[0]));
+        const uint32_t mn_a = opaque_u32(smem_u32(sm + lay.off_mn[0]));
+        const uint32_t mx_a = opaque_u32(smem_u32(sm + lay.off_mx[0]));
+        const uint32_t smask = (uint32_t)scap - 1u;
+        // the rest of a probe whose first slot held another key (or nothing): walk on, claim an empty slot
+        auto probe_on = [&](unsigned long long k, uint32_t s, unsigned long long cur) -> uint32_t {
+            if (k == kEmptyKey()) return 0xffffffffu;                        // the marker itself cannot live in this table
+#pragma unroll 1
+            for (int p = 0; p < kLeanProbes; ++p) {
+                if (cur == k) return s;
+                if (cur == kEmptyKey()) {
+                    const unsigned long long old = atomicCAS(&skeys[s], kEmptyKey(), k);
+                    if (old == kEmptyKey() || old == k) return s;
+                }
+                s = (s + 1u) & smask;
+                cur = lds_u64(keys_a + s * 8u);
+            }
+            return 0xffffffffu;
+        };
+        auto add_row = [&](uint32_t s, unsigned long long vbits) {
+            const double v = __longlong_as_double((long long)vbits);
+            if (v != v) return;                                               // skipna: the group exists, nothing to add
+            const uint32_t o8 = s * 8u;
+            if (need & NEED_SUM) reds_add_f64(sum_a + o8, v);
+            if (need & NEED_CNT) reds_add_u32(cnt_a + s * 4u, 1u);
+            if (need & (NEED_MIN | NEED_MAX)) {
+                const unsigned long long o = f64_to_ordered(v);
+                if (need & NEED_MIN) { if (o < lds_u64(mn_a + o8)) reds_min_u64(mn_a + o8, o); }
+                if (need & NEED_MAX) { if (o > lds_u64(mx_a + o8)) reds_max_u64(mx_a + o8, o); }
+            }
+        };
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int64_t base = tile * kSmTile;
+            unsigned long long kb[kRows], v0[kRows];
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) { kb[e] = kbn[e]; v0[e] = v0n[e]; }
+            if (tile + gridDim.x < ntiles) {
+                const int64_t nbase = (tile + gridDim.x) * kSmTile;
+                load4<kSmThreads>(keys, nbase, n, tid, cols.vec_ok, kbn);
+                load4<kSmThreads>(cols.data[0], nbase, n, tid, cols.vec_ok, v0n);
+            }
+            const int ovf = *(volatile int*)t.overflow;      // consumed at the end of the iteration
+            // the four rows' first probes are independent loads, all in flight together; only a row whose first slot
+            // is not its key walks on, and the warp is whole again before the (expensive) shared atomics
+            const bool full = base + kSmTile <= n;
+            bool valid[kRows];
+            uint32_t sl[kRows];
+            unsigned long long cur[kRows];
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) {
+                unsigned long long k = 0;
+                valid[e] = (full || tile_row<kSmThreads>(base, tid, e) < n) && canon_key<KEY_F64>(kb[e], k);   // NaN key: row skipped
+                kb[e] = k;
+                sl[e] = (uint32_t)((k * 0x9E3779B97F4A7C15ull) >> 40) & smask;
+            }
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) cur[e] = lds_u64(keys_a + sl[e] * 8u);
+#pragma unroll
+            for (int e = 0; e < kRows; ++e)
+                if (valid[e] && (cur[e] != kb[e] || kb[e] == kEmptyKey())) sl[e] = probe_on(kb[e], sl[e], cur[e]);
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < kRows; ++e) {
+                if (!valid[e]) continue;
+                if (sl[e] == 0xffffffffu) *(volatile int*)t.overflow = 3;
+                else add_row(sl[e], v0[e]);
+            }
+            if (ovf) break;
+        }
     } else
     // ---- 2. aggregate (generic: hashed or direct slots, any columns; a LEAN instantiation lands here when the
-    //      sampled keys do not fit a direct window).  Direct slots use the lane-indexed copies as well.
+    //      sampled keys do not fit a direct window and the hashed lean loop is off or gave up).  Direct slots use the
+    //      lane-indexed copies as well.
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int gcopy = (int)(((unsigned)lane & (rf - 1u)) * (unsigned)drange);
         __syncwarp();
@@ -1955,7 +2040,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
     if (!big && key_mode != KEYS_GID)
         plan[nattempts++] = {false, worst, 1};      // small inputs: the worst-case table is cheap
 
-    int allow_direct = 1;
+    int allow_direct = 1, allow_lean_hash = 1;
     for (int attempt = 0; attempt < nattempts; ++attempt) {
         const Attempt& at = plan[attempt];
         TableMem mem;
@@ -2027,15 +2112,17 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             else if (spec == 15) kern = gb_smem_kernel<KEY_F64, 15>;
             // int64 keys / group ids: the instantiation with the lean loop for a direct window (it carries the generic
             // loop as well, for sampled keys that do not fit one)
+            // Keys that have no such window (sparse int64 keys, every float64 key column) take the same instantiation's
+            // hashed lean loop until it reports a key it could not place (overflow 3).
             bool lean = false;
-            if constexpr (!KEY_F64) {
-                if (spec >= 0 && allow_direct && gb_lean_enabled()) {
-                    lean = true;
-                    if (spec == 1) kern = gb_smem_kernel<false, 1, true>;
-                    else if (spec == 2) kern = gb_smem_kernel<false, 2, true>;
-                    else if (spec == 3) kern = gb_smem_kernel<false, 3, true>;
-                    else if (spec == 15) kern = gb_smem_kernel<false, 15, true>;
-                }
+            const bool want_direct = !KEY_F64 && allow_direct;
+            const bool want_hash = allow_lean_hash && key_mode == KEYS_PLAIN && gb_env_int("SDCB200_GB_LEAN_HASH", 1) != 0;
+            if (spec >= 0 && (want_direct || want_hash) && gb_lean_enabled()) {
+                lean = true;
+                if (spec == 1) kern = gb_smem_kernel<KEY_F64, 1, true>;
+                else if (spec == 2) kern = gb_smem_kernel<KEY_F64, 2, true>;
+                else if (spec == 3) kern = gb_smem_kernel<KEY_F64, 3, true>;
+                else if (spec == 15) kern = gb_smem_kernel<KEY_F64, 15, true>;
             }
             const int rf_max = gb_env_int("SDCB200_GB_RF", 32);
             // the lean loop fills whatever the table holds beyond the key window with lane-indexed copies of it
@@ -2075,6 +2162,8 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             fin.write_out = need_ssd ? 0 : 1;
             fin.rf_max = rf_max;
             fin.hot = gb_env_int("SDCB200_GB_HOT", 1);
+            // (a hint that already says the groups cannot fit the shared table keeps the generic loop and its global fallback)
+            fin.lean_hash = lean && want_hash && (expected_groups <= 0 || 2 * expected_groups <= (int64_t)lay.scap) ? 1 : 0;
             fin.dh.mode = key_mode;
             fin.dh.allow = allow_direct;
             fin.dh.range = key_mode == KEYS_GID ? (unsigned long long)expected_groups : 0ull;
@@ -2109,6 +2198,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
                 res->keys = res->vals = nullptr;
                 res->one_block = false;
                 if (ovf == 2 && allow_direct) { allow_direct = 0; --attempt; continue; }   // same table, hashing this time
+                if (ovf == 3 && allow_lean_hash) { allow_lean_hash = 0; --attempt; continue; }   // same table, generic loop
                 if (attempt + 1 < nattempts || big) continue;
                 set_error("groupby: hash table overflow at capacity %llu", t.cap);
                 return SDCB200_ERR_CAPACITY;

@@ -20,6 +20,8 @@
 //       are skipped, reference hpat_pandas_dataframe_functions.py:3088-3089).  The numeric groupby then
 //       runs on the ids (key dtype SDCB200_GID: direct-addressed table).
 //   sdcb200_str_gather     rows -> a new str_arr (lengths, exclusive scan, byte copy).
+#include <cmath>
+
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -355,7 +357,8 @@ int32_t sdcb200_str_gather_chars(const uint8_t* chars, const uint32_t* offsets, 
 // varying byte (8 passes of 16-byte rows for 8-character keys); instead the rows are factorized (one pass, ids in
 // [0, G)), the G distinct strings are sorted by the LSD sort, and the rows are ordered by a stable radix sort of their
 // strings' 32-bit RANKS, whose constant high digits cost nothing (2 passes of 8-byte rows for G = 1 K).  Taken when a
-// sample of the first rows holds at most 1/16 distinct strings; *used = 0 leaves the job to the LSD sort.
+// sample of the first rows says every string repeats often enough (see the estimate below); *used = 0 leaves the job
+// to the LSD sort.
 static int32_t str_argsort_by_rank(const uint8_t* chars, const uint32_t* offsets, int64_t n, bool ascending, uint64_t* index_out,
                                    cudaStream_t s, int32_t* used) {
     *used = 0;
@@ -368,10 +371,26 @@ static int32_t str_argsort_by_rank(const uint8_t* chars, const uint32_t* offsets
         SDC_TRY(sample_gid.alloc((size_t)kSample * 8, s));
         SDC_TRY(sdcb200_str_factorize(chars, offsets, nullptr, kSample, 0, sample_gid.as<int64_t>(), &ng, &handle, &cap, s));
         SDC_TRY(sdcb200_str_table_free(handle, s));
-        if (ng * 16 > kSample) return SDCB200_OK;
+    }
+    // d distinct strings among s sampled rows: few (d <= s / 16) means the sample has seen most of them; otherwise the
+    // number of distinct strings G of the column is estimated from the collisions inside the sample -- d = G (1 - exp(-s / G))
+    // for rows drawn uniformly from G strings, solved by bisection -- and the rank path is taken while the column still
+    // repeats every string some 32 times (200 M rows over 1 M strings: factorize + 3 passes over 32-bit ranks against
+    // 8 passes over 64-bit chunks).  A sample that is almost collision-free (d > 0.93 s) cannot tell and leaves the job to LSD.
+    int64_t expect = ng * 2;
+    if (ng * 16 > kSample) {
+        const double d = (double)ng, sn = (double)kSample;
+        if (d > 0.93 * sn) return SDCB200_OK;
+        double lo = d, hi = 64.0 * sn;
+        for (int it = 0; it < 60; ++it) {
+            const double g = 0.5 * (lo + hi);
+            if (g * (1.0 - exp(-sn / g)) < d) lo = g; else hi = g;
+        }
+        if (hi * 32.0 > (double)n) return SDCB200_OK;
+        expect = (int64_t)(hi * 1.25);
     }
     SDC_TRY(gid.alloc((size_t)n * 8, s));
-    SDC_TRY(sdcb200_str_factorize(chars, offsets, nullptr, n, ng * 2, gid.as<int64_t>(), &ng, &handle, &cap, s));
+    SDC_TRY(sdcb200_str_factorize(chars, offsets, nullptr, n, expect, gid.as<int64_t>(), &ng, &handle, &cap, s));
     int32_t rc = SDCB200_OK;
     Scratch ids, rows, soff, schars, order, rank, keys, kA, kB, pA, pB;
     auto body = [&]() -> int32_t {
@@ -577,9 +596,190 @@ __global__ void __launch_bounds__(256) str_lens_bitmap_kernel(const uint32_t* __
         bitmap[b] = (uint8_t)v;
     }
 }
+
+// ---- short string keys as 64-bit words (the hash groupby on a column whose strings all fit one word) ----
+// str_profile: shortest / longest string and the number of NA rows -- what decides whether a key column can go through
+// the numeric groupby as int64 words instead of being factorized first:
+//   * every string exactly 8 bytes, no NA, chars 8-byte aligned: the chars buffer IS the key column (no copy at all;
+//     C4's 8-character keys);
+//   * every string at most 7 bytes, no NA: word = bytes (little-endian, zero padded) | length << 56 -- the length byte
+//     keeps "a" and "a\0" apart, so the word is exactly the string.
+__global__ void __launch_bounds__(256) str_profile_kernel(const uint32_t* __restrict__ offsets, const uint8_t* __restrict__ bitmap,
+                                                          int64_t n, unsigned long long* __restrict__ out /* [3] min, max, n_na */) {
+    unsigned mx = 0, mn = 0xffffffffu;
+    unsigned long long na = 0;
+    const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    // 4 rows per step from one aligned 16-byte load (+ the next offset)
+    const int64_t n4 = n / 4;
+    for (int64_t q = t0; q < n4; q += step) {
+        const uint4 o = *reinterpret_cast<const uint4*>(offsets + 4 * q);
+        const uint32_t e = offsets[4 * q + 4];
+        const unsigned l0 = o.y - o.x, l1 = o.z - o.y, l2 = o.w - o.z, l3 = e - o.w;
+        mx = max(max(mx, l0), max(l1, max(l2, l3)));
+        mn = min(min(mn, l0), min(l1, min(l2, l3)));
+    }
+    for (int64_t i = 4 * n4 + t0; i < n; i += step) {
+        const unsigned len = offsets[i + 1] - offsets[i];
+        mx = max(mx, len);
+        mn = min(mn, len);
+    }
+    if (bitmap) {
+        const int64_t nb = (n + 7) / 8;
+        for (int64_t b = t0; b < nb; b += step) {
+            unsigned v = bitmap[b];
+            if (b == nb - 1 && (n & 7)) v |= 0xffu << (n & 7);          // bits beyond row n - 1 do not count
+            na += 8u - (unsigned)__popc(v & 0xffu);
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) na += __shfl_xor_sync(0xffffffffu, na, d);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, (unsigned long long)mn);
+        atomicMax(out + 1, (unsigned long long)mx);
+        if (na) atomicAdd(out + 2, na);
+    }
+}
+
+// words[i] = the string's bytes (little-endian, zero padded) | length << 56; lengths are at most 7 (the caller profiled)
+__global__ void __launch_bounds__(256) str_pack_words_kernel(const uint8_t* __restrict__ chars, const uint32_t* __restrict__ offsets,
+                                                             int64_t n, unsigned long long* __restrict__ words) {
+    const uint64_t total = offsets[n];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t beg = offsets[i];
+        uint32_t len = offsets[i + 1] - beg;
+        len = len > 7u ? 7u : len;
+        // the 8 bytes at the aligned address below `beg` and the 8 after them cover any 7 bytes starting at `beg`
+        const uint64_t a = (uint64_t)beg & ~7ull;
+        const unsigned sh = ((unsigned)beg & 7u) * 8u;
+        unsigned long long w = 0;
+        if (len) {
+            const unsigned long long lo = *reinterpret_cast<const unsigned long long*>(chars + a);
+            w = lo >> sh;
+            if (sh && a + 8 < total) w |= *reinterpret_cast<const unsigned long long*>(chars + a + 8) << (64u - sh);
+            w &= (1ull << (8u * len)) - 1ull;
+        }
+        words[i] = w | ((unsigned long long)len << 56);
+    }
+}
+
+// result keys back into a str_arr: lengths (scanned into offsets by the caller's device_exclusive_scan), then the bytes
+struct WordLenLoad {
+    const unsigned long long* words;
+    int fixed8;
+    __device__ unsigned long long operator()(int64_t i) const { return fixed8 ? 8ull : (words[i] >> 56); }
+};
+// order-preserving unsigned image of a key word: byte-lexicographic string order, a proper prefix first
+__global__ void __launch_bounds__(256) str_words_sortkeys_kernel(const unsigned long long* __restrict__ words, int64_t m, int fixed8,
+                                                                 unsigned long long* __restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = words[i];
+        const unsigned long long body = fixed8 ? w : (w & 0x00ffffffffffffffull);
+        const unsigned long long be = ((unsigned long long)__byte_perm((unsigned)body, 0u, 0x0123) << 32) |
+                                      (unsigned long long)__byte_perm((unsigned)(body >> 32), 0u, 0x0123);
+        keys[i] = fixed8 ? be : (be | (w >> 56));        // bytes 0..6 big-endian in the top 56 bits, the length below them
+    }
+}
+__global__ void __launch_bounds__(256) str_fixed8_offsets_kernel(uint32_t* __restrict__ offsets, int64_t m) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= m; i += (int64_t)gridDim.x * blockDim.x)
+        offsets[i] = (uint32_t)(8 * i);
+}
+__global__ void __launch_bounds__(256) str_unpack_words_kernel(const unsigned long long* __restrict__ words, int64_t m, int fixed8,
+                                                               const uint32_t* __restrict__ offsets, uint8_t* __restrict__ chars) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = words[i];
+        const unsigned len = fixed8 ? 8u : (unsigned)(w >> 56);
+        const uint32_t ob = offsets[i];
+        for (unsigned b = 0; b < len; ++b) chars[ob + b] = (uint8_t)(w >> (8u * b));
+    }
+}
 }}
 
 extern "C" {
+
+int32_t sdcb200_str_profile(const uint32_t* offsets, const uint8_t* bitmap, int64_t n, int64_t* out3, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(n >= 0 && out3 != nullptr, "args");
+    out3[0] = out3[1] = out3[2] = 0;
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(offsets != nullptr, "null offsets");
+    SDC_ARG_CHECK((reinterpret_cast<uintptr_t>(offsets) & 15) == 0, "offsets must be 16-byte aligned");
+    Scratch meta;
+    SDC_TRY(meta.alloc(24, s));
+    const unsigned long long init[3] = {~0ull, 0ull, 0ull};
+    SDC_CUDA_TRY(cudaMemcpyAsync(meta.p, init, 24, cudaMemcpyHostToDevice, s));
+    str_profile_kernel<<<grid_for(n / 4 + 1, 256, 8), 256, 0, s>>>(offsets, bitmap, n, meta.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    unsigned long long h[3];
+    SDC_CUDA_TRY(cudaMemcpyAsync(h, meta.p, 24, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    out3[0] = (int64_t)h[0];
+    out3[1] = (int64_t)h[1];
+    out3[2] = (int64_t)h[2];
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_pack_words(const uint8_t* chars, const uint32_t* offsets, int64_t n, uint64_t* words_out, void* stream) {
+    SDC_ARG_CHECK(n >= 0, "n");
+    if (n == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(chars != nullptr && offsets != nullptr && words_out != nullptr, "null pointer");
+    SDC_ARG_CHECK((reinterpret_cast<uintptr_t>(chars) & 7) == 0, "chars must be 8-byte aligned");
+    str_pack_words_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(chars, offsets, n,
+                                                                                reinterpret_cast<unsigned long long*>(words_out));
+    SDC_CHECK_LAUNCH();
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_unpack_words(const uint64_t* words, int64_t m, int32_t fixed8, uint32_t* offsets_out, uint8_t* chars_out,
+                                 int64_t* total_chars, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(m >= 0 && offsets_out != nullptr && total_chars != nullptr, "args");
+    *total_chars = 0;
+    if (m == 0) {
+        SDC_CUDA_TRY(cudaMemsetAsync(offsets_out, 0, 4, s));
+        return SDCB200_OK;
+    }
+    SDC_ARG_CHECK(words != nullptr && chars_out != nullptr, "null pointer");
+    SDC_ARG_CHECK(m < (int64_t)(0xffffffffull / 8), "result chars exceed the uint32 offset range (sdc_str_arr.hpp:206)");
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(words);
+    if (fixed8) {
+        // every string is 8 bytes: offsets and total are known without a scan or a read-back
+        str_fixed8_offsets_kernel<<<grid_for(m + 1, 256, 8), 256, 0, s>>>(offsets_out, m);
+        SDC_CHECK_LAUNCH();
+        SDC_CUDA_TRY(cudaMemcpyAsync(chars_out, w, (size_t)m * 8, cudaMemcpyDeviceToDevice, s));
+        *total_chars = 8 * m;
+        return SDCB200_OK;
+    }
+    Scratch tsum;
+    SDC_TRY(tsum.alloc((size_t)(ceil_div(m, kScanTile) + 1) * 8, s));
+    SDC_TRY(device_exclusive_scan(WordLenLoad{w, fixed8}, OffsetStore{offsets_out}, m, tsum.as<unsigned long long>(), s));
+    str_unpack_words_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(w, m, fixed8, offsets_out, chars_out);
+    SDC_CHECK_LAUNCH();
+    unsigned long long total = 0;
+    SDC_CUDA_TRY(cudaMemcpyAsync(&total, tsum.as<unsigned long long>() + ceil_div(m, kScanTile), 8, cudaMemcpyDeviceToHost, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    const uint32_t t32 = (uint32_t)total;
+    SDC_CUDA_TRY(cudaMemcpyAsync(offsets_out + m, &t32, 4, cudaMemcpyHostToDevice, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));
+    *total_chars = (int64_t)total;
+    return SDCB200_OK;
+}
+
+int32_t sdcb200_str_words_order(const uint64_t* words, int64_t m, int32_t fixed8, int64_t* order_out, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    SDC_ARG_CHECK(m >= 0, "m");
+    if (m == 0) return SDCB200_OK;
+    SDC_ARG_CHECK(words != nullptr && order_out != nullptr, "null pointer");
+    Scratch keys;
+    SDC_TRY(keys.alloc((size_t)m * 8, s));
+    str_words_sortkeys_kernel<<<grid_for(m, 256, 8), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(words), m, fixed8,
+                                                                keys.as<unsigned long long>());
+    SDC_CHECK_LAUNCH();
+    SDC_TRY(argsort_device(SDCB200_U64, keys.p, m, true, order_out, s));
+    SDC_CUDA_TRY(cudaStreamSynchronize(s));      // the key scratch goes out of scope
+    return SDCB200_OK;
+}
 
 int32_t sdcb200_str_hash(const uint8_t* chars, const uint32_t* offsets, const uint8_t* bitmap, int64_t n, uint64_t* out, void* stream) {
     SDC_ARG_CHECK(n >= 0, "n");

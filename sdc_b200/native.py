@@ -75,6 +75,10 @@ SIGNATURES = {
     "sdcb200_str_table_free": (_i32, [_i64, _vp]),
     "sdcb200_str_gather_sizes": (_i32, [_vp, _vp, _i64, _vp, ct.POINTER(_i64), _vp]),
     "sdcb200_str_gather_chars": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "sdcb200_str_profile": (_i32, [_vp, _vp, _i64, ct.POINTER(_i64), _vp]),
+    "sdcb200_str_pack_words": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "sdcb200_str_unpack_words": (_i32, [_vp, _i64, _i32, _vp, _vp, ct.POINTER(_i64), _vp]),
+    "sdcb200_str_words_order": (_i32, [_vp, _i64, _i32, _vp, _vp]),
     "sdcb200_str_hash": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "sdcb200_str_pack_lens": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "sdcb200_str_unpack_lens": (_i32, [_vp, _i64, _vp, _vp, ct.POINTER(_i64), _vp]),

@@ -156,6 +156,58 @@ class StringArray:
                                                       out_bm.data_ptr(), stream))
         return StringArray(out_off, out_chars[:total.value] if total.value else out_chars[:0], out_bm[:(m + 7) // 8], m)
 
+    def profile(self):
+        """-> (shortest length, longest length, number of NA rows): one pass over offsets + bitmap, kept on the column
+        (a str_arr is immutable: the reference never writes into one after it is built)."""
+        prof = getattr(self, "_profile", None)
+        if prof is None:
+            torch = _torch()
+            lib = native.load()
+            d = self.cuda()
+            out = (ct.c_int64 * 3)()
+            with torch.cuda.device(d.offsets.device):
+                native.check(lib.sdcb200_str_profile(d.offsets.data_ptr(), d.bitmap.data_ptr(), d.n, out,
+                                                     native.current_stream_ptr()))
+            prof = self._profile = (int(out[0]), int(out[1]), int(out[2]))
+        return prof
+
+    def key_words(self):
+        """The column as int64 key words for the numeric hash groupby, or None when its strings do not all fit one:
+        -> (int64 CUDA tensor[n], fixed8).  Exactly-8-byte strings: a zero-copy view of the chars; at most 7 bytes:
+        bytes | length << 56 (csrc/strings.cu str_pack_words).  NA rows would have to be skipped: such columns are
+        factorized instead."""
+        torch = _torch()
+        d = self.cuda()
+        if d.n == 0 or d.offsets.data_ptr() % 16:
+            return None
+        mn, mx, n_na = d.profile()
+        if n_na:
+            return None
+        if mn == 8 and mx == 8 and d.chars.data_ptr() % 16 == 0:
+            return d.chars[:8 * d.n].view(torch.int64), True
+        if mx <= 7 and d.chars.data_ptr() % 8 == 0:
+            words = torch.empty(d.n, dtype=torch.int64, device=d.offsets.device)
+            with torch.cuda.device(d.offsets.device):
+                native.check(native.load().sdcb200_str_pack_words(d.chars.data_ptr(), d.offsets.data_ptr(), d.n,
+                                                                  words.data_ptr(), native.current_stream_ptr()))
+            return words, False
+        return None
+
+    @classmethod
+    def from_key_words(cls, words, fixed8):
+        """Result key words of the numeric groupby back into a device str_arr (no NA rows)."""
+        torch = _torch()
+        lib = native.load()
+        m = words.shape[0]
+        dev = words.device
+        off = torch.empty(m + 1, dtype=torch.int32, device=dev)
+        chars = torch.empty(max(1, 8 * m), dtype=torch.uint8, device=dev)
+        total = ct.c_int64(0)
+        with torch.cuda.device(dev):
+            native.check(lib.sdcb200_str_unpack_words(words.data_ptr() if m else None, m, 1 if fixed8 else 0, off.data_ptr(),
+                                                      chars.data_ptr(), ct.byref(total), native.current_stream_ptr()))
+        return cls(off, chars[:total.value], torch.full((max(1, (m + 7) // 8),), 0xFF, dtype=torch.uint8, device=dev)[:(m + 7) // 8], m)
+
     def factorize(self, expected_groups=0):
         """-> (gid int64 CUDA tensor with -1 for NA rows, n_groups, table handle, table capacity)."""
         torch = _torch()
@@ -170,17 +222,34 @@ class StringArray:
         return gid, ng.value, handle.value, cap.value
 
 
-def groupby_str_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0):
+def groupby_str_device(keys, cols, aggs, sort=True, ddof=1, expected_groups=0, short_keys=True):
     """Hash groupby with a string key column: factorize -> numeric groupby on the ids -> key strings.
 
     keys: StringArray (device);  cols: list of CUDA tensors -> (result key StringArray, {agg: [tensor per column]})
-    sort=True orders the groups by the reference's string order, sort=False by first appearance."""
+    sort=True orders the groups by the reference's string order, sort=False by first appearance.
+    short_keys=False keeps a column of one-word strings on the factorize path as well (A/B measurements, tests)."""
     torch = _torch()
     lib = native.load()
     from .groupby import groupby_device
     from .sort import gather_device
     d = keys.cuda()
     dev = d.offsets.device
+    kw = d.key_words() if short_keys else None
+    if kw is not None:
+        # strings that fit one word: the numeric hash groupby on the words themselves (no factorize pass, no id column);
+        # sort=True orders the few result rows by string order below, sort=False keeps first appearance
+        words, fixed8 = kw
+        gk, res = groupby_device(words, cols, aggs, bool(sort), ddof, expected_groups)
+        if sort and gk.shape[0] > 1:
+            # the aggregate ordered the groups by the words' integer value; string order is the order of their
+            # big-endian image (the length below it), sorted on the few result rows
+            order = torch.empty(gk.shape[0], dtype=torch.int64, device=dev)
+            with torch.cuda.device(dev):
+                native.check(lib.sdcb200_str_words_order(gk.data_ptr(), gk.shape[0], 1 if fixed8 else 0, order.data_ptr(),
+                                                         native.current_stream_ptr()))
+            gk = gather_device(gk, order)
+            res = {a: [gather_device(t, order) for t in ts] for a, ts in res.items()}
+        return StringArray.from_key_words(gk, fixed8), res
     gid, ng, handle, cap = d.factorize(expected_groups)
     try:
         # ids are dense, in [0, ng); NA rows carry -1 and are skipped by the aggregate (SDCB200_GID keys: a

@@ -263,14 +263,18 @@ def test_c1_full_size_sum_and_multi():
             np.testing.assert_array_equal(res[agg][0].cpu().numpy(), want[agg].to_numpy())
 
 
-@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide", "few", "zipf", "hotnan", "nanzero"])
+@pytest.mark.parametrize("keys_kind", ["dense", "skewed", "sparse", "float", "outliers", "wide", "few", "zipf", "hotnan", "nanzero",
+                                       "sparse_many", "sparse_nanzero", "float_zipf", "marker_key"])
 def test_single_f64_column_specialised_kernels(keys_kind):
     """One float64 column with sum / mean / the five-aggregate set takes gb_smem_kernel's compile-time specialised
     loops (SPEC 1 / 3 / 15): dense keys inside the sampled direct window, a hot key, hashed keys, float keys, keys
     outside the sampled span (rerun with hashing), more groups than shared slots (global-table fallback); a handful
     of groups (the direct window is copied 32 times across the shared table, one copy per lane), Zipf-distributed keys
     (the most frequent sampled keys are aggregated in registers) and a hot key whose values are all NaN (the group
-    must still appear: sum 0, count 0, min / max / mean NaN)."""
+    must still appear: sum 0, count 0, min / max / mean NaN).  Sparse int64 keys and float64 keys take the HASHED lean
+    loop (slot from a probe of the CTA's shared key table): more sparse groups than the shared table holds (overflow 3,
+    rerun with the generic loop), groups whose values are all NaN / zeros, skewed float keys with -0.0 == +0.0, and a
+    key equal to the table's empty marker."""
     rng = np.random.default_rng(23)
     n = 300_000
     if keys_kind == "dense":
@@ -294,6 +298,17 @@ def test_single_f64_column_specialised_kernels(keys_kind):
         a = np.where(rng.random(n) < 0.3, 41, rng.integers(0, 1000, n))
     elif keys_kind == "nanzero":
         a = rng.integers(0, 1000, n)
+    elif keys_kind == "sparse_many":
+        a = rng.integers(0, 3000, n) * 1000003 - 5
+    elif keys_kind == "sparse_nanzero":
+        a = rng.integers(0, 900, n) * 7_000_000_019 + 11
+    elif keys_kind == "float_zipf":
+        a = (np.minimum(rng.zipf(1.3, n), 500) - 1).astype(np.float64) * 0.5 - 3.0
+        a[a == 0.0] = np.where(rng.random(int((a == 0.0).sum())) < 0.5, 0.0, -0.0)
+        a[rng.integers(0, n, 50)] = np.nan
+    elif keys_kind == "marker_key":
+        a = rng.integers(0, 500, n) * 1000003
+        a[rng.integers(0, n, 40)] = 0x7ff8dead0000beef          # csrc/groupby.cu kEmptyKey
     else:
         a = rng.integers(0, 3000, n)
     b = rng.standard_normal(n) * 50
@@ -301,6 +316,11 @@ def test_single_f64_column_specialised_kernels(keys_kind):
     b[rng.integers(0, n, 20)] = np.inf
     if keys_kind == "hotnan":
         b[a == 41] = np.nan
+    if keys_kind == "sparse_nanzero":
+        u = np.unique(a)
+        b[a == u[5]] = np.nan
+        b[a == u[6]] = 0.0
+        b[a == u[7]] = -0.0
     if keys_kind == "nanzero":        # groups the lean loop's implicit presence (count / sum changed) cannot see
         b[a == 5] = np.nan
         b[a == 6] = 0.0
@@ -358,7 +378,7 @@ def test_several_f64_columns_take_the_lean_loop_per_column(keys_kind):
 def test_measurement_switches_give_the_same_result(monkeypatch):
     """The A/B switches of DESIGN 6 (read on every call) select other code paths of the same kernel family -- window
     copies off, hot keys off, control block through a copy-engine read-back, the generic loop for several columns:
-    every one of them must give what the default path gives."""
+    every one of them must give what the default path gives (sparse keys: the hashed lean loop against the generic one)."""
     import torch
     from sdc_b200.groupby import groupby_device
     rng = np.random.default_rng(5)
@@ -368,14 +388,14 @@ def test_measurement_switches_give_the_same_result(monkeypatch):
     cols[0][::77] = float("nan")
     aggs = ("sum", "mean", "min", "max", "count")
 
-    def run(ncols):
-        k, r = groupby_device(a, cols[:ncols], aggs, True, 1, 0)
-        return k.clone(), {g: [t.clone() for t in r[g]] for g in aggs}
-
-    for ncols in (1, 2):
+    sparse = a * 1_000_003 + 17
+    for ncols, keys in ((1, a), (2, a), (1, sparse)):
+        def run(ncols, keys=keys):
+            k, r = groupby_device(keys, cols[:ncols], aggs, True, 1, 0)
+            return k.clone(), {g: [t.clone() for t in r[g]] for g in aggs}
         base_k, base = run(ncols)
         for name, value in (("SDCB200_GB_RF", "1"), ("SDCB200_GB_HOT", "0"), ("SDCB200_GB_MAPPED", "0"),
-                            ("SDCB200_GB_SPLIT_COLS", "0")):
+                            ("SDCB200_GB_SPLIT_COLS", "0"), ("SDCB200_GB_LEAN_HASH", "0")):
             monkeypatch.setenv(name, value)
             k, r = run(ncols)
             monkeypatch.delenv(name)

@@ -162,6 +162,79 @@ def test_groupby_string_keys_inline_and_hashed_slots():
     np.testing.assert_array_equal(res["count"][0].cpu().numpy(), cnt)
 
 
+@pytest.mark.parametrize("kind", ["upto7", "fixed8", "mixed8", "upto7_na", "fixed8_unaligned_view"])
+def test_groupby_short_string_keys_as_words(kind):
+    """Strings that all fit one 64-bit word go through the numeric hash groupby as int64 words (str_arr.key_words:
+    exactly 8 bytes = a view of the chars, at most 7 bytes = bytes | length << 56 so that "a" and "a\0" stay apart);
+    anything else -- an 8-byte string among shorter ones, NA rows -- is factorized.  Every path against the oracle and
+    against the factorize path, sort=True and first-appearance order."""
+    import torch
+    from sdc_b200.str_arr import StringArray, groupby_str_device
+    rng = np.random.default_rng(17)
+    n = 60_000
+    if kind in ("upto7", "upto7_na"):
+        pool = ["", "a", "a\x00", "a\x00\x00", "\x00", "\x00\x00a", "ab", "abcdefg", "abcdef\x00", "zzzzzzz", "\u00e9t\u00e9", "Zq9"]
+        pool += _rand_strings(rng, 300, 7, "abcXYZ019")
+    elif kind == "mixed8":
+        pool = ["abcdefgh", "abcdefg", "abcdefg\x00", "a", ""] + _rand_strings(rng, 200, 8, "abcXYZ019")
+    else:
+        pool = ["abcdefgh", "abcdefg\x00", "\x00" * 8, "\u00e9t\u00e9xy!"]
+        pool += ["".join(rng.choice(list("abcXYZ019"), 8)) for _ in range(400)]
+        assert all(len(p.encode()) == 8 for p in pool)
+    keys = [pool[i] for i in rng.integers(0, len(pool), n)]
+    if kind == "upto7_na":
+        keys[11] = None
+        keys[4000] = None
+    v = rng.standard_normal(n)
+    v[rng.integers(0, n, n // 30)] = np.nan
+    sa = StringArray.from_pylist(keys).cuda()
+    if kind == "fixed8_unaligned_view":            # chars at an address that is not 16-byte aligned: no zero-copy view
+        buf = torch.empty(sa.chars.shape[0] + 8, dtype=torch.uint8, device="cuda")
+        buf[8:] = sa.chars
+        sa = StringArray(sa.offsets, buf[8:], sa.bitmap, sa.n)
+    kw = sa.key_words()
+    assert (kw is not None) == (kind in ("upto7", "fixed8")), kind
+    if kw is not None:
+        assert kw[1] == (kind == "fixed8")
+    val = torch.from_numpy(v).cuda()
+    aggs = ("sum", "mean", "min", "max", "count")
+    for sort in (True, False):
+        wants = {agg: ogroupby.groupby_agg(keys, {"v": v}, agg, sort) for agg in aggs}
+        for hint in (0, len(pool)):
+            rk, res = groupby_str_device(sa, [val], aggs, sort, 1, hint)
+            fk, fres = groupby_str_device(sa, [val], aggs, sort, 1, hint, short_keys=False)
+            got_keys = rk.to_pylist()
+            assert got_keys == fk.to_pylist(), (kind, sort, hint)
+            assert got_keys == list(wants["count"][0]), (kind, sort, hint)
+            for agg in aggs:
+                want = wants[agg][1]
+                g = res[agg][0].cpu().numpy()
+                if agg in ("min", "max", "count"):
+                    np.testing.assert_array_equal(g, want["v"], err_msg="%s %s" % (kind, agg))
+                    np.testing.assert_array_equal(g, fres[agg][0].cpu().numpy())
+                else:
+                    np.testing.assert_allclose(g, want["v"], rtol=1e-9, atol=1e-12, equal_nan=True, err_msg="%s %s" % (kind, agg))
+
+
+def test_str_profile_and_word_round_trip():
+    """sdcb200_str_profile (shortest / longest / NA count) against numpy, str_pack_words -> str_unpack_words is the identity."""
+    from sdc_b200.str_arr import StringArray
+    rng = np.random.default_rng(3)
+    for n, maxlen, na in ((1, 3, 0), (5, 7, 2), (4099, 7, 0), (100_003, 5, 17), (33, 40, 1)):
+        vals = _rand_strings(rng, n, maxlen)
+        for i in rng.integers(0, n, na):
+            vals[i] = None
+        sa = StringArray.from_pylist(vals)
+        lens = np.diff(sa.offsets.astype(np.int64))
+        assert sa.cuda().profile() == (int(lens.min()), int(lens.max()), sum(x is None for x in vals)), (n, maxlen)
+        if maxlen <= 7 and not any(x is None for x in vals):
+            d = sa.cuda()
+            words, fixed8 = d.key_words()
+            assert not fixed8
+            back = StringArray.from_key_words(words, False)
+            assert back.to_pylist() == vals
+
+
 def test_groupby_string_keys_skewed_one_float_column():
     """Half of the rows share one string: the dense ids go through the lean loop, whose hot-key search samples the ids
     (group-id keys have no window search of their own) and keeps the hot group's sum / count in registers."""
