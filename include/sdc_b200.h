@@ -306,6 +306,23 @@ int32_t sdcb200_str_words_order(const uint64_t* words, int64_t m, int32_t fixed8
 /* the reference's own symbol (HOST buffers, void return), exactly as sdc/str_arr_ext.py:94-99 declares it */
 void stable_argsort(const char* data, const uint32_t* offsets, uint64_t len, int8_t ascending, uint64_t* result);
 
+/* ------------------------------------------------------------------ CSV text -> numeric columns on the device
+ * Replaces, for numeric tables, the reference's CSV ingest: pd.read_csv lowered to pyarrow.csv.read_csv on the host
+ * (sdc/io/csv_ext.py:93-110, option mapping :174-272; sdc/native/arrow_reader.cpp), then boxing into NumPy.  Here the
+ * file's bytes sit in device memory and are decoded there (csrc/csv.cu); number conversion is bit-identical to Arrow's
+ * (int64 with overflow check; float64 correctly rounded, csrc/num_parse.cuh), empty lines are skipped, CRLF accepted,
+ * Arrow's null spellings give NaN in a float64 column.
+ *   csv_open      index the data rows of `data` (the bytes AFTER any header / skipped lines): *nrows_out rows
+ *   csv_classify  kinds_out[c] (host) = OR over the rows of 1 int64 | 2 float64 | 4 null | 8 other -- Arrow's inference:
+ *                 int64 if only 1 (and no 4), float64 if only 1 | 2 | 4, otherwise not a numeric column
+ *   csv_parse     col_types[c]: 0 skip, 1 int64, 2 float64; out_cols[c] = device column of nrows elements.  A field
+ *                 that does not convert makes the call fail with its row / column / reason in sdcb200_last_error()
+ *   csv_close     releases the index (runs on the stream given to csv_open)                                         */
+int32_t sdcb200_csv_open(const uint8_t* data, int64_t nbytes, int64_t* handle_out, int64_t* nrows_out, void* stream);
+int32_t sdcb200_csv_classify(int64_t handle, int32_t ncols, int32_t delimiter, uint32_t* kinds_out);
+int32_t sdcb200_csv_parse(int64_t handle, int32_t ncols, int32_t delimiter, const int32_t* col_types, void* const* out_cols);
+int32_t sdcb200_csv_close(int64_t handle);
+
 /* ------------------------------------------------------------------ multi-GPU hash shuffle
  * Partition step of the reference's (dead) MPI shuffle (sdc/shuffle_utils.py:119-163: per-row destination
  * and per-destination counts); the exchange -- c_alltoall of the counts and c_alltoallv per column,

@@ -38,7 +38,7 @@ def _digest(paths):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(ROOT, "include", "sdc_b200.h"))
     jobs = []
     for src in sources():

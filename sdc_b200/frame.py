@@ -376,11 +376,38 @@ class DeviceFrame:
         return pa.table(arrays, names=names)
 
     @classmethod
-    def read_csv(cls, path, read_options=None, parse_options=None, convert_options=None):
-        """CSV file -> device columns through Arrow's multithreaded reader (what `pd.read_csv` is lowered to in the
-        reference: sdc/io/csv_ext.py + native/arrow_reader.cpp; census_benchmark.py:84-85 starts this way).  Like
-        pandas, an empty field of a string column is a missing value unless `convert_options` says otherwise."""
+    def read_csv(cls, path, read_options=None, parse_options=None, convert_options=None, engine="auto", sep=",",
+                 delimiter=None, names=None, usecols=None, dtype=None, skiprows=None):
+        """CSV file -> device columns (what `pd.read_csv` is lowered to in the reference: sdc/io/csv_ext.py +
+        native/arrow_reader.cpp; census_benchmark.py:84-85 starts this way).
+        engine="device": the file's bytes are copied to the GPU and decoded there (sdc_b200/csv.py, csrc/csv.cu;
+        numeric columns, bit-identical to Arrow's conversion); engine="arrow": Arrow's multithreaded host reader, then
+        one copy per column -- string columns keep Arrow's buffers, which are the str_arr layout; engine="auto": the
+        device reader unless Arrow options are passed or the file turns out to hold a non-numeric column.  Like pandas,
+        an empty field of a string column is a missing value unless `convert_options` says otherwise."""
         import pyarrow.csv as pacsv
+        arrow_opts = read_options is not None or parse_options is not None or convert_options is not None
+        if engine not in ("auto", "device", "arrow"):
+            raise ValueError("read_csv: engine must be 'auto', 'device' or 'arrow'")
+        if engine == "device" or (engine == "auto" and not arrow_opts):
+            from .csv import NotNumericCSV, read_csv_device
+            try:
+                cols, _ = read_csv_device(path, sep=sep, delimiter=delimiter, names=names, usecols=usecols, dtype=dtype,
+                                          skiprows=skiprows)
+                return cls(cols)
+            except NotNumericCSV:
+                if engine == "device":
+                    raise
+        if not arrow_opts:
+            delim = delimiter if delimiter is not None else sep
+            read_options = pacsv.ReadOptions(skip_rows=int(skiprows or 0), column_names=list(names) if names is not None else None)
+            parse_options = pacsv.ParseOptions(delimiter=delim)
+            import pyarrow as pa
+            ctypes_ = None
+            if isinstance(dtype, dict):
+                ctypes_ = {k: pa.from_numpy_dtype(np.dtype(v)) for k, v in dtype.items()}
+            convert_options = pacsv.ConvertOptions(strings_can_be_null=True, column_types=ctypes_,
+                                                   include_columns=list(usecols) if usecols is not None else None)
         if convert_options is None:
             convert_options = pacsv.ConvertOptions(strings_can_be_null=True)
         return cls.from_arrow(pacsv.read_csv(path, read_options=read_options, parse_options=parse_options,

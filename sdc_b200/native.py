@@ -79,6 +79,10 @@ SIGNATURES = {
     "sdcb200_str_pack_words": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "sdcb200_str_unpack_words": (_i32, [_vp, _i64, _i32, _vp, _vp, ct.POINTER(_i64), _vp]),
     "sdcb200_str_words_order": (_i32, [_vp, _i64, _i32, _vp, _vp]),
+    "sdcb200_csv_open": (_i32, [_vp, _i64, ct.POINTER(_i64), ct.POINTER(_i64), _vp]),
+    "sdcb200_csv_classify": (_i32, [_i64, _i32, _i32, _vp]),
+    "sdcb200_csv_parse": (_i32, [_i64, _i32, _i32, _vp, _vp]),
+    "sdcb200_csv_close": (_i32, [_i64]),
     "sdcb200_str_hash": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "sdcb200_str_pack_lens": (_i32, [_vp, _vp, _i64, _vp, _vp]),
     "sdcb200_str_unpack_lens": (_i32, [_vp, _i64, _vp, _vp, ct.POINTER(_i64), _vp]),
