@@ -333,6 +333,39 @@ def bench_other_ops(dev, peak, cpu_legs=True):
                                "frac_of_measured_peak": 1.6e9 / (meda * 1e-3) / 1e9 / peak,
                                "frac_per_pass": 2.4e9 / (meda * 1e-3 / 8) / 1e9 / peak}
     del ks
+
+    # C4: 200 M rows with 8-character string keys drawn from 1 K distinct strings (str_arr offsets + chars built on the
+    # device): sort_values' argsort and the five-aggregate groupby; checked through totals (tests/test_strings_gpu.py
+    # holds the full parity run).  alg bytes: argsort = offsets + chars in, int64 rows out; groupby = offsets + chars + value
+    from sdc_b200.str_arr import StringArray, groupby_str_device
+    n4, g4 = 200_000_000, 1000
+    alphabet = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789", dtype=np.uint8)
+    dic = torch.from_numpy(alphabet[np.random.default_rng(4).integers(0, alphabet.size, (g4, 8))]).to(dev)
+    ids = torch.randint(0, g4, (n4,), device=dev, generator=torch.Generator(device=dev).manual_seed(4))
+    chars = dic[ids].reshape(-1).contiguous()
+    del ids
+    offsets = (torch.arange(n4 + 1, device=dev, dtype=torch.int64) * 8).to(torch.int32)
+    bitmap = torch.full(((n4 + 7) // 8,), 0xFF, dtype=torch.uint8, device=dev)
+    sa = StringArray(offsets, chars, bitmap, n4)
+    vals = torch.rand(n4, device=dev, dtype=torch.float64)
+    aggs = ("sum", "mean", "min", "max", "count")
+
+    def c4_groupby():
+        sa._profile = None                   # the column's length profile is part of the measured call
+        return groupby_str_device(sa, [vals], aggs, True, 1, g4)
+    medg, _ = _event_times(c4_groupby, 3, warm=1)
+    rk, res = c4_groupby()
+    ok = rk.n <= g4 and int(res["count"][0].sum().item()) == n4 and \
+        abs(float(res["sum"][0].sum().item()) - float(vals.sum().item())) <= 1e-9 * n4
+    keys_sorted = rk.to_pylist()
+    ok = ok and keys_sorted == sorted(keys_sorted, key=lambda t: t.encode())
+    meds, _ = _event_times(lambda: sa.argsort(True), 3, warm=1)
+    out["strings_c4"] = {
+        "workload": "C4: 200M rows, 8-char string keys from 1K distinct strings: five-aggregate groupby (sum, mean, min, max, count), stable argsort",
+        "groupby_ms": medg, "groupby_rows_per_s": n4 / (medg * 1e-3), "groupby_frac_of_measured_peak": n4 * 20 / (medg * 1e-3) / 1e9 / peak,
+        "argsort_ms": meds, "argsort_rows_per_s": n4 / (meds * 1e-3), "argsort_frac_of_measured_peak": n4 * 20 / (meds * 1e-3) / 1e9 / peak,
+        "totals_ok": bool(ok)}
+    del sa, vals, chars, offsets, bitmap, rk, res
     return out
 
 

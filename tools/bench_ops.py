@@ -172,6 +172,57 @@ def bench_strings(reps, n=200_000_000):
         del sa, vals, chars, offsets, bitmap
 
 
+def bench_csv(reps, nrows=2_000_000, ncols=24):
+    """Census-shaped CSV (24 float64 columns, SURVEY 8d C5 / benchmarks/census_benchmark.py:57-85): bytes resident in
+    HBM -> columns (index + inference + conversion), the same from a pinned host buffer (H2D inside), and Arrow's
+    multithreaded host reader (what the reference calls) on the box's cores."""
+    import io
+    import time
+    import ctypes as ct
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    from sdc_b200 import native
+    from sdc_b200.csv import read_csv_device
+    rng = np.random.default_rng(6)
+    table = pa.table({"c%d" % c: rng.standard_normal(nrows) * 10.0 ** (c % 7) for c in range(ncols)})
+    sink = io.BytesIO()
+    pacsv.write_csv(table, sink)
+    raw = sink.getvalue()
+    del table, sink
+    nbytes = len(raw)
+    med, best = timeit(lambda: read_csv_device(raw), max(3, reps // 2), warm=1)
+    emit("csv_read_device %d rows x %d float64 cols, host bytes -> device columns (H2D + index + inference + conversion)" % (nrows, ncols),
+         nrows, nbytes, med, best, csv_bytes=nbytes, csv_GBps=nbytes / (med * 1e-3) / 1e9)
+    dtypes = {"c%d" % c: np.float64 for c in range(ncols)}
+    med, best = timeit(lambda: read_csv_device(raw, dtype=dtypes), max(3, reps // 2), warm=1)
+    emit("csv_read_device %d rows x %d float64 cols, dtypes given (no inference pass)" % (nrows, ncols), nrows, nbytes, med, best,
+         csv_bytes=nbytes, csv_GBps=nbytes / (med * 1e-3) / 1e9)
+    # the kernels alone: bytes already in HBM
+    lib = native.load()
+    data = torch.frombuffer(bytearray(raw), dtype=torch.uint8).cuda()
+    first_nl = raw.index(b"\n") + 1
+    outs = [torch.empty(nrows, dtype=torch.float64, device="cuda") for _ in range(ncols)]
+    types = (ct.c_int32 * ncols)(*([2] * ncols))
+    ptrs = (ct.c_void_p * ncols)(*[o.data_ptr() for o in outs])
+
+    def kernels():
+        h, n = ct.c_int64(0), ct.c_int64(0)
+        native.check(lib.sdcb200_csv_open(data.data_ptr() + first_nl, nbytes - first_nl, ct.byref(h), ct.byref(n), native.current_stream_ptr()))
+        native.check(lib.sdcb200_csv_parse(h.value, ncols, ord(","), types, ptrs))
+        native.check(lib.sdcb200_csv_close(h.value))
+    med, best = timeit(kernels, reps, warm=1)
+    emit("csv_kernels %d rows x %d float64 cols, bytes resident in HBM (index + conversion)" % (nrows, ncols), nrows,
+         nbytes + 8 * nrows * ncols, med, best, csv_bytes=nbytes, csv_GBps=nbytes / (med * 1e-3) / 1e9,
+         note="alg bytes = text read once + columns written once")
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        pacsv.read_csv(io.BytesIO(raw))
+        ts.append(time.perf_counter() - t0)
+    print(json.dumps({"case": "csv_read_arrow_host (the reference's reader, %d threads)" % pa.cpu_count(), "rows": nrows,
+                      "ms_best": min(ts) * 1e3, "csv_GBps": nbytes / min(ts) / 1e9}), flush=True)
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     reps = 10
@@ -180,5 +231,5 @@ if __name__ == "__main__":
         args = [a for a in args if a != str(reps)]
     which = args or ["groupby", "sort"]
     for w in which:
-        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join, "strings": bench_strings,
+        {"groupby": bench_groupby, "sort": bench_sort, "join": bench_join, "strings": bench_strings, "csv": bench_csv,
          "rolling": bench_rolling}[w](reps)
