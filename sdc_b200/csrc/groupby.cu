@@ -1433,7 +1433,7 @@ struct GroupbyResult {
     unsigned long long* keys = nullptr;    // [ngcap]
     unsigned long long* vals = nullptr;    // [popc(agg_mask) * ncols * ngcap]
     bool one_block = false;                // vals lives in the allocation keys points at (low-cardinality path)
-    bool lean_direct = false;              // produced by gb_smem_kernel's lean loop over a direct window
+    bool lean_direct = false;              // produced by one of gb_smem_kernel's lean loops (direct window or hashed slots)
     struct PendingSmall* pending = nullptr;   // sdcb200_groupby_begin: the kernel is in flight, sdcb200_groupby_end finishes
     cudaStream_t stream = nullptr;            // the caller's stream the result was produced on: the buffers are handed out
                                               // as zero-copy views and consumed there, so they are freed in ITS order
@@ -1585,7 +1585,7 @@ struct PendingSmall {
     unsigned long long* slot = nullptr;     // pinned control-block copy (host address)
     void* table = nullptr;                  // the table allocation (stream-ordered), released by _end
     cudaStream_t stream = nullptr;
-    bool lean = false;
+    bool lean = false, lean_hash = false;
     // what a rerun needs when the optimistic attempt overflowed (a key outside the sampled window, too many groups):
     // the caller keeps the input columns alive until sdcb200_groupby_end
     const void* keys = nullptr;
@@ -2184,6 +2184,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
                 ps->table = mem.detach();
                 ps->stream = s;
                 ps->lean = lean;
+                ps->lean_hash = fin.lean_hash != 0;
                 ps->keys = keys; ps->n = n; ps->cols = cols; ps->agg_mask = agg_mask; ps->sort = sort; ps->ddof = ddof;
                 ps->key_dtype = key_dtype; ps->key_mode = key_mode; ps->expected_groups = expected_groups;
                 *pend = ps;
@@ -2205,7 +2206,7 @@ int32_t run_groupby(const void* keys, int64_t n, Cols cols, unsigned agg_mask, b
             }
             if (!need_ssd) {
                 res->ngroups = (int64_t)hmeta[16];
-                res->lean_direct = lean && hmeta[19] != 0ull;
+                res->lean_direct = lean && (hmeta[19] != 0ull || fin.lean_hash != 0);
                 return SDCB200_OK;
             }
             dlo = hmeta[18];
@@ -2479,7 +2480,7 @@ int32_t sdcb200_groupby_end(int64_t handle, int64_t* ngroups_out) {
                                           ps->expected_groups, ps->stream, r);
         } else {
             r->ngroups = ng;
-            r->lean_direct = ps->lean && direct;
+            r->lean_direct = ps->lean && (direct || ps->lean_hash);
         }
         delete ps;
         if (rc != SDCB200_OK) return rc;

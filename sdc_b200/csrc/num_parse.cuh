@@ -6,8 +6,9 @@
 // (Lemire, "Number parsing at a gigabyte per second", 2021; Mushtak & Lemire, "Fast number parsing without fallback",
 // 2023 -- no fallback is needed for up to 19 significant digits) over a 128-bit table of powers of five
 // (pow5_table.inc, produced by tools/gen_pow5_table.py).  Longer digit strings are truncated to 19 digits and
-// converted as w and w + 1: when both round to the same double that is the answer, otherwise the field is reported as
-// NP_AMBIG (the caller fails loudly; Arrow resolves those with big-decimal arithmetic).
+// converted as w and w + 1: when both round to the same double that is the answer, otherwise (about one such field in
+// a thousand) the full digit string is compared with the midpoint of the two candidates in exact big-integer
+// arithmetic (round_long_decimal below) -- what Arrow's fast_float does with its big-decimal fallback.
 //
 // Grammar = what Arrow accepts for a numeric column (probed against pyarrow 24, tests/test_csv_*):
 //   float  : blanks* [+-]? ( digit+ ('.' digit*)? | '.' digit+ ) ([eE] [+-]? digit+)? blanks*
@@ -158,6 +159,102 @@ SDC_HD int parse_int64_field(const uint8_t* s, int len, int64_t* out) {
     return NP_OK;
 }
 
+// ---- more than 19 significant digits whose 19-digit bracket [w, w + 1] straddles a rounding boundary ----
+// The two candidates are adjacent doubles b and b + 1 ulp; the answer depends on which side of their midpoint the
+// full decimal value lies.  Both are compared exactly as big integers (32-bit limbs):
+//     D * 10^q   against   (2 m + 1) * 2^(e - 1)          (b = m * 2^e, D = all significant digits)
+// with the powers of five multiplied onto the side where their exponent is positive and the powers of two applied as
+// one shift.  Up to kBigDigits digits take part; non-zero digits beyond them only matter for a tie (they break it
+// upwards).  A rare path (about one in a thousand fields with more than 19 digits): kept out of line.
+constexpr int kBigLimbs = 192;               // 6144 bits: 800 digits (2658 bits) * 5^308 (716 bits) shifted by up to 2^1140
+constexpr int kBigDigits = 800;
+
+struct BigNum {
+    uint32_t v[kBigLimbs];
+    int n;                                   // limbs in use (v[n - 1] != 0), 0 = zero
+};
+SDC_HD void big_set(BigNum& a, uint64_t x) {
+    a.n = 0;
+    while (x) { a.v[a.n++] = (uint32_t)x; x >>= 32; }
+}
+SDC_HD void big_mul_add(BigNum& a, uint32_t mul, uint32_t add) {
+    uint64_t carry = add;
+    for (int i = 0; i < a.n; ++i) {
+        const uint64_t t = (uint64_t)a.v[i] * mul + carry;
+        a.v[i] = (uint32_t)t;
+        carry = t >> 32;
+    }
+    if (carry && a.n < kBigLimbs) a.v[a.n++] = (uint32_t)carry;
+}
+SDC_HD void big_mul_pow5(BigNum& a, int64_t p) {
+    while (p >= 13) { big_mul_add(a, 1220703125u, 0u); p -= 13; }          // 5^13
+    uint32_t m = 1;
+    while (p-- > 0) m *= 5u;
+    if (m > 1) big_mul_add(a, m, 0u);
+}
+SDC_HD void big_shl(BigNum& a, int64_t bits) {
+    if (a.n == 0 || bits <= 0) return;
+    const int limbs = (int)(bits >> 5), r = (int)(bits & 31);
+    if (a.n + limbs + 1 > kBigLimbs) return;                                // cannot happen within the documented bounds
+    for (int i = a.n - 1; i >= 0; --i) {
+        const uint64_t t = (uint64_t)a.v[i] << r;
+        if (i == a.n - 1) a.v[i + limbs + 1] = (uint32_t)(t >> 32);
+        else a.v[i + limbs + 1] |= (uint32_t)(t >> 32);
+        a.v[i + limbs] = (uint32_t)t;
+    }
+    for (int i = 0; i < limbs; ++i) a.v[i] = 0;
+    a.n += limbs + 1;
+    while (a.n > 0 && a.v[a.n - 1] == 0) --a.n;
+}
+SDC_HD int big_cmp(const BigNum& a, const BigNum& b) {
+    if (a.n != b.n) return a.n < b.n ? -1 : 1;
+    for (int i = a.n - 1; i >= 0; --i)
+        if (a.v[i] != b.v[i]) return a.v[i] < b.v[i] ? -1 : 1;
+    return 0;
+}
+
+// s[0, len): the digits part of the field ("123.456", sign and exponent stripped), exp_explicit the written exponent,
+// lower = eisel_lemire(w, ...) of the 19-digit truncation (w <= true value).  -> the correctly rounded bits
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+uint64_t round_long_decimal(const uint8_t* s, int len, int64_t exp_explicit, uint64_t lower) {
+    BigNum A, B;
+    A.n = 0;
+    int nd = 0;
+    int64_t q = exp_explicit;
+    bool sticky = false, frac = false;
+    for (int i = 0; i < len; ++i) {
+        if (s[i] == '.') { frac = true; continue; }
+        const uint32_t d = (uint32_t)s[i] - '0';
+        if (nd < kBigDigits) {
+            if (A.n == 0) { if (d) { A.v[0] = d; A.n = 1; } }
+            else big_mul_add(A, 10u, d);
+            nd += (A.n != 0);
+            if (frac) --q;
+        } else {
+            sticky |= d != 0u;
+            if (!frac) ++q;
+        }
+    }
+    // b = m * 2^e; the midpoint to the next double is (2 m + 1) * 2^(e - 1)
+    const uint64_t frac_bits = lower & 0x000fffffffffffffull;
+    const int64_t bexp = (int64_t)(lower >> 52);
+    const uint64_t m = bexp ? (frac_bits | (1ull << 52)) : frac_bits;
+    const int64_t e = (bexp ? bexp : 1) - 1075;
+    big_set(B, 2ull * m + 1ull);
+    int64_t two = q - (e - 1);              // A * 5^q * 2^two  vs  B   (q >= 0)   |   A * 2^two  vs  B * 5^-q   (q < 0)
+    if (q >= 0) big_mul_pow5(A, q); else big_mul_pow5(B, -q);
+    if (two >= 0) big_shl(A, two); else big_shl(B, -two);
+    int c = big_cmp(A, B);
+    if (c == 0 && sticky) c = 1;
+    if (c > 0) return lower + 1ull;
+    if (c < 0) return lower;
+    return (lower & 1ull) ? lower + 1ull : lower;          // an exact tie: to even
+}
+
 // kind of a field for type inference: 1 = int64, 2 = float64 (not an int), 4 = null token, 8 = anything else
 SDC_HD int parse_f64_field(const uint8_t* s, int len, const uint64_t* __restrict__ pow5, double* out, bool* was_int = nullptr) {
     const uint64_t kNaN = 0x7ff8000000000000ull;
@@ -179,7 +276,8 @@ SDC_HD int parse_f64_field(const uint8_t* s, int len, const uint64_t* __restrict
     // up to 19 significant digits into w; further ones only move the exponent (and are remembered when non-zero)
     uint64_t w = 0;
     int nd = 0;                 // significant digits held in w
-    int64_t exp10 = 0;
+    int64_t exp10 = 0, exp_explicit = 0;
+    const int digits_begin = i;
     bool truncated = false, any_digit = false, plain_int = true;
     for (; i < len; ++i) {
         const unsigned d = (unsigned)s[i] - '0';
@@ -200,6 +298,7 @@ SDC_HD int parse_f64_field(const uint8_t* s, int len, const uint64_t* __restrict
         }
     }
     if (!any_digit) return NP_BAD;
+    const int digits_end = i;
     if (i < len && (s[i] == 'e' || s[i] == 'E')) {
         plain_int = false;
         ++i;
@@ -212,12 +311,14 @@ SDC_HD int parse_f64_field(const uint8_t* s, int len, const uint64_t* __restrict
             if (d > 9u) return NP_BAD;
             if (e < 100000) e = e * 10 + d;
         }
-        exp10 += eneg ? -e : e;
+        exp_explicit = eneg ? -e : e;
+        exp10 += exp_explicit;
     }
     if (i != len) return NP_BAD;
     if (was_int) *was_int = plain_int && !(signed_ && !neg);              // "+12" is a float to Arrow, not an int
     uint64_t bits = eisel_lemire(w, exp10, pow5);
-    if (truncated && eisel_lemire(w + 1ull, exp10, pow5) != bits) return NP_AMBIG;
+    if (truncated && eisel_lemire(w + 1ull, exp10, pow5) != bits)
+        bits = round_long_decimal(s + digits_begin, digits_end - digits_begin, exp_explicit, bits);
     *out = bits_to_f64(sign | bits);
     return NP_OK;
 }

@@ -14,7 +14,6 @@ is not numeric (strings, quoted fields, dates) makes `read_csv_device` raise; `D
 hands such files to Arrow's reader, whose string buffers are the str_arr layout.
 """
 import ctypes as ct
-import io
 import os
 
 import numpy as np
@@ -34,28 +33,52 @@ def _torch():
     return torch
 
 
-def _read_bytes_pinned(filepath_or_buffer):
-    """-> pinned uint8 torch tensor holding the file's bytes."""
+_CHUNK = 32 << 20
+
+
+def _stage_to_device(filepath_or_buffer, dev):
+    """File (or bytes) -> (uint8 CUDA tensor, the first MiB as host bytes, byte count).  The bytes pass through a pinned
+    staging buffer in 32 MiB pieces: a few threads fill the pieces (file reads / memcpy release the GIL) while the pieces
+    already filled are on their way to the device."""
+    import concurrent.futures as cf
     torch = _torch()
+    fd = None
     if isinstance(filepath_or_buffer, (bytes, bytearray, memoryview)):
-        raw = bytes(filepath_or_buffer)
-        buf = torch.empty(max(1, len(raw)), dtype=torch.uint8, pin_memory=True)
-        buf.numpy()[:len(raw)] = np.frombuffer(raw, dtype=np.uint8)
-        return buf, len(raw)
-    if isinstance(filepath_or_buffer, io.IOBase) or hasattr(filepath_or_buffer, "read"):
-        return _read_bytes_pinned(filepath_or_buffer.read() if not isinstance(filepath_or_buffer, io.TextIOBase)
-                                  else filepath_or_buffer.read().encode("utf-8"))
-    n = os.path.getsize(filepath_or_buffer)
-    buf = torch.empty(max(1, n), dtype=torch.uint8, pin_memory=True)
-    with open(filepath_or_buffer, "rb", buffering=0) as f:
-        view = memoryview(buf.numpy())[:n]
-        got = 0
-        while got < n:
-            k = f.readinto(view[got:])
-            if not k:
-                break
-            got += k
-    return buf, n
+        raw = np.frombuffer(filepath_or_buffer, dtype=np.uint8)
+        n = raw.shape[0]
+    elif hasattr(filepath_or_buffer, "read"):
+        data = filepath_or_buffer.read()
+        return _stage_to_device(data.encode("utf-8") if isinstance(data, str) else data, dev)
+    else:
+        fd = os.open(filepath_or_buffer, os.O_RDONLY)
+        n = os.fstat(fd).st_size
+    try:
+        pinned = torch.empty(max(1, n), dtype=torch.uint8, pin_memory=True)
+        out = torch.empty(max(16, n), dtype=torch.uint8, device=dev)
+        host = pinned.numpy()
+
+        def fill(a, b):
+            if fd is None:
+                np.copyto(host[a:b], raw[a:b])
+            else:
+                view, got = memoryview(host)[a:b], 0
+                while got < b - a:
+                    k = os.preadv(fd, [view[got:]], a + got)
+                    if k <= 0:
+                        raise IOError("read_csv: short read")
+                    got += k
+            return a, b
+        spans = [(a, min(n, a + _CHUNK)) for a in range(0, n, _CHUNK)]
+        with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(spans)))) as pool:
+            for a, b in pool.map(lambda ab: fill(*ab), spans):            # in file order, as they complete
+                out[a:b].copy_(pinned[a:b], non_blocking=True)
+        head = bytes(host[:min(n, 1 << 20)])
+        # the pinned buffer goes back to torch's caching host allocator only after the copies that read it are done
+        torch.cuda.current_stream(dev).synchronize()
+    finally:
+        if fd is not None:
+            os.close(fd)
+    return out, head, n
 
 
 def _header_split(host_bytes, nbytes, skiprows, want_header, delimiter):
@@ -91,16 +114,13 @@ def read_csv_device(filepath_or_buffer, sep=",", delimiter=None, names=None, use
     if not isinstance(delimiter, str) or len(delimiter.encode("utf-8")) != 1:
         raise ValueError("read_csv: the delimiter must be one byte")
     dbyte = delimiter.encode("utf-8")
-    pinned, nbytes = _read_bytes_pinned(filepath_or_buffer)
-    host = pinned.numpy()
-    head = bytes(host[:min(nbytes, 1 << 20)])                       # column names live in the first lines
-    start, file_names = _header_split(head, len(head), skiprows, names is None, dbyte)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    data, head, nbytes = _stage_to_device(filepath_or_buffer, dev)
+    start, file_names = _header_split(head, len(head), skiprows, names is None, dbyte)     # column names live in the first lines
     if names is None and file_names is None:
         return {}, 0
     col_names = list(names) if names is not None else file_names
     ncols = len(col_names)
-    dev = torch.device("cuda", torch.cuda.current_device())
-    data = pinned.to(dev, non_blocking=True)
     handle, nrows = ct.c_int64(0), ct.c_int64(0)
     stream = native.current_stream_ptr()
     native.check(lib.sdcb200_csv_open(data.data_ptr() + start, nbytes - start, ct.byref(handle), ct.byref(nrows), stream))

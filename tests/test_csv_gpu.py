@@ -83,6 +83,26 @@ def test_random_tables_bit_exact(shape):
     assert n == nrows
 
 
+def test_long_digit_strings_on_the_device():
+    """Fields with more than 19 significant digits, ties and near-ties included: the device's big-integer tie-break
+    (num_parse.cuh round_long_decimal, local memory) gives Arrow's bits."""
+    from fractions import Fraction
+    import random
+    rng = random.Random(5)
+    fields = []
+    for _ in range(3000):
+        m = rng.getrandbits(53) | (1 << 52)
+        e = rng.randint(-1000, 900)
+        v = Fraction(2 * m + 1, 2) * (Fraction(2) ** e)
+        k2 = v.denominator.bit_length() - 1
+        digits = str(v.numerator * 5 ** k2)
+        fields.append(digits + ("e-%d" % k2 if k2 else ""))
+        fields.append(digits + "0000001" + "e-%d" % (k2 + 7))
+        fields.append("%.30e" % struct.unpack("<d", struct.pack("<Q", rng.getrandbits(62)))[0])
+    data = ("x\n" + "\n".join(fields) + "\n").encode()
+    _check(data)
+
+
 def test_errors_are_loud():
     from sdc_b200.csv import NotNumericCSV, read_csv_device
     with pytest.raises(NotNumericCSV):

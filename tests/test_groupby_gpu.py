@@ -337,7 +337,7 @@ def test_single_f64_column_specialised_kernels(keys_kind):
                 _compare(rk, res[agg], wk, want, agg, "%s %s hint=%d" % (keys_kind, aggs, hint))
 
 
-@pytest.mark.parametrize("keys_kind", ["uniform", "zipf", "few", "wide"])
+@pytest.mark.parametrize("keys_kind", ["uniform", "zipf", "few", "wide", "sparse"])
 def test_several_f64_columns_take_the_lean_loop_per_column(keys_kind):
     """>= 4 Mi rows, several float64 columns, low-cardinality int64 keys: run_groupby_int_keys aggregates column by
     column with the one-column lean loop and assembles the result rows; "wide" keys (no direct window) must fall back
@@ -352,6 +352,8 @@ def test_several_f64_columns_take_the_lean_loop_per_column(keys_kind):
         a = np.minimum(rng.zipf(1.3, n), 1000) - 1
     elif keys_kind == "few":
         a = rng.integers(0, 6, n)
+    elif keys_kind == "sparse":                           # no direct window: the hashed lean loop, column by column
+        a = rng.integers(0, 800, n) * 1000003 - 17
     else:
         a = rng.integers(0, 3000, n) * 1000003
     cols = [rng.standard_normal(n) * 10 for _ in range(3)]
