@@ -119,8 +119,10 @@ __global__ void __launch_bounds__(kRowThreads) csv_rows_kernel(const uint8_t* __
     // the CTA's rows are the bytes [lo, hi) of the file; staged from the 16-byte boundary below lo
     const int64_t lo = (int64_t)row_start[r0];
     const int64_t hi = r1 < nrows ? (int64_t)row_start[r1] : nbytes;
-    const int64_t alo = lo & ~(int64_t)15;
-    const bool staged = hi - alo <= (int64_t)smem_bytes && (reinterpret_cast<uintptr_t>(d) & 15) == 0;
+    // (the 16-byte granule is taken on the ADDRESS: `d` is usually the buffer's start plus the header's length; a granule
+    // that holds a byte of the data lies in the same allocation page, so reading it whole is safe)
+    const int64_t alo = lo - (int64_t)(reinterpret_cast<uintptr_t>(d + lo) & 15);
+    const bool staged = hi - alo <= (int64_t)smem_bytes;
     if (staged) {
         const int64_t nvec = (hi - alo) >> 4;                 // whole 16-byte words, then the tail byte by byte
         const uint4* src = reinterpret_cast<const uint4*>(d + alo);
@@ -255,12 +257,12 @@ static int32_t csv_run(CsvIndex* ix, bool classify, int32_t ncols, uint8_t delim
     cudaStream_t s = ix->stream;
     auto kern = classify ? csv_rows_kernel<true> : csv_rows_kernel<false>;
     SDC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem));
-    // rows per CTA and staging bytes from the average row length (x 1.5 for the spread): narrow rows 256 per CTA,
+    // rows per CTA and staging bytes from the average row length (x 1.25 for the spread): narrow rows 256 per CTA,
     // wide ones (census-shaped: 24 float columns, ~450 bytes) fewer, so that the CTA's byte range still fits
     const double avg = ix->nrows > 0 ? (double)ix->nbytes / (double)ix->nrows : 1.0;
     int threads = kRowThreads;
-    while (threads > 32 && avg * 1.5 * threads + 64 > (double)kRowSmem) threads >>= 1;
-    int smem = (int)(avg * 1.5 * threads) + 64;
+    while (threads > 32 && avg * 1.25 * threads + 64 > (double)kRowSmem) threads >>= 1;
+    int smem = (int)(avg * 1.25 * threads) + 64;
     smem = smem < 8192 ? 8192 : (smem > kRowSmem ? kRowSmem : smem);
     smem = (smem + 15) & ~15;
     Scratch dtypes, dout, dkinds, derr;

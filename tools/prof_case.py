@@ -29,6 +29,25 @@ elif what in ("groupby_100m", "groupby_100m_5agg"):
     aggs = ("sum",) if what == "groupby_100m" else ("sum", "mean", "min", "max", "count")
     for _ in range(reps):
         groupby_device(a, [b], aggs, True, 1, 1000)
+elif what == "groupby_sparse_5agg":
+    # 1 K groups under sparse int64 keys: the hashed lean loop of gb_smem_kernel (regime 1b)
+    from sdc_b200.groupby import groupby_device
+    n = 100_000_000
+    a = torch.from_numpy(rng.integers(0, 1000, n, dtype=np.int64) * 1000003 + 17).cuda()
+    b = torch.from_numpy(rng.random(n)).cuda()
+    for _ in range(reps):
+        groupby_device(a, [b], ("sum", "mean", "min", "max", "count"), True, 1, 1000)
+elif what == "csv":
+    import io
+    import pyarrow as pa
+    import pyarrow.csv as pacsv
+    from sdc_b200.csv import read_csv_device
+    table = pa.table({"c%d" % c: rng.standard_normal(500_000) * 10.0 ** (c % 7) for c in range(24)})
+    sink = io.BytesIO()
+    pacsv.write_csv(table, sink)
+    raw = sink.getvalue()
+    for _ in range(reps):
+        read_csv_device(raw)
 elif what == "groupby_small":
     from sdc_b200.groupby import groupby_device
     n = 200_000
