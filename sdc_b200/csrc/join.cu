@@ -66,20 +66,49 @@ __device__ __forceinline__ unsigned long long canon_key(unsigned long long b) {
 
 struct JTable {
     ulonglong2* slots;          // hash mode: [cap + 1]
+    ulonglong2* spare;          // the slot of a key equal to kEmptyKey: slots + cap, except in the grouped partitioned flow
+                                // (run_join_grouped), where `slots` is an offset view of one bucket group's table
     unsigned long long cap;     // power of two
     unsigned long long* dense;  // dense mode: val of key k at dense[k - dlo]
     uint32_t* dense32;          // dense mode with unique build keys: right row + 1 (0 = absent), 4 bytes per key
     unsigned long long dlo, drange;   // drange == 0: hash mode
-    int shift;                  // hash mode: 0 -> slot = low bits of jmix64(key); else slot = hash_mix64(key) >> shift (the TOP
-                                // bits: rows partitioned by the top byte of the same hash, radix_sort.cuh, walk the table
-                                // one contiguous 1/256 slice after the other -- the partitioned join)
+    int shift;                  // hash mode: 0 -> slot = low bits of jmix64(key), cap a power of two; else slot =
+                                // hash_mix64(key) * cap >> 64 (monotonic in the hash, so rows partitioned by the top byte of
+                                // the same hash, radix_sort.cuh, walk the table one contiguous 1/256 slice after the other --
+                                // the partitioned join; cap is then any even number: load factor 0.5 exactly, not 0.25-0.5)
 };
 
 // Home slots are EVEN: a lookup reads the 32-byte pair {slot, slot + 1} with one 256-bit load (one sector either way),
 // so a probe chain is half as many dependent round trips long -- the probe kernels are bound by the LONGEST chain among
 // a warp's 32 lanes, not by the average.
-__device__ __forceinline__ unsigned long long jt_home(const JTable& t, unsigned long long key) {
-    return (t.shift ? (hash_mix64(key) >> t.shift) : (jmix64(key) & (t.cap - 1))) & ~1ull;
+// Partitioned mode (t.shift): cap is a multiple of 512, bucket b of the top hash byte owns the slice of cap / 256 slots
+// [b * slice, (b + 1) * slice) -- exactly the slots hash * cap >> 64 can give its keys -- and probing WRAPS INSIDE THE
+// SLICE: every bucket is a hash table of its own, initialised and filled by one CTA (jt_build_part_kernel).
+struct JHome {
+    unsigned long long s;
+    uint32_t h32;            // partitioned mode: the top 32 bits of the hash (slice bounds are only worked out when a probe walks on)
+};
+__device__ __forceinline__ JHome jt_home(const JTable& t, unsigned long long key) {
+    JHome h;
+    if (t.shift) {
+        // cap < 2^32 (run_join checks): slot = top 32 hash bits * cap >> 32, one IMAD.HI
+        h.h32 = (uint32_t)(hash_mix64(key) >> 32);
+        h.s = (unsigned long long)(__umulhi(h.h32, (uint32_t)t.cap) & ~1u);
+    } else {
+        h.h32 = 0;
+        h.s = jmix64(key) & (t.cap - 1) & ~1ull;
+    }
+    return h;
+}
+// the slot after s + step - 1, wrapping inside the bucket's slice (partitioned) or the table
+__device__ __forceinline__ unsigned long long jt_next(const JTable& t, const JHome& h, unsigned long long s, unsigned step) {
+    s += step;
+    if (t.shift) {
+        const unsigned long long slice = t.cap >> 8;
+        const unsigned long long lo = (unsigned long long)(h.h32 >> 24) * slice;
+        return s >= lo + slice ? lo : s;
+    }
+    return s >= t.cap ? 0ull : s;
 }
 __device__ __forceinline__ void ld_slot_pair(const ulonglong2* p, ulonglong2& a, ulonglong2& b) {
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a.x), "=l"(a.y), "=l"(b.x), "=l"(b.y) : "l"(p));
@@ -87,7 +116,8 @@ __device__ __forceinline__ void ld_slot_pair(const ulonglong2* p, ulonglong2& a,
 
 __device__ __forceinline__ unsigned long long jt_upsert(const JTable& t, unsigned long long key) {
     if (key == kEmptyKey) return t.cap;
-    unsigned long long s = jt_home(t, key);
+    const JHome h = jt_home(t, key);
+    unsigned long long s = h.s;
     while (true) {
         const unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&t.slots[s].x);
         if (cur == key) return s;
@@ -95,7 +125,23 @@ __device__ __forceinline__ unsigned long long jt_upsert(const JTable& t, unsigne
             const unsigned long long old = atomicCAS(&t.slots[s].x, kEmptyKey, key);
             if (old == kEmptyKey || old == key) return s;
         }
-        s = (s + 1) & (t.cap - 1);
+        s = jt_next(t, h, s, 1);
+    }
+}
+
+// hashed table -> val of the key's slot, 0 when the key is absent.  One exit test per pair of slots: the four compares
+// become predicates and selects (the chain of four early returns cost 30 instructions per lookup and a divergent branch
+// each).
+__device__ __forceinline__ unsigned long long jt_lookup_hash(const JTable& t, unsigned long long key) {
+    if (key == kEmptyKey) return t.spare->y;
+    const JHome h = jt_home(t, key);
+    unsigned long long s = h.s;
+    while (true) {
+        ulonglong2 a, b;
+        ld_slot_pair(&t.slots[s], a, b);
+        const bool ma = a.x == key, ea = a.x == kEmptyKey, mb = b.x == key, eb = b.x == kEmptyKey;
+        if (ma | ea | mb | eb) return ma ? a.y : ((mb && !ea) ? b.y : 0ull);
+        s = jt_next(t, h, s, 2);
     }
 }
 
@@ -105,17 +151,7 @@ __device__ __forceinline__ unsigned long long jt_lookup(const JTable& t, unsigne
         const unsigned long long d = key - t.dlo;
         return d < t.drange ? __ldg(t.dense + d) : 0ull;
     }
-    if (key == kEmptyKey) return t.slots[t.cap].y;
-    unsigned long long s = jt_home(t, key);
-    while (true) {
-        ulonglong2 a, b;
-        ld_slot_pair(&t.slots[s], a, b);
-        if (a.x == key) return a.y;
-        if (a.x == kEmptyKey) return 0ull;
-        if (b.x == key) return b.y;
-        if (b.x == kEmptyKey) return 0ull;
-        s = (s + 2) & (t.cap - 1);
-    }
+    return jt_lookup_hash(t, key);
 }
 
 __global__ void jt_init_kernel(JTable t) {
@@ -143,9 +179,10 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
             s = jt_upsert(t, k);
             // one add carries the count (low word) AND the row (high word): with unique build keys the slot then
             // already reads row << 32 | 1 -- no scan, no scatter, and the probe needs no row-id indirection.  With
-            // duplicates the high words are garbage; the scan below rebuilds them from the counts.
+            // duplicates the high words are garbage; the scan below rebuilds them from the counts.  (Key and value word
+            // entering with ONE 16-byte compare-and-swap measured slower: 416 against 370 us per 10 M rows.)
             const unsigned long long row = rowmap ? (unsigned long long)rowmap[j] : (unsigned long long)j;
-            rank = atomicAdd(&t.slots[s].y, (row << 32) | 1ull) & 0xffffffffull;
+            rank = atomicAdd(s == t.cap ? &t.spare->y : &t.slots[s].y, (row << 32) | 1ull) & 0xffffffffull;
             if (rank) *dup_flag = 1ull;
         }
         __syncwarp();
@@ -154,6 +191,13 @@ __global__ void __launch_bounds__(kJoinThreads) jt_insert_kernel(const unsigned 
             rrank[j] = (uint32_t)rank;
         }
     }
+}
+
+// slots [0, n) of one bucket group's table (run_join_grouped)
+__global__ void jt_init_range_kernel(ulonglong2* __restrict__ slots, unsigned long long n) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        slots[i] = make_ulonglong2(kEmptyKey, 0ull);
 }
 
 // ---- dense mode ----
@@ -655,6 +699,110 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_compact_kernel(cons
     }
 }
 
+// Row-set inner join (SDCB200_JOIN_ANY_ORDER) over the partitioned probe side, ONE pass: the pairs may come out in any
+// order, so a tile needs no prefix over the tiles before it -- it takes its output range with one atomic add on the
+// running total once its hits are counted, and stores the pairs straight from registers like pass 2 above.  Against the
+// two passes this drops the `right row + 1` word per left row (written, then read back) and the second read of the
+// left rows' map: 2.8 GB instead of 4.0 GB of traffic per 100 M probes.  (For the dense table in left-row order the
+// single pass measured slower than the two passes -- there the second pass is cheap and the order is part of the
+// contract)
+template <bool KEY_F64>
+__global__ void __launch_bounds__(kJoinThreads) probe_unique_any_kernel(const unsigned long long* __restrict__ keys, int64_t n,
+                                                                        JTable t, const uint32_t* __restrict__ rid,
+                                                                        unsigned long long* __restrict__ total,
+                                                                        int64_t* __restrict__ lidx, int64_t* __restrict__ ridx,
+                                                                        const uint32_t* __restrict__ lmap,
+                                                                        const long long* __restrict__ lids,
+                                                                        const long long* __restrict__ rids, int vec,
+                                                                        int64_t first /* rows [first, n): one bucket group */) {
+    constexpr int kWarps = kJoinThreads / 32;
+    __shared__ unsigned wcnt[kWarps];
+    __shared__ unsigned long long s_base;
+    const uint64_t stream_pol = l2_policy_evict_first();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int64_t tile0 = (first & ~int64_t(1)) + (int64_t)blockIdx.x * kTile;      // even: the pair loads stay aligned
+    unsigned long long k[kItems];
+    uint32_t row1[kItems];
+    load_probe_keys<KEY_F64>(keys, tile0, warp, lane, n, vec != 0, stream_pol, k);
+    // the left rows travel beside the partitioned keys: loaded before the probes so that they are not waited for later
+    uint32_t lrow[kItems];
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const int64_t r = probe_row(tile0, warp, lane, 2 * j);
+        lrow[2 * j] = (uint32_t)r;
+        lrow[2 * j + 1] = (uint32_t)(r + 1);
+        if (lmap) {
+            if (r + 1 < n) {
+                const uint2 m = __ldcs(reinterpret_cast<const uint2*>(lmap + r));
+                lrow[2 * j] = m.x;
+                lrow[2 * j + 1] = m.y;
+            } else if (r < n) {
+                lrow[2 * j] = lmap[r];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < kItems; ++e) {
+        const int64_t r = probe_row(tile0, warp, lane, e);
+        row1[e] = 0u;
+        if (r >= first && r < n) {
+            const unsigned long long v = jt_lookup_hash(t, k[e]);      // unique build keys: row << 32 | 1 straight from the insert
+            row1[e] = (unsigned)v ? (uint32_t)(v >> 32) + 1u : 0u;
+        }
+        __syncwarp();                                  // hash probes end at different times per lane
+    }
+    unsigned rank[kItems], wtot = 0, fullmask = 0;
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const unsigned ba = __ballot_sync(0xffffffffu, row1[2 * j] != 0u);
+        const unsigned bb = __ballot_sync(0xffffffffu, row1[2 * j + 1] != 0u);
+        rank[2 * j] = wtot + __popc(ba & lt_mask) + __popc(bb & lt_mask);
+        rank[2 * j + 1] = rank[2 * j] + (row1[2 * j] != 0u ? 1u : 0u);
+        if ((ba & bb) == 0xffffffffu && !(wtot & 1u)) fullmask |= 1u << j;
+        wtot += __popc(ba) + __popc(bb);
+    }
+    if (lane == 0) wcnt[warp] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) tot += wcnt[w];
+        s_base = tot ? atomicAdd(total, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long base = s_base;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if (w < warp) base += wcnt[w];
+    const bool even = !(base & 1ull);
+#pragma unroll
+    for (int j = 0; j < kItems / 2; ++j) {
+        const unsigned long long p0 = base + rank[2 * j];
+        int64_t l0 = (int64_t)lrow[2 * j], l1 = (int64_t)lrow[2 * j + 1];
+        int64_t r0 = (int64_t)row1[2 * j] - 1, r1 = (int64_t)row1[2 * j + 1] - 1;
+        if (lids) {                                   // caller's ids in place of the local row numbers (sdcb200_join_ids)
+            if (row1[2 * j]) l0 = lids[l0];
+            if (row1[2 * j + 1]) l1 = lids[l1];
+        }
+        if (rids) {
+            if (row1[2 * j]) r0 = rids[r0];
+            if (row1[2 * j + 1]) r1 = rids[r1];
+        }
+        if (((fullmask >> j) & 1u) && even) {
+            st_hint_v2s64(lidx + p0, l0, l1, stream_pol);
+            st_hint_v2s64(ridx + p0, r0, r1, stream_pol);
+        } else {
+            if (row1[2 * j]) { lidx[p0] = l0; ridx[p0] = r0; }
+            if (row1[2 * j + 1]) {
+                const unsigned long long p1 = base + rank[2 * j + 1];
+                lidx[p1] = l1;
+                ridx[p1] = r1;
+            }
+        }
+    }
+}
+
 // how='left' with unique build keys: output row i = left row i, no scan
 template <bool KEY_F64>
 __global__ void __launch_bounds__(kJoinThreads) probe_unique_left_kernel(const unsigned long long* __restrict__ keys, int64_t n,
@@ -745,7 +893,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     // ---- build ----
     JTable t;
     memset(&t, 0, sizeof(t));
-    Scratch slots, slots32, rslot, rrank, rid, tsum_b, meta, rk2, rrow2, lk2, lrow2, pbeg;
+    Scratch slots, slots_fb, slots32, rslot, rrank, rid, tsum_b, meta, rk2, rrow2, lk2, lrow2, pbeg;
     const unsigned long long* rk = r;          // the build / probe key columns the kernels read: the caller's, or the
     const unsigned long long* lk = l;          // copies partitioned by hash bucket
     const uint32_t* rmap = nullptr;            // partitioned: original row of every partitioned position
@@ -804,7 +952,7 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     } else {
         t.cap = 1024;
         while (t.cap < 2ull * (unsigned long long)nr) t.cap <<= 1;         // load factor <= 0.5: short chains (see jt_home)
-        const int64_t nslots = (int64_t)t.cap + 1;
+        int64_t nslots = (int64_t)t.cap + 1;
         // Partitioned join (inner joins over keys with no dense range): once the table is far larger than L2 every
         // probe is a random HBM burst (154 B of DRAM traffic per probe measured).  Both sides are first split into the 256
         // buckets of the top hash byte (one unordered partition pass each, row numbers riding along as 32-bit payload)
@@ -813,12 +961,22 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
         // an inner join's contract is the row SET; how='left' keeps left-row order and stays on the direct path.
         const int part_on = [] { const char* e = getenv("SDCB200_JOIN_PART"); return e ? atoi(e) : 1; }();   // 0 off, 2 always (tests)
         static const bool chained = [] { const char* e = getenv("SDCB200_JOIN_INNER"); return e && !strcmp(e, "chained"); }();
-        part = part_on && !chained && !LEFT && any_order && extra == 0 && nl < 0xffffffffll &&
+        part = part_on && !chained && !LEFT && any_order && extra == 0 && nl < 0xffffffffll && nl > 0 && nr > 0 &&
                (part_on == 2 || ((int64_t)t.cap * 16 >= (int64_t(48) << 20) && nl >= (int64_t(1) << 22)));
+        unsigned long long c_part = 0;
         if (part) {
-            int lg = 0;
-            while ((1ull << lg) < t.cap) ++lg;
-            t.shift = 64 - lg;
+            // slots by multiply-shift: the capacity need not be a power of two, so the load factor is what is asked for
+            // (SDCB200_JOIN_LF percent, default 30) instead of whatever the next power of two leaves -- 320 MB instead of
+            // 537 MB of table to initialise and walk for C3's 10 M build keys
+            static const int lf = [] { const char* e = getenv("SDCB200_JOIN_LF"); const int v = e ? atoi(e) : 0; return (v >= 10 && v <= 90) ? v : 30; }();
+            unsigned long long& c = c_part;
+            c = ((unsigned long long)nr * 100ull + (unsigned long long)lf - 1) / (unsigned long long)lf;
+            c = (c + 511ull) & ~511ull;
+            if (c >= (1ull << 32)) part = false;       // jt_home takes the slot from 32-bit arithmetic
+        }
+        if (part) {
+            t.cap = c_part < 1024 ? 1024 : c_part;
+            t.shift = 1;
             SDC_TRY(pbeg.alloc(2 * 257 * 8, s));
             if (nr > 0) {
                 SDC_TRY(rk2.alloc((size_t)nr * 8, s));
@@ -828,18 +986,128 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                 rmap = rrow2.as<uint32_t>();
             }
         }
+        nslots = (int64_t)t.cap + 1;
         SDC_TRY(rslot.alloc((size_t)nr * 4 + 16, s));
         SDC_TRY(rrank.alloc((size_t)nr * 4 + 16, s));
-        SDC_TRY(slots.alloc((size_t)nslots * 16, s));
-        t.slots = slots.as<ulonglong2>();
-        SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
-        jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
-        SDC_CHECK_LAUNCH();
-        if (nr > 0) {
-            jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(rk, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2, rmap);
-            SDC_CHECK_LAUNCH();
-            SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+        if (!part) {
+            SDC_TRY(slots.alloc((size_t)nslots * 16, s));
+            t.slots = slots.as<ulonglong2>();
+            t.spare = t.slots + t.cap;
+        }
+        if (part) {
+            // ---- grouped flow: the table of one GROUP of buckets at a time, in a buffer that is reused from group to
+            // group and never leaves L2.  Per group: initialise the buffer, insert the group's build rows, probe the
+            // group's left rows.  A table-wide build followed by a table-wide probe wrote the whole table (533 MB for
+            // C3's 10 M build keys), read every 64-byte burst of it back for its first insert and once more for the
+            // probe: 0.46 ms of build for 10 M rows and 0.47 GB of extra reads in the probe under ncu.
+            SDC_TRY(lk2.alloc((size_t)nl * 8, s));
+            SDC_TRY(lrow2.alloc((size_t)nl * 4 + 16, s));
+            SDC_TRY(hash_partition_pass(l, KEY_F64, lk2.p, 4, nullptr, lrow2.p, nl, true, pbeg.as<unsigned long long>() + 257, s));
+            lk = lk2.as<unsigned long long>();
+            lmap = lrow2.as<uint32_t>();
+            unsigned long long hb[2 * 257];
+            SDC_CUDA_TRY(cudaMemcpyAsync(hb, pbeg.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
             SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            const unsigned long long* rb = hb;
+            const unsigned long long* lb = hb + 257;
+            const unsigned long long slice = t.cap >> 8;
+            const unsigned long long room = slice - ((slice >> 3) > 2 ? (slice >> 3) : 2);     // a slice never fills up
+            bool skew = false;
+            for (int b = 0; b < 256; ++b) skew = skew || (rb[b + 1] - rb[b] > room);
+            if (skew) {
+                // the build keys' hashes pile up in one bucket: back to the table-wide path over the caller's rows
+                part = false;
+                rk = r;
+                lk = l;
+                rmap = lmap = nullptr;
+                t.shift = 0;
+                t.cap = 1024;
+                while (t.cap < 2ull * (unsigned long long)nr) t.cap <<= 1;
+                nslots = (int64_t)t.cap + 1;
+                SDC_TRY(slots_fb.alloc((size_t)nslots * 16, s));
+                t.slots = slots_fb.as<ulonglong2>();
+                t.spare = t.slots + t.cap;
+            } else {
+                // SDCB200_JOIN_GROUP_MB: the table bytes built and probed at a time (-1, the default: all of it -- see below)
+                const long long group_mb = [] { const char* e = getenv("SDCB200_JOIN_GROUP_MB"); return e ? atoll(e) : -1ll; }();
+                int G = 1;
+                while (group_mb >= 0 && G < 256 && (long long)(t.cap * 16ull / (unsigned long long)G) > (group_mb << 20)) G <<= 1;
+                const int bpg = 256 / G;
+                const unsigned long long gslots = slice * (unsigned long long)bpg;
+                Scratch gbuf, spare;
+                SDC_TRY(gbuf.alloc((size_t)gslots * 16, s));
+                SDC_TRY(spare.alloc(16, s));
+                const unsigned long long spare_init[2] = {kEmptyKey, 0ull};
+                SDC_CUDA_TRY(cudaMemcpyAsync(spare.p, spare_init, 16, cudaMemcpyHostToDevice, s));
+                void* po = nullptr;
+                SDC_TRY(dev_alloc(&po, (size_t)nl * 8, s));
+                res->lidx = reinterpret_cast<int64_t*>(po);
+                SDC_TRY(dev_alloc(&po, (size_t)nl * 8, s));
+                res->ridx = reinterpret_cast<int64_t*>(po);
+                const int vec = (reinterpret_cast<uintptr_t>(lk) & 15) == 0;
+                unsigned long long hdup_g = 0;
+                for (int g = 0; g < G && hdup_g == 0; ++g) {
+                    JTable tg = t;
+                    // global slot numbers: the group's first slot lands on gbuf[0]
+                    tg.slots = reinterpret_cast<ulonglong2*>(reinterpret_cast<uintptr_t>(gbuf.p) - (uintptr_t)g * gslots * 16);
+                    tg.spare = spare.as<ulonglong2>();
+                    const int64_t r0 = (int64_t)rb[g * bpg], r1 = (int64_t)rb[(g + 1) * bpg];
+                    const int64_t l0 = (int64_t)lb[g * bpg], l1 = (int64_t)lb[(g + 1) * bpg];
+                    if (l1 == l0) continue;                    // nobody asks for these build rows
+                    jt_init_range_kernel<<<(unsigned)(ceil_div((int64_t)gslots, 256) < wide ? ceil_div((int64_t)gslots, 256) : wide), 256, 0, s>>>(
+                        gbuf.as<ulonglong2>(), gslots);
+                    SDC_CHECK_LAUNCH();
+                    if (r1 > r0) {
+                        const int ig = (int)(ceil_div(r1 - r0, kJoinThreads) < wide ? ceil_div(r1 - r0, kJoinThreads) : wide);
+                        jt_insert_kernel<KEY_F64><<<ig, kJoinThreads, 0, s>>>(rk + r0, r1 - r0, tg, rslot.as<uint32_t>() + r0,
+                                                                              rrank.as<uint32_t>() + r0, dmeta + 2, rmap + r0);
+                        SDC_CHECK_LAUNCH();
+                    }
+                    if (g == 0 && G > 1) {
+                        // duplicate build keys usually show in the first group already: leave before the probes are wasted
+                        SDC_CUDA_TRY(cudaMemcpyAsync(&hdup_g, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+                        SDC_CUDA_TRY(cudaStreamSynchronize(s));
+                        if (hdup_g) break;
+                    }
+                    const int64_t base = l0 & ~int64_t(1);
+                    probe_unique_any_kernel<KEY_F64><<<(unsigned)ceil_div(l1 - base, kTile), kJoinThreads, 0, s>>>(
+                        lk, l1, tg, rid.as<uint32_t>(), dmeta + 1, res->lidx, res->ridx, lmap, ids_applied ? lids : nullptr,
+                        ids_applied ? rids : nullptr, vec, l0);
+                    SDC_CHECK_LAUNCH();
+                }
+                unsigned long long h[2] = {0, 0};
+                SDC_CUDA_TRY(cudaMemcpyAsync(h, dmeta + 1, 16, cudaMemcpyDeviceToHost, s));
+                SDC_CUDA_TRY(cudaStreamSynchronize(s));
+                if (h[1] == 0) {
+                    if (ids_applied) *ids_applied = true;
+                    res->n_out = (int64_t)h[0];
+                    return SDCB200_OK;
+                }
+                // duplicate build keys: every left row may have several partners -- the table-wide count / scan / emit
+                // path below, over the partitioned rows
+                dev_free(res->lidx, s);
+                dev_free(res->ridx, s);
+                res->lidx = res->ridx = nullptr;
+                const unsigned long long zero2[2] = {0, 0};
+                SDC_CUDA_TRY(cudaMemcpyAsync(dmeta + 1, zero2, 16, cudaMemcpyHostToDevice, s));
+                SDC_TRY(slots.alloc((size_t)nslots * 16, s));
+                t.slots = slots.as<ulonglong2>();
+                t.spare = t.slots + t.cap;
+            }
+        }
+        const bool built = false;
+        SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
+        if (!built) {
+            jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
+            SDC_CHECK_LAUNCH();
+        }
+        if (nr > 0) {
+            if (!built) {
+                jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(rk, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2, rmap);
+                SDC_CHECK_LAUNCH();
+                SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+                SDC_CUDA_TRY(cudaStreamSynchronize(s));
+            }
             if (hdup != 0) {
                 // duplicate build keys: counts -> starts, right rows grouped by key
                 SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
@@ -854,13 +1122,6 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
     if (nl == 0) return SDCB200_OK;
     const int64_t nt = ceil_div(nl, kTile);
     void* p = nullptr;
-    if (part) {
-        SDC_TRY(lk2.alloc((size_t)nl * 8, s));
-        SDC_TRY(lrow2.alloc((size_t)nl * 4 + 16, s));
-        SDC_TRY(hash_partition_pass(l, KEY_F64, lk2.p, 4, nullptr, lrow2.p, nl, true, pbeg.as<unsigned long long>() + 257, s));
-        lk = lk2.as<unsigned long long>();
-        lmap = lrow2.as<uint32_t>();
-    }
     if (unique) {
         // every left row has at most one partner: one kernel, n_out <= nl
         SDC_TRY(dev_alloc(&p, (size_t)(nl + extra) * 8, s));

@@ -19,10 +19,11 @@ int32_t radix_sort_core(int dtype, const void* src, void* bufA, void* bufB, int 
 // idx64_out (4-byte payload only): the LAST pass writes no keys and stores the payload as int64 into idx64_out
 // (*rkeys is then null, *rpay == idx64_out) -- what an argsort wants.
 
-// One stable partition pass of 8-byte keys (raw bits; key_f64: canonicalise -0.0 / NaN first) and their payload
+// One UNORDERED partition pass of 8-byte keys (raw bits; key_f64: canonicalise -0.0 / NaN first) and their payload
 // (pay_bytes 0 / 4 / 8; iota: the payload is the row number) into 256 buckets by the TOP byte of
 // hash_mix64(canonical key) (common.cuh).  part_begin: device u64[257], bucket b = [part_begin[b], part_begin[b+1]).
-// Rows of one bucket keep their input order.  Hash tables whose slot index is taken from the top bits of the same
+// Rows of one bucket arrive in no particular order (a tile claims its range of every bucket with one atomic add on
+// the bucket's cursor; inside a tile one shared atomic per row).  Hash tables whose slot index is taken from the top bits of the same
 // hash are then touched one contiguous 1/256 slice at a time (join / groupby with keys that have no dense range).
 int32_t hash_partition_pass(const void* keys, bool key_f64, void* keys_out, int pay_bytes, const void* pay, void* pay_out,
                             int64_t n, bool iota, unsigned long long* part_begin, cudaStream_t s);

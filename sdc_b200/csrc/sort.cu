@@ -201,8 +201,11 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t ntiles = (n + TILE - 1) / TILE;
+    // CLAIM (unordered partition passes): a tile takes its range of every bucket with one atomic add on the bucket's
+    // cursor -- no look-back chain, no status words, and no ticket either (tiles do not depend on one another)
+    constexpr bool CLAIM = !DIG::kStable;
     if (tid == 0) {
-        const unsigned t = atomicAdd(ticket, 1u);
+        const unsigned t = CLAIM ? blockIdx.x : atomicAdd(ticket, 1u);
         warp_tot[8] = t;
         if (use_tma) {
             mbar_init(&bars[0], 1);
@@ -315,7 +318,13 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             run = wh[d];
         }
         cnt = run;
-        lb[(size_t)tile * 256 + d] = lb_pack(cnt, tile == 0 ? 2u : 1u, epoch);
+        if (CLAIM) {
+            // the bucket's cursor started at the bucket's first row (hash_scan_kernel); the add is in flight while the
+            // tile is staged
+            if (cnt) cnt = atomicAdd(const_cast<unsigned long long*>(gbase) + d, cnt);
+        } else {
+            lb[(size_t)tile * 256 + d] = lb_pack(cnt, tile == 0 ? 2u : 1u, epoch);
+        }
         }
         unsigned x = run;
 #pragma unroll
@@ -363,7 +372,9 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             if (wbase + i * 32 + lane < tile_n) spay[slot[i]] = pay[i];
     }
     // ---- decoupled look-back per digit, four predecessors per round trip ----
-    if (tid < 256) {
+    if (CLAIM) {
+        if (tid < 256) digit_dst[tid] = (long long)cnt - (long long)tile_off[tid];      // cnt: the claimed range's first row
+    } else if (tid < 256) {
         const int d = tid;
         unsigned long long excl = 0;
         if (tile != 0) {
@@ -581,8 +592,8 @@ int32_t sort_dispatch_pay(const void* src, void* bufA, void* bufB, int pay_bytes
     return SDCB200_ERR_ARG;
 }
 
-// ---- one stable partition pass by hash bucket (HashTopDigit): 256 buckets, bucket b = rows whose
-// hash_mix64(canonical key) has top byte b, in input order.  part_begin (device, u64[257]) receives the bucket starts.
+// ---- one unordered partition pass by hash bucket (HashTopDigit): 256 buckets, bucket b = rows whose
+// hash_mix64(canonical key) has top byte b, in no particular order.  part_begin (device, u64[257]) receives the bucket starts.
 template <typename DIG>
 __global__ void __launch_bounds__(kHistThreads) hash_hist_kernel(const unsigned long long* __restrict__ keys, int64_t n, DIG dig,
                                                                  unsigned long long* __restrict__ ghist) {
@@ -595,7 +606,8 @@ __global__ void __launch_bounds__(kHistThreads) hash_hist_kernel(const unsigned 
     for (int i = threadIdx.x; i < 256; i += kHistThreads)
         if (sh[i]) atomicAdd(&ghist[i], (unsigned long long)sh[i]);
 }
-__global__ void __launch_bounds__(256) hash_scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase) {
+__global__ void __launch_bounds__(256) hash_scan_kernel(const unsigned long long* __restrict__ ghist, unsigned long long* __restrict__ gbase,
+                                                        unsigned long long* __restrict__ cursor /* the partition pass's bucket cursors */) {
     __shared__ unsigned long long warp_tot[8];
     const int d = threadIdx.x, lane = d & 31, w = d >> 5;
     const unsigned long long v = ghist[d];
@@ -610,6 +622,7 @@ __global__ void __launch_bounds__(256) hash_scan_kernel(const unsigned long long
     unsigned long long add = 0;
     for (int i = 0; i < w; ++i) add += warp_tot[i];
     gbase[d] = add + x - v;
+    cursor[d] = add + x - v;
     if (d == 255) gbase[256] = add + x;
 }
 
@@ -654,7 +667,7 @@ int32_t argsort_device(int dtype, const void* keys, int64_t n, bool ascending, i
     return SDCB200_OK;
 }
 
-// One stable partition pass of 8-byte keys (+ payload) into the 256 buckets of HashTopDigit.
+// One unordered partition pass of 8-byte keys (+ payload) into the 256 buckets of a digit functor.
 namespace {
 template <typename DIG>
 int32_t partition_pass_impl(DIG dig, const void* keys, void* keys_out, int pay_bytes, const void* pay, void* pay_out, int64_t n,
@@ -667,24 +680,25 @@ int32_t partition_pass_impl(DIG dig, const void* keys, void* keys_out, int pay_b
     // slower (2.83 / 2.64 against 2.55 ms for the partitioned C3 join)
     const int TILE = 4096;
     const int64_t ntiles = ceil_div(n, TILE);
-    Scratch meta, lb;
-    SDC_TRY(meta.alloc(256 * 8 + 16, s));
-    SDC_TRY(lb.alloc((size_t)ntiles * 256 * 8, s));
+    static_assert(!DIG::kStable, "partition passes claim their bucket ranges with atomics (no look-back buffer)");
+    (void)ntiles;
+    Scratch meta;
+    SDC_TRY(meta.alloc(2 * 256 * 8 + 16, s));
     unsigned long long* ghist = meta.as<unsigned long long>();
-    unsigned* ticket = reinterpret_cast<unsigned*>(ghist + 256);
-    SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, 256 * 8 + 16, s));
-    SDC_CUDA_TRY(cudaMemsetAsync(lb.p, 0, (size_t)ntiles * 256 * 8, s));
+    unsigned long long* cursor = ghist + 256;          // bucket d's next free row: starts at part_begin[d]
+    unsigned* ticket = reinterpret_cast<unsigned*>(cursor + 256);
+    SDC_CUDA_TRY(cudaMemsetAsync(meta.p, 0, 2 * 256 * 8 + 16, s));
     int hgrid = (int)(ceil_div(n, kHistThreads * 8) < (int64_t)sm_count() * 4 ? ceil_div(n, kHistThreads * 8) : (int64_t)sm_count() * 4);
     if (hgrid < 1) hgrid = 1;
     const unsigned long long* k = reinterpret_cast<const unsigned long long*>(keys);
     hash_hist_kernel<DIG><<<hgrid, kHistThreads, 0, s>>>(k, n, dig, ghist);
     SDC_CHECK_LAUNCH();
-    hash_scan_kernel<<<1, 256, 0, s>>>(ghist, part_begin);
+    hash_scan_kernel<<<1, 256, 0, s>>>(ghist, part_begin, cursor);
     SDC_CHECK_LAUNCH();
     unsigned long long* ko = reinterpret_cast<unsigned long long*>(keys_out);
     typedef unsigned long long K;
 #define SDC_PART(P_, HAS_, pin_) \
-    launch_cfg<K, P_, HAS_, DIG, 256, 16, (sizeof(P_) > 4 ? 2 : 3), false>(k, ko, pin_, pay_out, n, iota, part_begin, lb.as<K>(), 1u, ticket, dig, s)
+    launch_cfg<K, P_, HAS_, DIG, 256, 16, (sizeof(P_) > 4 ? 2 : 3), false>(k, ko, pin_, pay_out, n, iota, cursor, nullptr, 1u, ticket, dig, s)
     if (pay_bytes == 0) return SDC_PART(uint32_t, false, (const uint32_t*)nullptr);
     if (pay_bytes == 4) return SDC_PART(uint32_t, true, reinterpret_cast<const uint32_t*>(pay));
     if (pay_bytes == 8) return SDC_PART(K, true, reinterpret_cast<const K*>(pay));

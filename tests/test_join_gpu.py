@@ -190,12 +190,28 @@ def test_partitioned_inner_join_matches_oracle(monkeypatch):
     f[::50] = np.nan
     cases.append((f, np.concatenate([f[:5_000] * 1.0, [np.nan, -0.0, 0.0]])))
     cases.append((np.array([1, 2, 3], dtype=np.int64), np.array([], dtype=np.int64)))
-    for l, r in cases:
-        li, ri = join_device(torch.from_numpy(np.ascontiguousarray(l)).cuda(), torch.from_numpy(np.ascontiguousarray(r)).cuda(), "inner")
-        got = ojoin.canonical(li.cpu().numpy(), ri.cpu().numpy())
-        want = ojoin.join_indexers(l, r, "inner")
-        np.testing.assert_array_equal(got[0], want[0])
-        np.testing.assert_array_equal(got[1], want[1])
+    # the table can be built and probed one group of buckets at a time: one group (the default), 256 groups
+    for group_mb in ("-1", "0"):
+        monkeypatch.setenv("SDCB200_JOIN_GROUP_MB", group_mb)
+        for l, r in cases:
+            li, ri = join_device(torch.from_numpy(np.ascontiguousarray(l)).cuda(), torch.from_numpy(np.ascontiguousarray(r)).cuda(), "inner")
+            got = ojoin.canonical(li.cpu().numpy(), ri.cpu().numpy())
+            want = ojoin.join_indexers(l, r, "inner")
+            np.testing.assert_array_equal(got[0], want[0])
+            np.testing.assert_array_equal(got[1], want[1])
+    # keys whose hashes all fall into ONE bucket (top byte of (x ^ x >> 32) * 0x9e3779b97f4a7c15 == 0, common.cuh
+    # hash_mix64): the bucket's slice cannot hold them and the build falls back to the table-wide path
+    ginv = pow(0x9e3779b97f4a7c15, -1, 1 << 64)
+    h = rng.integers(0, 1 << 56, 60_000, dtype=np.uint64)
+    y = np.array([(int(v) * ginv) & ((1 << 64) - 1) for v in np.unique(h)], dtype=np.uint64)
+    x = (y ^ (y >> np.uint64(32))).view(np.int64)                                  # x ^ (x >> 32) == y
+    assert (((x.view(np.uint64) ^ (x.view(np.uint64) >> np.uint64(32))) * np.uint64(0x9e3779b97f4a7c15)) >> np.uint64(56)).max() == 0
+    lx = np.concatenate([x[rng.integers(0, len(x), 300_000)], rng.integers(0, 1 << 40, 50_000, dtype=np.int64)])
+    li, ri = join_device(torch.from_numpy(lx).cuda(), torch.from_numpy(x).cuda(), "inner")
+    got = ojoin.canonical(li.cpu().numpy(), ri.cpu().numpy())
+    want = ojoin.join_indexers(lx, x, "inner")
+    np.testing.assert_array_equal(got[0], want[0])
+    np.testing.assert_array_equal(got[1], want[1])
     # how='left' keeps left-row order whatever the switch says
     l, r = cases[0]
     li, _ = join_device(torch.from_numpy(l).cuda(), torch.from_numpy(r).cuda(), "left")
