@@ -742,6 +742,8 @@ __global__ void __launch_bounds__(kJoinThreads) probe_unique_any_kernel(const un
             }
         }
     }
+    // (asking for all eight home pairs with prefetches before the first lookup measured slower, 2.49 against 2.19 ms:
+    // the kernel is bound by L1TEX requests -- one sector per random lookup -- not by their latency)
 #pragma unroll
     for (int e = 0; e < kItems; ++e) {
         const int64_t r = probe_row(tile0, warp, lane, e);

@@ -193,7 +193,8 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
     unsigned* wh = reinterpret_cast<unsigned*>(spay + (HAS_PAY ? TILE : 0));  // [WARPS][256]
     unsigned* tile_off = wh + WARPS * 256;                              // [256]
     long long* digit_dst = reinterpret_cast<long long*>(tile_off + 256);    // [256]
-    unsigned* warp_tot = reinterpret_cast<unsigned*>(digit_dst + 256);      // [8 digit warps] + s_tile at [8]
+    unsigned* dst32 = reinterpret_cast<unsigned*>(digit_dst + 256);         // [256] low words of digit_dst
+    unsigned* warp_tot = dst32 + 256;                                       // [8 digit warps] + s_tile at [8]
     uint64_t* bars = reinterpret_cast<uint64_t*>(warp_tot + 16);            // [2]
     unsigned char* sdig = reinterpret_cast<unsigned char*>(bars + 2);       // [TILE] digit of the staged row
     P* pout = reinterpret_cast<P*>(pout_raw);
@@ -266,16 +267,19 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
                 unsigned m;
-                // one predicate-setting LOP3, one VOTE and the select-and-mask per bit
+                // per bit: the predicate (all eight come from one R2P), one VOTE, one SELP and ONE LOP3 --
+                // peers &= ballot ^ (bit ? 0 : ~0), i.e. the ballot for lanes whose bit is set, its complement for the
+                // others (the predicated and / and-not pair compiled to two LOP3 and a SEL: the ALU pipe is this kernel's
+                // busiest unit, 64 % under ncu)
                 asm volatile(
                     "{\n"
                     ".reg .pred p;\n"
-                    ".reg .b32 t;\n"
+                    ".reg .b32 t, x;\n"
                     "and.b32 t, %2, %3;\n"
                     "setp.ne.u32 p, t, 0;\n"
                     "vote.sync.ballot.b32 %0, p, 0xffffffff;\n"
-                    "@p and.b32 %1, %1, %0;\n"
-                    "@!p lop3.b32 %1, %1, %0, 0, 0x30;\n"           // a & ~b
+                    "selp.b32 x, 0, 0xffffffff, p;\n"
+                    "lop3.b32 %1, %1, %0, x, 0x60;\n"               // a & (b ^ c)
                     "}\n"
                     : "=&r"(m), "+r"(peers)
                     : "r"(d), "r"(1u << b));
@@ -372,8 +376,14 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             if (wbase + i * 32 + lane < tile_n) spay[slot[i]] = pay[i];
     }
     // ---- decoupled look-back per digit, four predecessors per round trip ----
+    // fewer than 2^32 rows: the scatter below works on the low words of the destinations (dst32)
+    const bool n32 = n <= 0xffffffffll;
     if (CLAIM) {
-        if (tid < 256) digit_dst[tid] = (long long)cnt - (long long)tile_off[tid];      // cnt: the claimed range's first row
+        if (tid < 256) {
+            const long long dd = (long long)cnt - (long long)tile_off[tid];             // cnt: the claimed range's first row
+            digit_dst[tid] = dd;
+            dst32[tid] = (unsigned)dd;
+        }
     } else if (tid < 256) {
         const int d = tid;
         unsigned long long excl = 0;
@@ -400,10 +410,25 @@ onesweep_kernel(const U* __restrict__ kin, U* __restrict__ kout, const P* __rest
             }
             lb[(size_t)tile * 256 + d] = lb_pack(excl + cnt, 2u, epoch);
         }
-        digit_dst[d] = (long long)(gbase[d] + excl) - (long long)tile_off[d];
+        const long long dd = (long long)(gbase[d] + excl) - (long long)tile_off[d];
+        digit_dst[d] = dd;
+        dst32[d] = (unsigned)dd;
     }
     __syncthreads();
     // ---- scatter: consecutive staged slots of one bucket go to consecutive global slots ----
+    if (n32) {
+        // 32-bit destinations: one add and one IMAD.WIDE per address instead of four 64-bit add / shift instructions
+        // each on the ALU pipe, this kernel's busiest unit
+        for (int p = tid; p < tile_n; p += THREADS) {
+            const unsigned dst = dst32[sdig[p]] + (unsigned)p;
+            if (!LAST_IDX) kout[dst] = skeys[p];
+            if (HAS_PAY) {
+                if (LAST_IDX) pout64[dst] = (long long)spay[p];
+                else pout[dst] = spay[p];
+            }
+        }
+        return;
+    }
     for (int p = tid; p < tile_n; p += THREADS) {
         const long long dst = digit_dst[sdig[p]] + p;
         if (!LAST_IDX) kout[dst] = skeys[p];
@@ -441,7 +466,7 @@ int sort_use_tma() { static const int v = sort_env("SDCB200_SORT_TMA", 1); retur
 template <typename U, typename P, bool HAS_PAY, int THREADS, int ITEMS>
 constexpr size_t onesweep_smem() {
     return (size_t)THREADS * ITEMS * (sizeof(U) + (HAS_PAY ? sizeof(P) : 0) + 1) + (size_t)(THREADS / 32) * 256 * 4 + 256 * 4 +
-           256 * 8 + 16 * 4 + 2 * 8;
+           256 * 8 + 256 * 4 + 16 * 4 + 2 * 8;
 }
 
 // tile geometry: rows per tile are the same for every configuration (look-back buffers are sized by it)
