@@ -219,6 +219,36 @@ def bench_other_ops(dev, peak, cpu_legs=True):
     gb["rows_per_s_100M"] = n2 / (med2 * 1e-3)
     gb["frac_of_measured_peak_100M"] = 16 * n2 / (med2 * 1e-3) / 1e9 / peak
     del a2, b2
+    # "launch overhead matters at this size: also report 100 M and 1 B rows" -- 1 B rows = 16 GB in HBM,
+    # generated on the device (same distributions: uniform keys in [0, 1000), uniform values in [0, 1))
+    n3 = 1_000_000_000
+    g3 = torch.Generator(device=dev).manual_seed(0)
+    a3 = torch.randint(0, 1000, (n3,), device=dev, dtype=torch.int64, generator=g3)
+    b3 = torch.rand(n3, device=dev, dtype=torch.float64, generator=g3)
+    med3, _ = _event_times(lambda: groupby_device(a3, [b3], ("sum",), True, 1, 1000), 5, warm=2)
+    k3, r3 = groupby_device(a3, [b3], ("sum",), True, 1, 1000)
+    gb["rows_per_s_1B"] = n3 / (med3 * 1e-3)
+    gb["ms_1B"] = med3
+    gb["frac_of_measured_peak_1B"] = 16 * n3 / (med3 * 1e-3) / 1e9 / peak
+    gb["check_1B"] = {"groups": int(k3.shape[0]), "sum_of_sums_rel_err": abs(float(r3["sum"][0].sum()) - float(b3.sum())) / float(b3.sum())}
+    del a3, b3, k3, r3
+    # C5's census shape on one GPU (24 float64 columns, 125 M rows per GPU = 24 GB + 1 GB of keys): every
+    # column summed per key, K = 1 K -- the local aggregate of the combiner path
+    nc, ncols = 125_000_000, 24
+    a4 = torch.randint(0, 1000, (nc,), device=dev, dtype=torch.int64, generator=g3)
+    cols4 = [torch.rand(nc, device=dev, dtype=torch.float64, generator=g3) for _ in range(ncols)]
+    med4, _ = _event_times(lambda: groupby_device(a4, cols4, ("sum",), True, 1, 1000), 3, warm=1)
+    k4, r4 = groupby_device(a4, cols4, ("sum",), True, 1, 1000)
+    bytes4 = nc * 8 * (ncols + 1)
+    out["groupby_sum_census24"] = {
+        "workload": "C5 census shape on one GPU: df.groupby('A').sum() over 24 float64 columns, 125M rows, 1K int64 groups",
+        "ms_median": med4, "rows_per_s": nc / (med4 * 1e-3), "algorithmic_bytes": bytes4,
+        "frac_of_measured_peak": bytes4 / (med4 * 1e-3) / 1e9 / peak,
+        "check": {"groups": int(k4.shape[0]),
+                  "max_rel_err_of_column_totals": max(abs(float(r4["sum"][i].sum()) - float(cols4[i].sum())) / float(cols4[i].sum())
+                                                      for i in range(ncols))}}
+    del a4, cols4, k4, r4
+    torch.cuda.empty_cache()
     if cpu_legs:
         import numba
         import pandas as pd
