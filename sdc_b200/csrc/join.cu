@@ -997,11 +997,13 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
             t.spare = t.slots + t.cap;
         }
         if (part) {
-            // ---- grouped flow: the table of one GROUP of buckets at a time, in a buffer that is reused from group to
-            // group and never leaves L2.  Per group: initialise the buffer, insert the group's build rows, probe the
-            // group's left rows.  A table-wide build followed by a table-wide probe wrote the whole table (533 MB for
-            // C3's 10 M build keys), read every 64-byte burst of it back for its first insert and once more for the
-            // probe: 0.46 ms of build for 10 M rows and 0.47 GB of extra reads in the probe under ncu.
+            // ---- unique build keys, both sides partitioned: build, then probe + emit in ONE pass (a tile takes its output
+            // range with one atomic).  The table can also be built and probed one GROUP of buckets at a time in a buffer
+            // that is reused from group to group and so never leaves L2 (SDCB200_JOIN_GROUP_MB): the table-wide form
+            // writes the whole table (533 MB for C3's 10 M build keys), reads every 64-byte burst of it back for its
+            // first insert and once more for the probe.  Measured, the sixteen small builds and probes that L2-sized
+            // groups take cost more than those reads (2.73 against 2.32 ms), so the default is one group; the switch
+            // stays for tables that dwarf this one and is covered by the tests.
             SDC_TRY(lk2.alloc((size_t)nl * 8, s));
             SDC_TRY(lrow2.alloc((size_t)nl * 4 + 16, s));
             SDC_TRY(hash_partition_pass(l, KEY_F64, lk2.p, 4, nullptr, lrow2.p, nl, true, pbeg.as<unsigned long long>() + 257, s));
@@ -1097,19 +1099,15 @@ int32_t run_join(const unsigned long long* l, int64_t nl, const unsigned long lo
                 t.spare = t.slots + t.cap;
             }
         }
-        const bool built = false;
+        // ---- table-wide build: every path but the unique-key partitioned one, which returned above
         SDC_TRY(tsum_b.alloc((size_t)(ceil_div(nslots, kTile) + 1) * 8, s));
-        if (!built) {
-            jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
-            SDC_CHECK_LAUNCH();
-        }
+        jt_init_kernel<<<(unsigned)(ceil_div(nslots, 256) < wide ? ceil_div(nslots, 256) : wide), 256, 0, s>>>(t);
+        SDC_CHECK_LAUNCH();
         if (nr > 0) {
-            if (!built) {
-                jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(rk, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2, rmap);
-                SDC_CHECK_LAUNCH();
-                SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
-                SDC_CUDA_TRY(cudaStreamSynchronize(s));
-            }
+            jt_insert_kernel<KEY_F64><<<bgrid, kJoinThreads, 0, s>>>(rk, nr, t, rslot.as<uint32_t>(), rrank.as<uint32_t>(), dmeta + 2, rmap);
+            SDC_CHECK_LAUNCH();
+            SDC_CUDA_TRY(cudaMemcpyAsync(&hdup, dmeta + 2, 8, cudaMemcpyDeviceToHost, s));
+            SDC_CUDA_TRY(cudaStreamSynchronize(s));
             if (hdup != 0) {
                 // duplicate build keys: counts -> starts, right rows grouped by key
                 SDC_TRY(device_exclusive_scan(SlotCountLoad{t.slots}, SlotStartStore{t.slots}, nslots,
