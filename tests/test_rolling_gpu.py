@@ -210,6 +210,34 @@ def test_c2_full_size_mean_sum_std():
         assert err < 1e-9, (op, err)
 
 
+def test_std_is_the_square_root_of_var():
+    """The std kernel takes a run's square roots together with a branch-free form of sqrt()'s own chain
+    (csrc/rolling.cu sqrt_batch).  It must give what sqrt() gives: the var kernel's output through torch.sqrt -- clean
+    tiles (the batched roots) and NaN-bearing tiles (sqrt() itself), variances that are subnormal, huge, exactly zero
+    and negative from cancellation (-> NaN, as the reference's var ** 0.5)."""
+    import torch
+    from sdc_b200.rolling import rolling_device
+    rng = np.random.default_rng(11)
+    n = 3_000_000
+    base = rng.standard_normal(n)
+    cases = [base * s for s in (1.0, 1e-160, 1e150)]
+    cases.append(np.repeat(rng.standard_normal(n // 500), 500))          # constant runs: variance 0 or a rounding residue
+    holes = base.copy()
+    holes[rng.integers(0, n, n // 1000)] = np.nan
+    holes[rng.integers(0, n, 5)] = np.inf
+    cases.append(holes)
+    for x in cases:
+        d = _dev(x)
+        for win, minp in ((2, 2), (7, 3), (100, 100)):
+            var = rolling_device(d, "var", win, minp, 1)
+            std = rolling_device(d, "std", win, minp, 1)
+            want = torch.sqrt(var)
+            assert torch.equal(torch.isnan(std), torch.isnan(want))
+            ok = ~torch.isnan(want)
+            ulp = (std[ok].view(torch.int64) - want[ok].view(torch.int64)).abs()
+            assert int(ulp.max()) <= 1, (win, int(ulp.max()))
+
+
 def test_adversarial_reference_perf_data():
     """The reference perf generator's data (choice over test_global_input_data_float64): exact ops."""
     from sdc_b200.rolling import rolling_device
