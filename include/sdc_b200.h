@@ -214,9 +214,10 @@ int32_t sdcb200_combine_ids(const int64_t* a, const int64_t* b, int64_t nb, int6
  * how = SDCB200_JOIN_INNER | SDCB200_JOIN_ANY_ORDER: the caller takes the pairs as a row SET (what SURVEY 8(d) C3
  * compares, and all an aggregate or a further join downstream needs) -- they may come out in any order, and the order
  * may differ between two calls.  Keys with no dense range then take the partitioned join (both sides bucketed by hash
- * so that the table slice in use stays in L2; pairs come out bucket by bucket).  Measured and dropped for dense keys: a
- * single-pass probe in which a tile takes its output range with one atomic (1.12 ms against the two-pass probe's 1.04 ms
- * on C3 -- the probe is bound by L2 sector requests, not by its scan).                                */
+ * so that the table slice in use stays in L2; probe and emit in one pass, a tile taking its output range with one
+ * atomic -- pairs come out roughly bucket by bucket, in no fixed order inside).  For dense keys the same single-pass
+ * probe measured slower than the two passes that keep left-row order (1.12 against 1.04 ms on C3 -- the probe is bound
+ * by L2 sector requests, not by its scan), so dense keys keep the two passes under this flag as well.          */
 #define SDCB200_JOIN_INNER 0
 #define SDCB200_JOIN_LEFT  1
 #define SDCB200_JOIN_RIGHT 2   /* every right row: a left join with the sides swapped */

@@ -25,7 +25,7 @@ def _torch():
 def join_device(left_keys, right_keys, how="inner", ordered=False, left_ids=None, right_ids=None):
     """-> (left_idx, right_idx): int64 CUDA tensors of the joined row positions (right_idx == -1 where a left row has
     no partner under how='left').  how='inner' returns the pairs as a row SET by default (SDCB200_JOIN_ANY_ORDER: keys
-    with no dense range may take the partitioned join, whose pairs come out bucket by bucket); ordered=True asks for
+    with no dense range may take the partitioned join, whose pairs come out in no fixed order); ordered=True asks for
     left-row order as pandas.merge gives it.  The other joins always come out in the order include/sdc_b200.h states.
     left_ids / right_ids (int64 CUDA tensors, one id per row): the result holds these ids instead of local row numbers
     (sdcb200_join_ids: rows that arrived through a shuffle carry their global row numbers)."""
