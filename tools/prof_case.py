@@ -75,14 +75,14 @@ elif what == "rolling":
     out = torch.empty_like(x)
     for _ in range(reps):
         rolling_device(x, "mean", 100, 100, 1, out=out)
-elif what in ("rolling_std", "rolling_min", "rolling_mean_nan"):
+elif what in ("rolling_std", "rolling_min", "rolling_mean_nan", "rolling_var", "rolling_sum"):
     from sdc_b200.rolling import rolling_device
     x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
     if what == "rolling_mean_nan":
         x[::1000] = float("nan")
     out = torch.empty_like(x)
     for _ in range(reps):
-        rolling_device(x, {"rolling_std": "std", "rolling_min": "min", "rolling_mean_nan": "mean"}[what], 100, 100, 1, out=out)
+        rolling_device(x, {"rolling_std": "std", "rolling_min": "min", "rolling_mean_nan": "mean", "rolling_var": "var", "rolling_sum": "sum"}[what], 100, 100, 1, out=out)
 elif what == "rolling_skew":
     from sdc_b200.rolling import rolling_moments_device
     x = torch.from_numpy(np.random.default_rng(1).random(100_000_000)).cuda()
